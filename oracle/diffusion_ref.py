@@ -1,0 +1,171 @@
+"""Oracle (test infrastructure): schedule, posterior coefficients and the sampling loop.
+
+Restates ``/root/reference/v_diffusion/diffusion.py`` (get_logsnr_schedule 42-112,
+stable_log1mexp 115-123, logsnr_to_posterior 126-163, logsnr_to_posterior_ddim
+169-203, pred_x0_from_* 206-234, p_mean_var 317-356, p_sample_step 360-392,
+p_sample 394-414) and ``functions.py`` get_timestep_embedding (11-29).
+
+Scalars follow the reference's rounding chain exactly: log-SNR in
+fp64 -> rounded to fp32 by ``broadcast_to`` -> re-upcast to fp64 inside the posterior
+-> coefficients rounded to fp32; alpha/sigma evaluated in fp32 on the fp32 log-SNR.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+
+# ----------------------------------------------------------------------------- schedule
+def logsnr_schedule(t, schedule: str = "cosine", logsnr_min: float = -20., logsnr_max: float = 20.):
+    """fp64 log-SNR at time t in [0,1] (diffusion.py:42-112; rescale is off in every config)."""
+    t = np.asarray(t, dtype=np.float64)
+    if schedule == "cosine":
+        t_from = np.arctan(np.exp(-0.5 * logsnr_max)) / (0.5 * np.pi)
+        t_to = np.arctan(np.exp(-0.5 * logsnr_min)) / (0.5 * np.pi)
+        tt = t_from + t * (t_to - t_from)            # torch.lerp(start, end, w) = start + w (end-start)
+        return -2.0 * np.log(np.tan(tt * np.pi * 0.5))
+    if schedule == "linear":
+        sig = lambda z: 1.0 / (1.0 + np.exp(-z))
+        t_from, t_to = sig(logsnr_max), sig(logsnr_min)
+        tt = t_from + t * (t_to - t_from)
+        return np.log(tt) - np.log1p(-tt)
+    if schedule == "sigmoid":
+        rng = logsnr_max - logsnr_min
+        t_from, t_to = 0.0, 1.0
+        tt = t_from + t * (t_to - t_from)
+        return logsnr_max - tt * rng
+    if schedule == "legacy":
+        x_from = x_max = 0.9999
+        x_min, slope = 0.98, -0.0199
+        x_to = x_max + t * (x_min - x_max)
+        log_alpha = 1000 / slope * (x_to * np.log(x_to) - x_to - x_from * np.log(x_from) + x_from)
+        return log_alpha - _log1mexp(log_alpha - 1e-9)
+    raise NotImplementedError(schedule)
+
+
+def _logsigmoid(x):
+    x = np.asarray(x, dtype=np.float64)
+    return -np.logaddexp(0.0, -x)
+
+
+def _log1mexp(x):
+    x = np.asarray(x, dtype=np.float64)
+    assert np.all(x < 0)                             # diffusion.py:119
+    with np.errstate(divide="ignore"):
+        return np.where(x < -9, np.log1p(-np.exp(x)), np.log(-np.expm1(x)))
+
+
+def step_coefficients(T: int, use_ddim: bool, var_type: str = "fixed_large", intp_frac=None,
+                      schedule: str = "cosine", logsnr_min: float = -20., logsnr_max: float = 20.):
+    """Per-step fp32 scalars for step index i = 0..T-1 (the loop visits T-1 .. 0).
+
+    Returns dict of float32 arrays of length T: ``logsnr_s, logsnr_t, alpha_t, sigma_t
+    (fp32 math on the fp32 log-SNR: diffusion.py:233-234), c1, c2, logvar, std``
+    (std = exp(0.5 logvar) in fp32, 0 for DDIM) and fp64 ``t_model`` = (i+1)/T, the time
+    fed to the network (diffusion.py:364, 374)."""
+    i = np.arange(T, dtype=np.float64)
+    s, t = i / T, (i + 1) / T
+    ls32 = logsnr_schedule(s, schedule, logsnr_min, logsnr_max).astype(np.float32)
+    lt32 = logsnr_schedule(t, schedule, logsnr_min, logsnr_max).astype(np.float32)
+    ls, lt = ls32.astype(np.float64), lt32.astype(np.float64)
+    logr = lt - ls
+    if use_ddim:                                     # eta = 0 branch, diffusion.py:178-187
+        c1 = np.exp(0.5 * (_logsigmoid(-ls) - _logsigmoid(-lt)))
+        c2 = np.exp(_log1mexp(0.5 * logr) + 0.5 * _logsigmoid(ls))
+        logvar = np.full(T, -np.inf)
+    else:                                            # diffusion.py:133-161
+        log_alpha_st = 0.5 * (_logsigmoid(ls) - _logsigmoid(lt))
+        l1mr = _log1mexp(logr)
+        c1 = np.exp(logr + log_alpha_st)
+        c2 = np.exp(l1mr + 0.5 * _logsigmoid(ls))
+        if var_type == "fixed_large":
+            logvar = l1mr + _logsigmoid(-lt)
+        elif var_type == "fixed_small":
+            logvar = l1mr + _logsigmoid(-ls)
+        elif var_type == "fixed_medium":
+            lo, hi = l1mr + _logsigmoid(-ls), l1mr + _logsigmoid(-lt)
+            logvar = lo + intp_frac * (hi - lo)
+        else:
+            raise NotImplementedError(var_type)
+    lt_t = torch.from_numpy(lt32)
+    alpha = torch.sigmoid(lt_t).sqrt().numpy()
+    sigma = torch.sigmoid(-lt_t).sqrt().numpy()
+    logvar32 = logvar.astype(np.float32)
+    std = torch.exp(0.5 * torch.from_numpy(logvar32)).numpy()
+    return dict(logsnr_s=ls32, logsnr_t=lt32, alpha_t=alpha, sigma_t=sigma,
+                c1=c1.astype(np.float32), c2=c2.astype(np.float32), logvar=logvar32, std=std,
+                t_model=t)
+
+
+# ----------------------------------------------------------------------------- embedding
+def timestep_embedding(t: torch.Tensor, dim: int, scale: float = 1000.) -> torch.Tensor:
+    """[sin | cos] of scale*t*exp(-k ln(1e4)/(half-1)), evaluated in t's dtype, cast to
+    fp32 (functions.py:11-29)."""
+    t = t.reshape(-1)
+    half = dim // 2
+    f = torch.exp(-torch.arange(half, dtype=t.dtype) * (math.log(10000) / (half - 1)))
+    ang = torch.outer(scale * t, f)
+    e = torch.cat([torch.sin(ang), torch.cos(ang)], dim=1).to(torch.float32)
+    if dim % 2 == 1:
+        e = torch.nn.functional.pad(e, [0, 1])
+    return e
+
+
+# ----------------------------------------------------------------------------- sampler
+def _pred_x0(x_t, out, lt, model_out_type):
+    if model_out_type == "x0":
+        return out
+    if model_out_type == "v":                        # diffusion.py:233-234
+        return x_t * torch.sigmoid(lt).sqrt() - out * torch.sigmoid(-lt).sqrt()
+    if model_out_type == "eps":                      # diffusion.py:207-208
+        return x_t * torch.sigmoid(lt).rsqrt() - out * (-lt * 0.5).exp()
+    if model_out_type == "both":                     # diffusion.py:211-214
+        x0, eps = out.chunk(2, dim=1)
+        x0e = x_t * torch.sigmoid(lt).rsqrt() - eps * (-lt * 0.5).exp()
+        return x0 * torch.sigmoid(-lt) + x0e * torch.sigmoid(lt)
+    raise NotImplementedError(model_out_type)
+
+
+@torch.no_grad()
+def p_sample(denoise_fn: Callable, shape, noise: torch.Tensor, label: Optional[torch.Tensor], *,
+             T: int, model_out_type: str, w_guide: float = 0., use_ddim: bool = True,
+             var_type: str = "fixed_large", intp_frac=None, step_noise: Optional[torch.Tensor] = None,
+             schedule: str = "cosine", logsnr_min: float = -20., logsnr_max: float = 20.,
+             record: Optional[list] = None) -> torch.Tensor:
+    """Reverse loop (diffusion.py:394-414 + 360-392).  ``noise``: initial x_T.
+    ``step_noise``: (T, B, C, H, W) pre-drawn per-step normal draws, indexed by the step
+    index ti (required for ancestral sampling so both sides inject identical noise);
+    DDIM multiplies them by exp(-inf)=0.  ``record`` collects (ti, model_out)."""
+    B = shape[0]
+    co = step_coefficients(T, use_ddim, var_type, intp_frac, schedule, logsnr_min, logsnr_max)
+    x_t = noise.clone().float()
+    use_cfg = (w_guide > 0) and (label is not None)
+    for ti in reversed(range(T)):
+        lt = torch.tensor(co["logsnr_t"][ti])
+        c1, c2 = float(co["c1"][ti]), float(co["c2"][ti])
+        t = torch.full((B,), co["t_model"][ti], dtype=torch.float64)
+        if use_cfg:                                   # rows 2i cond, 2i+1 uncond (diffusion.py:368-372)
+            xin = x_t.repeat_interleave(2, dim=0)
+            tin = t.repeat_interleave(2)
+            yin = label.repeat_interleave(2, dim=0).clone()
+            yin[1::2] = 0
+        else:
+            xin, tin, yin = x_t, t, label
+        out = denoise_fn(xin, tin, yin)
+        if record is not None:
+            record.append((ti, out.clone()))
+        x0 = _pred_x0(xin, out, lt, model_out_type).clamp(-1., 1.)
+        mean = torch.tensor(c1) * xin + torch.tensor(c2) * x0
+        if ti == 0:                                   # where(cond, mean, pred_x_0)  diffusion.py:378
+            mean = x0
+        if use_cfg:
+            mc, mu = mean[0::2], mean[1::2]
+            mean = mc + w_guide * (mc - mu)           # not re-clipped
+        if ti > 0 and not use_ddim:
+            assert step_noise is not None, "ancestral sampling needs injected step noise"
+            mean = mean + torch.tensor(co["std"][ti]) * step_noise[ti]
+        x_t = mean
+    return x_t

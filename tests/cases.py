@@ -1,0 +1,83 @@
+"""Shared definitions of the seeded parity cases.
+
+Used by ``tests/golden/make_golden.py`` (which runs the unmodified reference on them in
+the build container) and by the CPU / GPU tests (which run the oracle and the CUDA path
+on the very same inputs).  Everything is regenerated from integer seeds with CPU
+generators, so only outputs need to be stored under ``tests/golden/``.
+"""
+import torch
+
+
+def _cfg(in_channels=3, hid=64, out_channels=3, mult=(1, 2), nrb=2, attn=(False, True),
+         embedding_dim=None, head_dim=None, num_heads=1, num_classes=0, multitags=False):
+    if head_dim is None and num_heads is None:
+        num_heads = 1
+    return dict(in_channels=in_channels, hid_channels=hid, out_channels=out_channels,
+                ch_multipliers=list(mult), num_res_blocks=nrb, apply_attn=list(attn),
+                embedding_dim=embedding_dim or 4 * hid, head_dim=head_dim, num_heads=num_heads,
+                num_classes=num_classes, multitags=multitags)
+
+
+# cifar10_{cond,uncond}.json + defaults.json -> UNet ctor integers (checked against
+# tests/golden/merged_configs.json by test_config_merge)
+CIFAR_COND = _cfg(hid=256, mult=(1, 1, 1), nrb=3, attn=(False, True, True), num_heads=1, num_classes=10)
+CIFAR_UNCOND = _cfg(hid=256, mult=(1, 1, 1), nrb=3, attn=(False, True, True), num_heads=1, num_classes=0)
+CELEBA = _cfg(hid=192, out_channels=6, mult=(1, 2, 3, 4), nrb=3, attn=(False, True, True, True),
+              embedding_dim=768, head_dim=64, num_heads=1, num_classes=0)
+
+UNET_CASES = {
+    # small: two levels, concat widths 192/256/128 (6-channel groups straddling the concat seam)
+    "small_cond": dict(cfg=_cfg(num_classes=10), seed=11, B=3, res=16, labels=[0, 3, 10],
+                       trace=["in_conv", "downsamples.level_0.0", "downsamples.level_0.2",
+                              "downsamples.level_1.0", "middle", "upsamples.level_1.0",
+                              "upsamples.level_1.3", "upsamples.level_0.2"]),
+    # three levels with an attention-bearing resample block (N = 1024 / 256 / 64 tokens), head_dim 64
+    "small_hd64": dict(cfg=_cfg(out_channels=6, mult=(1, 1, 2), nrb=1, attn=(False, True, True),
+                                embedding_dim=192, head_dim=64, num_heads=1),
+                       seed=12, B=2, res=32, labels=None, trace=[]),
+    # the real CIFAR-10 conditional network (BASELINE configs[1]) at batch 2
+    "cifar_cond": dict(cfg=CIFAR_COND, seed=13, B=2, res=32, labels=[7, 0], trace=["middle"]),
+}
+
+SAMPLE_CASES = {
+    # BASELINE configs[1] in miniature: v-prediction, CFG w=1, DDIM
+    "ddim_cfg_v": dict(unet="small_cond", seed=21, B=4, res=16, T=8, model_out_type="v", w_guide=1.0,
+                       use_ddim=True, var_type="fixed_medium", intp_frac=0.3, labels=[1, 5, 10, 2]),
+    # BASELINE configs[0] in miniature: x0-prediction, unconditional, DDIM
+    "ddim_x0_uncond": dict(unet="small_hd64_x0", seed=22, B=3, res=32, T=6, model_out_type="x0",
+                           w_guide=0.0, use_ddim=True, var_type="fixed_large", labels=None),
+    # BASELINE configs[3] in miniature: ancestral, CFG w=3, injected per-step noise
+    "ancestral_cfg_v": dict(unet="small_cond", seed=23, B=2, res=16, T=10, model_out_type="v", w_guide=3.0,
+                            use_ddim=False, var_type="fixed_medium", intp_frac=0.3, labels=[4, 9]),
+    # CelebA-style "both" output (2C channels), ancestral fixed_large
+    "ancestral_both": dict(unet="small_hd64", seed=24, B=2, res=32, T=5, model_out_type="both", w_guide=0.0,
+                           use_ddim=False, var_type="fixed_large", labels=None),
+}
+UNET_CASES["small_hd64_x0"] = dict(cfg=_cfg(out_channels=3, mult=(1, 1, 2), nrb=1, attn=(False, True, True),
+                                            embedding_dim=192, head_dim=64, num_heads=1),
+                                   seed=14, B=2, res=32, labels=None, trace=[])
+
+
+def build_inputs(case):
+    """x fp32 NCHW, t fp64 in (0,1], y int64 | None — seeded, CPU."""
+    g = torch.Generator().manual_seed(case["seed"] + 1000)
+    cfg = case["cfg"]
+    x = torch.randn(case["B"], cfg["in_channels"], case["res"], case["res"], generator=g)
+    t = torch.rand(case["B"], generator=g, dtype=torch.float64) * 0.98 + 0.01
+    y = torch.tensor(case["labels"], dtype=torch.int64) if case["labels"] is not None else None
+    return x, t, y
+
+
+def build_sample_inputs(case, cfg):
+    """initial noise, labels, and the per-step draws the reference would take from
+    ``torch.Generator('cpu').manual_seed(seed)``: one ``empty(shape).normal_()`` per step in loop
+    order ti = T-1 .. 0 (diffusion.py:389, 410), stored at index ti."""
+    g0 = torch.Generator().manual_seed(case["seed"] + 2000)
+    shape = (case["B"], cfg["in_channels"], case["res"], case["res"])
+    noise = torch.randn(shape, generator=g0)
+    label = torch.tensor(case["labels"], dtype=torch.int64) if case["labels"] is not None else None
+    g = torch.Generator().manual_seed(case["seed"])
+    step_noise = torch.empty((case["T"],) + shape)
+    for ti in reversed(range(case["T"])):
+        step_noise[ti] = torch.empty(shape).normal_(generator=g)
+    return noise, label, step_noise

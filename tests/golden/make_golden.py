@@ -1,0 +1,133 @@
+"""Generate the golden fixtures in this directory FROM THE UNMODIFIED REFERENCE.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports tqch/v-diffusion-torch from /root/reference (matplotlib stubbed),
+loads the oracle's deterministic synthetic state_dict into the reference's own ``UNet`` (strict
+load: proves the key/shape layout), runs ``UNet.forward`` and ``GaussianDiffusion.p_sample`` on
+seeded inputs and stores inputs + outputs as .npz.  The fixtures pin ``oracle/`` (CPU tests) and
+the CUDA path (gpu tests); the GPU box never sees /root/reference.
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+_m = types.ModuleType("matplotlib"); _m.rcParams = {}
+sys.modules.setdefault("matplotlib", _m)
+sys.modules.setdefault("matplotlib.pyplot", types.ModuleType("matplotlib.pyplot"))
+sys.path.insert(0, REF)
+from v_diffusion import UNet, GaussianDiffusion, get_logsnr_schedule, fill_with_defaults  # noqa: E402
+from v_diffusion.diffusion import logsnr_to_posterior, logsnr_to_posterior_ddim  # noqa: E402
+from v_diffusion.functions import get_timestep_embedding  # noqa: E402
+
+from oracle.unet_ref import make_state_dict, state_dict_shapes  # noqa: E402
+from tests.cases import UNET_CASES, SAMPLE_CASES, build_inputs, build_sample_inputs  # noqa: E402
+
+torch.set_num_threads(os.cpu_count())
+
+
+def ref_unet(cfg, seed):
+    net = UNet(cfg["in_channels"], cfg["hid_channels"], cfg["out_channels"], cfg["ch_multipliers"],
+               cfg["num_res_blocks"], cfg["apply_attn"], embedding_dim=cfg["embedding_dim"],
+               head_dim=cfg["head_dim"], num_heads=cfg["num_heads"], num_classes=cfg["num_classes"],
+               multitags=cfg["multitags"])
+    ref_shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert ref_shapes == state_dict_shapes(cfg), "state_dict layout mismatch vs reference"
+    net.load_state_dict(make_state_dict(cfg, seed), strict=True)
+    return net.eval()
+
+
+def main():
+    # ---- UNet forward goldens
+    for name, case in UNET_CASES.items():
+        cfg = case["cfg"]
+        net = ref_unet(cfg, case["seed"])
+        x, t, y = build_inputs(case)
+        feats = {}
+        hooks = []
+        for mod_name in case.get("trace", []):
+            mod = net.get_submodule(mod_name)
+            hooks.append(mod.register_forward_hook(
+                lambda m, i, o, n=mod_name: feats.__setitem__(n, o.detach().clone())))
+        with torch.no_grad():
+            out = net(x, t, y)
+        for h in hooks:
+            h.remove()
+        arrs = {"out": out.numpy()}
+        for k, v in feats.items():
+            arrs["trace:" + k] = v.numpy()
+        np.savez_compressed(os.path.join(HERE, f"unet_{name}.npz"), **arrs)
+        print(name, tuple(out.shape), float(out.abs().mean()), float(out.abs().max()))
+
+    # ---- sampler goldens
+    for name, case in SAMPLE_CASES.items():
+        cfg = UNET_CASES[case["unet"]]["cfg"]
+        net = ref_unet(cfg, UNET_CASES[case["unet"]]["seed"])
+        noise, label, step_noise = build_sample_inputs(case, cfg)
+        logsnr_fn = get_logsnr_schedule("cosine", -20., 20., rescale=False)
+        diff = GaussianDiffusion(
+            logsnr_fn=logsnr_fn, sample_timesteps=case["T"], model_out_type=case["model_out_type"],
+            model_var_type=case["var_type"], reweight_type="snr_trunc", loss_type="mse",
+            intp_frac=case.get("intp_frac"), w_guide=case["w_guide"])
+        outs = []
+
+        def rec(x, t, y):
+            o = net(x, t, y)
+            outs.append(o.clone())
+            return o
+        # the reference draws one normal_ per step from Generator(seed) (diffusion.py:389);
+        # build_sample_inputs replays exactly that sequence into step_noise.
+        x = diff.p_sample(rec, shape=tuple(noise.shape), noise=noise, label=label, device="cpu",
+                          seed=case["seed"], use_ddim=case["use_ddim"])
+        np.savez_compressed(os.path.join(HERE, f"sample_{name}.npz"), out=x.numpy(),
+                            model_out=torch.stack(outs).numpy())
+        print(name, tuple(x.shape), float(x.abs().mean()), float(x.abs().max()))
+
+    # ---- coefficient known answers (T = 100, cosine +-20) straight from the reference functions
+    T = 100
+    logsnr_fn = get_logsnr_schedule("cosine", -20., 20., rescale=False)
+    step = torch.arange(T, dtype=torch.float64)
+    ls = logsnr_fn(step / T).to(torch.float32).reshape(-1, 1, 1, 1)
+    lt = logsnr_fn((step + 1) / T).to(torch.float32).reshape(-1, 1, 1, 1)
+    co = {"logsnr_s": ls.flatten().numpy(), "logsnr_t": lt.flatten().numpy()}
+    c1, c2, _ = logsnr_to_posterior_ddim(ls, lt, eta=0.)
+    co["ddim_c1"], co["ddim_c2"] = c1.flatten().numpy(), c2.flatten().numpy()
+    for vt in ("fixed_small", "fixed_large", "fixed_medium"):
+        c1, c2, lv = logsnr_to_posterior(ls, lt, vt, intp_frac=0.3)
+        co[f"{vt}_c1"], co[f"{vt}_c2"], co[f"{vt}_logvar"] = (
+            c1.flatten().numpy(), c2.flatten().numpy(), lv.flatten().numpy())
+    co["alpha_t"] = torch.sigmoid(lt).sqrt().flatten().numpy()
+    co["sigma_t"] = torch.sigmoid(-lt).sqrt().flatten().numpy()
+    tt = torch.tensor([0.37, 0.01, 1.0, 0.5], dtype=torch.float64)
+    co["temb_t"] = tt.numpy()
+    co["temb_256"] = get_timestep_embedding(tt, 256).numpy()
+    co["temb_64"] = get_timestep_embedding(tt, 64).numpy()
+    np.savez_compressed(os.path.join(HERE, "coefs_T100.npz"), **co)
+
+    # ---- config merge known answer (utils.py:193-201 on the shipped JSONs)
+    merged = {}
+    for n in ("cifar10_cond", "cifar10_uncond", "celeba"):
+        with open(f"{REF}/configs/{n}.json") as f:
+            c = json.load(f)
+        with open(f"{REF}/configs/defaults.json") as f:
+            d = json.load(f)
+        fill_with_defaults(c, d)
+        merged[n] = {"model": c["model"], "diffusion": c["diffusion"], "conditional": c["conditional"]}
+    with open(os.path.join(HERE, "merged_configs.json"), "w") as f:
+        json.dump(merged, f, indent=1, sort_keys=True)
+    print("done")
+
+
+if __name__ == "__main__":
+    main()

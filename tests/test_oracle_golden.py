@@ -1,0 +1,102 @@
+"""CPU: the oracle restatement against fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  This is what pins the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_forward, make_state_dict, step_coefficients, p_sample, timestep_embedding
+from oracle.unet_ref import unet_config_from_json
+from tests.cases import UNET_CASES, SAMPLE_CASES, CIFAR_COND, CIFAR_UNCOND, CELEBA, build_inputs, build_sample_inputs
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.mark.parametrize("name", sorted(UNET_CASES))
+def test_unet_forward_matches_reference(golden_dir, name):
+    case = UNET_CASES[name]
+    g = _load(golden_dir, f"unet_{name}.npz")
+    sd = make_state_dict(case["cfg"], case["seed"])
+    x, t, y = build_inputs(case)
+    trace = {}
+    out = unet_forward(sd, case["cfg"], x, t, y, trace=trace)
+    ref = torch.from_numpy(g["out"])
+    assert out.shape == ref.shape
+    # same fp32 library kernels, different op grouping -> tiny reassociation differences only
+    assert (out - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+    for key in g.files:
+        if key.startswith("trace:"):
+            mod = key[len("trace:"):]
+            got = trace[mod] if mod in trace else trace[mod + ".1"] if mod + ".1" in trace else None
+            if mod == "middle":
+                got = trace["middle.2"]
+            elif got is None:
+                got = trace[mod + ".0"]
+            r = torch.from_numpy(g[key])
+            assert (got - r).abs().max().item() <= 2e-4 * max(1.0, r.abs().max().item()), mod
+
+
+@pytest.mark.parametrize("name", sorted(SAMPLE_CASES))
+def test_sampler_matches_reference(golden_dir, name):
+    case = SAMPLE_CASES[name]
+    ucase = UNET_CASES[case["unet"]]
+    cfg = ucase["cfg"]
+    g = _load(golden_dir, f"sample_{name}.npz")
+    sd = make_state_dict(cfg, ucase["seed"])
+    noise, label, step_noise = build_sample_inputs(case, cfg)
+    rec = []
+    out = p_sample(lambda x, t, y: unet_forward(sd, cfg, x, t, y), tuple(noise.shape), noise, label,
+                   T=case["T"], model_out_type=case["model_out_type"], w_guide=case["w_guide"],
+                   use_ddim=case["use_ddim"], var_type=case["var_type"], intp_frac=case.get("intp_frac"),
+                   step_noise=step_noise, record=rec)
+    ref = torch.from_numpy(g["out"])
+    assert (out - ref).abs().max().item() <= 5e-4
+    mo = torch.from_numpy(g["model_out"])
+    assert len(rec) == mo.shape[0] == case["T"]
+    for i, (ti, o) in enumerate(rec):
+        assert ti == case["T"] - 1 - i
+        rel = (o - mo[i]).norm() / mo[i].norm()
+        assert rel.item() <= 1e-4
+
+
+def test_step_coefficients_known_answers(golden_dir):
+    g = _load(golden_dir, "coefs_T100.npz")
+    dd = step_coefficients(100, use_ddim=True)
+    np.testing.assert_array_equal(dd["logsnr_s"], g["logsnr_s"])
+    np.testing.assert_array_equal(dd["logsnr_t"], g["logsnr_t"])
+    np.testing.assert_allclose(dd["c1"], g["ddim_c1"], rtol=2e-7, atol=0)
+    np.testing.assert_allclose(dd["c2"], g["ddim_c2"], rtol=2e-7, atol=1e-12)
+    np.testing.assert_array_equal(dd["alpha_t"], g["alpha_t"])
+    np.testing.assert_array_equal(dd["sigma_t"], g["sigma_t"])
+    assert np.all(dd["std"] == 0)
+    for vt in ("fixed_small", "fixed_large", "fixed_medium"):
+        an = step_coefficients(100, use_ddim=False, var_type=vt, intp_frac=0.3)
+        np.testing.assert_allclose(an["c1"], g[f"{vt}_c1"], rtol=2e-7, atol=1e-12)
+        np.testing.assert_allclose(an["c2"], g[f"{vt}_c2"], rtol=2e-7, atol=1e-12)
+        np.testing.assert_allclose(an["logvar"], g[f"{vt}_logvar"], rtol=2e-7, atol=1e-9)
+    # SURVEY §10.2 table (values printed by the reference)
+    assert abs(dd["c1"][50] - 0.984656036) < 1e-7 and abs(dd["c2"][50] - 0.021871394) < 1e-7
+    assert abs(dd["alpha_t"][1] - 0.999505162) < 1e-7 and abs(dd["sigma_t"][1] - 0.031454321) < 1e-7
+    an = step_coefficients(100, use_ddim=False, var_type="fixed_medium", intp_frac=0.3)
+    assert abs(an["c1"][50] - 0.954199851) < 1e-7 and abs(an["logvar"][1] - (-8.175132)) < 1e-5
+
+
+def test_timestep_embedding_known_answers(golden_dir):
+    g = _load(golden_dir, "coefs_T100.npz")
+    t = torch.from_numpy(g["temb_t"])
+    np.testing.assert_allclose(timestep_embedding(t, 256).numpy(), g["temb_256"], rtol=0, atol=1e-7)
+    np.testing.assert_allclose(timestep_embedding(t, 64).numpy(), g["temb_64"], rtol=0, atol=1e-7)
+    e = timestep_embedding(torch.tensor([0.37], dtype=torch.float64), 256)[0]
+    assert abs(e[0].item() - (-0.650264919)) < 1e-6 and abs(e[128].item() - 0.759707510) < 1e-6
+
+
+def test_config_merge_gives_case_configs(golden_dir):
+    with open(os.path.join(golden_dir, "merged_configs.json")) as f:
+        merged = json.load(f)
+    assert unet_config_from_json(merged["cifar10_cond"]["model"], 3, 3, num_classes=10) == CIFAR_COND
+    assert unet_config_from_json(merged["cifar10_uncond"]["model"], 3, 3) == CIFAR_UNCOND
+    assert unet_config_from_json(merged["celeba"]["model"], 3, 6) == CELEBA
