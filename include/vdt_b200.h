@@ -1,0 +1,123 @@
+/* vdt_b200.h — C ABI of the B200-native sampling hot path for tqch/v-diffusion-torch.
+ *
+ * The reference has no FFI: its boundary for this path is a Python object protocol
+ * (SURVEY.md §8b).  Each entry point below names the reference interface it stands in for;
+ * the Python shim in v-diffusion-torch_b200/ (UNet, GaussianDiffusion) binds them with ctypes
+ * and INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (vdt_last_error() gives the
+ * message, thread-local).  Unless the name ends in _host, data pointers are DEVICE pointers on the
+ * current CUDA device and the call is stream-ordered on `stream` (a cudaStream_t, may be NULL).
+ * A plan owns its workspace; calls on one plan must not overlap in time.
+ */
+#ifndef VDT_B200_H
+#define VDT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDT_MAX_LEVELS 8
+
+/* UNet constructor integers — v_diffusion/models/unet.py:155-171 (UNet.__init__), as they arrive from
+ * config["model"] after the defaults merge (generate.py:86-91).  head_dim / num_heads: 0 = None. */
+typedef struct vdt_unet_config {
+    int32_t in_channels;
+    int32_t hid_channels;
+    int32_t out_channels;
+    int32_t num_levels;
+    int32_t ch_multipliers[VDT_MAX_LEVELS];
+    int32_t num_res_blocks;
+    int32_t apply_attn[VDT_MAX_LEVELS];
+    int32_t embedding_dim;        /* 0 = 4 * hid_channels */
+    int32_t head_dim;
+    int32_t num_heads;
+    int32_t num_classes;
+    int32_t multitags;            /* not supported yet: must be 0 */
+    int32_t resolution;           /* H = W of the images this plan serves (DATA_INFO[...]["resolution"]) */
+    int32_t max_rows;             /* UNet batch rows processed per pass; larger batches are chunked */
+} vdt_unet_config;
+
+/* GaussianDiffusion constructor + get_logsnr_schedule arguments — diffusion.py:260-291, 42-112. */
+enum { VDT_OUT_X0 = 0, VDT_OUT_EPS = 1, VDT_OUT_BOTH = 2, VDT_OUT_V = 3 };
+enum { VDT_VAR_FIXED_SMALL = 0, VDT_VAR_FIXED_LARGE = 1, VDT_VAR_FIXED_MEDIUM = 2 };
+enum { VDT_SCHED_COSINE = 0, VDT_SCHED_LINEAR = 1, VDT_SCHED_SIGMOID = 2, VDT_SCHED_LEGACY = 3 };
+typedef struct vdt_sampler_config {
+    int32_t sample_timesteps;     /* T */
+    int32_t model_out_type;       /* VDT_OUT_* */
+    int32_t model_var_type;       /* VDT_VAR_* */
+    int32_t logsnr_schedule;      /* VDT_SCHED_* */
+    int32_t use_ddim;             /* p_sample(..., use_ddim=) */
+    int32_t reserved;
+    double intp_frac;
+    double logsnr_min, logsnr_max;
+    double w_guide;
+    uint64_t seed;                /* on-device noise stream for ancestral sampling without injected noise */
+} vdt_sampler_config;
+
+typedef struct vdt_plan vdt_plan;
+
+const char* vdt_last_error(void);
+int vdt_version(void);
+
+/* UNet(...) — unet.py:155-283.  Builds the block list, the weight table and (lazily) the workspace. */
+int vdt_plan_create(const vdt_unet_config* cfg, vdt_plan** out);
+void vdt_plan_destroy(vdt_plan* plan);
+
+/* state_dict layout — SURVEY §8b.  Enumerate the expected keys / shapes (OIHW fp32 like the reference). */
+int vdt_plan_num_weights(const vdt_plan* plan);
+const char* vdt_plan_weight_name(const vdt_plan* plan, int index);
+int vdt_plan_weight_shape(const vdt_plan* plan, int index, int64_t* shape4, int* ndim);
+
+/* load_state_dict — generate.py:92-98.  `data` is contiguous fp32 with the reference's shape;
+ * on_device != 0: device pointer, else host pointer.  Re-loading a key re-packs it. */
+int vdt_plan_load_weight(vdt_plan* plan, const char* key, const float* data, int64_t numel, int on_device);
+/* After all keys are loaded: pack bf16 GEMM operands.  Fails listing the first missing key. */
+int vdt_plan_finalize(vdt_plan* plan);
+
+/* UNet.forward(x, t, y) — unet.py:286-322.  x fp32 NCHW [B, in, R, R]; t fp64 [B]; y int64 [B] or NULL;
+ * out fp32 NCHW [B, out, R, R]. */
+int vdt_unet_forward(vdt_plan* plan, const float* x, const double* t, const int64_t* y, float* out, int32_t batch,
+                     void* stream);
+
+/* GaussianDiffusion.p_sample(denoise_fn=UNet, shape, noise, label, use_ddim) — diffusion.py:394-414,
+ * with p_sample_step (360-392) and p_mean_var (317-356) fused into one kernel per step and the step
+ * captured as a CUDA graph.  noise fp32 [B, C, R, R] (x_T); label int64 [B] or NULL; step_noise NULL or
+ * fp32 [T, B, C, R, R] (the per-step normal draws of diffusion.py:389, indexed by step); out fp32 [B, C, R, R]. */
+int vdt_p_sample(vdt_plan* plan, const vdt_sampler_config* sc, const float* noise, const int64_t* label,
+                 const float* step_noise, float* out, int32_t batch, void* stream);
+/* Same with HOST buffers (pinned or pageable); copies in/out inside the call and synchronises. */
+int vdt_p_sample_host(vdt_plan* plan, const vdt_sampler_config* sc, const float* noise, const int64_t* label,
+                      const float* step_noise, float* out, int32_t batch);
+
+/* logsnr schedule + posterior coefficients — diffusion.py:42-112, 126-203 (host, fp64 with the reference's
+ * fp32 rounding points).  out: [T][12] floats: alpha_t, sigma_t, rsqrt(sigmoid l_t), exp(-l_t/2), sigmoid(l_t),
+ * sigmoid(-l_t), c1, c2, std, logvar, logsnr_s, logsnr_t. */
+int vdt_step_coefficients(const vdt_sampler_config* sc, float* out);
+
+/* Counters: kernels launched by this library since process start (graph replays count their nodes). */
+uint64_t vdt_kernel_launches(void);
+
+/* ---- kernel-level entry points (used by the parity tests; device pointers) ------------------------- */
+/* conv2d(k x k, pad k/2) on bf16 NHWC input with fp32 OIHW weights -> fp32 NHWC (+bias, +residual). */
+int vdt_op_conv(const void* x_bf16_nhwc, int32_t batch, int32_t h, int32_t w, int32_t cin, const float* w_oihw,
+                int32_t cout, int32_t ksize, const float* bias, const float* residual, float* out_nhwc, void* stream);
+/* GroupNorm(32, 1e-6) [+FiLM] [+SiLU] [+resample 0 none / 1 avgpool2 / 2 nearest x2] over concat(src1, src2). */
+int vdt_op_groupnorm(const float* src1, int32_t c1, const float* src2, int32_t c2, int32_t batch, int32_t h, int32_t w,
+                     const float* gamma, const float* beta, const float* film, int32_t film_stride, int32_t film_off,
+                     int32_t silu, int32_t resample, void* out_act_bf16, void* out_raw_bf16, float* out_res,
+                     void* stream);
+/* attention on qk bf16 [B*N, 2*hid], v^T bf16 [B*hid, N] -> bf16 [B*N, hid] */
+int vdt_op_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf16, int32_t batch, int32_t n, int32_t heads,
+                     int32_t d, void* stream);
+/* one sampler update with explicit step index; coef = one row of vdt_step_coefficients (host pointer). */
+int vdt_op_sampler_step(const float* model_out, const float* x_t, const float* noise, float* x_s, int32_t batch,
+                        int32_t c, int32_t hw, int32_t cfg, int32_t model_out_type, int32_t step, const float* coef_host,
+                        float w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDT_B200_H */

@@ -1,0 +1,80 @@
+"""CPU: the C-ABI library loads, exports every symbol include/vdt_b200.h declares, and its host-side
+schedule code agrees with the reference-generated known answers (no GPU work)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import torch
+
+from v_diffusion_b200 import _lib, GaussianDiffusion, get_logsnr_schedule, fill_with_defaults, UNet
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    hdr = open(_lib.INCLUDE).read()
+    declared = set(re.findall(r"\b(vdt_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.vdt_version() == 1
+
+
+def test_struct_layout_matches_header():
+    assert C.sizeof(_lib.UNetConfig) == 4 * (4 + 8 + 1 + 8 + 7)
+    assert C.sizeof(_lib.SamplerConfig) == 6 * 4 + 4 * 8 + 8
+
+
+def test_step_coefficients_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "coefs_T100.npz"))
+    d = GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), 100, "v", "fixed_medium", "snr_trunc", "mse",
+                          intp_frac=0.3, w_guide=1.0)
+    dd = d.step_coefficients(use_ddim=True).numpy()
+    np.testing.assert_allclose(dd[:, 10], g["logsnr_s"], rtol=1e-6)
+    np.testing.assert_allclose(dd[:, 11], g["logsnr_t"], rtol=1e-6)
+    np.testing.assert_allclose(dd[:, 0], g["alpha_t"], rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(dd[:, 1], g["sigma_t"], rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(dd[:, 6], g["ddim_c1"], rtol=2e-6)
+    np.testing.assert_allclose(dd[:, 7], g["ddim_c2"], rtol=2e-6, atol=1e-10)
+    assert np.all(dd[:, 8] == 0)
+    for vt in ("fixed_small", "fixed_large", "fixed_medium"):
+        d.model_var_type = vt
+        an = d.step_coefficients(use_ddim=False).numpy()
+        np.testing.assert_allclose(an[:, 6], g[f"{vt}_c1"], rtol=2e-6, atol=1e-10)
+        np.testing.assert_allclose(an[:, 7], g[f"{vt}_c2"], rtol=2e-6, atol=1e-10)
+        np.testing.assert_allclose(an[:, 9], g[f"{vt}_logvar"], rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(an[:, 8], np.exp(0.5 * g[f"{vt}_logvar"]), rtol=1e-5)
+
+
+def test_error_behaviour_mirrors_reference():
+    import pytest
+    with pytest.raises(NotImplementedError):
+        get_logsnr_schedule("quadratic")                         # diffusion.py:96
+    with pytest.raises(NotImplementedError):
+        GaussianDiffusion(get_logsnr_schedule("cosine"), 10, "w", "fixed_large", "snr", "mse")   # diffusion.py:253
+    d = GaussianDiffusion(get_logsnr_schedule("cosine"), 10, "v", "learned", "snr", "mse")
+    with pytest.raises(NotImplementedError):
+        d.sampler_config(use_ddim=False)                         # diffusion.py:161
+    net = UNet(3, 64, 3, (1, 2), 1, (False, True)).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 3, 16, 16), torch.zeros(1, dtype=torch.float64))    # no CPU fallback
+    with pytest.raises(RuntimeError, match="CUDA"):
+        d.p_sample(net, (1, 3, 16, 16), device="cpu", use_ddim=True)
+
+
+def test_reference_init_semantics():
+    torch.manual_seed(0)
+    net = UNet(3, 64, 3, (1, 2), 2, (False, True), num_classes=10)
+    sd = net.state_dict()
+    zero = [k for k, v in sd.items() if v.ndim >= 2 and not bool(v.any())]
+    # conv2 of every res block, proj_out of every attention block, the last conv
+    assert all(k.endswith(("conv2.weight", "proj_out.weight", "out_conv.2.weight")) for k in zero) and len(zero) > 0
+    assert sd["class_embed.1.weight"].shape == (256, 10)
+    w = sd["in_conv.weight"]
+    assert abs(w.std().item() * (27 ** 0.5) - 0.88) < 0.1       # truncated normal at 2 sigma: std ~0.88/sqrt(fan_in)
+
+
+def test_fill_with_defaults_semantics():
+    cfg = {"a": None, "b": {"c": 1, "d": None}}
+    fill_with_defaults(cfg, {"a": 2, "b": {"c": 3, "d": 4, "e": 5}, "f": 6})
+    assert cfg == {"a": 2, "b": {"c": 1, "d": 4, "e": 5}, "f": 6}     # utils.py:204-224 demo

@@ -1,0 +1,175 @@
+"""GPU parity of each hand-written kernel, called through the C ABI (vdt_op_*), against a plain PyTorch
+fp32 reference of the same op on the same (bf16-rounded) operands."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from v_diffusion_b200 import _lib
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return _lib.lib()
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _check(L, rc):
+    assert rc == 0, L.vdt_last_error().decode()
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+CONV_CASES = [
+    # B, H, cin, cout, k, residual
+    (2, 32, 256, 256, 3, True),
+    (3, 16, 256, 256, 3, False),
+    (3, 8, 256, 256, 3, True),       # two images per tile, odd batch -> zero-filled tail
+    (1, 8, 128, 64, 3, False),       # single image: half-empty tile
+    (2, 32, 512, 256, 3, False),
+    (2, 16, 192, 64, 3, True),
+    (2, 32, 64, 128, 3, False),
+    (2, 32, 512, 256, 1, False),
+    (3, 8, 256, 768, 1, False),      # three N tiles
+    (2, 16, 128, 384, 1, False),     # N tile of 192
+    (2, 64, 192, 192, 3, True),      # CelebA-style 64x64, 2 image rows per tile
+]
+
+
+@pytest.mark.parametrize("B,H,cin,cout,k,res", CONV_CASES)
+def test_conv_gemm(L, B, H, cin, cout, k, res):
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H + cin + cout + k)
+    x = torch.randn(B, cin, H, H, device="cuda", generator=g)
+    w = torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    resid = torch.randn(B, H, H, cout, device="cuda", generator=g) if res else None
+    xb = x.to(torch.bfloat16)
+    x_nhwc = xb.permute(0, 2, 3, 1).contiguous()
+    out = torch.full((B, H, H, cout), float("nan"), device="cuda")
+    _check(L, L.vdt_op_conv(_p(x_nhwc), B, H, H, cin, _p(w), cout, k, _p(bias), _p(resid), _p(out), None))
+    torch.cuda.synchronize()
+    ref = F.conv2d(xb.double(), w.to(torch.bfloat16).double(), bias.double(), padding=k // 2).permute(0, 2, 3, 1)
+    if res:
+        ref = ref + resid.double()
+    assert torch.isfinite(out).all()
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 2e-3, f"max abs err {err}"       # fp32 accumulation over K <= 4608 products of O(1/sqrt(K)) terms
+
+
+GN_CASES = [
+    # B, H, c1, c2, film, silu, resample, want_raw, want_res
+    (3, 32, 256, 0, False, True, 0, False, False),
+    (2, 16, 256, 256, False, True, 0, True, False),
+    (2, 16, 128, 64, True, True, 0, True, False),     # 6 channels per group straddling the concat seam
+    (3, 8, 256, 0, True, True, 0, False, False),
+    (2, 32, 256, 0, False, True, 1, False, True),     # avg-pool
+    (2, 8, 64, 0, False, True, 2, False, True),       # nearest upsample
+    (2, 16, 128, 0, False, False, 0, False, False),   # attention norm: no activation
+    (2, 16, 576, 0, False, True, 0, False, False),    # 18 channels per group
+]
+
+
+@pytest.mark.parametrize("B,H,c1,c2,film,silu,resample,want_raw,want_res", GN_CASES)
+def test_groupnorm(L, B, H, c1, c2, film, silu, resample, want_raw, want_res):
+    g = torch.Generator(device="cuda").manual_seed(H * 7 + c1 + c2)
+    C_ = c1 + c2
+    s1 = torch.randn(B, H, H, c1, device="cuda", generator=g) * 2 + 0.5
+    s2 = torch.randn(B, H, H, c2, device="cuda", generator=g) if c2 else None
+    gamma = 1 + 0.2 * torch.randn(C_, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(C_, device="cuda", generator=g)
+    stride, off = 3 * 2 * C_, 2 * C_
+    ftab = torch.randn(B, stride, device="cuda", generator=g) * 0.3 if film else None
+    Ho = H // 2 if resample == 1 else H * 2 if resample == 2 else H
+    out_act = torch.zeros(B, Ho, Ho, C_, device="cuda", dtype=torch.bfloat16)
+    out_raw = torch.zeros(B, H, H, C_, device="cuda", dtype=torch.bfloat16) if want_raw else None
+    out_res = torch.zeros(B, Ho, Ho, C_, device="cuda") if want_res else None
+    _check(L, L.vdt_op_groupnorm(_p(s1), c1, _p(s2), c2, B, H, H, _p(gamma), _p(beta), _p(ftab), stride, off,
+                                 int(silu), resample, _p(out_act), _p(out_raw), _p(out_res), None))
+    torch.cuda.synchronize()
+    x = torch.cat([s1, s2], dim=3) if c2 else s1
+    xn = x.permute(0, 3, 1, 2).double()
+    y = F.group_norm(xn, 32, gamma.double(), beta.double(), 1e-6)
+    if film:
+        shift = ftab[:, off:off + C_].double()[:, :, None, None]
+        scale = ftab[:, off + C_:off + 2 * C_].double()[:, :, None, None]
+        y = (1 + scale) * y + shift
+    if silu:
+        y = F.silu(y)
+    rs = (lambda z: F.avg_pool2d(z, 2)) if resample == 1 else (lambda z: F.interpolate(z, scale_factor=2, mode="nearest")) if resample == 2 else (lambda z: z)
+    y = rs(y).permute(0, 2, 3, 1)
+    err = (out_act.double() - y).abs().max().item()
+    assert err <= 4e-2 * max(1.0, y.abs().max().item() / 4), f"act err {err}"      # bf16 output rounding
+    assert _rel(out_act, y) <= 4e-3
+    if want_raw:
+        assert torch.equal(out_raw, x.to(torch.bfloat16))
+    if want_res:
+        r = rs(xn).permute(0, 2, 3, 1)
+        assert (out_res.double() - r).abs().max().item() <= 1e-5
+
+
+ATTN_CASES = [(2, 1024, 1, 256), (3, 256, 1, 256), (3, 64, 1, 256), (2, 256, 1, 64), (2, 64, 2, 64), (1, 4096, 1, 64),
+              (2, 128, 1, 128)]
+
+
+@pytest.mark.parametrize("B,N,heads,d", ATTN_CASES)
+def test_attention(L, B, N, heads, d):
+    g = torch.Generator(device="cuda").manual_seed(N + heads * 3 + d)
+    hid = heads * d
+    q = torch.randn(B, N, heads, d, device="cuda", generator=g).to(torch.bfloat16)
+    k = torch.randn(B, N, heads, d, device="cuda", generator=g).to(torch.bfloat16)
+    v = torch.randn(B, N, heads, d, device="cuda", generator=g).to(torch.bfloat16)
+    # make the softmax peaky in places so the lazy rescale path (row max jumps by > 2^8) is exercised
+    q[:, : N // 2] *= 3.0
+    k[:, N // 2:] *= 2.0
+    qk = torch.cat([q.reshape(B * N, hid), k.reshape(B * N, hid)], dim=1).contiguous()
+    vt = v.permute(0, 2, 3, 1).reshape(B * hid, N).contiguous()
+    out = torch.zeros(B * N, hid, device="cuda", dtype=torch.bfloat16)
+    _check(L, L.vdt_op_attention(_p(qk), _p(vt), _p(out), B, N, heads, d, None))
+    torch.cuda.synchronize()
+    qd, kd, vd = (z.double().permute(0, 2, 1, 3) for z in (q, k, v))           # B, h, N, d
+    w = torch.softmax(qd @ kd.transpose(-1, -2) / math.sqrt(d), dim=-1)
+    ref = (w @ vd).permute(0, 2, 1, 3).reshape(B * N, hid)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) <= 1e-2, _rel(out, ref)           # P and the output are rounded to bf16
+    assert (out.double() - ref).abs().max().item() <= 6e-2
+
+
+@pytest.mark.parametrize("mot,cfg,last", [(3, 1, False), (3, 1, True), (0, 0, False), (1, 0, False), (2, 0, False),
+                                          (2, 1, True), (3, 0, False)])
+def test_sampler_step(L, mot, cfg, last):
+    from oracle.diffusion_ref import _pred_x0
+    from v_diffusion_b200 import GaussianDiffusion, get_logsnr_schedule
+    T, B, Cc, H = 20, 3, 3, 8
+    names = {0: "x0", 1: "eps", 2: "both", 3: "v"}
+    diff = GaussianDiffusion(get_logsnr_schedule("cosine"), T, names[mot], "fixed_medium", "snr_trunc", "mse",
+                             intp_frac=0.3, w_guide=1.5)
+    coefs = diff.step_coefficients(use_ddim=False)
+    step = 0 if last else 7
+    g = torch.Generator(device="cuda").manual_seed(mot * 10 + cfg)
+    rep, Cm = 1 + cfg, (2 * Cc if mot == 2 else Cc)
+    mo = torch.randn(B * rep, Cm, H, H, device="cuda", generator=g)
+    x = torch.randn(B, Cc, H, H, device="cuda", generator=g)
+    z = torch.randn(B, Cc, H, H, device="cuda", generator=g)
+    out = torch.zeros_like(x)
+    _check(L, L.vdt_op_sampler_step(_p(mo), _p(x), _p(z), _p(out), B, Cc, H * H, cfg, mot, step,
+                                    _p(coefs[step].contiguous()), 1.5, None))
+    torch.cuda.synchronize()
+    row = coefs[step]
+    lt = row[11].cuda()
+    xin = x.repeat_interleave(rep, dim=0)
+    x0 = _pred_x0(xin, mo, lt, names[mot]).clamp(-1, 1)
+    mean = x0 if last else row[6].cuda() * xin + row[7].cuda() * x0
+    if cfg:
+        mean = mean[0::2] + 1.5 * (mean[0::2] - mean[1::2])
+    if not last:
+        mean = mean + row[8].cuda() * z
+    assert (out - mean).abs().max().item() <= 2e-5

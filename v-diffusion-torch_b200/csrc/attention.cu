@@ -1,0 +1,255 @@
+// Fused self-attention for sm_100a: softmax(q^T k / sqrt(d)) v per image and head, flash-style.
+//
+// Replaces BaseAttentionBlock.scaled_dot_product (unet.py:55-64: two einsums + a softmax that
+// materialise the N x N score matrix in HBM).  Here one CTA owns 128 query rows; S = Q K^T and
+// O += P V run on tcgen05 with S and O resident in TMEM, the softmax runs in registers (one thread
+// per query row, fp32, exp2 with the 1/sqrt(d) scale folded in), P is re-quantised to bf16 into
+// swizzled shared memory as the A operand of the second MMA.  O is rescaled lazily (only when a
+// row maximum grows by more than 2^8), so the TMEM round trip is rare.
+//
+// Operands (written by the proj_in GEMM epilogue): QK bf16 [B*N, 2*hid] (q | k, heads contiguous,
+// unet.py:76-78) and V^T bf16 [B*hid, N], so every MMA operand is K-major.
+//
+//   warp 0     TMA producer (Q once, then 64-key K / V^T tiles through a 2-stage ring)
+//   warp 1     MMA issuer
+//   warps 2-5  softmax + final normalise/store (thread = query row = TMEM lane)
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace vdt {
+namespace {
+
+constexpr int kQRows = 128;
+constexpr int kKeys = 64;                      // keys per tile = one 128-byte swizzle row of P / V^T
+constexpr int kThreads = 192;
+constexpr float kRescaleThreshold = 8.0f;      // log2 units
+
+struct Smem {
+    uint8_t* q; uint8_t* k[2]; uint8_t* v[2]; uint8_t* p[2];
+    uint64_t* q_full; uint64_t* k_full; uint64_t* v_full; uint64_t* kv_empty; uint64_t* s_full; uint64_t* p_full;
+    uint32_t* tmem_slot;
+};
+
+__host__ __device__ inline int attn_smem_bytes(int d) {
+    // Q d/64 x 16K | K 2 x d/64 x 8K | V 2 x d*128 | P 2 x 16K | barriers | align slack
+    return (d / 64) * 16384 + 2 * (d / 64) * 8192 + 2 * d * 128 + 2 * 16384 + 256 + 1024;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int d = p.d, dch = d / 64;
+    Smem sm;
+    sm.q = base; base += dch * 16384;
+    sm.k[0] = base; base += dch * 8192;
+    sm.k[1] = base; base += dch * 8192;
+    sm.v[0] = base; base += d * 128;
+    sm.v[1] = base; base += d * 128;
+    sm.p[0] = base; base += 16384;
+    sm.p[1] = base; base += 16384;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base);
+    sm.q_full = bars; sm.k_full = bars + 1; sm.v_full = bars + 3; sm.kv_empty = bars + 5; sm.s_full = bars + 7;
+    sm.p_full = bars + 8;
+    sm.tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = p.N;
+    const int ipc = (N >= kQRows) ? 1 : kQRows / N;        // images per CTA
+    const int qtiles = (N >= kQRows) ? N / kQRows : 1;
+    const int nt = (N >= kQRows) ? N / kKeys : kQRows / kKeys;
+    // blockIdx.x -> (image group, head, q tile)
+    const int qt = blockIdx.x % qtiles;
+    const int h = (blockIdx.x / qtiles) % p.heads;
+    const int b0 = (blockIdx.x / (qtiles * p.heads)) * ipc;
+    const long long row0 = static_cast<long long>(b0) * N + static_cast<long long>(qt) * kQRows;   // first query row
+    const long long krow0 = static_cast<long long>(b0) * N;                                          // first key row
+    uint32_t tmem_cols = 128; while (tmem_cols < static_cast<uint32_t>(d + kKeys)) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        mbar_init(sm.q_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.k_full[s], 1); mbar_init(&sm.v_full[s], 1); mbar_init(&sm.kv_empty[s], 1);
+                                      mbar_init(&sm.p_full[s], 128); }
+        mbar_init(sm.s_full, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&p.qk_map); tma_prefetch_desc(&p.k_map); tma_prefetch_desc(&p.vt_map);
+    }
+    if (warp == 1) tmem_alloc(sm.tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *sm.tmem_slot;
+    const uint32_t tmem_o = tmem_base;                      // columns [0, d)
+    const uint32_t tmem_s = tmem_base + static_cast<uint32_t>(d);   // columns [d, d+64)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(sm.q_full, static_cast<uint32_t>(dch * 16384));
+            for (int c = 0; c < dch; ++c)
+                tma_load_2d(sm.q + c * 16384, &p.qk_map, sm.q_full, h * d + c * 64, static_cast<int>(row0));
+            for (int j = 0; j < nt; ++j) {
+                const int s = j & 1;
+                mbar_wait(&sm.kv_empty[s], ((j >> 1) & 1) ^ 1);
+                mbar_expect_tx(&sm.k_full[s], static_cast<uint32_t>(dch * 8192));
+                for (int c = 0; c < dch; ++c)
+                    tma_load_2d(sm.k[s] + c * 8192, &p.k_map, &sm.k_full[s], p.hid + h * d + c * 64,
+                                static_cast<int>(krow0) + j * kKeys);
+                const int img = b0 + (j * kKeys) / N;
+                const int koff = (N >= kQRows) ? j * kKeys : (j * kKeys) % N;
+                mbar_expect_tx(&sm.v_full[s], static_cast<uint32_t>(d * 128));
+                tma_load_2d(sm.v[s], &p.vt_map, &sm.v_full[s], koff, (img * p.heads + h) * d);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = umma_idesc_bf16(kQRows, kKeys);
+            const uint32_t idesc_o = umma_idesc_bf16(kQRows, d);
+            auto issue_s = [&](int j) {
+                const int s = j & 1;
+                mbar_wait(&sm.k_full[s], (j >> 1) & 1);
+                tc_fence_after();
+                for (int kk = 0; kk < d / 16; ++kk) {
+                    const uint64_t ad = umma_desc_sw128(smem_u32(sm.q + (kk >> 2) * 16384)) + 2 * (kk & 3);
+                    const uint64_t bd = umma_desc_sw128(smem_u32(sm.k[s] + (kk >> 2) * 8192)) + 2 * (kk & 3);
+                    umma_bf16(tmem_s, ad, bd, idesc_s, kk != 0);
+                }
+                umma_commit(sm.s_full);
+            };
+            mbar_wait(sm.q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < nt; ++j) {
+                const int s = j & 1;
+                mbar_wait(&sm.p_full[s], (j >> 1) & 1);   // P_j in smem, S_j consumed, O rescaled if needed
+                tc_fence_after();
+                if (j + 1 < nt) issue_s(j + 1);
+                mbar_wait(&sm.v_full[s], (j >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < kKeys / 16; ++kk) {
+                    const uint64_t ad = umma_desc_sw128(smem_u32(sm.p[s])) + 2 * kk;
+                    const uint64_t bd = umma_desc_sw128(smem_u32(sm.v[s])) + 2 * kk;
+                    umma_bf16(tmem_o, ad, bd, idesc_o, (j | kk) != 0);
+                }
+                umma_commit(&sm.kv_empty[s]);             // K_j / V_j / P_j free, O updated
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+        const long long grow = row0 + row;
+        const bool row_ok = grow < static_cast<long long>(p.B) * N;
+        const int row_img = row / N;                        // only meaningful when N < 128
+        const float c = p.scale_log2e;
+        float m_used = -INFINITY, l = 0.f;
+        for (int j = 0; j < nt; ++j) {
+            mbar_wait(sm.s_full, j & 1);
+            tc_fence_after();
+            uint32_t r0[32], r1[32];
+            tmem_ld32(tmem_s + lane_off, r0);
+            tmem_ld32(tmem_s + lane_off + 32, r1);
+            tmem_ld_wait();
+            float sv[64];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { sv[i] = __uint_as_float(r0[i]); sv[32 + i] = __uint_as_float(r1[i]); }
+            bool tile_valid = true;
+            if (N < kQRows) tile_valid = ((j * kKeys) / N) == row_img;    // kKeys <= N: a tile lies in one image
+            float m_tile = -INFINITY;
+            if (tile_valid) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) m_tile = fmaxf(m_tile, sv[i]);
+            }
+            float factor = 1.f;
+            bool need = false;
+            if (m_tile > m_used) {
+                if (m_used == -INFINITY) {
+                    m_used = m_tile;                        // nothing accumulated yet for this row (O row == 0, l == 0)
+                } else if ((m_tile - m_used) * c > kRescaleThreshold) {
+                    factor = exp2f((m_used - m_tile) * c);
+                    m_used = m_tile;
+                    need = true;
+                }
+            }
+            if (__any_sync(0xffffffffu, need)) {
+                // O must be complete through PV_{j-1} before it is rescaled
+                mbar_wait(&sm.kv_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                tc_fence_after();
+                for (int c0 = 0; c0 < d; c0 += 32) {
+                    uint32_t o[32];
+                    tmem_ld32(tmem_o + lane_off + c0, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                    tmem_st32(tmem_o + lane_off + c0, o);
+                }
+                tmem_st_wait();
+                l *= factor;
+            }
+            const float mc = (m_used == -INFINITY) ? 0.f : m_used * c;
+            uint8_t* prow = sm.p[j & 1] + row * 128;
+            float lsum = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                float e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    e[i] = tile_valid ? exp2f(sv[ch * 8 + i] * c - mc) : 0.f;
+                    lsum += e[i];
+                }
+                *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) =
+                    make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+            }
+            l += lsum;
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&sm.p_full[j & 1]);
+        }
+        // ---- final: O / l -> bf16
+        mbar_wait(&sm.kv_empty[(nt - 1) & 1], ((nt - 1) >> 1) & 1);
+        tc_fence_after();
+        const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+        for (int c0 = 0; c0 < d; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld32(tmem_o + lane_off + c0, o);
+            tmem_ld_wait();
+            if (row_ok) {
+                uint4* dst = reinterpret_cast<uint4*>(p.out + grow * p.hid + h * d + c0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    dst[i] = make_uint4(pack_bf16(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l),
+                                        pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l),
+                                        pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l),
+                                        pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
+    if (p.d % 64 != 0 || p.d > 256 || p.N % kKeys != 0 || p.N < kKeys) return cudaErrorInvalidValue;
+    if (p.N > kQRows && p.N % kQRows != 0) return cudaErrorInvalidValue;
+    const int smem = attn_smem_bytes(p.d);
+    static int smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        smem_set = smem;
+    }
+    const int ipc = (p.N >= kQRows) ? 1 : kQRows / p.N;
+    const int qtiles = (p.N >= kQRows) ? p.N / kQRows : 1;
+    const int groups = (p.B + ipc - 1) / ipc;
+    const long long grid = static_cast<long long>(groups) * p.heads * qtiles;
+    if (grid <= 0) return cudaSuccess;
+    attention_kernel<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace vdt

@@ -1,0 +1,231 @@
+// Fused GroupNorm(32 groups, eps 1e-6) + optional FiLM (1+scale)*y+shift + optional SiLU + optional
+// 2x average-pool / 2x nearest-upsample, fp32 NHWC in -> bf16 NHWC out (the next conv's operand).
+//
+// Replaces nn.GroupNorm + SiLU + (1+scale)*x+shift + AvgPool2d/Upsample of the reference
+// (unet.py:28-30, 119-124, 127-132, 141-146; AttentionBlock.norm unet.py:52,76; out_conv unet.py:229-231)
+// and the channel concat feeding it (unet.py:315) by reading two sources.
+//
+// One CTA per sample.  Thread t owns VEC consecutive channels (always inside one group) and every
+// PPH-th pixel, so per-group statistics are private fp32 partials combined once through shared
+// memory in a fixed order (deterministic).  Pass 2 re-reads the sample (L2-resident) and writes the
+// normalised operand; optionally also the raw concat in bf16 (operand of the 1x1 skip conv) and the
+// resampled raw input in fp32 (identity-skip residual of a resampling block).
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace vdt {
+namespace {
+
+constexpr int kGroups = 32;
+constexpr float kEps = 1e-6f;
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { typedef float4 type; };
+template <> struct VecT<2> { typedef float2 type; };
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
+    typename VecT<VEC>::type t = __ldg(reinterpret_cast<const typename VecT<VEC>::type*>(p));
+    const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = f[i];
+}
+template <int VEC>
+__device__ __forceinline__ void store_bf16(bf16* p, const float (&v)[VEC]) {
+    if (VEC == 4) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+    } else {
+        *reinterpret_cast<uint32_t*>(p) = pack_bf16(v[0], v[1]);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void store_f32(float* p, const float (&v)[VEC]) {
+    if (VEC == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParams p, int CV, int PPH) {
+    extern __shared__ float2 part[];                 // [CV * PPH] partial (sum, sumsq); then [32] (mean, rstd)
+    __shared__ float2 stat[kGroups];
+    const int b = blockIdx.x;
+    const int C = p.C1 + p.C2;
+    const int HW = p.H * p.W;
+    const int cpg = C / kGroups;
+    const int tid = threadIdx.x;
+    const bool active = tid < CV * PPH;
+    const int cv = active ? tid % CV : 0;
+    const int pp = active ? tid / CV : 0;
+    const int c = cv * VEC;                          // first channel owned by this thread
+    const bool from1 = c < p.C1;
+    const float* src = from1 ? p.src1 + static_cast<size_t>(b) * HW * p.C1 + c
+                             : p.src2 + static_cast<size_t>(b) * HW * p.C2 + (c - p.C1);
+    const int sC = from1 ? p.C1 : p.C2;
+
+    // ---- pass 1: statistics
+    float s = 0.f, ss = 0.f;
+    if (active) {
+        int pix = pp;
+        for (; pix + 3 * PPH < HW; pix += 4 * PPH) {
+            float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
+            load_vec<VEC>(src + static_cast<size_t>(pix) * sC, v0);
+            load_vec<VEC>(src + static_cast<size_t>(pix + PPH) * sC, v1);
+            load_vec<VEC>(src + static_cast<size_t>(pix + 2 * PPH) * sC, v2);
+            load_vec<VEC>(src + static_cast<size_t>(pix + 3 * PPH) * sC, v3);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                s += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+                ss += (v0[i] * v0[i] + v1[i] * v1[i]) + (v2[i] * v2[i] + v3[i] * v3[i]);
+            }
+        }
+        for (; pix < HW; pix += PPH) {
+            float v0[VEC];
+            load_vec<VEC>(src + static_cast<size_t>(pix) * sC, v0);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) { s += v0[i]; ss += v0[i] * v0[i]; }
+        }
+        part[tid] = make_float2(s, ss);
+    }
+    __syncthreads();
+    if (tid < kGroups) {
+        const int vpg = cpg / VEC;                   // vectors per group per pixel
+        double ds = 0.0, dss = 0.0;
+        for (int ph = 0; ph < PPH; ++ph)
+            for (int j = 0; j < vpg; ++j) {
+                const float2 t = part[ph * CV + tid * vpg + j];
+                ds += t.x; dss += t.y;
+            }
+        const double n = static_cast<double>(cpg) * HW;
+        const double mean = ds / n;
+        double var = dss / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stat[tid] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(kEps))));
+    }
+    __syncthreads();
+    if (!active) return;
+
+    // ---- pass 2: apply
+    const float2 st = stat[c / cpg];
+    float ga[VEC], be[VEC], fs[VEC], fb[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const float g = __ldg(p.gamma + c + i) * st.y;
+        ga[i] = g;
+        be[i] = __ldg(p.beta + c + i) - st.x * g;
+        fs[i] = 1.f; fb[i] = 0.f;
+    }
+    if (p.film) {
+        const int r = p.film_row ? __ldg(p.film_row + b) : b;
+        const float* f = p.film + static_cast<size_t>(r) * p.film_stride + p.film_off;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            fb[i] = __ldg(f + c + i);                // shift first, scale second (unet.py:145)
+            fs[i] = 1.f + __ldg(f + C + c + i);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { ga[i] *= fs[i]; be[i] = be[i] * fs[i] + fb[i]; }
+
+    auto norm_act = [&](const float (&x)[VEC], float (&y)[VEC]) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float t = x[i] * ga[i] + be[i];
+            y[i] = p.silu ? t / (1.f + expf(-t)) : t;
+        }
+    };
+
+    if (p.resample == kResDown) {
+        const int Wo = p.W / 2, HWo = HW / 4;
+        bf16* oa = p.out_act + static_cast<size_t>(b) * HWo * C + c;
+        float* orr = p.out_res ? p.out_res + static_cast<size_t>(b) * HWo * C + c : nullptr;
+        for (int po = pp; po < HWo; po += PPH) {
+            const int ho = po / Wo, wo = po % Wo;
+            float acc[VEC], racc[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) { acc[i] = 0.f; racc[i] = 0.f; }
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int pix = (2 * ho + (d >> 1)) * p.W + 2 * wo + (d & 1);
+                float x[VEC], y[VEC];
+                load_vec<VEC>(src + static_cast<size_t>(pix) * sC, x);
+                norm_act(x, y);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { acc[i] += y[i]; racc[i] += x[i]; }
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) { acc[i] *= 0.25f; racc[i] *= 0.25f; }
+            store_bf16<VEC>(oa + static_cast<size_t>(po) * C, acc);
+            if (orr) store_f32<VEC>(orr + static_cast<size_t>(po) * C, racc);
+        }
+    } else if (p.resample == kResUp) {
+        const int Wo = p.W * 2;
+        bf16* oa = p.out_act + static_cast<size_t>(b) * HW * 4 * C + c;
+        float* orr = p.out_res ? p.out_res + static_cast<size_t>(b) * HW * 4 * C + c : nullptr;
+        for (int pix = pp; pix < HW; pix += PPH) {
+            const int h = pix / p.W, w = pix % p.W;
+            float x[VEC], y[VEC];
+            load_vec<VEC>(src + static_cast<size_t>(pix) * sC, x);
+            norm_act(x, y);
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const size_t po = static_cast<size_t>(2 * h + (d >> 1)) * Wo + 2 * w + (d & 1);
+                store_bf16<VEC>(oa + po * C, y);
+                if (orr) store_f32<VEC>(orr + po * C, x);
+            }
+        }
+    } else {
+        bf16* oa = p.out_act + static_cast<size_t>(b) * HW * C + c;
+        bf16* ow = p.out_raw ? p.out_raw + static_cast<size_t>(b) * HW * C + c : nullptr;
+        int pix = pp;
+        for (; pix + PPH < HW; pix += 2 * PPH) {
+            float x0[VEC], x1[VEC], y0[VEC], y1[VEC];
+            load_vec<VEC>(src + static_cast<size_t>(pix) * sC, x0);
+            load_vec<VEC>(src + static_cast<size_t>(pix + PPH) * sC, x1);
+            norm_act(x0, y0);
+            norm_act(x1, y1);
+            store_bf16<VEC>(oa + static_cast<size_t>(pix) * C, y0);
+            store_bf16<VEC>(oa + static_cast<size_t>(pix + PPH) * C, y1);
+            if (ow) {
+                store_bf16<VEC>(ow + static_cast<size_t>(pix) * C, x0);
+                store_bf16<VEC>(ow + static_cast<size_t>(pix + PPH) * C, x1);
+            }
+        }
+        for (; pix < HW; pix += PPH) {
+            float x0[VEC], y0[VEC];
+            load_vec<VEC>(src + static_cast<size_t>(pix) * sC, x0);
+            norm_act(x0, y0);
+            store_bf16<VEC>(oa + static_cast<size_t>(pix) * C, y0);
+            if (ow) store_bf16<VEC>(ow + static_cast<size_t>(pix) * C, x0);
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream) {
+    const int C = p.C1 + p.C2;
+    if (C % kGroups != 0 || p.B <= 0) return cudaErrorInvalidValue;
+    const int cpg = C / kGroups;
+    const int vec = (cpg % 4 == 0 && p.C1 % 4 == 0) ? 4 : 2;
+    if (cpg % vec != 0 || p.C1 % vec != 0) return cudaErrorInvalidValue;
+    const int CV = C / vec;
+    if (CV > 1024) return cudaErrorInvalidValue;
+    int PPH = 1024 / CV;
+    const int HW = p.H * p.W;
+    const int work = (p.resample == kResDown) ? HW / 4 : HW;
+    if (PPH > work) PPH = work;
+    if (PPH > 8) PPH = 8;                             // >= 8 pixels of work per thread at 32x32 / 256 ch
+    if (PPH < 1) PPH = 1;
+    const int threads = ((CV * PPH + 31) / 32) * 32;
+    const size_t smem = static_cast<size_t>(CV) * PPH * sizeof(float2);
+    if (vec == 4)
+        groupnorm_kernel<4><<<p.B, threads, smem, stream>>>(p, CV, PPH);
+    else
+        groupnorm_kernel<2><<<p.B, threads, smem, stream>>>(p, CV, PPH);
+    return cudaGetLastError();
+}
+
+}  // namespace vdt

@@ -1,0 +1,140 @@
+// Launch-parameter structs and launcher prototypes shared by the kernels (.cu) and the host
+// runtime (plan.cu).  All pointers are device pointers; all launchers are stream-ordered and
+// return the cudaError_t of the launch.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace vdt {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution / linear layer on tcgen05 (conv_gemm.cu)
+//   D[M, Cout] = sum over K-segments  A_seg[M, taps*Cin_seg] * W[Cout, K_total]^T  (+ epilogue)
+// M rows are NHWC pixels (or batch rows for a linear layer).  A tile of 128 rows is `box_n` images
+// x `box_h` image rows x W pixels; a 3x3 tap is a shifted TMA box whose out-of-bounds part the
+// hardware zero-fills (= the conv padding).
+// ------------------------------------------------------------------------------------------------
+constexpr int kConvMaxSegs = 3;
+
+enum ConvOutMode : int {
+    kOutF32 = 0,        // fp32 [M, ld]            (+bias, +residual, optional SiLU)
+    kOutBF16 = 1,       // bf16 [M, ld] for columns < split_col; columns >= split_col are written
+                        // transposed per image: out_t[(img * (Cout - split_col) + col - split_col) * HW + pix]
+    kOutNCHW = 2,       // fp32 [img, Cout, HW]    (network output, Cout may be tiny)
+};
+
+struct alignas(64) ConvParams {
+    CUtensorMap a_map[kConvMaxSegs];   // 4-D (C, W, H, N) bf16, box (64, W, box_h, box_n), SWIZZLE_128B
+    CUtensorMap b_map;                 // 2-D (K_total, Cout) bf16, box (64, block_n), SWIZZLE_128B
+    int num_segs;
+    int seg_taps[kConvMaxSegs];        // 9 (3x3, pad 1) or 1 (pointwise)
+    int seg_kblocks[kConvMaxSegs];     // Cin_seg / 64
+    int pointwise;                     // 1: A is a plain [M, C] matrix, tile row origin = m_tile * 128
+    int tiles_per_image;               // H / box_h  (when box_n == 1), else 1
+    int box_h, box_n;
+    int rows_per_tile;                 // box_n * box_h * W  (<= 128)
+    int num_m_tiles, num_n_tiles, block_n;
+    int M, Cout;                       // valid rows / columns
+    int out_mode;
+    int ld;                            // row stride (elements) of out_f32 / out_bf16 / residual
+    int split_col, HW;
+    int act_silu;
+    const float* bias;                 // [Cout]
+    const float* residual;             // fp32 [M, ld] or null
+    float* out_f32;
+    bf16* out_bf16;
+    bf16* out_t;
+};
+cudaError_t launch_conv_gemm(const ConvParams& p, int num_sms, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm(32, eps 1e-6) [+ FiLM (1+scale)*y+shift] [+ SiLU] [+ 2x avg-pool | 2x nearest upsample]
+// over an fp32 NHWC tensor that may be the channel concat of two tensors (groupnorm.cu).
+// ------------------------------------------------------------------------------------------------
+enum Resample : int { kResNone = 0, kResDown = 1, kResUp = 2 };
+
+struct GroupNormParams {
+    const float* src1; int C1;         // fp32 [B, HW, C1]
+    const float* src2; int C2;         // fp32 [B, HW, C2] or null: channels C1..C1+C2 (virtual concat)
+    int B, H, W;
+    const float* gamma; const float* beta;   // [C1 + C2]
+    const float* film;                 // null or fp32 table; row r holds [shift(C) | scale(C)] at film_off
+    const int* film_row;               // [B] row index per sample (null: row = sample index)
+    int film_stride, film_off;
+    int silu;
+    int resample;                      // applied after norm+act (unet.py:141)
+    bf16* out_act;                     // bf16 [B, H'W', C]   normalised (+FiLM, +SiLU), resampled
+    bf16* out_raw;                     // optional bf16 [B, HW, C]: the un-normalised concat (skip-conv operand)
+    float* out_res;                    // optional fp32 [B, H'W', C]: resampled raw input (identity-skip residual)
+};
+cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// Self-attention softmax(q^T k / sqrt(d)) v per image and head, flash-style on tcgen05 (attention.cu)
+// ------------------------------------------------------------------------------------------------
+struct alignas(64) AttnParams {
+    CUtensorMap qk_map;                // 2-D (2*hid, B*N) bf16, box (64, 128): q at col h*d, k at hid + h*d
+    CUtensorMap k_map;                 // same tensor, box (64, 64)
+    CUtensorMap vt_map;                // 2-D (N, B*hid) bf16, box (64, d): V^T per image/head
+    int B, N, heads, d, hid;
+    float scale_log2e;                 // log2(e) / sqrt(d)
+    bf16* out;                         // bf16 [B*N, hid]
+};
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// Small kernels (pointwise.cu)
+// ------------------------------------------------------------------------------------------------
+// x fp32 NCHW [B, C, H, W] (9*C <= 64) -> bf16 patch matrix [B*rep*H*W, 64]: column (r*3+s)*C + c =
+// x[b, c, h+r-1, w+s-1] (zero outside); output image i reads input image i / rep (the CFG
+// repeat-interleave of diffusion.py:30-35, 370).
+cudaError_t launch_im2col3x3(const float* x, bf16* out, int B, int rep, int C, int H, int W, cudaStream_t stream);
+
+// sinusoidal embedding evaluated in fp64 like functions.py:11-29 -> fp32 [rows, dim]
+cudaError_t launch_timestep_embedding(const double* t, float* out, int rows, int dim, cudaStream_t stream);
+
+// out[r, n] = act( sum_k x[r, k] * W[n, k] + b[n] )   fp32 CUDA-core path for the embedding MLP
+// (time_embed, fc of every ResidualBlock: unet.py:201-205, 122, 142); rows are few (one per distinct
+// (t, class) pair in the sampler), so this is weight-bandwidth bound and kept in exact fp32.
+cudaError_t launch_linear_f32(const float* x, const float* W, const float* b, float* out, int rows, int K, int N,
+                              int silu_out, cudaStream_t stream);
+
+// e[r, :] = SiLU( e[r, :] + (y ? (y[r] > 0 ? W_cls[:, y[r]-1] : 0) + b_cls : 0) )   (unet.py:289-295, modules.py:184-201;
+// the SiLU is the act1 applied before every fc, unet.py:142)
+cudaError_t launch_class_embed_silu(const float* e, const int64_t* y, const float* w_cls, const float* b_cls,
+                                    int num_classes, float* out, int rows, int E, cudaStream_t stream);
+
+// Per-step device-side sampler state: everything that changes from step to step lives here so one
+// captured CUDA graph can be replayed for every step.
+struct SamplerState {
+    int next_step;                     // step index the next begin_step will consume (T-1 .. 0)
+    int step;                          // step index of the step in flight
+    int img0;                          // first image of the current chunk (offset into injected noise)
+    int pad;
+    float coef[12];                    // alpha_t, sigma_t, rsqrt_sig, exp_half_neg, sig_pos, sig_neg, c1, c2, std, 0...
+};
+constexpr int kCoefStride = 12;
+// single-thread kernel: st->step = st->next_step--, copies the coefficient row, writes t_rows[r] = (step+1)/T
+cudaError_t launch_sampler_begin_step(SamplerState* st, const float* coef_table, double* t_rows, int nrows, int T,
+                                      cudaStream_t stream);
+
+struct SamplerStepParams {
+    const float* model_out;            // fp32 NCHW [B*(1+cfg), Cm, HW]; cond rows even, uncond rows odd
+    const float* x_t;                  // fp32 NCHW [B, C, HW]
+    float* x_s;                        // fp32 NCHW [B, C, HW]  (may alias x_t)
+    const float* noise;                // injected per-step noise [T, Btotal, C, HW] or null
+    long long noise_step_stride;       // elements between steps (Btotal*C*HW)
+    const SamplerState* st;
+    unsigned long long seed;           // on-device Philox noise when `noise` is null and std > 0
+    int B, C, HW;
+    int cfg;                           // 1: classifier-free guidance pair per sample
+    int model_out_type;                // 0 x0, 1 eps, 2 both, 3 v
+    float w;
+};
+cudaError_t launch_sampler_step(const SamplerStepParams& p, cudaStream_t stream);
+
+}  // namespace vdt

@@ -1,0 +1,1157 @@
+// Host runtime behind the C ABI (include/vdt_b200.h): UNet plan (block list mirroring
+// unet.py:155-322), weight table with the reference's state_dict keys, bf16 weight packing,
+// TMA tensor maps, per-batch-size execution lists captured as CUDA graphs, and the sampling
+// driver (diffusion.py:360-414).  No torch types; device memory via the CUDA runtime.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vdt_b200.h"
+#include "kernels.cuh"
+
+using namespace vdt;
+
+// ================================================================================================ errors
+static thread_local char g_err[1024] = "";
+static uint64_t g_launches = 0;
+
+static int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define CKI(expr)                       \
+    do {                                \
+        int _r = (expr);                \
+        if (_r != 0) return _r;         \
+    } while (0)
+
+extern "C" const char* vdt_last_error(void) { return g_err; }
+extern "C" int vdt_version(void) { return 1; }
+extern "C" uint64_t vdt_kernel_launches(void) { return g_launches; }
+
+// ================================================================================================ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encoder() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return fail("cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return 0;
+}
+
+// bf16 tensor, innermost dimension first; strides in elements for dims 1..rank-1
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                    const uint32_t* box) {
+    CKI(get_encoder());
+    cuuint64_t gdim[4], gstr[3];
+    cuuint32_t bdim[4], estr[4];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_elems[i] * 2;
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u", (int)r, rank,
+                    (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                    (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                    rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return 0;
+}
+
+// A operand of a 3x3 (or geometric 1x1) conv: NHWC bf16 [n, h, w, c]
+static int make_map_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, int c, int box_h, int box_n) {
+    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)c, (uint64_t)w * c, (uint64_t)h * w * c};
+    const uint32_t box[4] = {64, (uint32_t)w, (uint32_t)box_h, (uint32_t)box_n};
+    return make_map(m, base, 4, dims, str, box);
+}
+// plain row-major [rows, ld] matrix viewed through the 4-D path of the conv kernel (cols columns used)
+static int make_map_rows4d(CUtensorMap* m, const void* base, long long rows, int cols, int ld) {
+    const uint64_t dims[4] = {(uint64_t)cols, (uint64_t)rows, 1, 1};
+    const uint64_t str[3] = {(uint64_t)ld, (uint64_t)rows * ld, (uint64_t)rows * ld};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    return make_map(m, base, 4, dims, str, box);
+}
+static int make_map_2d(CUtensorMap* m, const void* base, long long rows, int cols, int ld, int box_rows) {
+    const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+    const uint64_t str[1] = {(uint64_t)ld};
+    const uint32_t box[2] = {64, (uint32_t)box_rows};
+    return make_map(m, base, 2, dims, str, box);
+}
+
+// ================================================================================================ pack kernels
+__global__ void pack_conv_w_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I, int taps,
+                                   int ktot, int koff) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n = (long long)O * I * taps;
+    if (idx >= n) return;
+    const int i = (int)(idx % I);
+    const int tap = (int)((idx / I) % taps);
+    const int o = (int)(idx / ((long long)I * taps));
+    dst[(long long)o * ktot + koff + tap * I + i] = __float2bfloat16(src[((long long)o * I + i) * taps + tap]);
+}
+// in_conv: [O][C][3][3] -> [O][64], column tap*C + c (matches im2col3x3), zero padded
+__global__ void pack_inconv_w_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int O, int C) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= O * 64) return;
+    const int o = idx / 64, col = idx % 64;
+    float v = 0.f;
+    if (col < 9 * C) { const int tap = col / C, c = col % C; v = src[((long long)o * C + c) * 9 + tap]; }
+    dst[idx] = __float2bfloat16(v);
+}
+__global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
+}
+__global__ void film_rows_kernel(const int64_t* __restrict__ label, int* __restrict__ film_row, int rows, int rep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    int r = 0;
+    if (label != nullptr && !(rep == 2 && (i & 1))) r = (int)label[i / rep];   // odd rows: y = 0 (diffusion.py:372)
+    film_row[i] = r;
+}
+__global__ void sampler_init_state_kernel(SamplerState* st, int next_step, int img0) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { st->next_step = next_step; st->step = next_step; st->img0 = img0; st->pad = 0; }
+}
+__global__ void iota_i64_kernel(int64_t* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// ================================================================================================ plan
+struct Weight {
+    std::string name;
+    std::vector<int64_t> shape;
+    int64_t numel = 0;
+    float* dev = nullptr;
+    bool loaded = false;
+};
+
+struct Block {
+    int kind;            // 0 res, 1 attn
+    std::string name;
+    int cin, cout;
+    int resample;        // kResNone/Down/Up
+    bool concat, push;
+    int res_in;          // input resolution
+    int film_off = 0;
+    // packed
+    bf16* w1 = nullptr;  // conv1 [cout][9*cin]            | proj_in [3*hid][cin]
+    bf16* w2 = nullptr;  // conv2 (+skip) [cout][9*cout(+cin)] | proj_out [cin][hid]
+    float* bias2 = nullptr;   // conv2.bias (+ skip.bias)
+};
+
+enum StepKind { S_CONV, S_GN, S_ATTN, S_IM2COL, S_TEMB, S_LINEAR, S_CLSEMB, S_BEGIN, S_SAMPLE };
+struct LinearArgs { const float *x, *W, *b; float* out; int rows, K, N, silu; };
+struct Im2colArgs { const float* x; bf16* out; int B, rep, C, H, W; };
+struct TembArgs { const double* t; float* out; int rows, dim; };
+struct ClsArgs { const float* e; const int64_t* y; const float *w, *b; int ncls; float* out; int rows, E; };
+struct BeginArgs { SamplerState* st; const float* table; double* t_rows; int nrows, T; };
+
+struct Step { StepKind kind; int idx; };
+
+struct Exec {
+    int rows = 0;          // UNet batch rows
+    int emb_rows = 0;
+    bool sampler = false;
+    bool has_y = false;
+    std::vector<void*> bufs;
+    std::vector<size_t> buf_bytes;
+    std::vector<char> buf_free;
+    std::vector<Step> steps;
+    std::vector<std::unique_ptr<ConvParams>> convs;
+    std::vector<GroupNormParams> gns;
+    std::vector<std::unique_ptr<AttnParams>> attns;
+    std::vector<LinearArgs> linears;
+    std::vector<Im2colArgs> im2cols;
+    std::vector<TembArgs> tembs;
+    std::vector<ClsArgs> clss;
+    std::vector<BeginArgs> begins;
+    std::vector<SamplerStepParams> samples;
+    // fixed I/O staging
+    float* xin = nullptr;        // forward: fp32 NCHW [rows, Cin, HW] | sampler: x_t [rows/rep, C, HW]
+    float* yout = nullptr;       // fp32 NCHW [rows, Cout, HW]
+    double* t_rows = nullptr;    // [emb_rows]
+    int64_t* y_rows = nullptr;   // [emb_rows]
+    int* film_row = nullptr;     // [rows] (sampler)
+    SamplerState* state = nullptr;
+    float* coef_table = nullptr; // [T][12] (sampler)
+    // sampler signature this exec was built for
+    vdt_sampler_config sc{};
+    int rep = 1;
+    const float* noise_ptr = nullptr; long long noise_stride = 0;
+    cudaGraphExec_t graph = nullptr;
+    bool graph_failed = false;
+    int runs = 0;
+
+    ~Exec() {
+        if (graph) cudaGraphExecDestroy(graph);
+        for (void* b : bufs) cudaFree(b);
+    }
+    int acquire(size_t bytes, void** out) {
+        bytes = (bytes + 1023) & ~size_t(1023);
+        int best = -1;
+        for (size_t i = 0; i < bufs.size(); ++i)
+            if (buf_free[i] && buf_bytes[i] >= bytes && buf_bytes[i] <= bytes + bytes / 2 &&
+                (best < 0 || buf_bytes[i] < buf_bytes[best]))
+                best = (int)i;
+        if (best < 0) {
+            void* p = nullptr;
+            CK(cudaMalloc(&p, bytes));
+            CK(cudaMemset(p, 0, bytes));
+            bufs.push_back(p); buf_bytes.push_back(bytes); buf_free.push_back(0);
+            best = (int)bufs.size() - 1;
+        }
+        buf_free[best] = 0;
+        *out = bufs[best];
+        return 0;
+    }
+    void release(void* p) {
+        for (size_t i = 0; i < bufs.size(); ++i)
+            if (bufs[i] == p) { buf_free[i] = 1; return; }
+    }
+};
+
+struct vdt_plan {
+    vdt_unet_config cfg{};
+    int E = 0, hid = 0, levels = 0;
+    int num_sms = 148;
+    std::vector<Weight> weights;
+    std::unordered_map<std::string, int> windex;
+    std::vector<Block> blocks;
+    int film_total = 0;
+    bool finalized = false;
+    // packed globals
+    bf16* w_in = nullptr;                 // in_conv [hid][64]
+    bf16* w_out = nullptr;                // out_conv.2 [Cout][9*c0]
+    float* w_fc_all = nullptr;            // [film_total][E]
+    float* b_fc_all = nullptr;            // [film_total]
+    std::vector<void*> owned;
+    std::map<std::string, std::unique_ptr<Exec>> execs;
+    bool use_graph = true;
+    // all work runs on an internal stream (the caller's may be the legacy default stream, which
+    // cannot be captured); ordering against the caller's stream is kept with two events
+    cudaStream_t work = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+
+    ~vdt_plan() {
+        if (work) cudaStreamSynchronize(work);
+        execs.clear();
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_out) cudaEventDestroy(ev_out);
+        if (work) cudaStreamDestroy(work);
+        for (auto& w : weights) if (w.dev) cudaFree(w.dev);
+        for (void* p : owned) cudaFree(p);
+    }
+    const float* W(const std::string& k) const { return weights[windex.at(k)].dev; }
+    bool has(const std::string& k) const { return windex.count(k) != 0; }
+};
+
+static int enter_work(vdt_plan* p, cudaStream_t user) {
+    if (!p->work) {
+        CK(cudaStreamCreateWithFlags(&p->work, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(p->ev_in, user));
+    CK(cudaStreamWaitEvent(p->work, p->ev_in, 0));
+    return 0;
+}
+static int leave_work(vdt_plan* p, cudaStream_t user) {
+    CK(cudaEventRecord(p->ev_out, p->work));
+    CK(cudaStreamWaitEvent(user, p->ev_out, 0));
+    return 0;
+}
+
+static void add_weight(vdt_plan* p, const std::string& name, std::vector<int64_t> shape) {
+    Weight w;
+    w.name = name; w.shape = shape; w.numel = 1;
+    for (auto s : shape) w.numel *= s;
+    p->windex[name] = (int)p->weights.size();
+    p->weights.push_back(w);
+}
+
+static void attn_dims(const vdt_unet_config& c, int ch, int* hd, int* nh) {   // unet.py:43-53
+    int head_dim = c.head_dim, num_heads = c.num_heads;
+    if (head_dim == 0 && num_heads == 0) num_heads = 1;
+    if (head_dim == 0) head_dim = ch / num_heads;
+    if (num_heads == 0) num_heads = ch / head_dim;
+    *hd = head_dim; *nh = num_heads;
+}
+
+// Execution order of UNet.forward (unet.py:250-283, 297-321)
+static void build_blocks(vdt_plan* p) {
+    const vdt_unet_config& c = p->cfg;
+    const int L = c.num_levels, nrb = c.num_res_blocks, hid = c.hid_channels;
+    std::vector<int> chs(L);
+    for (int i = 0; i < L; ++i) chs[i] = hid * c.ch_multipliers[i];
+    int res = c.resolution;
+    auto add = [&](const std::string& prefix, int cin, int cout, int level, int resample, bool concat, bool push) {
+        const bool has_attn = level >= 0 && c.apply_attn[level];
+        Block b{};
+        b.kind = 0; b.name = prefix + (has_attn ? ".0" : ""); b.cin = cin; b.cout = cout; b.resample = resample;
+        b.concat = concat; b.push = push && !has_attn; b.res_in = res;
+        p->blocks.push_back(b);
+        if (resample == kResDown) res /= 2;
+        if (resample == kResUp) res *= 2;
+        if (has_attn) {
+            Block a{};
+            a.kind = 1; a.name = prefix + ".1"; a.cin = cout; a.cout = cout; a.resample = kResNone; a.concat = false;
+            a.push = push; a.res_in = res;
+            p->blocks.push_back(a);
+        }
+    };
+    auto lvl = [](const char* side, int i, int j) {
+        char buf[64];
+        snprintf(buf, sizeof(buf), "%s.level_%d.%d", side, i, j);
+        return std::string(buf);
+    };
+    for (int i = 0; i < L; ++i) {
+        const int prev = i ? chs[i - 1] : hid;
+        add(lvl("downsamples", i, 0), prev, chs[i], i, kResNone, false, true);
+        for (int j = 1; j < nrb; ++j) add(lvl("downsamples", i, j), chs[i], chs[i], i, kResNone, false, true);
+        if (i != L - 1) add(lvl("downsamples", i, nrb), chs[i], chs[i], i, kResDown, false, true);
+    }
+    const int mid = chs[L - 1];
+    { Block b{}; b.kind = 0; b.name = "middle.0"; b.cin = b.cout = mid; b.res_in = res; p->blocks.push_back(b); }
+    { Block b{}; b.kind = 1; b.name = "middle.1"; b.cin = b.cout = mid; b.res_in = res; p->blocks.push_back(b); }
+    { Block b{}; b.kind = 0; b.name = "middle.2"; b.cin = b.cout = mid; b.res_in = res; p->blocks.push_back(b); }
+    for (int i = L - 1; i >= 0; --i) {
+        const int nxt = i == 0 ? hid : chs[i - 1];
+        const int prev = i == L - 1 ? chs[L - 1] : chs[i + 1];
+        const int cur = chs[i];
+        add(lvl("upsamples", i, 0), prev + cur, cur, i, kResNone, true, false);
+        for (int j = 1; j < nrb; ++j) add(lvl("upsamples", i, j), 2 * cur, cur, i, kResNone, true, false);
+        add(lvl("upsamples", i, nrb), nxt + cur, cur, i, kResNone, true, false);
+        if (i != 0) add(lvl("upsamples", i, nrb + 1), cur, cur, i, kResUp, false, false);
+    }
+}
+
+extern "C" int vdt_plan_create(const vdt_unet_config* cfg, vdt_plan** out) {
+    if (!cfg || !out) return fail("null argument");
+    const vdt_unet_config& c = *cfg;
+    if (c.num_levels < 1 || c.num_levels > VDT_MAX_LEVELS) return fail("num_levels out of range");
+    if (c.multitags) return fail("multitags (multi-hot labels) is not supported yet");
+    if (c.hid_channels % 64 != 0) return fail("hid_channels must be a multiple of 64 (got %d)", c.hid_channels);
+    if (9 * c.in_channels > 64) return fail("in_channels must be <= 7");
+    if (c.out_channels > 16) return fail("out_channels must be <= 16");
+    if (c.max_rows < 1) return fail("max_rows must be >= 1");
+    const int minres = c.resolution >> (c.num_levels - 1);
+    if ((minres << (c.num_levels - 1)) != c.resolution) return fail("resolution must be divisible by 2^(levels-1)");
+    for (int i = 0, r = c.resolution; i < c.num_levels; ++i, r /= 2) {
+        const bool pow2 = (r & (r - 1)) == 0;
+        if (!pow2 || r < 8 || r > 128) return fail("unsupported feature-map size %d (need a power of two in [8, 128])", r);
+    }
+    std::unique_ptr<vdt_plan> p(new vdt_plan());
+    p->cfg = c;
+    p->hid = c.hid_channels;
+    p->E = c.embedding_dim ? c.embedding_dim : 4 * c.hid_channels;
+    p->levels = c.num_levels;
+    const char* ng = getenv("VDT_NO_GRAPH");
+    p->use_graph = !(ng && ng[0] == '1');
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) p->num_sms = n;
+    } else {
+        cudaGetLastError();
+    }
+    build_blocks(p.get());
+    const int E = p->E, hid = p->hid;
+    add_weight(p.get(), "time_embed.0.weight", {E, hid});
+    add_weight(p.get(), "time_embed.0.bias", {E});
+    add_weight(p.get(), "time_embed.2.weight", {E, E});
+    add_weight(p.get(), "time_embed.2.bias", {E});
+    if (c.num_classes > 0) {
+        add_weight(p.get(), "class_embed.1.weight", {E, c.num_classes});
+        add_weight(p.get(), "class_embed.1.bias", {E});
+    }
+    add_weight(p.get(), "in_conv.weight", {hid, c.in_channels, 3, 3});
+    add_weight(p.get(), "in_conv.bias", {hid});
+    int film = 0;
+    for (auto& b : p->blocks) {
+        const std::string& n = b.name;
+        if (b.kind == 0) {
+            if (b.cin % 64 || b.cout % 64) return fail("channel counts must be multiples of 64 (%s: %d -> %d)", n.c_str(), b.cin, b.cout);
+            add_weight(p.get(), n + ".norm1.weight", {b.cin}); add_weight(p.get(), n + ".norm1.bias", {b.cin});
+            add_weight(p.get(), n + ".conv1.weight", {b.cout, b.cin, 3, 3}); add_weight(p.get(), n + ".conv1.bias", {b.cout});
+            add_weight(p.get(), n + ".fc.weight", {2 * b.cout, E}); add_weight(p.get(), n + ".fc.bias", {2 * b.cout});
+            add_weight(p.get(), n + ".norm2.weight", {b.cout}); add_weight(p.get(), n + ".norm2.bias", {b.cout});
+            add_weight(p.get(), n + ".conv2.weight", {b.cout, b.cout, 3, 3}); add_weight(p.get(), n + ".conv2.bias", {b.cout});
+            if (b.cin != b.cout) {
+                add_weight(p.get(), n + ".skip.weight", {b.cout, b.cin, 1, 1}); add_weight(p.get(), n + ".skip.bias", {b.cout});
+            }
+            b.film_off = film;
+            film += 2 * b.cout;
+        } else {
+            int hd, nh;
+            attn_dims(c, b.cin, &hd, &nh);
+            if (hd % 64 || hd > 256) return fail("head_dim must be a multiple of 64 and <= 256 (got %d)", hd);
+            const int tokens = b.res_in * b.res_in;
+            if (tokens % 64) return fail("attention needs a multiple of 64 tokens (got %d)", tokens);
+            add_weight(p.get(), n + ".norm.weight", {b.cin}); add_weight(p.get(), n + ".norm.bias", {b.cin});
+            add_weight(p.get(), n + ".proj_in.weight", {3 * hd * nh, b.cin, 1, 1}); add_weight(p.get(), n + ".proj_in.bias", {3 * hd * nh});
+            add_weight(p.get(), n + ".proj_out.weight", {b.cin, hd * nh, 1, 1}); add_weight(p.get(), n + ".proj_out.bias", {b.cin});
+        }
+    }
+    p->film_total = film;
+    const int c0 = hid * c.ch_multipliers[0];
+    add_weight(p.get(), "out_conv.0.weight", {c0}); add_weight(p.get(), "out_conv.0.bias", {c0});
+    add_weight(p.get(), "out_conv.2.weight", {c.out_channels, c0, 3, 3}); add_weight(p.get(), "out_conv.2.bias", {c.out_channels});
+    *out = p.release();
+    return 0;
+}
+
+extern "C" void vdt_plan_destroy(vdt_plan* plan) { delete plan; }
+extern "C" int vdt_plan_num_weights(const vdt_plan* plan) { return plan ? (int)plan->weights.size() : 0; }
+extern "C" const char* vdt_plan_weight_name(const vdt_plan* plan, int i) {
+    if (!plan || i < 0 || i >= (int)plan->weights.size()) return nullptr;
+    return plan->weights[i].name.c_str();
+}
+extern "C" int vdt_plan_weight_shape(const vdt_plan* plan, int i, int64_t* shape4, int* ndim) {
+    if (!plan || i < 0 || i >= (int)plan->weights.size()) return fail("weight index out of range");
+    const Weight& w = plan->weights[i];
+    *ndim = (int)w.shape.size();
+    for (size_t k = 0; k < w.shape.size(); ++k) shape4[k] = w.shape[k];
+    return 0;
+}
+
+extern "C" int vdt_plan_load_weight(vdt_plan* plan, const char* key, const float* data, int64_t numel, int on_device) {
+    if (!plan || !key || !data) return fail("null argument");
+    auto it = plan->windex.find(key);
+    if (it == plan->windex.end()) return fail("unexpected key in state_dict: %s", key);
+    Weight& w = plan->weights[it->second];
+    if (numel != w.numel) return fail("size mismatch for %s: expected %lld elements, got %lld", key, (long long)w.numel, (long long)numel);
+    if (!w.dev) CK(cudaMalloc(&w.dev, sizeof(float) * (size_t)w.numel));
+    CK(cudaMemcpy(w.dev, data, sizeof(float) * (size_t)w.numel, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    w.loaded = true;
+    plan->finalized = false;
+    return 0;
+}
+
+template <typename T>
+static int dev_alloc(vdt_plan* p, T** out, size_t count) {
+    void* ptr = nullptr;
+    CK(cudaMalloc(&ptr, count * sizeof(T)));
+    CK(cudaMemset(ptr, 0, count * sizeof(T)));
+    p->owned.push_back(ptr);
+    *out = reinterpret_cast<T*>(ptr);
+    return 0;
+}
+
+static int pack_conv(const float* src, bf16* dst, int O, int I, int taps, int ktot, int koff) {
+    const long long n = (long long)O * I * taps;
+    pack_conv_w_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src, dst, O, I, taps, ktot, koff);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vdt_plan_finalize(vdt_plan* p) {
+    if (!p) return fail("null plan");
+    for (auto& w : p->weights)
+        if (!w.loaded) return fail("missing key in state_dict: %s", w.name.c_str());
+    p->execs.clear();
+    for (void* q : p->owned) cudaFree(q);
+    p->owned.clear();
+    const vdt_unet_config& c = p->cfg;
+    const int E = p->E, hid = p->hid;
+    CKI(dev_alloc(p, &p->w_in, (size_t)hid * 64));
+    pack_inconv_w_kernel<<<(hid * 64 + 255) / 256, 256>>>(p->W("in_conv.weight"), p->w_in, hid, c.in_channels);
+    CK(cudaGetLastError());
+    CKI(dev_alloc(p, &p->w_fc_all, (size_t)p->film_total * E));
+    CKI(dev_alloc(p, &p->b_fc_all, (size_t)p->film_total));
+    for (auto& b : p->blocks) {
+        const std::string& n = b.name;
+        if (b.kind == 0) {
+            CKI(dev_alloc(p, &b.w1, (size_t)b.cout * 9 * b.cin));
+            CKI(pack_conv(p->W(n + ".conv1.weight"), b.w1, b.cout, b.cin, 9, 9 * b.cin, 0));
+            const bool skipconv = b.cin != b.cout;
+            const int k2 = 9 * b.cout + (skipconv ? b.cin : 0);
+            CKI(dev_alloc(p, &b.w2, (size_t)b.cout * k2));
+            CKI(pack_conv(p->W(n + ".conv2.weight"), b.w2, b.cout, b.cout, 9, k2, 0));
+            if (skipconv) CKI(pack_conv(p->W(n + ".skip.weight"), b.w2, b.cout, b.cin, 1, k2, 9 * b.cout));
+            CKI(dev_alloc(p, &b.bias2, (size_t)b.cout));
+            add_vec_kernel<<<(b.cout + 255) / 256, 256>>>(p->W(n + ".conv2.bias"), skipconv ? p->W(n + ".skip.bias") : nullptr,
+                                                          b.bias2, b.cout);
+            CK(cudaGetLastError());
+            CK(cudaMemcpy(p->w_fc_all + (size_t)b.film_off * E, p->W(n + ".fc.weight"), sizeof(float) * 2 * b.cout * E,
+                          cudaMemcpyDeviceToDevice));
+            CK(cudaMemcpy(p->b_fc_all + b.film_off, p->W(n + ".fc.bias"), sizeof(float) * 2 * b.cout, cudaMemcpyDeviceToDevice));
+        } else {
+            int hd, nh;
+            attn_dims(c, b.cin, &hd, &nh);
+            const int hidd = hd * nh;
+            CKI(dev_alloc(p, &b.w1, (size_t)3 * hidd * b.cin));
+            CKI(pack_conv(p->W(n + ".proj_in.weight"), b.w1, 3 * hidd, b.cin, 1, b.cin, 0));
+            CKI(dev_alloc(p, &b.w2, (size_t)b.cin * hidd));
+            CKI(pack_conv(p->W(n + ".proj_out.weight"), b.w2, b.cin, hidd, 1, hidd, 0));
+        }
+    }
+    const int c0 = hid * c.ch_multipliers[0];
+    // out_conv weight rows are padded to 16 output channels (zero rows) so the TMA box never leaves the tensor
+    CKI(dev_alloc(p, &p->w_out, (size_t)16 * 9 * c0));
+    CKI(pack_conv(p->W("out_conv.2.weight"), p->w_out, c.out_channels, c0, 9, 9 * c0, 0));
+    CK(cudaDeviceSynchronize());
+    p->finalized = true;
+    return 0;
+}
+
+// ================================================================================================ conv setup
+static int pick_block_n(int cout) {
+    if (cout <= 16) return 16;
+    if (cout <= 256) return cout;
+    for (int bn = 256; bn >= 32; bn -= 32)
+        if (cout % bn == 0) return bn;
+    return 0;
+}
+
+struct ConvGeom { int box_h, box_n, tiles_per_image, rows_per_tile, num_m_tiles; };
+static int conv_geom(int n, int h, int w, ConvGeom* g) {
+    if (w > 128 || 128 % w != 0) return fail("unsupported feature-map width %d", w);
+    if (w * h >= 128) {
+        g->box_h = 128 / w; g->box_n = 1;
+        if (h % g->box_h) return fail("unsupported feature-map height %d", h);
+        g->tiles_per_image = h / g->box_h; g->rows_per_tile = 128; g->num_m_tiles = n * g->tiles_per_image;
+    } else {
+        g->box_h = h; g->box_n = 128 / (w * h); g->tiles_per_image = 1; g->rows_per_tile = 128;
+        g->num_m_tiles = (n + g->box_n - 1) / g->box_n;
+    }
+    return 0;
+}
+
+// 3x3 conv (optionally with an appended pointwise K-segment) or pure pointwise GEMM
+struct ConvSpec {
+    const bf16* a3 = nullptr; int c3 = 0;       // 3x3 segment: NHWC [n,h,w,c3]
+    const bf16* a1 = nullptr; int c1 = 0;       // pointwise segment: [n*h*w, c1] with row stride ld1
+    int ld1 = 0;
+    int n = 0, h = 0, w = 0;
+    const bf16* wpacked = nullptr; int cout = 0; int wrows = 0;   // weight rows actually allocated
+    const float* bias = nullptr; const float* residual = nullptr;
+    int out_mode = kOutF32; float* out_f32 = nullptr; bf16* out_bf16 = nullptr; bf16* out_t = nullptr;
+    int ld = 0, split_col = 0, act_silu = 0;
+};
+
+static int setup_conv(const ConvSpec& s, ConvParams* cp) {
+    memset(cp, 0, sizeof(*cp));
+    const long long M = (long long)s.n * s.h * s.w;
+    int seg = 0, ktot = 0;
+    if (s.a3) {
+        ConvGeom g;
+        CKI(conv_geom(s.n, s.h, s.w, &g));
+        CKI(make_map_nhwc(&cp->a_map[seg], s.a3, s.n, s.h, s.w, s.c3, g.box_h, g.box_n));
+        cp->seg_taps[seg] = 9; cp->seg_kblocks[seg] = s.c3 / 64; ktot += 9 * s.c3; ++seg;
+        cp->pointwise = 0; cp->tiles_per_image = g.tiles_per_image; cp->box_h = g.box_h; cp->box_n = g.box_n;
+        cp->rows_per_tile = g.rows_per_tile; cp->num_m_tiles = g.num_m_tiles;
+        if (s.a1) {
+            // the appended pointwise segment walks the same tiles through the geometric view
+            CKI(make_map_nhwc(&cp->a_map[seg], s.a1, s.n, s.h, s.w, s.c1, g.box_h, g.box_n));
+            cp->seg_taps[seg] = 1; cp->seg_kblocks[seg] = s.c1 / 64; ktot += s.c1; ++seg;
+        }
+    } else {
+        CKI(make_map_rows4d(&cp->a_map[seg], s.a1, M, s.c1, s.ld1));
+        cp->seg_taps[seg] = 1; cp->seg_kblocks[seg] = s.c1 / 64; ktot += s.c1; ++seg;
+        cp->pointwise = 1; cp->tiles_per_image = 1; cp->box_h = 1; cp->box_n = 1; cp->rows_per_tile = 128;
+        cp->num_m_tiles = (int)((M + 127) / 128);
+    }
+    cp->num_segs = seg;
+    cp->block_n = pick_block_n(s.cout);
+    if (cp->block_n == 0) return fail("unsupported output channel count %d", s.cout);
+    cp->num_n_tiles = (s.cout + cp->block_n - 1) / cp->block_n;
+    CKI(make_map_2d(&cp->b_map, s.wpacked, s.wrows, ktot, ktot, cp->block_n));
+    cp->M = (int)M; cp->Cout = s.cout; cp->out_mode = s.out_mode; cp->ld = s.ld;
+    cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu;
+    cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t;
+    if (s.out_mode != kOutNCHW && s.cout % 32 != 0) return fail("output channels must be a multiple of 32 (got %d)", s.cout);
+    return 0;
+}
+
+// ================================================================================================ exec build
+static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int* film_row) {
+    const vdt_unet_config& c = p->cfg;
+    const int R = ex->rows, hid = p->hid;
+    int res = c.resolution;
+    auto add_conv = [&](const ConvSpec& s) -> int {
+        std::unique_ptr<ConvParams> cp(new ConvParams());
+        CKI(setup_conv(s, cp.get()));
+        ex->convs.push_back(std::move(cp));
+        ex->steps.push_back({S_CONV, (int)ex->convs.size() - 1});
+        return 0;
+    };
+    auto add_gn = [&](const GroupNormParams& g) {
+        ex->gns.push_back(g);
+        ex->steps.push_back({S_GN, (int)ex->gns.size() - 1});
+    };
+    // ---- in_conv
+    bf16* patches; float* h;
+    const size_t hw0 = (size_t)res * res;
+    CKI(ex->acquire((size_t)R * hw0 * 64 * 2, (void**)&patches));
+    ex->im2cols.push_back({ex->xin, patches, R / ex->rep, ex->rep, c.in_channels, res, res});
+    ex->steps.push_back({S_IM2COL, (int)ex->im2cols.size() - 1});
+    CKI(ex->acquire((size_t)R * hw0 * hid * 4, (void**)&h));
+    {
+        ConvSpec s;
+        s.a1 = patches; s.c1 = 64; s.ld1 = 64; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_in; s.cout = hid; s.wrows = hid;
+        s.bias = p->W("in_conv.bias"); s.out_mode = kOutF32; s.out_f32 = h; s.ld = hid;
+        CKI(add_conv(s));
+    }
+    ex->release(patches);
+    struct Skip { float* ptr; int ch; };
+    std::vector<Skip> stack;
+    stack.push_back({h, hid});
+    bool h_on_stack = true;      // h aliases the top stack entry -> must not be released when replaced
+    int hch = hid;
+
+    for (auto& b : p->blocks) {
+        const std::string& n = b.name;
+        const int HW = res * res;
+        if (b.kind == 0) {
+            const float* src2 = nullptr; int c2 = 0; float* src2_buf = nullptr;
+            if (b.concat) { Skip sk = stack.back(); stack.pop_back(); src2 = sk.ptr; c2 = sk.ch; src2_buf = sk.ptr; }
+            const int cin = hch + c2;
+            if (cin != b.cin) return fail("internal: channel bookkeeping mismatch at %s (%d vs %d)", n.c_str(), cin, b.cin);
+            const bool skipconv = b.cin != b.cout;
+            const int ro = b.resample == kResDown ? res / 2 : b.resample == kResUp ? res * 2 : res;
+            const size_t HWo = (size_t)ro * ro;
+            bf16 *a1, *xraw = nullptr; float* xres = nullptr;
+            CKI(ex->acquire((size_t)R * HWo * cin * 2, (void**)&a1));
+            if (skipconv) CKI(ex->acquire((size_t)R * HW * cin * 2, (void**)&xraw));
+            if (b.resample != kResNone) CKI(ex->acquire((size_t)R * HWo * cin * 4, (void**)&xres));
+            GroupNormParams g{};
+            g.src1 = h; g.C1 = hch; g.src2 = src2; g.C2 = c2; g.B = R; g.H = res; g.W = res;
+            g.gamma = p->W(n + ".norm1.weight"); g.beta = p->W(n + ".norm1.bias");
+            g.silu = 1; g.resample = b.resample; g.out_act = a1; g.out_raw = xraw; g.out_res = xres;
+            add_gn(g);
+            // conv1
+            float* h1;
+            CKI(ex->acquire((size_t)R * HWo * b.cout * 4, (void**)&h1));
+            {
+                ConvSpec s;
+                s.a3 = a1; s.c3 = cin; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w1; s.cout = b.cout; s.wrows = b.cout;
+                s.bias = p->W(n + ".conv1.bias"); s.out_mode = kOutF32; s.out_f32 = h1; s.ld = b.cout;
+                CKI(add_conv(s));
+            }
+            ex->release(a1);
+            // norm2 + FiLM + SiLU
+            bf16* a2;
+            CKI(ex->acquire((size_t)R * HWo * b.cout * 2, (void**)&a2));
+            GroupNormParams g2{};
+            g2.src1 = h1; g2.C1 = b.cout; g2.B = R; g2.H = ro; g2.W = ro;
+            g2.gamma = p->W(n + ".norm2.weight"); g2.beta = p->W(n + ".norm2.bias");
+            g2.film = film; g2.film_row = film_row; g2.film_stride = p->film_total; g2.film_off = b.film_off;
+            g2.silu = 1; g2.resample = kResNone; g2.out_act = a2;
+            add_gn(g2);
+            ex->release(h1);
+            // conv2 (+ fused 1x1 skip conv as extra K) + residual
+            float* hout;
+            CKI(ex->acquire((size_t)R * HWo * b.cout * 4, (void**)&hout));
+            {
+                ConvSpec s;
+                s.a3 = a2; s.c3 = b.cout; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w2; s.cout = b.cout; s.wrows = b.cout;
+                if (skipconv) { s.a1 = xraw; s.c1 = cin; s.ld1 = cin; }
+                s.bias = b.bias2;
+                s.residual = skipconv ? nullptr : (b.resample != kResNone ? xres : h);
+                s.out_mode = kOutF32; s.out_f32 = hout; s.ld = b.cout;
+                CKI(add_conv(s));
+            }
+            ex->release(a2);
+            if (xraw) ex->release(xraw);
+            if (xres) ex->release(xres);
+            if (src2_buf) ex->release(src2_buf);
+            if (!h_on_stack) ex->release(h);
+            h = hout; hch = b.cout; h_on_stack = false; res = ro;
+        } else {
+            int hd, nh;
+            attn_dims(c, b.cin, &hd, &nh);
+            const int hidd = hd * nh, N = HW;
+            bf16 *a, *qk, *vt, *o;
+            CKI(ex->acquire((size_t)R * HW * b.cin * 2, (void**)&a));
+            GroupNormParams g{};
+            g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
+            g.gamma = p->W(n + ".norm.weight"); g.beta = p->W(n + ".norm.bias");
+            g.silu = 0; g.resample = kResNone; g.out_act = a;
+            add_gn(g);
+            CKI(ex->acquire((size_t)R * N * 2 * hidd * 2, (void**)&qk));
+            CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&vt));
+            {
+                ConvSpec s;
+                s.a1 = a; s.c1 = b.cin; s.ld1 = b.cin; s.n = R; s.h = res; s.w = res; s.wpacked = b.w1; s.cout = 3 * hidd;
+                s.wrows = 3 * hidd; s.bias = p->W(n + ".proj_in.bias"); s.out_mode = kOutBF16; s.out_bf16 = qk; s.out_t = vt;
+                s.ld = 2 * hidd; s.split_col = 2 * hidd;
+                CKI(add_conv(s));
+            }
+            ex->release(a);
+            CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&o));
+            {
+                std::unique_ptr<AttnParams> ap(new AttnParams());
+                memset(ap.get(), 0, sizeof(AttnParams));
+                CKI(make_map_2d(&ap->qk_map, qk, (long long)R * N, 2 * hidd, 2 * hidd, 128));
+                CKI(make_map_2d(&ap->k_map, qk, (long long)R * N, 2 * hidd, 2 * hidd, 64));
+                CKI(make_map_2d(&ap->vt_map, vt, (long long)R * hidd, N, N, hd));
+                ap->B = R; ap->N = N; ap->heads = nh; ap->d = hd; ap->hid = hidd;
+                ap->scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)hd));
+                ap->out = o;
+                ex->attns.push_back(std::move(ap));
+                ex->steps.push_back({S_ATTN, (int)ex->attns.size() - 1});
+            }
+            ex->release(qk); ex->release(vt);
+            float* hout;
+            CKI(ex->acquire((size_t)R * HW * b.cin * 4, (void**)&hout));
+            {
+                ConvSpec s;
+                s.a1 = o; s.c1 = hidd; s.ld1 = hidd; s.n = R; s.h = res; s.w = res; s.wpacked = b.w2; s.cout = b.cin; s.wrows = b.cin;
+                s.bias = p->W(n + ".proj_out.bias"); s.residual = h; s.out_mode = kOutF32; s.out_f32 = hout; s.ld = b.cin;
+                CKI(add_conv(s));
+            }
+            ex->release(o);
+            if (!h_on_stack) ex->release(h);
+            h = hout; h_on_stack = false;
+        }
+        if (b.push) { stack.push_back({h, hch}); h_on_stack = true; }
+    }
+    if (!stack.empty()) return fail("internal: skip stack not empty (%d)", (int)stack.size());
+    // ---- out_conv
+    {
+        const int HW = res * res;
+        bf16* a;
+        CKI(ex->acquire((size_t)R * HW * hch * 2, (void**)&a));
+        GroupNormParams g{};
+        g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
+        g.gamma = p->W("out_conv.0.weight"); g.beta = p->W("out_conv.0.bias");
+        g.silu = 1; g.resample = kResNone; g.out_act = a;
+        add_gn(g);
+        ConvSpec s;
+        s.a3 = a; s.c3 = hch; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_out; s.cout = c.out_channels; s.wrows = 16;
+        s.bias = p->W("out_conv.2.bias"); s.out_mode = kOutNCHW; s.out_f32 = ex->yout; s.ld = 0;
+        CKI(add_conv(s));
+        ex->release(a);
+        if (!h_on_stack) ex->release(h);
+    }
+    return 0;
+}
+
+static int add_embedding_steps(vdt_plan* p, Exec* ex, float* film, bool has_y) {
+    const int E = p->E, hid = p->hid, ER = ex->emb_rows;
+    float *temb, *e1, *e2, *act;
+    CKI(ex->acquire((size_t)ER * hid * 4, (void**)&temb));
+    CKI(ex->acquire((size_t)ER * E * 4, (void**)&e1));
+    CKI(ex->acquire((size_t)ER * E * 4, (void**)&e2));
+    CKI(ex->acquire((size_t)ER * E * 4, (void**)&act));
+    ex->tembs.push_back({ex->t_rows, temb, ER, hid});
+    ex->steps.push_back({S_TEMB, (int)ex->tembs.size() - 1});
+    ex->linears.push_back({temb, p->W("time_embed.0.weight"), p->W("time_embed.0.bias"), e1, ER, hid, E, 1});
+    ex->steps.push_back({S_LINEAR, (int)ex->linears.size() - 1});
+    ex->linears.push_back({e1, p->W("time_embed.2.weight"), p->W("time_embed.2.bias"), e2, ER, E, E, 0});
+    ex->steps.push_back({S_LINEAR, (int)ex->linears.size() - 1});
+    const bool cls = p->cfg.num_classes > 0 && has_y;
+    ex->clss.push_back({e2, cls ? ex->y_rows : nullptr, cls ? p->W("class_embed.1.weight") : nullptr,
+                        cls ? p->W("class_embed.1.bias") : nullptr, p->cfg.num_classes, act, ER, E});
+    ex->steps.push_back({S_CLSEMB, (int)ex->clss.size() - 1});
+    ex->linears.push_back({act, p->w_fc_all, p->b_fc_all, film, ER, E, p->film_total, 0});
+    ex->steps.push_back({S_LINEAR, (int)ex->linears.size() - 1});
+    // temb/e1/e2/act stay allocated for the life of the exec (tiny)
+    return 0;
+}
+
+static int run_steps(vdt_plan* p, Exec* ex, cudaStream_t st) {
+    for (const Step& s : ex->steps) {
+        cudaError_t e = cudaSuccess;
+        switch (s.kind) {
+            case S_CONV: e = launch_conv_gemm(*ex->convs[s.idx], p->num_sms, st); break;
+            case S_GN: e = launch_groupnorm(ex->gns[s.idx], st); break;
+            case S_ATTN: e = launch_attention(*ex->attns[s.idx], st); break;
+            case S_IM2COL: { auto& a = ex->im2cols[s.idx]; e = launch_im2col3x3(a.x, a.out, a.B, a.rep, a.C, a.H, a.W, st); break; }
+            case S_TEMB: { auto& a = ex->tembs[s.idx]; e = launch_timestep_embedding(a.t, a.out, a.rows, a.dim, st); break; }
+            case S_LINEAR: { auto& a = ex->linears[s.idx]; e = launch_linear_f32(a.x, a.W, a.b, a.out, a.rows, a.K, a.N, a.silu, st); break; }
+            case S_CLSEMB: { auto& a = ex->clss[s.idx]; e = launch_class_embed_silu(a.e, a.y, a.w, a.b, a.ncls, a.out, a.rows, a.E, st); break; }
+            case S_BEGIN: { auto& a = ex->begins[s.idx]; e = launch_sampler_begin_step(a.st, a.table, a.t_rows, a.nrows, a.T, st); break; }
+            case S_SAMPLE: e = launch_sampler_step(ex->samples[s.idx], st); break;
+        }
+        if (e != cudaSuccess) return fail("kernel launch failed (step kind %d): %s", (int)s.kind, cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+// Run the exec's step list, through a CUDA graph when enabled.
+static int run_exec(vdt_plan* p, Exec* ex, cudaStream_t st) {
+    // first run is eager (sets function attributes, surfaces launch errors); the second run captures
+    if (p->use_graph && !ex->graph && !ex->graph_failed && ex->runs++ >= 1) {
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            const int r = run_steps(p, ex, st);
+            cudaError_t e2 = cudaStreamEndCapture(st, &g);
+            if (r != 0) { if (g) cudaGraphDestroy(g); return r; }
+            if (e2 == cudaSuccess && g) {
+                if (cudaGraphInstantiate(&ex->graph, g, 0) != cudaSuccess) { ex->graph = nullptr; ex->graph_failed = true; }
+                cudaGraphDestroy(g);
+            } else {
+                ex->graph_failed = true;
+            }
+        } else {
+            ex->graph_failed = true;
+        }
+        cudaGetLastError();
+    }
+    g_launches += ex->steps.size();
+    if (ex->graph) {
+        CK(cudaGraphLaunch(ex->graph, st));
+        return 0;
+    }
+    return run_steps(p, ex, st);
+}
+
+static int get_forward_exec(vdt_plan* p, int rows, bool has_y, Exec** out) {
+    char key[64];
+    snprintf(key, sizeof(key), "fwd:%d:%d", rows, (int)has_y);
+    auto it = p->execs.find(key);
+    if (it != p->execs.end()) { *out = it->second.get(); return 0; }
+    if (p->execs.size() >= 4) p->execs.clear();
+    std::unique_ptr<Exec> ex(new Exec());
+    const vdt_unet_config& c = p->cfg;
+    const size_t HW = (size_t)c.resolution * c.resolution;
+    ex->rows = rows; ex->emb_rows = rows; ex->sampler = false; ex->has_y = has_y; ex->rep = 1;
+    CKI(ex->acquire(rows * HW * c.in_channels * 4, (void**)&ex->xin));
+    CKI(ex->acquire(rows * HW * c.out_channels * 4, (void**)&ex->yout));
+    CKI(ex->acquire(rows * sizeof(double), (void**)&ex->t_rows));
+    CKI(ex->acquire(rows * sizeof(int64_t), (void**)&ex->y_rows));
+    float* film;
+    CKI(ex->acquire((size_t)rows * p->film_total * 4, (void**)&film));
+    CKI(add_embedding_steps(p, ex.get(), film, has_y));
+    CKI(build_unet_steps(p, ex.get(), film, nullptr));
+    *out = ex.get();
+    p->execs[key] = std::move(ex);
+    return 0;
+}
+
+extern "C" int vdt_unet_forward(vdt_plan* p, const float* x, const double* t, const int64_t* y, float* out, int32_t batch,
+                                void* stream) {
+    if (!p || !x || !t || !out) return fail("null argument");
+    if (!p->finalized) return fail("plan not finalized (load every state_dict key, then vdt_plan_finalize)");
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    CKI(enter_work(p, user));
+    cudaStream_t st = p->work;
+    const vdt_unet_config& c = p->cfg;
+    const size_t HW = (size_t)c.resolution * c.resolution;
+    for (int b0 = 0; b0 < batch; b0 += c.max_rows) {
+        const int rows = std::min(c.max_rows, batch - b0);
+        Exec* ex;
+        CKI(get_forward_exec(p, rows, y != nullptr, &ex));
+        CK(cudaMemcpyAsync(ex->xin, x + (size_t)b0 * c.in_channels * HW, rows * HW * c.in_channels * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ex->t_rows, t + b0, rows * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        if (y) CK(cudaMemcpyAsync(ex->y_rows, y + b0, rows * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        CKI(run_exec(p, ex, st));
+        CK(cudaMemcpyAsync(out + (size_t)b0 * c.out_channels * HW, ex->yout, rows * HW * c.out_channels * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return leave_work(p, user);
+}
+
+// ================================================================================================ schedule (host, fp64)
+static double logsigmoid_d(double x) { return std::fmin(x, 0.0) - std::log1p(std::exp(-std::fabs(x))); }
+static double log1mexp_d(double x) { return x < -9.0 ? std::log1p(-std::exp(x)) : std::log(-std::expm1(x)); }
+static double lerp_d(double a, double b, double w) { return w < 0.5 ? a + w * (b - a) : b - (b - a) * (1.0 - w); }
+
+static int logsnr_d(const vdt_sampler_config& sc, double t, double* out) {
+    const double PI = 3.14159265358979323846;
+    switch (sc.logsnr_schedule) {
+        case VDT_SCHED_COSINE: {
+            const double t_from = std::atan(std::exp(-0.5 * sc.logsnr_max)) / (0.5 * PI);
+            const double t_to = std::atan(std::exp(-0.5 * sc.logsnr_min)) / (0.5 * PI);
+            *out = -2.0 * std::log(std::tan(lerp_d(t_from, t_to, t) * PI * 0.5));
+            return 0;
+        }
+        case VDT_SCHED_LINEAR: {
+            const double t_from = 1.0 / (1.0 + std::exp(-sc.logsnr_max)), t_to = 1.0 / (1.0 + std::exp(-sc.logsnr_min));
+            const double tt = lerp_d(t_from, t_to, t);
+            *out = std::log(tt) - std::log1p(-tt);
+            return 0;
+        }
+        case VDT_SCHED_SIGMOID: {
+            *out = sc.logsnr_max - lerp_d(0.0, 1.0, t) * (sc.logsnr_max - sc.logsnr_min);
+            return 0;
+        }
+        case VDT_SCHED_LEGACY: {
+            const double x_from = 0.9999, x_max = 0.9999, x_min = 0.98, slope = -0.0199;
+            const double x_to = lerp_d(x_max, x_min, t);
+            const double la = 1000.0 / slope * (x_to * std::log(x_to) - x_to - x_from * std::log(x_from) + x_from);
+            *out = la - log1mexp_d(la - 1e-9);
+            return 0;
+        }
+    }
+    return fail("unknown logsnr schedule %d", sc.logsnr_schedule);   // NotImplementedError, diffusion.py:96
+}
+
+extern "C" int vdt_step_coefficients(const vdt_sampler_config* scp, float* out) {
+    if (!scp || !out) return fail("null argument");
+    const vdt_sampler_config& sc = *scp;
+    const int T = sc.sample_timesteps;
+    if (T < 1) return fail("sample_timesteps must be >= 1");
+    for (int i = 0; i < T; ++i) {
+        double ls_d, lt_d;
+        CKI(logsnr_d(sc, (double)i / (double)T, &ls_d));
+        CKI(logsnr_d(sc, (double)(i + 1) / (double)T, &lt_d));
+        const float ls32 = (float)ls_d, lt32 = (float)lt_d;     // broadcast_to casts to x.dtype (diffusion.py:23-26)
+        const double ls = ls32, lt = lt32;                      // re-upcast inside the posterior (131, 171)
+        const double logr = lt - ls;
+        if (!(logr < 0.0)) return fail("log-SNR schedule is not strictly decreasing at step %d", i);   // assert, diffusion.py:119
+        double c1, c2, logvar;
+        if (sc.use_ddim) {
+            c1 = std::exp(0.5 * (logsigmoid_d(-ls) - logsigmoid_d(-lt)));
+            c2 = std::exp(log1mexp_d(0.5 * logr) + 0.5 * logsigmoid_d(ls));
+            logvar = -INFINITY;
+        } else {
+            const double l1mr = log1mexp_d(logr);
+            c1 = std::exp(logr + 0.5 * (logsigmoid_d(ls) - logsigmoid_d(lt)));
+            c2 = std::exp(l1mr + 0.5 * logsigmoid_d(ls));
+            const double lo = l1mr + logsigmoid_d(-ls), hi = l1mr + logsigmoid_d(-lt);
+            if (sc.model_var_type == VDT_VAR_FIXED_LARGE) logvar = hi;
+            else if (sc.model_var_type == VDT_VAR_FIXED_SMALL) logvar = lo;
+            else if (sc.model_var_type == VDT_VAR_FIXED_MEDIUM) logvar = lo + sc.intp_frac * (hi - lo);
+            else return fail("unknown model_var_type %d", sc.model_var_type);   // NotImplementedError, diffusion.py:161
+        }
+        float* o = out + (size_t)i * kCoefStride;
+        const float sig_pos = 1.0f / (1.0f + std::exp(-lt32)), sig_neg = 1.0f / (1.0f + std::exp(lt32));
+        o[0] = std::sqrt(sig_pos);
+        o[1] = std::sqrt(sig_neg);
+        o[2] = 1.0f / std::sqrt(sig_pos);
+        o[3] = std::exp(-0.5f * lt32);
+        o[4] = sig_pos;
+        o[5] = sig_neg;
+        o[6] = (float)c1;
+        o[7] = (float)c2;
+        const float lv32 = (float)logvar;
+        o[8] = std::isinf(lv32) ? 0.0f : std::exp(0.5f * lv32);
+        o[9] = lv32;
+        o[10] = ls32;
+        o[11] = lt32;
+    }
+    return 0;
+}
+
+// ================================================================================================ sampler
+static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs, bool has_label, const float* step_noise,
+                            long long noise_stride, Exec** out) {
+    const bool cfg = sc.w_guide > 0.0 && has_label;            // diffusion.py:368
+    const int rep = cfg ? 2 : 1;
+    char key[160];
+    snprintf(key, sizeof(key), "smp:%d:%d:%d:%d:%d:%d:%d:%.17g:%.17g:%.17g:%.17g:%llu:%p:%lld", imgs, (int)has_label,
+             sc.sample_timesteps, sc.model_out_type, sc.model_var_type, sc.logsnr_schedule, sc.use_ddim, sc.intp_frac,
+             sc.logsnr_min, sc.logsnr_max, sc.w_guide, (unsigned long long)sc.seed, (const void*)step_noise, noise_stride);
+    auto it = p->execs.find(key);
+    if (it != p->execs.end()) { *out = it->second.get(); return 0; }
+    if (p->execs.size() >= 4) p->execs.clear();
+    const vdt_unet_config& c = p->cfg;
+    const int Cm = sc.model_out_type == VDT_OUT_BOTH ? 2 * c.in_channels : c.in_channels;
+    if (Cm != c.out_channels)
+        return fail("model_out_type needs %d output channels but the UNet has %d", Cm, c.out_channels);
+    std::unique_ptr<Exec> ex(new Exec());
+    const size_t HW = (size_t)c.resolution * c.resolution;
+    const int T = sc.sample_timesteps;
+    ex->rows = imgs * rep; ex->rep = rep; ex->sampler = true; ex->has_y = has_label; ex->sc = sc;
+    const bool cond_model = c.num_classes > 0 && has_label;
+    ex->emb_rows = cond_model ? c.num_classes + 1 : 1;
+    CKI(ex->acquire(imgs * HW * c.in_channels * 4, (void**)&ex->xin));
+    CKI(ex->acquire((size_t)ex->rows * HW * c.out_channels * 4, (void**)&ex->yout));
+    CKI(ex->acquire(ex->emb_rows * sizeof(double), (void**)&ex->t_rows));
+    CKI(ex->acquire(ex->emb_rows * sizeof(int64_t), (void**)&ex->y_rows));
+    CKI(ex->acquire(ex->rows * sizeof(int), (void**)&ex->film_row));
+    CKI(ex->acquire(sizeof(SamplerState), (void**)&ex->state));
+    CKI(ex->acquire((size_t)T * kCoefStride * 4, (void**)&ex->coef_table));
+    iota_i64_kernel<<<(ex->emb_rows + 127) / 128, 128>>>(ex->y_rows, ex->emb_rows);
+    CK(cudaGetLastError());
+    std::vector<float> coefs((size_t)T * kCoefStride);
+    CKI(vdt_step_coefficients(&sc, coefs.data()));
+    CK(cudaMemcpy(ex->coef_table, coefs.data(), coefs.size() * 4, cudaMemcpyHostToDevice));
+    float* film;
+    CKI(ex->acquire((size_t)ex->emb_rows * p->film_total * 4, (void**)&film));
+    ex->begins.push_back({ex->state, ex->coef_table, ex->t_rows, ex->emb_rows, T});
+    ex->steps.push_back({S_BEGIN, 0});
+    CKI(add_embedding_steps(p, ex.get(), film, cond_model));
+    CKI(build_unet_steps(p, ex.get(), film, ex->film_row));
+    SamplerStepParams sp{};
+    sp.model_out = ex->yout; sp.x_t = ex->xin; sp.x_s = ex->xin; sp.noise = step_noise; sp.noise_step_stride = noise_stride;
+    sp.st = ex->state; sp.seed = sc.seed; sp.B = imgs; sp.C = c.in_channels; sp.HW = (int)HW; sp.cfg = cfg ? 1 : 0;
+    sp.model_out_type = sc.model_out_type; sp.w = (float)sc.w_guide;
+    ex->samples.push_back(sp);
+    ex->steps.push_back({S_SAMPLE, 0});
+    *out = ex.get();
+    p->execs[key] = std::move(ex);
+    return 0;
+}
+
+extern "C" int vdt_p_sample(vdt_plan* p, const vdt_sampler_config* scp, const float* noise, const int64_t* label,
+                            const float* step_noise, float* out, int32_t batch, void* stream) {
+    if (!p || !scp || !noise || !out) return fail("null argument");
+    if (!p->finalized) return fail("plan not finalized (load every state_dict key, then vdt_plan_finalize)");
+    const vdt_sampler_config& sc = *scp;
+    if (sc.model_out_type < 0 || sc.model_out_type > 3) return fail("unknown model_out_type %d", sc.model_out_type);
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    CKI(enter_work(p, user));
+    cudaStream_t st = p->work;
+    const vdt_unet_config& c = p->cfg;
+    const size_t CHW = (size_t)c.in_channels * c.resolution * c.resolution;
+    const bool cfg = sc.w_guide > 0.0 && label != nullptr;
+    const int64_t* row_label = c.num_classes > 0 ? label : nullptr;   // an unconditional UNet ignores y (unet.py:289)
+    const int rep = cfg ? 2 : 1;
+    const int chunk = std::max(1, c.max_rows / rep);
+    const int T = sc.sample_timesteps;
+    for (int i0 = 0; i0 < batch; i0 += chunk) {
+        const int imgs = std::min(chunk, batch - i0);
+        Exec* ex;
+        CKI(get_sampler_exec(p, sc, imgs, label != nullptr, step_noise, (long long)batch * (long long)CHW, &ex));
+        CK(cudaMemcpyAsync(ex->xin, noise + (size_t)i0 * CHW, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
+        film_rows_kernel<<<(ex->rows + 127) / 128, 128, 0, st>>>(row_label ? row_label + i0 : nullptr, ex->film_row, ex->rows, rep);
+        CK(cudaGetLastError());
+        sampler_init_state_kernel<<<1, 32, 0, st>>>(ex->state, T - 1, i0);
+        CK(cudaGetLastError());
+        g_launches += 2;
+        for (int step = 0; step < T; ++step) CKI(run_exec(p, ex, st));
+        CK(cudaMemcpyAsync(out + (size_t)i0 * CHW, ex->xin, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return leave_work(p, user);
+}
+
+extern "C" int vdt_p_sample_host(vdt_plan* p, const vdt_sampler_config* scp, const float* noise, const int64_t* label,
+                                 const float* step_noise, float* out, int32_t batch) {
+    if (!p || !scp || !noise || !out) return fail("null argument");
+    const vdt_unet_config& c = p->cfg;
+    const size_t CHW = (size_t)c.in_channels * c.resolution * c.resolution;
+    const size_t n = (size_t)batch * CHW;
+    float *d_noise = nullptr, *d_out = nullptr, *d_sn = nullptr;
+    int64_t* d_label = nullptr;
+    int rc = 0;
+    cudaStream_t st = nullptr;
+    auto cleanup = [&]() { cudaFree(d_noise); cudaFree(d_out); cudaFree(d_sn); cudaFree(d_label); };
+#define CKH(expr)                                                                               \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) { cleanup(); return fail("%s failed: %s", #expr, cudaGetErrorString(_e)); } \
+    } while (0)
+    CKH(cudaMalloc(&d_noise, n * 4));
+    CKH(cudaMalloc(&d_out, n * 4));
+    CKH(cudaMemcpyAsync(d_noise, noise, n * 4, cudaMemcpyHostToDevice, st));
+    if (label) {
+        CKH(cudaMalloc(&d_label, batch * sizeof(int64_t)));
+        CKH(cudaMemcpyAsync(d_label, label, batch * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    }
+    if (step_noise) {
+        CKH(cudaMalloc(&d_sn, n * 4 * scp->sample_timesteps));
+        CKH(cudaMemcpyAsync(d_sn, step_noise, n * 4 * scp->sample_timesteps, cudaMemcpyHostToDevice, st));
+    }
+    rc = vdt_p_sample(p, scp, d_noise, d_label, d_sn, d_out, batch, st);
+    if (rc == 0) {
+        CKH(cudaMemcpyAsync(out, d_out, n * 4, cudaMemcpyDeviceToHost, st));
+        CKH(cudaStreamSynchronize(st));
+    }
+    cleanup();
+#undef CKH
+    return rc;
+}
+
+// ================================================================================================ kernel-level hooks
+extern "C" int vdt_op_conv(const void* x, int32_t batch, int32_t h, int32_t w, int32_t cin, const float* w_oihw, int32_t cout,
+                           int32_t ksize, const float* bias, const float* residual, float* out, void* stream) {
+    if (ksize != 1 && ksize != 3) return fail("ksize must be 1 or 3");
+    if (cin % 64) return fail("cin must be a multiple of 64");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int taps = ksize * ksize;
+    bf16* wp = nullptr;
+    const int wrows = std::max(cout, 16);
+    CK(cudaMalloc(&wp, (size_t)wrows * taps * cin * 2));
+    CK(cudaMemset(wp, 0, (size_t)wrows * taps * cin * 2));
+    int rc = pack_conv(w_oihw, wp, cout, cin, taps, taps * cin, 0);
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (rc == 0) {
+        ConvSpec s;
+        if (ksize == 3) { s.a3 = (const bf16*)x; s.c3 = cin; } else { s.a1 = (const bf16*)x; s.c1 = cin; s.ld1 = cin; }
+        s.n = batch; s.h = h; s.w = w; s.wpacked = wp; s.cout = cout; s.wrows = wrows; s.bias = bias; s.residual = residual;
+        s.out_mode = kOutF32; s.out_f32 = out; s.ld = cout;
+        std::unique_ptr<ConvParams> cp(new ConvParams());
+        rc = setup_conv(s, cp.get());
+        if (rc == 0) {
+            cudaError_t e = launch_conv_gemm(*cp, nsm, st);
+            ++g_launches;
+            if (e != cudaSuccess) rc = fail("conv launch failed: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(wp);
+    if (rc == 0 && e != cudaSuccess) return fail("conv kernel failed: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+extern "C" int vdt_op_groupnorm(const float* src1, int32_t c1, const float* src2, int32_t c2, int32_t batch, int32_t h,
+                                int32_t w, const float* gamma, const float* beta, const float* film, int32_t film_stride,
+                                int32_t film_off, int32_t silu, int32_t resample, void* out_act, void* out_raw, float* out_res,
+                                void* stream) {
+    GroupNormParams g{};
+    g.src1 = src1; g.C1 = c1; g.src2 = src2; g.C2 = c2; g.B = batch; g.H = h; g.W = w; g.gamma = gamma; g.beta = beta;
+    g.film = film; g.film_row = nullptr; g.film_stride = film_stride; g.film_off = film_off; g.silu = silu; g.resample = resample;
+    g.out_act = (bf16*)out_act; g.out_raw = (bf16*)out_raw; g.out_res = out_res;
+    cudaError_t e = launch_groupnorm(g, reinterpret_cast<cudaStream_t>(stream));
+    ++g_launches;
+    if (e != cudaSuccess) return fail("groupnorm launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int vdt_op_attention(const void* qk, const void* vt, void* out, int32_t batch, int32_t n, int32_t heads, int32_t d,
+                                void* stream) {
+    const int hid = heads * d;
+    std::unique_ptr<AttnParams> ap(new AttnParams());
+    memset(ap.get(), 0, sizeof(AttnParams));
+    CKI(make_map_2d(&ap->qk_map, qk, (long long)batch * n, 2 * hid, 2 * hid, 128));
+    CKI(make_map_2d(&ap->k_map, qk, (long long)batch * n, 2 * hid, 2 * hid, 64));
+    CKI(make_map_2d(&ap->vt_map, vt, (long long)batch * hid, n, n, d));
+    ap->B = batch; ap->N = n; ap->heads = heads; ap->d = d; ap->hid = hid;
+    ap->scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)d));
+    ap->out = (bf16*)out;
+    cudaError_t e = launch_attention(*ap, reinterpret_cast<cudaStream_t>(stream));
+    ++g_launches;
+    if (e != cudaSuccess) return fail("attention launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int vdt_op_sampler_step(const float* model_out, const float* x_t, const float* noise, float* x_s, int32_t batch,
+                                   int32_t c, int32_t hw, int32_t cfg, int32_t model_out_type, int32_t step,
+                                   const float* coef_host, float w, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    SamplerState hs{};
+    hs.next_step = step - 1; hs.step = step; hs.img0 = 0;
+    for (int i = 0; i < kCoefStride; ++i) hs.coef[i] = coef_host[i];
+    SamplerState* ds = nullptr;
+    CK(cudaMalloc(&ds, sizeof(SamplerState)));
+    CK(cudaMemcpy(ds, &hs, sizeof(hs), cudaMemcpyHostToDevice));
+    SamplerStepParams sp{};
+    sp.model_out = model_out; sp.x_t = x_t; sp.x_s = x_s; sp.noise = noise;
+    sp.noise_step_stride = 0; sp.st = ds; sp.seed = 0; sp.B = batch; sp.C = c; sp.HW = hw; sp.cfg = cfg;
+    sp.model_out_type = model_out_type; sp.w = w;
+    cudaError_t e = launch_sampler_step(sp, st);
+    ++g_launches;
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(ds);
+    if (e != cudaSuccess) return fail("sampler_step launch failed: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return fail("sampler_step failed: %s", cudaGetErrorString(e2));
+    return 0;
+}

@@ -1,0 +1,235 @@
+// Small kernels around the UNet: input patch extraction, timestep/class embedding MLP (fp32),
+// and the fused per-step sampler update (v/eps/x0 -> x0, clip, DDIM / ancestral posterior mean,
+// classifier-free-guidance combine, noise injection).
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace vdt {
+namespace {
+
+// ------------------------------------------------------------------------------------------ im2col
+__global__ void im2col3x3_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int rep, int C, int H,
+                                 int W) {
+    const long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long rows = static_cast<long long>(B) * rep * H * W;
+    if (row >= rows) return;
+    const int HW = H * W;
+    const int img = static_cast<int>(row / HW), pix = static_cast<int>(row % HW);
+    const int h = pix / W, w = pix % W;
+    const float* xi = x + static_cast<size_t>(img / rep) * C * HW;
+    float v[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+        for (int c = 0; c < C; ++c) v[tap * C + c] = __ldg(xi + static_cast<size_t>(c) * HW + hh * W + ww);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + row * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+}
+
+// ------------------------------------------------------------------------------------------ embedding
+__global__ void timestep_embedding_kernel(const double* __restrict__ t, float* __restrict__ out, int rows, int dim) {
+    const int half = dim / 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * half) return;
+    const int r = idx / half, k = idx % half;
+    const double c = log(10000.0) / static_cast<double>(half - 1);
+    const double ang = (1000.0 * t[r]) * exp(-static_cast<double>(k) * c);
+    out[static_cast<size_t>(r) * dim + k] = static_cast<float>(sin(ang));
+    out[static_cast<size_t>(r) * dim + half + k] = static_cast<float>(cos(ang));
+    if ((dim & 1) && k == 0) out[static_cast<size_t>(r) * dim + dim - 1] = 0.f;
+}
+
+constexpr int kLinRows = 8;
+// one warp per output feature n, kLinRows rows at a time
+__global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                         const float* __restrict__ b, float* __restrict__ out,
+                                                         int rows, int K, int N, int silu_out) {
+    extern __shared__ float xs[];                    // [kLinRows][K]
+    const int r0 = blockIdx.y * kLinRows;
+    const int nr = min(kLinRows, rows - r0);
+    for (int i = threadIdx.x; i < kLinRows * K; i += blockDim.x) {
+        const int r = i / K;
+        xs[i] = (r < nr) ? x[static_cast<size_t>(r0 + r) * K + (i % K)] : 0.f;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + warp;
+    if (n >= N) return;
+    float acc[kLinRows];
+#pragma unroll
+    for (int r = 0; r < kLinRows; ++r) acc[r] = 0.f;
+    const float* w = W + static_cast<size_t>(n) * K;
+    for (int k = lane; k < K; k += 32) {
+        const float wv = __ldg(w + k);
+#pragma unroll
+        for (int r = 0; r < kLinRows; ++r) acc[r] = fmaf(wv, xs[r * K + k], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kLinRows; ++r) {
+        float v = acc[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[r] = v;
+    }
+    if (lane < nr) {
+        float v = 0.f;
+#pragma unroll
+        for (int r = 0; r < kLinRows; ++r) if (lane == r) v = acc[r];
+        v += __ldg(b + n);
+        if (silu_out) v = v / (1.f + expf(-v));
+        out[static_cast<size_t>(r0 + lane) * N + n] = v;
+    }
+}
+
+__global__ void class_embed_silu_kernel(const float* __restrict__ e, const int64_t* __restrict__ y,
+                                        const float* __restrict__ w_cls, const float* __restrict__ b_cls,
+                                        int num_classes, float* __restrict__ out, int rows, int E) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * E) return;
+    const int r = idx / E, j = idx % E;
+    float v = e[idx];
+    if (y != nullptr) {
+        const long long cls = y[r];
+        float add = b_cls[j];
+        if (cls > 0) add += w_cls[static_cast<size_t>(j) * num_classes + (cls - 1)];
+        v += add;
+    }
+    out[idx] = v / (1.f + expf(-v));
+}
+
+// ------------------------------------------------------------------------------------------ sampler
+__global__ void sampler_begin_step_kernel(SamplerState* st, const float* __restrict__ coef_table, double* t_rows,
+                                          int nrows, int T) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int step = st->next_step;
+        st->step = step;
+        st->next_step = step - 1;
+        for (int i = 0; i < kCoefStride; ++i) st->coef[i] = coef_table[step * kCoefStride + i];
+        const double t = static_cast<double>(step + 1) / static_cast<double>(T);   // diffusion.py:364
+        for (int r = 0; r < nrows; ++r) t_rows[r] = t;
+    }
+}
+
+// Philox4x32-10 counter RNG + Box-Muller for on-device ancestral noise (used only when no noise
+// tensor is injected; the stream is this library's own, not torch's).
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float philox_normal(unsigned long long seed, uint32_t step, unsigned long long idx) {
+    const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(idx >> 1), static_cast<uint32_t>(idx >> 33), step, 0u),
+                               make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    const float u1 = (static_cast<float>(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = (static_cast<float>(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    return (idx & 1) ? rad * sn : rad * cs;
+}
+
+__device__ __forceinline__ float pred_x0(int type, float x, float o, float o2, const float* cf) {
+    float x0;
+    if (type == 3) x0 = x * cf[0] - o * cf[1];                       // v   (diffusion.py:233-234)
+    else if (type == 0) x0 = o;                                      // x0
+    else if (type == 1) x0 = x * cf[2] - o * cf[3];                  // eps (diffusion.py:207-208)
+    else { const float xe = x * cf[2] - o2 * cf[3]; x0 = o * cf[5] + xe * cf[4]; }   // both (211-214)
+    return fminf(fmaxf(x0, -1.f), 1.f);                              // clip_denoised (diffusion.py:327)
+}
+
+__global__ void sampler_step_kernel(const SamplerStepParams p) {
+    const long long n = static_cast<long long>(p.B) * p.C * p.HW;
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const float* cf = p.st->coef;
+    const int step = p.st->step;
+    const int chw = p.C * p.HW;
+    const int b = static_cast<int>(i / chw), e = static_cast<int>(i % chw);
+    const int Cm = (p.model_out_type == 2) ? 2 * p.C : p.C;
+    const int rep = 1 + p.cfg;
+    const float x = p.x_t[i];
+    const float* mo = p.model_out + static_cast<size_t>(b) * rep * Cm * p.HW + e;
+    const size_t second = static_cast<size_t>(p.C) * p.HW;           // "both": eps half follows the x0 half
+    const float o = mo[0];
+    const float o2 = (p.model_out_type == 2) ? mo[second] : 0.f;
+    const float c1 = cf[6], c2 = cf[7], sd = cf[8];
+    const bool last = (step == 0);
+    const float x0c = pred_x0(p.model_out_type, x, o, o2, cf);
+    float mean = last ? x0c : c1 * x + c2 * x0c;                     // where(cond, mean, pred_x_0)  (diffusion.py:378)
+    if (p.cfg) {
+        const float* mu = mo + static_cast<size_t>(Cm) * p.HW;
+        const float u = mu[0];
+        const float u2 = (p.model_out_type == 2) ? mu[second] : 0.f;
+        const float x0u = pred_x0(p.model_out_type, x, u, u2, cf);
+        const float mean_u = last ? x0u : c1 * x + c2 * x0u;
+        mean = mean + p.w * (mean - mean_u);                         // guided, not re-clipped (diffusion.py:384)
+    }
+    if (!last && sd > 0.f) {
+        float z;
+        if (p.noise) z = p.noise[static_cast<long long>(step) * p.noise_step_stride + static_cast<long long>(p.st->img0) * chw + i];
+        else z = philox_normal(p.seed, static_cast<uint32_t>(step), static_cast<unsigned long long>(p.st->img0) * chw + i);
+        mean += sd * z;
+    }
+    p.x_s[i] = mean;
+}
+
+}  // namespace
+
+cudaError_t launch_im2col3x3(const float* x, bf16* out, int B, int rep, int C, int H, int W, cudaStream_t stream) {
+    if (9 * C > 64) return cudaErrorInvalidValue;
+    const long long rows = static_cast<long long>(B) * rep * H * W;
+    if (rows == 0) return cudaSuccess;
+    im2col3x3_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, stream>>>(x, out, B, rep, C, H, W);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_timestep_embedding(const double* t, float* out, int rows, int dim, cudaStream_t stream) {
+    const int n = rows * (dim / 2);
+    if (n == 0) return cudaSuccess;
+    timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, stream>>>(t, out, rows, dim);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_linear_f32(const float* x, const float* W, const float* b, float* out, int rows, int K, int N,
+                              int silu_out, cudaStream_t stream) {
+    if (rows == 0) return cudaSuccess;
+    const size_t smem = static_cast<size_t>(kLinRows) * K * sizeof(float);
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    dim3 grid((N + 7) / 8, (rows + kLinRows - 1) / kLinRows);
+    linear_f32_kernel<<<grid, 256, smem, stream>>>(x, W, b, out, rows, K, N, silu_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_class_embed_silu(const float* e, const int64_t* y, const float* w_cls, const float* b_cls,
+                                    int num_classes, float* out, int rows, int E, cudaStream_t stream) {
+    const int n = rows * E;
+    if (n == 0) return cudaSuccess;
+    class_embed_silu_kernel<<<(n + 255) / 256, 256, 0, stream>>>(e, y, w_cls, b_cls, num_classes, out, rows, E);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sampler_begin_step(SamplerState* st, const float* coef_table, double* t_rows, int nrows, int T,
+                                      cudaStream_t stream) {
+    sampler_begin_step_kernel<<<1, 32, 0, stream>>>(st, coef_table, t_rows, nrows, T);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sampler_step(const SamplerStepParams& p, cudaStream_t stream) {
+    const long long n = static_cast<long long>(p.B) * p.C * p.HW;
+    if (n == 0) return cudaSuccess;
+    sampler_step_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace vdt

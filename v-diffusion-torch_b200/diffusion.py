@@ -1,0 +1,148 @@
+"""Drop-in for the sampling half of ``v_diffusion.diffusion`` (diffusion.py:42-112, 260-414).
+
+``GaussianDiffusion.p_sample`` keeps the reference signature.  When ``denoise_fn`` is this
+package's ``UNet`` the whole reverse loop runs inside the C library (one CUDA graph per step, the
+v->x0 / clip / posterior mean / guidance combine / noise update fused in one kernel).  Any other
+callable (e.g. a recording wrapper around the UNet) goes through the same fused update kernel one
+step at a time, so tests can observe per-step model outputs.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from .unet import UNet
+
+
+class LogSNRSchedule:
+    """Callable returned by get_logsnr_schedule; also carries the parameters the C side needs."""
+
+    def __init__(self, schedule, logsnr_min, logsnr_max):
+        if schedule not in _lib.SCHEDULES:
+            raise NotImplementedError(schedule)                     # diffusion.py:96
+        self.schedule, self.logsnr_min, self.logsnr_max = schedule, float(logsnr_min), float(logsnr_max)
+
+    def __call__(self, t):
+        tt = t.to(torch.float64)
+        lmin, lmax = self.logsnr_min, self.logsnr_max
+        if self.schedule == "cosine":
+            a = math.atan(math.exp(-0.5 * lmax)) / (0.5 * math.pi)
+            b = math.atan(math.exp(-0.5 * lmin)) / (0.5 * math.pi)
+            out = -2 * torch.log(torch.tan((a + tt * (b - a)) * math.pi * 0.5))
+        elif self.schedule == "linear":
+            a, b = 1 / (1 + math.exp(-lmax)), 1 / (1 + math.exp(-lmin))
+            out = torch.logit(a + tt * (b - a))
+        elif self.schedule == "sigmoid":
+            out = lmax - tt * (lmax - lmin)
+        else:
+            x_to = 0.9999 + tt * (0.98 - 0.9999)
+            la = 1000 / -0.0199 * (x_to * torch.log(x_to) - x_to - 0.9999 * math.log(0.9999) + 0.9999)
+            z = la - 1e-9
+            out = la - torch.where(z < -9, torch.log1p(-torch.exp(z)), torch.log(-torch.expm1(z)))
+        return out.to(t.dtype)
+
+
+def get_logsnr_schedule(schedule, logsnr_min: float = -20., logsnr_max: float = 20., rescale: bool = False):
+    if rescale:
+        raise NotImplementedError("allow_rescale is off in every reference config (defaults.json:45)")
+    return LogSNRSchedule(schedule, logsnr_min, logsnr_max)
+
+
+class GaussianDiffusion:
+    def __init__(self, logsnr_fn, sample_timesteps, model_out_type, model_var_type, reweight_type, loss_type,
+                 intp_frac=None, w_guide=0.1, p_uncond=0.1, x0eps_coef=False):
+        if not isinstance(logsnr_fn, LogSNRSchedule):
+            raise TypeError("logsnr_fn must come from v_diffusion_b200.get_logsnr_schedule")
+        if x0eps_coef:
+            raise NotImplementedError("x0eps_coef=True is not used by any reference config (defaults.json:52)")
+        if model_out_type not in _lib.OUT_TYPES:
+            raise NotImplementedError(model_out_type)               # diffusion.py:253-257
+        self.logsnr_fn = logsnr_fn
+        self.sample_timesteps = sample_timesteps
+        self.model_out_type, self.model_var_type = model_out_type, model_var_type
+        self.reweight_type, self.loss_type = reweight_type, loss_type
+        self.intp_frac, self.w_guide, self.p_uncond, self.x0eps_coef = intp_frac, w_guide, p_uncond, x0eps_coef
+
+    # ------------------------------------------------------------------ C structs
+    def sampler_config(self, use_ddim, seed=None):
+        if not use_ddim and self.model_var_type not in _lib.VAR_TYPES:
+            raise NotImplementedError(self.model_var_type)          # diffusion.py:161
+        if not use_ddim and self.model_var_type == "fixed_medium" and not isinstance(self.intp_frac, float):
+            raise AssertionError("fixed_medium needs a float intp_frac")   # diffusion.py:155
+        sc = _lib.SamplerConfig()
+        sc.sample_timesteps = int(self.sample_timesteps)
+        sc.model_out_type = _lib.OUT_TYPES[self.model_out_type]
+        sc.model_var_type = _lib.VAR_TYPES.get(self.model_var_type, 1)
+        sc.logsnr_schedule = _lib.SCHEDULES[self.logsnr_fn.schedule]
+        sc.use_ddim = int(bool(use_ddim))
+        sc.intp_frac = float(self.intp_frac or 0.)
+        sc.logsnr_min, sc.logsnr_max = self.logsnr_fn.logsnr_min, self.logsnr_fn.logsnr_max
+        sc.w_guide = float(self.w_guide)
+        sc.seed = int(seed or 0)
+        return sc
+
+    def step_coefficients(self, use_ddim):
+        """[T, 12] fp32 host table (include/vdt_b200.h: vdt_step_coefficients)."""
+        sc = self.sampler_config(use_ddim)
+        out = torch.empty((self.sample_timesteps, _lib.COEF_STRIDE), dtype=torch.float32)
+        _lib.check(_lib.lib().vdt_step_coefficients(C.byref(sc), _lib.ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ p_sample (diffusion.py:394-414)
+    @torch.no_grad()
+    def p_sample(self, denoise_fn, shape, noise=None, label=None, device="cpu", seed=None, use_ddim=False,
+                 step_noise=None):
+        """``step_noise`` (extension): optional (T, B, C, H, W) tensor of the per-step normal draws the
+        reference takes from its generator (diffusion.py:389), so both sides inject identical noise."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("v_diffusion_b200 samples on CUDA (sm_100a) only; there is no CPU fallback")
+        B = shape[0]
+        if noise is None:
+            gen = None if seed is None else torch.Generator(device).manual_seed(seed)
+            x_t = torch.randn(shape, device=device, generator=gen)
+        else:
+            x_t = noise.to(device)
+        x_t = x_t.to(torch.float32).contiguous()
+        if label is not None:
+            label = label.to(device=device, dtype=torch.int64).contiguous()
+        if step_noise is not None:
+            step_noise = step_noise.to(device=device, dtype=torch.float32).contiguous()
+        sc = self.sampler_config(use_ddim, seed)
+        L = _lib.lib()
+        if isinstance(denoise_fn, UNet):
+            plan = denoise_fn.plan_for(shape[2], device)
+            out = torch.empty_like(x_t)
+            with torch.cuda.device(device):
+                _lib.check(L.vdt_p_sample(plan, C.byref(sc), _lib.ptr(x_t), _lib.ptr(label), _lib.ptr(step_noise),
+                                          _lib.ptr(out), B, _lib.current_stream_ptr()))
+            return out.cpu()
+        # generic callable: same fused update kernel, one step at a time
+        coefs = self.step_coefficients(use_ddim)
+        use_cfg = (self.w_guide > 0) and (label is not None)        # diffusion.py:368
+        T = self.sample_timesteps
+        hw = shape[2] * shape[3]
+        if not use_ddim and step_noise is None:
+            gen = None if seed is None else torch.Generator(device).manual_seed(seed)
+        with torch.cuda.device(device):
+            for ti in reversed(range(T)):
+                t = torch.full((B,), (ti + 1) / T, dtype=torch.float64, device=device)
+                if use_cfg:
+                    xin, tin = x_t.repeat_interleave(2, dim=0), t.repeat_interleave(2)
+                    yin = label.repeat_interleave(2)
+                    yin[1::2] = 0
+                else:
+                    xin, tin, yin = x_t, t, label
+                model_out = denoise_fn(xin, tin, yin).to(torch.float32).contiguous()
+                z = None
+                if not use_ddim and ti > 0:
+                    z = step_noise[ti] if step_noise is not None else torch.randn(shape, device=device, generator=gen)
+                    z = z.contiguous()
+                x_s = torch.empty_like(x_t)
+                _lib.check(L.vdt_op_sampler_step(_lib.ptr(model_out), _lib.ptr(x_t), _lib.ptr(z), _lib.ptr(x_s), B,
+                                                 shape[1], hw, int(use_cfg), sc.model_out_type, ti,
+                                                 _lib.ptr(coefs[ti].contiguous()), float(self.w_guide),
+                                                 _lib.current_stream_ptr()))
+                x_t = x_s
+        return x_t.cpu()
