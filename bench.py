@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Headline benchmark: DDIM images/sec, CIFAR-10 class-conditional UNet, CFG w=1 (cond/uncond batched as 2B
+rows in one UNet call), 100-step DDIM, batch 4096 per GPU (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one denoising step of the real sampling loop over the whole per-GPU batch: one UNet forward on
+2*B rows plus the fused sampler update (diffusion.py:360-392).  100 such steps make B images, so
+images/s = N_gpus * B * K / (100 * t_K).  Inputs are synthetic (seeded normal noise, random labels, random
+non-zero weights of the reference architecture); every tensor a step touches is far larger than L2.
+One process per GPU; multi-GPU is weak scaling with no collective in the loop.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_STEPS = 100
+W_GUIDE = 1.0
+METRIC = "ddim_images_per_sec_cifar10_cfg_100step"
+# cifar10_cond.json merged with defaults.json (tests/golden/merged_configs.json pins this in the CPU tests)
+CIFAR_COND_MODEL = dict(in_channels=3, hid_channels=256, ch_multipliers=[1, 1, 1], num_res_blocks=3,
+                        apply_attn=[False, True, True], drop_rate=0.2, num_heads=1)
+FLOP_PER_ROW = 37.644423168e9          # conv 35.965 + attention 1.648 + linear 0.031 GF (vdt_plan_flops)
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(tflops=p["bf16_tflops_sustained"], tflops_burst=p["bf16_tflops"], hbm=p["hbm_gbs"], source="measured")
+    except Exception:
+        return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        busy = sorted(sm)[len(sm) // 4:]                     # drop idle samples at the edges
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 7)}
+
+
+def build_model(device, seed):
+    import torch
+    from v_diffusion_b200 import UNet, GaussianDiffusion, get_logsnr_schedule
+    torch.manual_seed(seed)
+    net = UNet(out_channels=3, num_classes=10, multitags=False, **CIFAR_COND_MODEL)
+    g = torch.Generator().manual_seed(seed + 7)
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            # the reference zero-initialises conv2 / proj_out / out_conv: a zero network would
+            # exercise nothing, so every all-zero matrix gets N(0, 1/fan_in) and biases / norms get jitter
+            if p.ndim >= 2 and not bool(p.any()):
+                fan_in = p[0].numel()
+                p.copy_(torch.randn(p.shape, generator=g) / fan_in ** 0.5)
+            elif p.ndim == 1:
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+    net = net.to(device).eval()
+    diff = GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), T_STEPS, "v", "fixed_medium", "snr_trunc",
+                             "mse", intp_frac=0.3, w_guide=W_GUIDE)
+    return net, diff
+
+
+def cpu_baseline(seconds_budget=20.0):
+    """Oracle port (oracle/unet_ref.py, plain PyTorch fp32 on the host cores) on a bounded sample of the same
+    workload: B=2 images -> 4 UNet rows per denoising step, a few steps, scaled by 100 steps / image."""
+    import torch
+    from oracle import unet_forward, make_state_dict
+    from oracle.unet_ref import unet_config_from_json
+    torch.set_num_threads(os.cpu_count())
+    cfg = unet_config_from_json(CIFAR_COND_MODEL, 3, 3, num_classes=10)
+    sd = make_state_dict(cfg, 0)
+    B = 2
+    x = torch.randn(2 * B, 3, 32, 32)
+    t = torch.full((2 * B,), 0.5, dtype=torch.float64)
+    y = torch.tensor([3, 0, 7, 0])
+    unet_forward(sd, cfg, x, t, y)                        # warm-up
+    n, t0 = 0, time.perf_counter()
+    while n < 2 or (time.perf_counter() - t0 < seconds_budget and n < 16):
+        unet_forward(sd, cfg, x, t, y)
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": B / (dt * T_STEPS), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle UNet forward on {2 * B} rows (B={B} images, CFG pair) x {n} denoising steps, "
+                      f"{dt:.3f} s/step, scaled by {T_STEPS} steps per image"}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is a Python/PyTorch
+    repo that cannot travel to the GPU box, so this times the oracle port (pinned to the reference by
+    tests/golden) with all host threads, same metric/config, on a bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import unet_forward, make_state_dict
+    from oracle.unet_ref import unet_config_from_json
+    from oracle.diffusion_ref import step_coefficients, _pred_x0
+    torch.set_num_threads(os.cpu_count())
+    cfg = unet_config_from_json(CIFAR_COND_MODEL, 3, 3, num_classes=10)
+    sd = make_state_dict(cfg, 0)
+    B = 2
+    g = torch.Generator().manual_seed(1234)
+    x_t = torch.randn(B, 3, 32, 32, generator=g)
+    label = torch.randint(10, (B,), generator=g) + 1
+    co = step_coefficients(T_STEPS, use_ddim=True)
+
+    def step(x_t, ti):
+        xin = x_t.repeat_interleave(2, dim=0)
+        yin = label.repeat_interleave(2).clone(); yin[1::2] = 0
+        t = torch.full((2 * B,), co["t_model"][ti], dtype=torch.float64)
+        out = unet_forward(sd, cfg, xin, t, yin)
+        x0 = _pred_x0(xin, out, torch.tensor(co["logsnr_t"][ti]), "v").clamp(-1, 1)
+        mean = float(co["c1"][ti]) * xin + float(co["c2"][ti]) * x0
+        return mean[0::2] + W_GUIDE * (mean[0::2] - mean[1::2])
+    ti = T_STEPS - 1
+    for _ in range(args.warmup):
+        x_t = step(x_t, ti); ti = max(ti - 1, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        x_t = step(x_t, ti); ti = max(ti - 1, 1)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = B / (dt * T_STEPS)
+    line = {"metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "CIFAR-10 cond UNet (cifar10_cond.json), CFG w=1 as 2B rows, 100-step DDIM; "
+                                   f"bounded sample B={B} images per step on the host CPU"},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"B={B} images (4 UNet rows) per denoising step, {args.steps} steps"},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world, local_rank):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from v_diffusion_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    L = _lib.lib()
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    net, diff = build_model(device, seed=0)
+    net.max_rows = args.max_rows
+    plan = net.plan_for(32, device)
+    sc = diff.sampler_config(use_ddim=True)
+    g = torch.Generator(device=device).manual_seed(1234 + rank)      # SURVEY §8d cfg 2: per-rank seeds 1234+rank
+    noise = torch.randn(B, 3, 32, 32, device=device, generator=g)
+    label = torch.randint(10, (B,), device=device, generator=g) + 1
+    stream = torch.cuda.current_stream()
+
+    def run_range(x, first, n):
+        _lib.check(L.vdt_p_sample_range(plan, C.byref(sc), _lib.ptr(x), _lib.ptr(label), None, B, first, n,
+                                        C.c_void_p(stream.cuda_stream)))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    x = noise.clone()
+    run_range(x, T_STEPS - 1, W)                                      # warm-up (eager pass + graph capture)
+    barrier()
+    x = noise.clone()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = L.vdt_kernel_launches()
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record(stream)
+        done, first = 0, T_STEPS - 1
+        while done < K:                                               # K may exceed one trajectory
+            n = min(K - done, first + 1)
+            run_range(x, first, n)
+            done += n
+            first = T_STEPS - 1 if first - n < 0 else first - n
+        ev1.record(stream)
+        barrier()
+    launches = L.vdt_kernel_launches() - n0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    ms_step = ms_total / K
+    value = world * B / (ms_step * 1e-3 * T_STEPS)
+
+    # ---- per-kernel-family timing of the same step (CUDA events around every launch, on the launching stream)
+    L.vdt_profile_enable(1)
+    xs = noise.clone()
+    run_range(xs, T_STEPS - 1, 1)
+    torch.cuda.synchronize()
+    fam_ms, fam_n = (C.c_double * 4)(), (C.c_uint64 * 4)()
+    L.vdt_profile_read(fam_ms, fam_n)
+    L.vdt_profile_enable(0)
+    fc, fa, fl = C.c_double(), C.c_double(), C.c_double()
+    L.vdt_plan_flops(plan, C.byref(fc), C.byref(fa), C.byref(fl))
+    rows = 2 * B
+    conv_tflops = fc.value * rows / (fam_ms[0] * 1e-3) / 1e12 if fam_ms[0] > 0 else 0.0
+    peaks = read_peaks()
+    prof_total = sum(fam_ms)
+    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all conv/1x1 launches of a step)",
+                "achieved": conv_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": conv_tflops / peaks["tflops"],
+                "peak_source": peaks["source"] + " sustained bf16 cuBLAS", "traffic": None,
+                "algorithmic_flop_per_launch_avg": fc.value * rows / max(1, fam_n[0]),
+                "avg_launch_ms": fam_ms[0] / max(1, fam_n[0]), "launches_per_step": int(fam_n[0]),
+                "step_share": {"conv": fam_ms[0] / prof_total, "groupnorm": fam_ms[1] / prof_total,
+                               "attention": fam_ms[2] / prof_total, "other": fam_ms[3] / prof_total},
+                "family_ms_per_step": {"conv": fam_ms[0], "groupnorm": fam_ms[1], "attention": fam_ms[2], "other": fam_ms[3]},
+                "unet_tflops_whole_step": FLOP_PER_ROW * rows / (ms_step * 1e-3) / 1e12,
+                "unet_frac_of_peak_whole_step": FLOP_PER_ROW * rows / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
+                "unet_frac_of_nominal_2250": FLOP_PER_ROW * rows / (ms_step * 1e-3) / 1e12 / 2250.0}
+
+    # ---- end to end through the public API: host noise/labels in (pinned), CPU images out, all 100 steps
+    noise_h = noise.cpu().pin_memory()
+    label_h = label.cpu().pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    imgs = diff.p_sample(net, (B, 3, 32, 32), noise=noise_h, label=label_h, device=device, use_ddim=True)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        gathered = [torch.empty_like(noise) for _ in range(world)]   # the only collective: final image gather
+        dist.all_gather(gathered, imgs.to(device))
+    assert torch.isfinite(imgs).all()
+    e2e = {"value": world * B / e2e_s.item(), "unit": "images/s",
+           "h2d_bytes_per_step": (noise_h.numel() * 4 + label_h.numel() * 8) / T_STEPS,
+           "d2h_bytes_per_step": imgs.numel() * 4 / T_STEPS,
+           "note": "one GaussianDiffusion.p_sample call = 100 denoising steps; bytes are per call / 100",
+           "seconds_per_call": e2e_s.item()}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "CIFAR-10 class-conditional UNet (cifar10_cond.json), CFG w=1 batched cond/uncond "
+                                       f"(2B rows), 100-step DDIM, batch {B} per GPU; step = one denoising step over the batch",
+                           "batch_per_gpu": B, "rows_per_unet_call": 2 * B, "chunk_rows": args.max_rows,
+                           "steps_per_image": T_STEPS, "l2": "inputs_exceed_l2", "parallelism": f"replicas x{world}",
+                           "accumulate": "fp32", "residual_stream": "fp32"},
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="images per GPU (BASELINE configs[1]: 4096)")
+    ap.add_argument("--max-rows", type=int, default=int(os.environ.get("VDT_MAX_ROWS", "1024")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run on this node
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

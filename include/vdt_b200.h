@@ -38,6 +38,8 @@ typedef struct vdt_unet_config {
     int32_t multitags;            /* not supported yet: must be 0 */
     int32_t resolution;           /* H = W of the images this plan serves (DATA_INFO[...]["resolution"]) */
     int32_t max_rows;             /* UNet batch rows processed per pass; larger batches are chunked */
+    int32_t operand_dtype;        /* 16-bit tensor-core operand format: 0 = fp16 (default), 1 = bf16; accumulation,
+                                     GroupNorm statistics, softmax and the residual stream are fp32 either way */
 } vdt_unet_config;
 
 /* GaussianDiffusion constructor + get_logsnr_schedule arguments — diffusion.py:260-291, 42-112. */
@@ -88,6 +90,12 @@ int vdt_unet_forward(vdt_plan* plan, const float* x, const double* t, const int6
  * fp32 [T, B, C, R, R] (the per-step normal draws of diffusion.py:389, indexed by step); out fp32 [B, C, R, R]. */
 int vdt_p_sample(vdt_plan* plan, const vdt_sampler_config* sc, const float* noise, const int64_t* label,
                  const float* step_noise, float* out, int32_t batch, void* stream);
+/* A slice of the same loop, in place on x (fp32 [B, C, R, R]): runs `num_steps` consecutive steps starting
+ * at step index `first_step` (T-1 is the first step of a trajectory) — p_sample_step (diffusion.py:360-392)
+ * applied num_steps times.  vdt_p_sample == copy noise, range(T-1, T), copy out.  Used by bench.py to time
+ * K denoising steps of the real loop. */
+int vdt_p_sample_range(vdt_plan* plan, const vdt_sampler_config* sc, float* x, const int64_t* label,
+                       const float* step_noise, int32_t batch, int32_t first_step, int32_t num_steps, void* stream);
 /* Same with HOST buffers (pinned or pageable); copies in/out inside the call and synchronises. */
 int vdt_p_sample_host(vdt_plan* plan, const vdt_sampler_config* sc, const float* noise, const int64_t* label,
                       const float* step_noise, float* out, int32_t batch);
@@ -100,18 +108,30 @@ int vdt_step_coefficients(const vdt_sampler_config* sc, float* out);
 /* Counters: kernels launched by this library since process start (graph replays count their nodes). */
 uint64_t vdt_kernel_launches(void);
 
+/* Algorithmic FLOPs (1 MAC = 2 FLOP) of one UNet.forward batch row, split like SURVEY §6:
+ * convolutions (incl. 1x1), attention matmuls, embedding linears. */
+int vdt_plan_flops(const vdt_plan* plan, double* conv, double* attn, double* linear);
+
+/* Per-kernel-family device timing.  While enabled, steps run eagerly (no graph) with a CUDA-event pair
+ * around every launch on the launching stream; vdt_profile_read returns accumulated milliseconds and launch
+ * counts for VDT_PROF_* families and resets them. */
+enum { VDT_PROF_CONV = 0, VDT_PROF_GROUPNORM = 1, VDT_PROF_ATTENTION = 2, VDT_PROF_OTHER = 3, VDT_PROF_FAMILIES = 4 };
+int vdt_profile_enable(int on);
+int vdt_profile_read(double* ms4, uint64_t* launches4);
+
 /* ---- kernel-level entry points (used by the parity tests; device pointers) ------------------------- */
-/* conv2d(k x k, pad k/2) on bf16 NHWC input with fp32 OIHW weights -> fp32 NHWC (+bias, +residual). */
+/* f16: 1 = fp16 operands, 0 = bf16.  conv2d(k x k, pad k/2) on 16-bit NHWC input with fp32 OIHW weights -> fp32 NHWC (+bias, +residual). */
 int vdt_op_conv(const void* x_bf16_nhwc, int32_t batch, int32_t h, int32_t w, int32_t cin, const float* w_oihw,
-                int32_t cout, int32_t ksize, const float* bias, const float* residual, float* out_nhwc, void* stream);
+                int32_t cout, int32_t ksize, const float* bias, const float* residual, float* out_nhwc, int32_t f16,
+                void* stream);
 /* GroupNorm(32, 1e-6) [+FiLM] [+SiLU] [+resample 0 none / 1 avgpool2 / 2 nearest x2] over concat(src1, src2). */
 int vdt_op_groupnorm(const float* src1, int32_t c1, const float* src2, int32_t c2, int32_t batch, int32_t h, int32_t w,
                      const float* gamma, const float* beta, const float* film, int32_t film_stride, int32_t film_off,
-                     int32_t silu, int32_t resample, void* out_act_bf16, void* out_raw_bf16, float* out_res,
-                     void* stream);
-/* attention on qk bf16 [B*N, 2*hid], v^T bf16 [B*hid, N] -> bf16 [B*N, hid] */
-int vdt_op_attention(const void* qk_bf16, const void* vt_bf16, void* out_bf16, int32_t batch, int32_t n, int32_t heads,
-                     int32_t d, void* stream);
+                     int32_t silu, int32_t resample, void* out_act_16, void* out_raw_16, float* out_res,
+                     int32_t f16, void* stream);
+/* attention on qk 16-bit [B*N, 2*hid], v^T 16-bit [B*hid, N] -> 16-bit [B*N, hid] */
+int vdt_op_attention(const void* qk_16, const void* vt_16, void* out_16, int32_t batch, int32_t n, int32_t heads,
+                     int32_t d, int32_t f16, void* stream);
 /* one sampler update with explicit step index; coef = one row of vdt_step_coefficients (host pointer). */
 int vdt_op_sampler_step(const float* model_out, const float* x_t, const float* noise, float* x_s, int32_t batch,
                         int32_t c, int32_t hw, int32_t cfg, int32_t model_out_type, int32_t step, const float* coef_host,

@@ -25,6 +25,11 @@ def _check(L, rc):
     assert rc == 0, L.vdt_last_error().decode()
 
 
+DT = {1: torch.float16, 0: torch.bfloat16}
+# rounding unit of the 16-bit operand formats relative to bf16
+EPS = {1: 0.25, 0: 1.0}
+
+
 def _rel(a, b):
     return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
 
@@ -45,19 +50,20 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize("f16", [1, 0])
 @pytest.mark.parametrize("B,H,cin,cout,k,res", CONV_CASES)
-def test_conv_gemm(L, B, H, cin, cout, k, res):
+def test_conv_gemm(L, B, H, cin, cout, k, res, f16):
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + H + cin + cout + k)
     x = torch.randn(B, cin, H, H, device="cuda", generator=g)
     w = torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k)
     bias = torch.randn(cout, device="cuda", generator=g)
     resid = torch.randn(B, H, H, cout, device="cuda", generator=g) if res else None
-    xb = x.to(torch.bfloat16)
+    xb = x.to(DT[f16])
     x_nhwc = xb.permute(0, 2, 3, 1).contiguous()
     out = torch.full((B, H, H, cout), float("nan"), device="cuda")
-    _check(L, L.vdt_op_conv(_p(x_nhwc), B, H, H, cin, _p(w), cout, k, _p(bias), _p(resid), _p(out), None))
+    _check(L, L.vdt_op_conv(_p(x_nhwc), B, H, H, cin, _p(w), cout, k, _p(bias), _p(resid), _p(out), f16, None))
     torch.cuda.synchronize()
-    ref = F.conv2d(xb.double(), w.to(torch.bfloat16).double(), bias.double(), padding=k // 2).permute(0, 2, 3, 1)
+    ref = F.conv2d(xb.double(), w.to(DT[f16]).double(), bias.double(), padding=k // 2).permute(0, 2, 3, 1)
     if res:
         ref = ref + resid.double()
     assert torch.isfinite(out).all()
@@ -78,8 +84,9 @@ GN_CASES = [
 ]
 
 
+@pytest.mark.parametrize("f16", [1, 0])
 @pytest.mark.parametrize("B,H,c1,c2,film,silu,resample,want_raw,want_res", GN_CASES)
-def test_groupnorm(L, B, H, c1, c2, film, silu, resample, want_raw, want_res):
+def test_groupnorm(L, B, H, c1, c2, film, silu, resample, want_raw, want_res, f16):
     g = torch.Generator(device="cuda").manual_seed(H * 7 + c1 + c2)
     C_ = c1 + c2
     s1 = torch.randn(B, H, H, c1, device="cuda", generator=g) * 2 + 0.5
@@ -89,11 +96,11 @@ def test_groupnorm(L, B, H, c1, c2, film, silu, resample, want_raw, want_res):
     stride, off = 3 * 2 * C_, 2 * C_
     ftab = torch.randn(B, stride, device="cuda", generator=g) * 0.3 if film else None
     Ho = H // 2 if resample == 1 else H * 2 if resample == 2 else H
-    out_act = torch.zeros(B, Ho, Ho, C_, device="cuda", dtype=torch.bfloat16)
-    out_raw = torch.zeros(B, H, H, C_, device="cuda", dtype=torch.bfloat16) if want_raw else None
+    out_act = torch.zeros(B, Ho, Ho, C_, device="cuda", dtype=DT[f16])
+    out_raw = torch.zeros(B, H, H, C_, device="cuda", dtype=DT[f16]) if want_raw else None
     out_res = torch.zeros(B, Ho, Ho, C_, device="cuda") if want_res else None
     _check(L, L.vdt_op_groupnorm(_p(s1), c1, _p(s2), c2, B, H, H, _p(gamma), _p(beta), _p(ftab), stride, off,
-                                 int(silu), resample, _p(out_act), _p(out_raw), _p(out_res), None))
+                                 int(silu), resample, _p(out_act), _p(out_raw), _p(out_res), f16, None))
     torch.cuda.synchronize()
     x = torch.cat([s1, s2], dim=3) if c2 else s1
     xn = x.permute(0, 3, 1, 2).double()
@@ -107,10 +114,10 @@ def test_groupnorm(L, B, H, c1, c2, film, silu, resample, want_raw, want_res):
     rs = (lambda z: F.avg_pool2d(z, 2)) if resample == 1 else (lambda z: F.interpolate(z, scale_factor=2, mode="nearest")) if resample == 2 else (lambda z: z)
     y = rs(y).permute(0, 2, 3, 1)
     err = (out_act.double() - y).abs().max().item()
-    assert err <= 4e-2 * max(1.0, y.abs().max().item() / 4), f"act err {err}"      # bf16 output rounding
-    assert _rel(out_act, y) <= 4e-3
+    assert err <= 4e-2 * EPS[f16] * max(1.0, y.abs().max().item() / 4), f"act err {err}"      # 16-bit output rounding
+    assert _rel(out_act, y) <= 4e-3 * EPS[f16]
     if want_raw:
-        assert torch.equal(out_raw, x.to(torch.bfloat16))
+        assert torch.equal(out_raw, x.to(DT[f16]))
     if want_res:
         r = rs(xn).permute(0, 2, 3, 1)
         assert (out_res.double() - r).abs().max().item() <= 1e-5
@@ -120,27 +127,28 @@ ATTN_CASES = [(2, 1024, 1, 256), (3, 256, 1, 256), (3, 64, 1, 256), (2, 256, 1, 
               (2, 128, 1, 128)]
 
 
+@pytest.mark.parametrize("f16", [1, 0])
 @pytest.mark.parametrize("B,N,heads,d", ATTN_CASES)
-def test_attention(L, B, N, heads, d):
+def test_attention(L, B, N, heads, d, f16):
     g = torch.Generator(device="cuda").manual_seed(N + heads * 3 + d)
     hid = heads * d
-    q = torch.randn(B, N, heads, d, device="cuda", generator=g).to(torch.bfloat16)
-    k = torch.randn(B, N, heads, d, device="cuda", generator=g).to(torch.bfloat16)
-    v = torch.randn(B, N, heads, d, device="cuda", generator=g).to(torch.bfloat16)
+    q = torch.randn(B, N, heads, d, device="cuda", generator=g).to(DT[f16])
+    k = torch.randn(B, N, heads, d, device="cuda", generator=g).to(DT[f16])
+    v = torch.randn(B, N, heads, d, device="cuda", generator=g).to(DT[f16])
     # make the softmax peaky in places so the lazy rescale path (row max jumps by > 2^8) is exercised
     q[:, : N // 2] *= 3.0
     k[:, N // 2:] *= 2.0
     qk = torch.cat([q.reshape(B * N, hid), k.reshape(B * N, hid)], dim=1).contiguous()
     vt = v.permute(0, 2, 3, 1).reshape(B * hid, N).contiguous()
-    out = torch.zeros(B * N, hid, device="cuda", dtype=torch.bfloat16)
-    _check(L, L.vdt_op_attention(_p(qk), _p(vt), _p(out), B, N, heads, d, None))
+    out = torch.zeros(B * N, hid, device="cuda", dtype=DT[f16])
+    _check(L, L.vdt_op_attention(_p(qk), _p(vt), _p(out), B, N, heads, d, f16, None))
     torch.cuda.synchronize()
     qd, kd, vd = (z.double().permute(0, 2, 1, 3) for z in (q, k, v))           # B, h, N, d
     w = torch.softmax(qd @ kd.transpose(-1, -2) / math.sqrt(d), dim=-1)
     ref = (w @ vd).permute(0, 2, 1, 3).reshape(B * N, hid)
     assert torch.isfinite(out.float()).all()
-    assert _rel(out, ref) <= 1e-2, _rel(out, ref)           # P and the output are rounded to bf16
-    assert (out.double() - ref).abs().max().item() <= 6e-2
+    assert _rel(out, ref) <= 1e-2 * EPS[f16], _rel(out, ref)           # P and the output are rounded to 16 bits
+    assert (out.double() - ref).abs().max().item() <= 6e-2 * EPS[f16]
 
 
 @pytest.mark.parametrize("mot,cfg,last", [(3, 1, False), (3, 1, True), (0, 0, False), (1, 0, False), (2, 0, False),

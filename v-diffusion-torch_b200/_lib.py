@@ -20,6 +20,7 @@ OUT_TYPES = {"x0": 0, "eps": 1, "both": 2, "v": 3}
 VAR_TYPES = {"fixed_small": 0, "fixed_large": 1, "fixed_medium": 2}
 SCHEDULES = {"cosine": 0, "linear": 1, "sigmoid": 2, "legacy": 3}
 COEF_STRIDE = 12
+OPERAND_DTYPES = {"fp16": 0, "bf16": 1}
 
 
 class UNetConfig(C.Structure):
@@ -28,7 +29,7 @@ class UNetConfig(C.Structure):
                 ("num_res_blocks", C.c_int32), ("apply_attn", C.c_int32 * VDT_MAX_LEVELS),
                 ("embedding_dim", C.c_int32), ("head_dim", C.c_int32), ("num_heads", C.c_int32),
                 ("num_classes", C.c_int32), ("multitags", C.c_int32), ("resolution", C.c_int32),
-                ("max_rows", C.c_int32)]
+                ("max_rows", C.c_int32), ("operand_dtype", C.c_int32)]
 
 
 class SamplerConfig(C.Structure):
@@ -98,11 +99,15 @@ def lib():
     L.vdt_plan_finalize.argtypes = [vp]
     L.vdt_unet_forward.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     L.vdt_p_sample.argtypes = [vp, C.POINTER(SamplerConfig), vp, vp, vp, vp, i32, vp]
+    L.vdt_p_sample_range.argtypes = [vp, C.POINTER(SamplerConfig), vp, vp, vp, i32, i32, i32, vp]
+    L.vdt_plan_flops.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.vdt_profile_enable.argtypes = [C.c_int]
+    L.vdt_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.vdt_p_sample_host.argtypes = [vp, C.POINTER(SamplerConfig), vp, vp, vp, vp, i32]
     L.vdt_step_coefficients.argtypes = [C.POINTER(SamplerConfig), vp]
-    L.vdt_op_conv.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp]
-    L.vdt_op_groupnorm.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
-    L.vdt_op_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    L.vdt_op_conv.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp, i32, vp]
+    L.vdt_op_groupnorm.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
+    L.vdt_op_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.vdt_op_sampler_step.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, C.c_float, vp]
     _lib = L
     return L
@@ -110,7 +115,8 @@ def lib():
 
 EXPORTS = ["vdt_last_error", "vdt_version", "vdt_kernel_launches", "vdt_plan_create", "vdt_plan_destroy",
            "vdt_plan_num_weights", "vdt_plan_weight_name", "vdt_plan_weight_shape", "vdt_plan_load_weight",
-           "vdt_plan_finalize", "vdt_unet_forward", "vdt_p_sample", "vdt_p_sample_host", "vdt_step_coefficients",
+           "vdt_plan_finalize", "vdt_unet_forward", "vdt_p_sample", "vdt_p_sample_range", "vdt_p_sample_host",
+           "vdt_step_coefficients", "vdt_plan_flops", "vdt_profile_enable", "vdt_profile_read",
            "vdt_op_conv", "vdt_op_groupnorm", "vdt_op_attention", "vdt_op_sampler_step"]
 
 

@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc_s = umma_idesc_bf16(kQRows, kKeys);
-            const uint32_t idesc_o = umma_idesc_bf16(kQRows, d);
+            const uint32_t idesc_s = umma_idesc_16(kQRows, kKeys, p.f16);
+            const uint32_t idesc_o = umma_idesc_16(kQRows, d, p.f16);
             auto issue_s = [&](int j) {
                 const int s = j & 1;
                 mbar_wait(&sm.k_full[s], (j >> 1) & 1);
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                 for (int kk = 0; kk < d / 16; ++kk) {
                     const uint64_t ad = umma_desc_sw128(smem_u32(sm.q + (kk >> 2) * 16384)) + 2 * (kk & 3);
                     const uint64_t bd = umma_desc_sw128(smem_u32(sm.k[s] + (kk >> 2) * 8192)) + 2 * (kk & 3);
-                    umma_bf16(tmem_s, ad, bd, idesc_s, kk != 0);
+                    umma_16(tmem_s, ad, bd, idesc_s, kk != 0);
                 }
                 umma_commit(sm.s_full);
             };
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                 for (int kk = 0; kk < kKeys / 16; ++kk) {
                     const uint64_t ad = umma_desc_sw128(smem_u32(sm.p[s])) + 2 * kk;
                     const uint64_t bd = umma_desc_sw128(smem_u32(sm.v[s])) + 2 * kk;
-                    umma_bf16(tmem_o, ad, bd, idesc_o, (j | kk) != 0);
+                    umma_16(tmem_o, ad, bd, idesc_o, (j | kk) != 0);
                 }
                 umma_commit(&sm.kv_empty[s]);             // K_j / V_j / P_j free, O updated
             }
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                     lsum += e[i];
                 }
                 *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) =
-                    make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+                    make_uint4(pack_16(e[0], e[1], p.f16), pack_16(e[2], e[3], p.f16), pack_16(e[4], e[5], p.f16), pack_16(e[6], e[7], p.f16));
             }
             l += lsum;
             fence_proxy_async_smem();
@@ -215,10 +215,10 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                 uint4* dst = reinterpret_cast<uint4*>(p.out + grow * p.hid + h * d + c0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    dst[i] = make_uint4(pack_bf16(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l),
-                                        pack_bf16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l),
-                                        pack_bf16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l),
-                                        pack_bf16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
+                    dst[i] = make_uint4(pack_16(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l, p.f16),
+                                        pack_16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l, p.f16),
+                                        pack_16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l, p.f16),
+                                        pack_16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l, p.f16));
             }
         }
     }

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(kBM, p.block_n);
+            const uint32_t idesc = umma_idesc_16(kBM, p.block_n, p.f16);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     const uint64_t bdesc = umma_desc_sw128(a_addr + kABytes);
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k)
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        umma_16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -182,14 +182,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                             uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + grow * p.ld + col0);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                                dst[j] = make_uint4(pack_16(v[8 * j], v[8 * j + 1], p.f16), pack_16(v[8 * j + 2], v[8 * j + 3], p.f16),
+                                                    pack_16(v[8 * j + 4], v[8 * j + 5], p.f16), pack_16(v[8 * j + 6], v[8 * j + 7], p.f16));
                         } else {
                             const long long img = grow / p.HW;
                             const int pix = static_cast<int>(grow - img * p.HW);
-                            bf16* dst = p.out_t + (img * (p.Cout - p.split_col) + (col0 - p.split_col)) * p.HW + pix;
+                            h16* dst = p.out_t + (img * (p.Cout - p.split_col) + (col0 - p.split_col)) * p.HW + pix;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.HW] = __float2bfloat16(v[j]);
+                            for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.HW] = cvt_16(v[j], p.f16);
                         }
                     }
                 } else {   // kOutNCHW

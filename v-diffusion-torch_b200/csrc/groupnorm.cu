@@ -31,11 +31,11 @@ __device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
     for (int i = 0; i < VEC; ++i) v[i] = f[i];
 }
 template <int VEC>
-__device__ __forceinline__ void store_bf16(bf16* p, const float (&v)[VEC]) {
+__device__ __forceinline__ void store_16(h16* p, const float (&v)[VEC], int f16) {
     if (VEC == 4) {
-        *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+        *reinterpret_cast<uint2*>(p) = make_uint2(pack_16(v[0], v[1], f16), pack_16(v[2], v[3], f16));
     } else {
-        *reinterpret_cast<uint32_t*>(p) = pack_bf16(v[0], v[1]);
+        *reinterpret_cast<uint32_t*>(p) = pack_16(v[0], v[1], f16);
     }
 }
 template <int VEC>
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
 
     if (p.resample == kResDown) {
         const int Wo = p.W / 2, HWo = HW / 4;
-        bf16* oa = p.out_act + static_cast<size_t>(b) * HWo * C + c;
+        h16* oa = p.out_act + static_cast<size_t>(b) * HWo * C + c;
         float* orr = p.out_res ? p.out_res + static_cast<size_t>(b) * HWo * C + c : nullptr;
         for (int po = pp; po < HWo; po += PPH) {
             const int ho = po / Wo, wo = po % Wo;
@@ -157,12 +157,12 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             }
 #pragma unroll
             for (int i = 0; i < VEC; ++i) { acc[i] *= 0.25f; racc[i] *= 0.25f; }
-            store_bf16<VEC>(oa + static_cast<size_t>(po) * C, acc);
+            store_16<VEC>(oa + static_cast<size_t>(po) * C, acc, p.f16);
             if (orr) store_f32<VEC>(orr + static_cast<size_t>(po) * C, racc);
         }
     } else if (p.resample == kResUp) {
         const int Wo = p.W * 2;
-        bf16* oa = p.out_act + static_cast<size_t>(b) * HW * 4 * C + c;
+        h16* oa = p.out_act + static_cast<size_t>(b) * HW * 4 * C + c;
         float* orr = p.out_res ? p.out_res + static_cast<size_t>(b) * HW * 4 * C + c : nullptr;
         for (int pix = pp; pix < HW; pix += PPH) {
             const int h = pix / p.W, w = pix % p.W;
@@ -172,13 +172,13 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 const size_t po = static_cast<size_t>(2 * h + (d >> 1)) * Wo + 2 * w + (d & 1);
-                store_bf16<VEC>(oa + po * C, y);
+                store_16<VEC>(oa + po * C, y, p.f16);
                 if (orr) store_f32<VEC>(orr + po * C, x);
             }
         }
     } else {
-        bf16* oa = p.out_act + static_cast<size_t>(b) * HW * C + c;
-        bf16* ow = p.out_raw ? p.out_raw + static_cast<size_t>(b) * HW * C + c : nullptr;
+        h16* oa = p.out_act + static_cast<size_t>(b) * HW * C + c;
+        h16* ow = p.out_raw ? p.out_raw + static_cast<size_t>(b) * HW * C + c : nullptr;
         int pix = pp;
         for (; pix + PPH < HW; pix += 2 * PPH) {
             float x0[VEC], x1[VEC], y0[VEC], y1[VEC];
@@ -186,19 +186,19 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             load_vec<VEC>(src + static_cast<size_t>(pix + PPH) * sC, x1);
             norm_act(x0, y0);
             norm_act(x1, y1);
-            store_bf16<VEC>(oa + static_cast<size_t>(pix) * C, y0);
-            store_bf16<VEC>(oa + static_cast<size_t>(pix + PPH) * C, y1);
+            store_16<VEC>(oa + static_cast<size_t>(pix) * C, y0, p.f16);
+            store_16<VEC>(oa + static_cast<size_t>(pix + PPH) * C, y1, p.f16);
             if (ow) {
-                store_bf16<VEC>(ow + static_cast<size_t>(pix) * C, x0);
-                store_bf16<VEC>(ow + static_cast<size_t>(pix + PPH) * C, x1);
+                store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, p.f16);
+                store_16<VEC>(ow + static_cast<size_t>(pix + PPH) * C, x1, p.f16);
             }
         }
         for (; pix < HW; pix += PPH) {
             float x0[VEC], y0[VEC];
             load_vec<VEC>(src + static_cast<size_t>(pix) * sC, x0);
             norm_act(x0, y0);
-            store_bf16<VEC>(oa + static_cast<size_t>(pix) * C, y0);
-            if (ow) store_bf16<VEC>(ow + static_cast<size_t>(pix) * C, x0);
+            store_16<VEC>(oa + static_cast<size_t>(pix) * C, y0, p.f16);
+            if (ow) store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, p.f16);
         }
     }
 }

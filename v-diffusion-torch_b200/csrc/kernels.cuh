@@ -9,7 +9,7 @@
 
 namespace vdt {
 
-typedef __nv_bfloat16 bf16;
+typedef uint16_t h16;   // storage of a 16-bit GEMM operand: IEEE fp16 (default) or bf16, per the launch's `f16` flag
 
 // ------------------------------------------------------------------------------------------------
 // Implicit-GEMM convolution / linear layer on tcgen05 (conv_gemm.cu)
@@ -22,7 +22,7 @@ constexpr int kConvMaxSegs = 3;
 
 enum ConvOutMode : int {
     kOutF32 = 0,        // fp32 [M, ld]            (+bias, +residual, optional SiLU)
-    kOutBF16 = 1,       // bf16 [M, ld] for columns < split_col; columns >= split_col are written
+    kOutBF16 = 1,       // 16-bit [M, ld] for columns < split_col; columns >= split_col are written
                         // transposed per image: out_t[(img * (Cout - split_col) + col - split_col) * HW + pix]
     kOutNCHW = 2,       // fp32 [img, Cout, HW]    (network output, Cout may be tiny)
 };
@@ -43,11 +43,12 @@ struct alignas(64) ConvParams {
     int ld;                            // row stride (elements) of out_f32 / out_bf16 / residual
     int split_col, HW;
     int act_silu;
+    int f16;                           // operand / 16-bit output format: 1 fp16, 0 bf16
     const float* bias;                 // [Cout]
     const float* residual;             // fp32 [M, ld] or null
     float* out_f32;
-    bf16* out_bf16;
-    bf16* out_t;
+    h16* out_bf16;
+    h16* out_t;
 };
 cudaError_t launch_conv_gemm(const ConvParams& p, int num_sms, cudaStream_t stream);
 
@@ -66,9 +67,10 @@ struct GroupNormParams {
     const int* film_row;               // [B] row index per sample (null: row = sample index)
     int film_stride, film_off;
     int silu;
+    int f16;                           // 16-bit output format: 1 fp16, 0 bf16
     int resample;                      // applied after norm+act (unet.py:141)
-    bf16* out_act;                     // bf16 [B, H'W', C]   normalised (+FiLM, +SiLU), resampled
-    bf16* out_raw;                     // optional bf16 [B, HW, C]: the un-normalised concat (skip-conv operand)
+    h16* out_act;                     // 16-bit [B, H'W', C]   normalised (+FiLM, +SiLU), resampled
+    h16* out_raw;                     // optional 16-bit [B, HW, C]: the un-normalised concat (skip-conv operand)
     float* out_res;                    // optional fp32 [B, H'W', C]: resampled raw input (identity-skip residual)
 };
 cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream);
@@ -81,18 +83,19 @@ struct alignas(64) AttnParams {
     CUtensorMap k_map;                 // same tensor, box (64, 64)
     CUtensorMap vt_map;                // 2-D (N, B*hid) bf16, box (64, d): V^T per image/head
     int B, N, heads, d, hid;
+    int f16;
     float scale_log2e;                 // log2(e) / sqrt(d)
-    bf16* out;                         // bf16 [B*N, hid]
+    h16* out;                         // 16-bit [B*N, hid]
 };
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // Small kernels (pointwise.cu)
 // ------------------------------------------------------------------------------------------------
-// x fp32 NCHW [B, C, H, W] (9*C <= 64) -> bf16 patch matrix [B*rep*H*W, 64]: column (r*3+s)*C + c =
+// x fp32 NCHW [B, C, H, W] (9*C <= 64) -> 16-bit patch matrix [B*rep*H*W, 64]: column (r*3+s)*C + c =
 // x[b, c, h+r-1, w+s-1] (zero outside); output image i reads input image i / rep (the CFG
 // repeat-interleave of diffusion.py:30-35, 370).
-cudaError_t launch_im2col3x3(const float* x, bf16* out, int B, int rep, int C, int H, int W, cudaStream_t stream);
+cudaError_t launch_im2col3x3(const float* x, h16* out, int B, int rep, int C, int H, int W, int f16, cudaStream_t stream);
 
 // sinusoidal embedding evaluated in fp64 like functions.py:11-29 -> fp32 [rows, dim]
 cudaError_t launch_timestep_embedding(const double* t, float* out, int rows, int dim, cudaStream_t stream);

@@ -1,5 +1,5 @@
 // Host runtime behind the C ABI (include/vdt_b200.h): UNet plan (block list mirroring
-// unet.py:155-322), weight table with the reference's state_dict keys, bf16 weight packing,
+// unet.py:155-322), weight table with the reference's state_dict keys, 16-bit weight packing,
 // TMA tensor maps, per-batch-size execution lists captured as CUDA graphs, and the sampling
 // driver (diffusion.py:360-414).  No torch types; device memory via the CUDA runtime.
 #include <cmath>
@@ -40,6 +40,19 @@ static int fail(const char* fmt, ...) {
         if (_r != 0) return _r;         \
     } while (0)
 
+static bool g_profile = false;
+static double g_prof_ms[VDT_PROF_FAMILIES] = {0, 0, 0, 0};
+static uint64_t g_prof_n[VDT_PROF_FAMILIES] = {0, 0, 0, 0};
+extern "C" int vdt_profile_enable(int on) { g_profile = on != 0; return 0; }
+extern "C" int vdt_profile_read(double* ms4, uint64_t* n4) {
+    for (int i = 0; i < VDT_PROF_FAMILIES; ++i) {
+        if (ms4) ms4[i] = g_prof_ms[i];
+        if (n4) n4[i] = g_prof_n[i];
+        g_prof_ms[i] = 0; g_prof_n[i] = 0;
+    }
+    return 0;
+}
+
 extern "C" const char* vdt_last_error(void) { return g_err; }
 extern "C" int vdt_version(void) { return 1; }
 extern "C" uint64_t vdt_kernel_launches(void) { return g_launches; }
@@ -60,9 +73,9 @@ static int get_encoder() {
     return 0;
 }
 
-// bf16 tensor, innermost dimension first; strides in elements for dims 1..rank-1
+// h16 tensor, innermost dimension first; strides in elements for dims 1..rank-1
 static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                    const uint32_t* box) {
+                    const uint32_t* box) {   // 2-byte elements; TMA only moves bytes, so fp16 and bf16 share the encoding
     CKI(get_encoder());
     cuuint64_t gdim[4], gstr[3];
     cuuint32_t bdim[4], estr[4];
@@ -79,7 +92,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
     return 0;
 }
 
-// A operand of a 3x3 (or geometric 1x1) conv: NHWC bf16 [n, h, w, c]
+// A operand of a 3x3 (or geometric 1x1) conv: NHWC h16 [n, h, w, c]
 static int make_map_nhwc(CUtensorMap* m, const void* base, int n, int h, int w, int c, int box_h, int box_n) {
     const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t str[3] = {(uint64_t)c, (uint64_t)w * c, (uint64_t)h * w * c};
@@ -101,24 +114,29 @@ static int make_map_2d(CUtensorMap* m, const void* base, long long rows, int col
 }
 
 // ================================================================================================ pack kernels
-__global__ void pack_conv_w_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I, int taps,
-                                   int ktot, int koff) {
+__device__ __forceinline__ h16 to_h16(float x, int f16) {
+    if (f16) { __half v = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); return *reinterpret_cast<h16*>(&v); }
+    __nv_bfloat16 v = __float2bfloat16(x);
+    return *reinterpret_cast<h16*>(&v);
+}
+__global__ void pack_conv_w_kernel(const float* __restrict__ src, h16* __restrict__ dst, int O, int I, int taps,
+                                   int ktot, int koff, int f16) {
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long n = (long long)O * I * taps;
     if (idx >= n) return;
     const int i = (int)(idx % I);
     const int tap = (int)((idx / I) % taps);
     const int o = (int)(idx / ((long long)I * taps));
-    dst[(long long)o * ktot + koff + tap * I + i] = __float2bfloat16(src[((long long)o * I + i) * taps + tap]);
+    dst[(long long)o * ktot + koff + tap * I + i] = to_h16(src[((long long)o * I + i) * taps + tap], f16);
 }
 // in_conv: [O][C][3][3] -> [O][64], column tap*C + c (matches im2col3x3), zero padded
-__global__ void pack_inconv_w_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int O, int C) {
+__global__ void pack_inconv_w_kernel(const float* __restrict__ src, h16* __restrict__ dst, int O, int C, int f16) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= O * 64) return;
     const int o = idx / 64, col = idx % 64;
     float v = 0.f;
     if (col < 9 * C) { const int tap = col / C, c = col % C; v = src[((long long)o * C + c) * 9 + tap]; }
-    dst[idx] = __float2bfloat16(v);
+    dst[idx] = to_h16(v, f16);
 }
 __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -157,14 +175,14 @@ struct Block {
     int res_in;          // input resolution
     int film_off = 0;
     // packed
-    bf16* w1 = nullptr;  // conv1 [cout][9*cin]            | proj_in [3*hid][cin]
-    bf16* w2 = nullptr;  // conv2 (+skip) [cout][9*cout(+cin)] | proj_out [cin][hid]
+    h16* w1 = nullptr;  // conv1 [cout][9*cin]            | proj_in [3*hid][cin]
+    h16* w2 = nullptr;  // conv2 (+skip) [cout][9*cout(+cin)] | proj_out [cin][hid]
     float* bias2 = nullptr;   // conv2.bias (+ skip.bias)
 };
 
 enum StepKind { S_CONV, S_GN, S_ATTN, S_IM2COL, S_TEMB, S_LINEAR, S_CLSEMB, S_BEGIN, S_SAMPLE };
 struct LinearArgs { const float *x, *W, *b; float* out; int rows, K, N, silu; };
-struct Im2colArgs { const float* x; bf16* out; int B, rep, C, H, W; };
+struct Im2colArgs { const float* x; h16* out; int B, rep, C, H, W, f16; };
 struct TembArgs { const double* t; float* out; int rows, dim; };
 struct ClsArgs { const float* e; const int64_t* y; const float *w, *b; int ncls; float* out; int rows, E; };
 struct BeginArgs { SamplerState* st; const float* table; double* t_rows; int nrows, T; };
@@ -243,13 +261,14 @@ struct vdt_plan {
     int film_total = 0;
     bool finalized = false;
     // packed globals
-    bf16* w_in = nullptr;                 // in_conv [hid][64]
-    bf16* w_out = nullptr;                // out_conv.2 [Cout][9*c0]
+    h16* w_in = nullptr;                 // in_conv [hid][64]
+    h16* w_out = nullptr;                // out_conv.2 [Cout][9*c0]
     float* w_fc_all = nullptr;            // [film_total][E]
     float* b_fc_all = nullptr;            // [film_total]
     std::vector<void*> owned;
     std::map<std::string, std::unique_ptr<Exec>> execs;
     bool use_graph = true;
+    int f16 = 1;                          // GEMM operand format: 1 fp16 (default), 0 bf16
     // all work runs on an internal stream (the caller's may be the legacy default stream, which
     // cannot be captured); ordering against the caller's stream is kept with two events
     cudaStream_t work = nullptr;
@@ -368,6 +387,8 @@ extern "C" int vdt_plan_create(const vdt_unet_config* cfg, vdt_plan** out) {
     p->hid = c.hid_channels;
     p->E = c.embedding_dim ? c.embedding_dim : 4 * c.hid_channels;
     p->levels = c.num_levels;
+    if (c.operand_dtype != 0 && c.operand_dtype != 1) return fail("operand_dtype must be 0 (fp16) or 1 (bf16)");
+    p->f16 = c.operand_dtype == 0;
     const char* ng = getenv("VDT_NO_GRAPH");
     p->use_graph = !(ng && ng[0] == '1');
     int dev = 0;
@@ -460,9 +481,9 @@ static int dev_alloc(vdt_plan* p, T** out, size_t count) {
     return 0;
 }
 
-static int pack_conv(const float* src, bf16* dst, int O, int I, int taps, int ktot, int koff) {
+static int pack_conv(const float* src, h16* dst, int O, int I, int taps, int ktot, int koff, int f16) {
     const long long n = (long long)O * I * taps;
-    pack_conv_w_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src, dst, O, I, taps, ktot, koff);
+    pack_conv_w_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src, dst, O, I, taps, ktot, koff, f16);
     CK(cudaGetLastError());
     return 0;
 }
@@ -477,7 +498,7 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
     const vdt_unet_config& c = p->cfg;
     const int E = p->E, hid = p->hid;
     CKI(dev_alloc(p, &p->w_in, (size_t)hid * 64));
-    pack_inconv_w_kernel<<<(hid * 64 + 255) / 256, 256>>>(p->W("in_conv.weight"), p->w_in, hid, c.in_channels);
+    pack_inconv_w_kernel<<<(hid * 64 + 255) / 256, 256>>>(p->W("in_conv.weight"), p->w_in, hid, c.in_channels, p->f16);
     CK(cudaGetLastError());
     CKI(dev_alloc(p, &p->w_fc_all, (size_t)p->film_total * E));
     CKI(dev_alloc(p, &p->b_fc_all, (size_t)p->film_total));
@@ -485,12 +506,12 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
         const std::string& n = b.name;
         if (b.kind == 0) {
             CKI(dev_alloc(p, &b.w1, (size_t)b.cout * 9 * b.cin));
-            CKI(pack_conv(p->W(n + ".conv1.weight"), b.w1, b.cout, b.cin, 9, 9 * b.cin, 0));
+            CKI(pack_conv(p->W(n + ".conv1.weight"), b.w1, b.cout, b.cin, 9, 9 * b.cin, 0, p->f16));
             const bool skipconv = b.cin != b.cout;
             const int k2 = 9 * b.cout + (skipconv ? b.cin : 0);
             CKI(dev_alloc(p, &b.w2, (size_t)b.cout * k2));
-            CKI(pack_conv(p->W(n + ".conv2.weight"), b.w2, b.cout, b.cout, 9, k2, 0));
-            if (skipconv) CKI(pack_conv(p->W(n + ".skip.weight"), b.w2, b.cout, b.cin, 1, k2, 9 * b.cout));
+            CKI(pack_conv(p->W(n + ".conv2.weight"), b.w2, b.cout, b.cout, 9, k2, 0, p->f16));
+            if (skipconv) CKI(pack_conv(p->W(n + ".skip.weight"), b.w2, b.cout, b.cin, 1, k2, 9 * b.cout, p->f16));
             CKI(dev_alloc(p, &b.bias2, (size_t)b.cout));
             add_vec_kernel<<<(b.cout + 255) / 256, 256>>>(p->W(n + ".conv2.bias"), skipconv ? p->W(n + ".skip.bias") : nullptr,
                                                           b.bias2, b.cout);
@@ -503,17 +524,47 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
             attn_dims(c, b.cin, &hd, &nh);
             const int hidd = hd * nh;
             CKI(dev_alloc(p, &b.w1, (size_t)3 * hidd * b.cin));
-            CKI(pack_conv(p->W(n + ".proj_in.weight"), b.w1, 3 * hidd, b.cin, 1, b.cin, 0));
+            CKI(pack_conv(p->W(n + ".proj_in.weight"), b.w1, 3 * hidd, b.cin, 1, b.cin, 0, p->f16));
             CKI(dev_alloc(p, &b.w2, (size_t)b.cin * hidd));
-            CKI(pack_conv(p->W(n + ".proj_out.weight"), b.w2, b.cin, hidd, 1, hidd, 0));
+            CKI(pack_conv(p->W(n + ".proj_out.weight"), b.w2, b.cin, hidd, 1, hidd, 0, p->f16));
         }
     }
     const int c0 = hid * c.ch_multipliers[0];
     // out_conv weight rows are padded to 16 output channels (zero rows) so the TMA box never leaves the tensor
     CKI(dev_alloc(p, &p->w_out, (size_t)16 * 9 * c0));
-    CKI(pack_conv(p->W("out_conv.2.weight"), p->w_out, c.out_channels, c0, 9, 9 * c0, 0));
+    CKI(pack_conv(p->W("out_conv.2.weight"), p->w_out, c.out_channels, c0, 9, 9 * c0, 0, p->f16));
     CK(cudaDeviceSynchronize());
     p->finalized = true;
+    return 0;
+}
+
+extern "C" int vdt_plan_flops(const vdt_plan* p, double* conv, double* attn, double* linear) {
+    if (!p) return fail("null plan");
+    const vdt_unet_config& c = p->cfg;
+    const double E = p->E, hid = p->hid;
+    double fc = 0, fa = 0, fl = 0;
+    double res = c.resolution;
+    fc += 2.0 * res * res * hid * 9 * c.in_channels;                       // in_conv
+    fl += 2.0 * (hid * E + E * E) + (c.num_classes > 0 ? 2.0 * c.num_classes * E : 0.0);
+    for (const auto& b : p->blocks) {
+        const double r = b.res_in, hw = r * r;
+        if (b.kind == 0) {
+            const double ro = b.resample == kResDown ? r / 2 : b.resample == kResUp ? r * 2 : r;
+            fc += 2.0 * ro * ro * b.cout * 9.0 * (b.cin + b.cout);          // conv1 + conv2
+            if (b.cin != b.cout) fc += 2.0 * ro * ro * b.cout * b.cin;     // 1x1 skip
+            fl += 2.0 * E * 2 * b.cout;                                    // fc
+        } else {
+            int hd, nh;
+            attn_dims(c, b.cin, &hd, &nh);
+            const double hidd = (double)hd * nh;
+            fc += 2.0 * hw * b.cin * 3 * hidd + 2.0 * hw * hidd * b.cin;   // proj_in + proj_out
+            fa += 2.0 * 2.0 * hw * hw * hidd;                              // q^T k and p v
+        }
+    }
+    fc += 2.0 * res * res * c.out_channels * 9.0 * hid * c.ch_multipliers[0];   // out_conv
+    if (conv) *conv = fc;
+    if (attn) *attn = fa;
+    if (linear) *linear = fl;
     return 0;
 }
 
@@ -542,14 +593,14 @@ static int conv_geom(int n, int h, int w, ConvGeom* g) {
 
 // 3x3 conv (optionally with an appended pointwise K-segment) or pure pointwise GEMM
 struct ConvSpec {
-    const bf16* a3 = nullptr; int c3 = 0;       // 3x3 segment: NHWC [n,h,w,c3]
-    const bf16* a1 = nullptr; int c1 = 0;       // pointwise segment: [n*h*w, c1] with row stride ld1
+    const h16* a3 = nullptr; int c3 = 0;       // 3x3 segment: NHWC [n,h,w,c3]
+    const h16* a1 = nullptr; int c1 = 0;       // pointwise segment: [n*h*w, c1] with row stride ld1
     int ld1 = 0;
     int n = 0, h = 0, w = 0;
-    const bf16* wpacked = nullptr; int cout = 0; int wrows = 0;   // weight rows actually allocated
+    const h16* wpacked = nullptr; int cout = 0; int wrows = 0;   // weight rows actually allocated
     const float* bias = nullptr; const float* residual = nullptr;
-    int out_mode = kOutF32; float* out_f32 = nullptr; bf16* out_bf16 = nullptr; bf16* out_t = nullptr;
-    int ld = 0, split_col = 0, act_silu = 0;
+    int out_mode = kOutF32; float* out_f32 = nullptr; h16* out_bf16 = nullptr; h16* out_t = nullptr;
+    int ld = 0, split_col = 0, act_silu = 0, f16 = 1;
 };
 
 static int setup_conv(const ConvSpec& s, ConvParams* cp) {
@@ -580,7 +631,7 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     cp->num_n_tiles = (s.cout + cp->block_n - 1) / cp->block_n;
     CKI(make_map_2d(&cp->b_map, s.wpacked, s.wrows, ktot, ktot, cp->block_n));
     cp->M = (int)M; cp->Cout = s.cout; cp->out_mode = s.out_mode; cp->ld = s.ld;
-    cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu;
+    cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16;
     cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t;
     if (s.out_mode != kOutNCHW && s.cout % 32 != 0) return fail("output channels must be a multiple of 32 (got %d)", s.cout);
     return 0;
@@ -603,14 +654,15 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
         ex->steps.push_back({S_GN, (int)ex->gns.size() - 1});
     };
     // ---- in_conv
-    bf16* patches; float* h;
+    h16* patches; float* h;
     const size_t hw0 = (size_t)res * res;
     CKI(ex->acquire((size_t)R * hw0 * 64 * 2, (void**)&patches));
-    ex->im2cols.push_back({ex->xin, patches, R / ex->rep, ex->rep, c.in_channels, res, res});
+    ex->im2cols.push_back({ex->xin, patches, R / ex->rep, ex->rep, c.in_channels, res, res, p->f16});
     ex->steps.push_back({S_IM2COL, (int)ex->im2cols.size() - 1});
     CKI(ex->acquire((size_t)R * hw0 * hid * 4, (void**)&h));
     {
         ConvSpec s;
+        s.f16 = p->f16;
         s.a1 = patches; s.c1 = 64; s.ld1 = 64; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_in; s.cout = hid; s.wrows = hid;
         s.bias = p->W("in_conv.bias"); s.out_mode = kOutF32; s.out_f32 = h; s.ld = hid;
         CKI(add_conv(s));
@@ -633,11 +685,12 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             const bool skipconv = b.cin != b.cout;
             const int ro = b.resample == kResDown ? res / 2 : b.resample == kResUp ? res * 2 : res;
             const size_t HWo = (size_t)ro * ro;
-            bf16 *a1, *xraw = nullptr; float* xres = nullptr;
+            h16 *a1, *xraw = nullptr; float* xres = nullptr;
             CKI(ex->acquire((size_t)R * HWo * cin * 2, (void**)&a1));
             if (skipconv) CKI(ex->acquire((size_t)R * HW * cin * 2, (void**)&xraw));
             if (b.resample != kResNone) CKI(ex->acquire((size_t)R * HWo * cin * 4, (void**)&xres));
             GroupNormParams g{};
+            g.f16 = p->f16;
             g.src1 = h; g.C1 = hch; g.src2 = src2; g.C2 = c2; g.B = R; g.H = res; g.W = res;
             g.gamma = p->W(n + ".norm1.weight"); g.beta = p->W(n + ".norm1.bias");
             g.silu = 1; g.resample = b.resample; g.out_act = a1; g.out_raw = xraw; g.out_res = xres;
@@ -647,15 +700,17 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire((size_t)R * HWo * b.cout * 4, (void**)&h1));
             {
                 ConvSpec s;
+                s.f16 = p->f16;
                 s.a3 = a1; s.c3 = cin; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w1; s.cout = b.cout; s.wrows = b.cout;
                 s.bias = p->W(n + ".conv1.bias"); s.out_mode = kOutF32; s.out_f32 = h1; s.ld = b.cout;
                 CKI(add_conv(s));
             }
             ex->release(a1);
             // norm2 + FiLM + SiLU
-            bf16* a2;
+            h16* a2;
             CKI(ex->acquire((size_t)R * HWo * b.cout * 2, (void**)&a2));
             GroupNormParams g2{};
+            g2.f16 = p->f16;
             g2.src1 = h1; g2.C1 = b.cout; g2.B = R; g2.H = ro; g2.W = ro;
             g2.gamma = p->W(n + ".norm2.weight"); g2.beta = p->W(n + ".norm2.bias");
             g2.film = film; g2.film_row = film_row; g2.film_stride = p->film_total; g2.film_off = b.film_off;
@@ -667,6 +722,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire((size_t)R * HWo * b.cout * 4, (void**)&hout));
             {
                 ConvSpec s;
+                s.f16 = p->f16;
                 s.a3 = a2; s.c3 = b.cout; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w2; s.cout = b.cout; s.wrows = b.cout;
                 if (skipconv) { s.a1 = xraw; s.c1 = cin; s.ld1 = cin; }
                 s.bias = b.bias2;
@@ -684,9 +740,10 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             int hd, nh;
             attn_dims(c, b.cin, &hd, &nh);
             const int hidd = hd * nh, N = HW;
-            bf16 *a, *qk, *vt, *o;
+            h16 *a, *qk, *vt, *o;
             CKI(ex->acquire((size_t)R * HW * b.cin * 2, (void**)&a));
             GroupNormParams g{};
+            g.f16 = p->f16;
             g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
             g.gamma = p->W(n + ".norm.weight"); g.beta = p->W(n + ".norm.bias");
             g.silu = 0; g.resample = kResNone; g.out_act = a;
@@ -695,6 +752,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&vt));
             {
                 ConvSpec s;
+                s.f16 = p->f16;
                 s.a1 = a; s.c1 = b.cin; s.ld1 = b.cin; s.n = R; s.h = res; s.w = res; s.wpacked = b.w1; s.cout = 3 * hidd;
                 s.wrows = 3 * hidd; s.bias = p->W(n + ".proj_in.bias"); s.out_mode = kOutBF16; s.out_bf16 = qk; s.out_t = vt;
                 s.ld = 2 * hidd; s.split_col = 2 * hidd;
@@ -708,7 +766,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
                 CKI(make_map_2d(&ap->qk_map, qk, (long long)R * N, 2 * hidd, 2 * hidd, 128));
                 CKI(make_map_2d(&ap->k_map, qk, (long long)R * N, 2 * hidd, 2 * hidd, 64));
                 CKI(make_map_2d(&ap->vt_map, vt, (long long)R * hidd, N, N, hd));
-                ap->B = R; ap->N = N; ap->heads = nh; ap->d = hd; ap->hid = hidd;
+                ap->B = R; ap->N = N; ap->heads = nh; ap->d = hd; ap->hid = hidd; ap->f16 = p->f16;
                 ap->scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)hd));
                 ap->out = o;
                 ex->attns.push_back(std::move(ap));
@@ -719,6 +777,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire((size_t)R * HW * b.cin * 4, (void**)&hout));
             {
                 ConvSpec s;
+                s.f16 = p->f16;
                 s.a1 = o; s.c1 = hidd; s.ld1 = hidd; s.n = R; s.h = res; s.w = res; s.wpacked = b.w2; s.cout = b.cin; s.wrows = b.cin;
                 s.bias = p->W(n + ".proj_out.bias"); s.residual = h; s.out_mode = kOutF32; s.out_f32 = hout; s.ld = b.cin;
                 CKI(add_conv(s));
@@ -733,14 +792,16 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
     // ---- out_conv
     {
         const int HW = res * res;
-        bf16* a;
+        h16* a;
         CKI(ex->acquire((size_t)R * HW * hch * 2, (void**)&a));
         GroupNormParams g{};
+        g.f16 = p->f16;
         g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
         g.gamma = p->W("out_conv.0.weight"); g.beta = p->W("out_conv.0.bias");
         g.silu = 1; g.resample = kResNone; g.out_act = a;
         add_gn(g);
         ConvSpec s;
+        s.f16 = p->f16;
         s.a3 = a; s.c3 = hch; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_out; s.cout = c.out_channels; s.wrows = 16;
         s.bias = p->W("out_conv.2.bias"); s.out_mode = kOutNCHW; s.out_f32 = ex->yout; s.ld = 0;
         CKI(add_conv(s));
@@ -773,14 +834,16 @@ static int add_embedding_steps(vdt_plan* p, Exec* ex, float* film, bool has_y) {
     return 0;
 }
 
-static int run_steps(vdt_plan* p, Exec* ex, cudaStream_t st) {
+static int run_steps(vdt_plan* p, Exec* ex, cudaStream_t st, std::vector<cudaEvent_t>* evs = nullptr) {
+    size_t ei = 0;
     for (const Step& s : ex->steps) {
         cudaError_t e = cudaSuccess;
+        if (evs) cudaEventRecord((*evs)[ei++], st);
         switch (s.kind) {
             case S_CONV: e = launch_conv_gemm(*ex->convs[s.idx], p->num_sms, st); break;
             case S_GN: e = launch_groupnorm(ex->gns[s.idx], st); break;
             case S_ATTN: e = launch_attention(*ex->attns[s.idx], st); break;
-            case S_IM2COL: { auto& a = ex->im2cols[s.idx]; e = launch_im2col3x3(a.x, a.out, a.B, a.rep, a.C, a.H, a.W, st); break; }
+            case S_IM2COL: { auto& a = ex->im2cols[s.idx]; e = launch_im2col3x3(a.x, a.out, a.B, a.rep, a.C, a.H, a.W, a.f16, st); break; }
             case S_TEMB: { auto& a = ex->tembs[s.idx]; e = launch_timestep_embedding(a.t, a.out, a.rows, a.dim, st); break; }
             case S_LINEAR: { auto& a = ex->linears[s.idx]; e = launch_linear_f32(a.x, a.W, a.b, a.out, a.rows, a.K, a.N, a.silu, st); break; }
             case S_CLSEMB: { auto& a = ex->clss[s.idx]; e = launch_class_embed_silu(a.e, a.y, a.w, a.b, a.ncls, a.out, a.rows, a.E, st); break; }
@@ -789,11 +852,34 @@ static int run_steps(vdt_plan* p, Exec* ex, cudaStream_t st) {
         }
         if (e != cudaSuccess) return fail("kernel launch failed (step kind %d): %s", (int)s.kind, cudaGetErrorString(e));
     }
+    if (evs) cudaEventRecord((*evs)[ei], st);
     return 0;
+}
+
+static int run_steps_profiled(vdt_plan* p, Exec* ex, cudaStream_t st) {
+    std::vector<cudaEvent_t> evs(ex->steps.size() + 1);
+    for (auto& e : evs) CK(cudaEventCreate(&e));
+    int rc = run_steps(p, ex, st, &evs);
+    if (rc == 0) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail("profiled step failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == 0) {
+        for (size_t i = 0; i < ex->steps.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+            const StepKind k = ex->steps[i].kind;
+            const int fam = k == S_CONV ? VDT_PROF_CONV : k == S_GN ? VDT_PROF_GROUPNORM : k == S_ATTN ? VDT_PROF_ATTENTION : VDT_PROF_OTHER;
+            g_prof_ms[fam] += ms; g_prof_n[fam] += 1;
+        }
+    }
+    for (auto& e : evs) cudaEventDestroy(e);
+    return rc;
 }
 
 // Run the exec's step list, through a CUDA graph when enabled.
 static int run_exec(vdt_plan* p, Exec* ex, cudaStream_t st) {
+    if (g_profile) { g_launches += ex->steps.size(); return run_steps_profiled(p, ex, st); }
     // first run is eager (sets function attributes, surfaces launch errors); the second run captures
     if (p->use_graph && !ex->graph && !ex->graph_failed && ex->runs++ >= 1) {
         cudaGraph_t g = nullptr;
@@ -999,12 +1085,15 @@ static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs,
     return 0;
 }
 
-extern "C" int vdt_p_sample(vdt_plan* p, const vdt_sampler_config* scp, const float* noise, const int64_t* label,
-                            const float* step_noise, float* out, int32_t batch, void* stream) {
-    if (!p || !scp || !noise || !out) return fail("null argument");
+extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, float* x, const int64_t* label,
+                                  const float* step_noise, int32_t batch, int32_t first_step, int32_t num_steps, void* stream) {
+    if (!p || !scp || !x) return fail("null argument");
     if (!p->finalized) return fail("plan not finalized (load every state_dict key, then vdt_plan_finalize)");
     const vdt_sampler_config& sc = *scp;
     if (sc.model_out_type < 0 || sc.model_out_type > 3) return fail("unknown model_out_type %d", sc.model_out_type);
+    const int T = sc.sample_timesteps;
+    if (first_step < 0 || first_step >= T || num_steps < 0 || first_step - num_steps < -1)
+        return fail("step range [%d, %d) steps leaves the trajectory of %d steps", first_step, num_steps, T);
     cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
     CKI(enter_work(p, user));
     cudaStream_t st = p->work;
@@ -1014,21 +1103,29 @@ extern "C" int vdt_p_sample(vdt_plan* p, const vdt_sampler_config* scp, const fl
     const int64_t* row_label = c.num_classes > 0 ? label : nullptr;   // an unconditional UNet ignores y (unet.py:289)
     const int rep = cfg ? 2 : 1;
     const int chunk = std::max(1, c.max_rows / rep);
-    const int T = sc.sample_timesteps;
     for (int i0 = 0; i0 < batch; i0 += chunk) {
         const int imgs = std::min(chunk, batch - i0);
         Exec* ex;
         CKI(get_sampler_exec(p, sc, imgs, label != nullptr, step_noise, (long long)batch * (long long)CHW, &ex));
-        CK(cudaMemcpyAsync(ex->xin, noise + (size_t)i0 * CHW, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ex->xin, x + (size_t)i0 * CHW, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
         film_rows_kernel<<<(ex->rows + 127) / 128, 128, 0, st>>>(row_label ? row_label + i0 : nullptr, ex->film_row, ex->rows, rep);
         CK(cudaGetLastError());
-        sampler_init_state_kernel<<<1, 32, 0, st>>>(ex->state, T - 1, i0);
+        sampler_init_state_kernel<<<1, 32, 0, st>>>(ex->state, first_step, i0);
         CK(cudaGetLastError());
         g_launches += 2;
-        for (int step = 0; step < T; ++step) CKI(run_exec(p, ex, st));
-        CK(cudaMemcpyAsync(out + (size_t)i0 * CHW, ex->xin, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
+        for (int step = 0; step < num_steps; ++step) CKI(run_exec(p, ex, st));
+        CK(cudaMemcpyAsync(x + (size_t)i0 * CHW, ex->xin, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
     }
     return leave_work(p, user);
+}
+
+extern "C" int vdt_p_sample(vdt_plan* p, const vdt_sampler_config* scp, const float* noise, const int64_t* label,
+                            const float* step_noise, float* out, int32_t batch, void* stream) {
+    if (!p || !scp || !noise || !out) return fail("null argument");
+    const size_t CHW = (size_t)p->cfg.in_channels * p->cfg.resolution * p->cfg.resolution;
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    if (out != noise) CK(cudaMemcpyAsync(out, noise, (size_t)batch * CHW * 4, cudaMemcpyDeviceToDevice, user));
+    return vdt_p_sample_range(p, scp, out, label, step_noise, batch, scp->sample_timesteps - 1, scp->sample_timesteps, stream);
 }
 
 extern "C" int vdt_p_sample_host(vdt_plan* p, const vdt_sampler_config* scp, const float* noise, const int64_t* label,
@@ -1070,22 +1167,23 @@ extern "C" int vdt_p_sample_host(vdt_plan* p, const vdt_sampler_config* scp, con
 
 // ================================================================================================ kernel-level hooks
 extern "C" int vdt_op_conv(const void* x, int32_t batch, int32_t h, int32_t w, int32_t cin, const float* w_oihw, int32_t cout,
-                           int32_t ksize, const float* bias, const float* residual, float* out, void* stream) {
+                           int32_t ksize, const float* bias, const float* residual, float* out, int32_t f16, void* stream) {
     if (ksize != 1 && ksize != 3) return fail("ksize must be 1 or 3");
     if (cin % 64) return fail("cin must be a multiple of 64");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int taps = ksize * ksize;
-    bf16* wp = nullptr;
+    h16* wp = nullptr;
     const int wrows = std::max(cout, 16);
     CK(cudaMalloc(&wp, (size_t)wrows * taps * cin * 2));
     CK(cudaMemset(wp, 0, (size_t)wrows * taps * cin * 2));
-    int rc = pack_conv(w_oihw, wp, cout, cin, taps, taps * cin, 0);
+    int rc = pack_conv(w_oihw, wp, cout, cin, taps, taps * cin, 0, f16);
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     if (rc == 0) {
         ConvSpec s;
-        if (ksize == 3) { s.a3 = (const bf16*)x; s.c3 = cin; } else { s.a1 = (const bf16*)x; s.c1 = cin; s.ld1 = cin; }
+        s.f16 = f16;
+        if (ksize == 3) { s.a3 = (const h16*)x; s.c3 = cin; } else { s.a1 = (const h16*)x; s.c1 = cin; s.ld1 = cin; }
         s.n = batch; s.h = h; s.w = w; s.wpacked = wp; s.cout = cout; s.wrows = wrows; s.bias = bias; s.residual = residual;
         s.out_mode = kOutF32; s.out_f32 = out; s.ld = cout;
         std::unique_ptr<ConvParams> cp(new ConvParams());
@@ -1105,11 +1203,12 @@ extern "C" int vdt_op_conv(const void* x, int32_t batch, int32_t h, int32_t w, i
 extern "C" int vdt_op_groupnorm(const float* src1, int32_t c1, const float* src2, int32_t c2, int32_t batch, int32_t h,
                                 int32_t w, const float* gamma, const float* beta, const float* film, int32_t film_stride,
                                 int32_t film_off, int32_t silu, int32_t resample, void* out_act, void* out_raw, float* out_res,
-                                void* stream) {
+                                int32_t f16, void* stream) {
     GroupNormParams g{};
+    g.f16 = f16;
     g.src1 = src1; g.C1 = c1; g.src2 = src2; g.C2 = c2; g.B = batch; g.H = h; g.W = w; g.gamma = gamma; g.beta = beta;
     g.film = film; g.film_row = nullptr; g.film_stride = film_stride; g.film_off = film_off; g.silu = silu; g.resample = resample;
-    g.out_act = (bf16*)out_act; g.out_raw = (bf16*)out_raw; g.out_res = out_res;
+    g.out_act = (h16*)out_act; g.out_raw = (h16*)out_raw; g.out_res = out_res;
     cudaError_t e = launch_groupnorm(g, reinterpret_cast<cudaStream_t>(stream));
     ++g_launches;
     if (e != cudaSuccess) return fail("groupnorm launch failed: %s", cudaGetErrorString(e));
@@ -1117,16 +1216,16 @@ extern "C" int vdt_op_groupnorm(const float* src1, int32_t c1, const float* src2
 }
 
 extern "C" int vdt_op_attention(const void* qk, const void* vt, void* out, int32_t batch, int32_t n, int32_t heads, int32_t d,
-                                void* stream) {
+                                int32_t f16, void* stream) {
     const int hid = heads * d;
     std::unique_ptr<AttnParams> ap(new AttnParams());
     memset(ap.get(), 0, sizeof(AttnParams));
     CKI(make_map_2d(&ap->qk_map, qk, (long long)batch * n, 2 * hid, 2 * hid, 128));
     CKI(make_map_2d(&ap->k_map, qk, (long long)batch * n, 2 * hid, 2 * hid, 64));
     CKI(make_map_2d(&ap->vt_map, vt, (long long)batch * hid, n, n, d));
-    ap->B = batch; ap->N = n; ap->heads = heads; ap->d = d; ap->hid = hid;
+    ap->B = batch; ap->N = n; ap->heads = heads; ap->d = d; ap->hid = hid; ap->f16 = f16;
     ap->scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)d));
-    ap->out = (bf16*)out;
+    ap->out = (h16*)out;
     cudaError_t e = launch_attention(*ap, reinterpret_cast<cudaStream_t>(stream));
     ++g_launches;
     if (e != cudaSuccess) return fail("attention launch failed: %s", cudaGetErrorString(e));

@@ -8,8 +8,8 @@ namespace vdt {
 namespace {
 
 // ------------------------------------------------------------------------------------------ im2col
-__global__ void im2col3x3_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int rep, int C, int H,
-                                 int W) {
+__global__ void im2col3x3_kernel(const float* __restrict__ x, h16* __restrict__ out, int B, int rep, int C, int H,
+                                 int W, int f16) {
     const long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long rows = static_cast<long long>(B) * rep * H * W;
     if (row >= rows) return;
@@ -28,8 +28,8 @@ __global__ void im2col3x3_kernel(const float* __restrict__ x, bf16* __restrict__
     uint4* dst = reinterpret_cast<uint4*>(out + row * 64);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-        dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        dst[j] = make_uint4(pack_16(v[8 * j], v[8 * j + 1], f16), pack_16(v[8 * j + 2], v[8 * j + 3], f16),
+                            pack_16(v[8 * j + 4], v[8 * j + 5], f16), pack_16(v[8 * j + 6], v[8 * j + 7], f16));
 }
 
 // ------------------------------------------------------------------------------------------ embedding
@@ -186,11 +186,11 @@ __global__ void sampler_step_kernel(const SamplerStepParams p) {
 
 }  // namespace
 
-cudaError_t launch_im2col3x3(const float* x, bf16* out, int B, int rep, int C, int H, int W, cudaStream_t stream) {
+cudaError_t launch_im2col3x3(const float* x, h16* out, int B, int rep, int C, int H, int W, int f16, cudaStream_t stream) {
     if (9 * C > 64) return cudaErrorInvalidValue;
     const long long rows = static_cast<long long>(B) * rep * H * W;
     if (rows == 0) return cudaSuccess;
-    im2col3x3_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, stream>>>(x, out, B, rep, C, H, W);
+    im2col3x3_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, stream>>>(x, out, B, rep, C, H, W, f16);
     return cudaGetLastError();
 }
 

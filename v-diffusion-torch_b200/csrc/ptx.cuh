@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cuda.h>          // CUtensorMap (type only; the encoder is fetched at run time, no -lcuda)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace vdt {
 
@@ -131,12 +132,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
-// Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, M x N.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+// Instruction descriptor, kind::f16: D fp32, A/B both fp16 (format 0) or both bf16 (format 1), both
+// K-major, M x N.
+__host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, int fp16) {
+    return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(m >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -154,9 +156,22 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 // ---- small math --------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+// fp32 pair -> packed 16-bit operand pair.  fp16 saturates at +-65504 instead of overflowing to inf.
+__device__ __forceinline__ uint32_t pack_16(float lo, float hi, int fp16) {
+    if (fp16) {
+        __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint16_t cvt_16(float x, int fp16) {
+    if (fp16) {
+        __half v = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+        return *reinterpret_cast<uint16_t*>(&v);
+    }
+    __nv_bfloat16 v = __float2bfloat16(x);
+    return *reinterpret_cast<uint16_t*>(&v);
 }
 
 }  // namespace vdt

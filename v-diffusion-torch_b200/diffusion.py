@@ -98,6 +98,8 @@ class GaussianDiffusion:
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("v_diffusion_b200 samples on CUDA (sm_100a) only; there is no CPU fallback")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         B = shape[0]
         if noise is None:
             gen = None if seed is None else torch.Generator(device).manual_seed(seed)

@@ -126,6 +126,9 @@ class UNet(nn.Module):
                                        _Affine((out_channels, chs[0], 3, 3), init_scale=0.)])
         # runtime state (not part of the reference surface)
         self.max_rows = int(os.environ.get("VDT_MAX_ROWS", "1024"))
+        # 16-bit tensor-core operand format: "fp16" (default: 10-bit mantissa like the TF32 the reference's own
+        # cuDNN convs use on GPU, same tcgen05 rate as bf16) or "bf16"
+        self.operand_dtype = os.environ.get("VDT_OPERAND", "fp16")
         self._plans = {}
 
     # ------------------------------------------------------------------ plan management
@@ -136,7 +139,9 @@ class UNet(nn.Module):
         """C-side plan (block list, packed bf16 weights, workspace) for one image resolution."""
         if device.type != "cuda":
             raise RuntimeError("v_diffusion_b200.UNet runs on CUDA (sm_100a) only; there is no CPU fallback")
-        key = (int(resolution), device.index if device.index is not None else torch.cuda.current_device(), int(self.max_rows))
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        key = (int(resolution), device.index, int(self.max_rows), self.operand_dtype)
         sig = self._weights_signature()
         ent = self._plans.get(key)
         L = _lib.lib()
@@ -153,6 +158,7 @@ class UNet(nn.Module):
             cfg.num_heads = self.num_heads or 0
             cfg.num_classes, cfg.multitags = self.num_classes, int(self.multitags)
             cfg.resolution, cfg.max_rows = int(resolution), int(self.max_rows)
+            cfg.operand_dtype = _lib.OPERAND_DTYPES[self.operand_dtype]
             handle = C.c_void_p()
             with torch.cuda.device(device):
                 _lib.check(L.vdt_plan_create(C.byref(cfg), C.byref(handle)))
