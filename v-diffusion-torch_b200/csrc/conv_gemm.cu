@@ -4,13 +4,19 @@
 // from unet.py:121,125,134,70-71,203-215,217,232).  NHWC bf16 operands, fp32 accumulation in
 // TMEM, fused epilogue (bias, residual add, SiLU, bf16 / transposed / NCHW stores).
 //
-// Persistent warp-specialised kernel, one CTA per SM, 192 threads:
-//   warp 0     TMA producer   : per K-block one 4-D box of the activation (shifted by the filter
-//                               tap; out-of-bounds rows/cols are zero-filled by TMA = padding) and
-//                               one 2-D box of the packed weight, into a 4-stage smem ring
-//   warp 1     MMA issuer     : tcgen05.mma.cta_group::1.kind::f16, M=128 x N=block_n x K=16,
-//                               accumulators double-buffered in TMEM (2 x 256 columns)
-//   warps 2-5  epilogue       : tcgen05.ld -> registers -> global, overlapping the next tile's mainloop
+// Persistent warp-specialised kernel, one CTA per SM, 192 threads, CTAs paired (cluster of 2) so
+// the tensor cores run in cta_group::2 mode: one 256 x N x 16 MMA spans both SMs, each CTA holding
+// its own 128 rows of A, half of the N rows of B and its 128 x N half of the accumulator.  Per SM
+// this halves the weight-tile fill (L2 -> smem) and the operand reads (smem -> tensor core) that
+// cap a single-CTA 128 x 256 tile at ~2/3 of the MMA rate.
+//   warp 0     TMA producer (both CTAs): per K-block one 4-D box of the activation (shifted by the
+//                               filter tap; out-of-bounds rows/cols are zero-filled by TMA = conv
+//                               padding) and this CTA's half of the packed-weight box, into a
+//                               6-stage smem ring; completion is signalled on the leader's barrier
+//   warp 1     MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::f16, accumulators
+//                               double-buffered in TMEM (2 x 256 columns per CTA)
+//   warps 2-9  epilogue (both CTAs): tcgen05.ld -> registers -> smem transposition -> coalesced global
+//                               stores (+bias, +residual), overlapping the next tile's main loop
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -20,13 +26,15 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;                       // bf16 elements per K-block = one 128-byte swizzle row
-constexpr int kStages = 4;
+constexpr int kStages = 6;
 constexpr int kMaxBN = 256;
 constexpr int kABytes = kBM * kBK * 2;        // 16 KiB
-constexpr int kBBytes = kMaxBN * kBK * 2;     // 32 KiB
+constexpr int kBBytes = (kMaxBN / 2) * kBK * 2;   // 16 KiB: this CTA's half of the N rows
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                    // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int kEpiBytes = kEpiWarps * 32 * 128; // per epilogue warp: 32 rows x 32 fp32 columns transposition tile
+constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 64 + 32 * 8;          // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kTmemCols = 512;
 
 struct TileCoord {
@@ -45,10 +53,12 @@ __device__ __forceinline__ TileCoord tile_origin(const ConvParams& p, int m_tile
     return t;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint8_t* epi_smem = smem + kStages * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + kEpiBytes);
     uint64_t* full_bar = bars;                    // [kStages] TMA -> MMA
     uint64_t* empty_bar = bars + kStages;         // [kStages] MMA -> TMA
     uint64_t* acc_full = bars + 2 * kStages;      // [2] MMA -> epilogue
@@ -57,21 +67,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int rank = static_cast<int>(cluster_ctarank());   // 0 / 1 inside the pair
+    const int pair = blockIdx.x >> 1, num_pairs_resident = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
+        // full / acc_empty are only used in the leader CTA (rank 0); empty / acc_full in both
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 2 * 32 * kEpiWarps); }
         fence_mbar_init();
         for (int s = 0; s < p.num_segs; ++s) tma_prefetch_desc(&p.a_map[s]);
         tma_prefetch_desc(&p.b_map);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == 1) tmem_alloc_2cta(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                                      // peer's barriers are initialised before any multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+    // work item w = (pair of M tiles, N tile); this CTA takes M tile 2*mp + rank (a phantom tile past the
+    // end is all zero-filled loads and masked stores)
+    const int total_items = ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles;
     int kblocks_total = 0;
     for (int s = 0; s < p.num_segs; ++s) kblocks_total += p.seg_taps[s] * p.seg_kblocks[s];
 
@@ -79,9 +95,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t tx_bytes = static_cast<uint32_t>(p.rows_per_tile * kBK * 2 + p.block_n * kBK * 2);
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+            const int half_n = p.block_n >> 1;
+            // both CTAs' boxes complete on the leader's barrier
+            const uint32_t tx_bytes = 2u * static_cast<uint32_t>(p.rows_per_tile * kBK * 2 + half_n * kBK * 2);
+            for (int w = pair; w < total_items; w += num_pairs_resident) {
+                const int m_tile = (w / p.num_n_tiles) * 2 + rank, n_tile = w % p.num_n_tiles;
                 const TileCoord o = tile_origin(p, m_tile);
                 int kcol = 0;
                 for (int s = 0; s < p.num_segs; ++s) {
@@ -93,9 +111,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* a_dst = smem + stage * kStageBytes;
                             uint8_t* b_dst = a_dst + kABytes;
-                            mbar_expect_tx(&full_bar[stage], tx_bytes);
-                            tma_load_4d(a_dst, &p.a_map[s], &full_bar[stage], kb * kBK, o.c1 + dx, o.c2 + dy, o.c3);
-                            tma_load_2d(b_dst, &p.b_map, &full_bar[stage], kcol, n_tile * p.block_n);
+                            if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
+                            tma_load_4d_2cta(a_dst, &p.a_map[s], &full_bar[stage], kb * kBK, o.c1 + dx, o.c2 + dy, o.c3);
+                            tma_load_2d_2cta(b_dst, &p.b_map, &full_bar[stage], kcol, n_tile * p.block_n + rank * half_n);
                             kcol += kBK;
                             if (++stage == kStages) { stage = 0; phase ^= 1; }
                         }
@@ -104,12 +122,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_16(kBM, p.block_n, p.f16);
+        // ------------------------------------------------------------------ MMA issuer (leader CTA)
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = umma_idesc_16(2 * kBM, p.block_n, p.f16);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int w = pair; w < total_items; w += num_pairs_resident) {
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
@@ -121,57 +139,81 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     const uint64_t bdesc = umma_desc_sw128(a_addr + kABytes);
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k)
-                        umma_16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
+                        umma_16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_2cta(&empty_bar[stage], static_cast<uint16_t>(3));        // frees the slot in both CTAs
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&acc_full[acc]);                 // accumulator complete -> epilogue
+                umma_commit_2cta(&acc_full[acc], static_cast<uint16_t>(3));       // both halves complete -> both epilogues
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        const int chunk_par = (warp - 2) >> 2;               // this warp takes the 32-column chunks of this parity
         const int row = q * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+        for (int w = pair; w < total_items; w += num_pairs_resident) {
+            const int m_tile = (w / p.num_n_tiles) * 2 + rank, n_tile = w % p.num_n_tiles;
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const long long grow = static_cast<long long>(m_tile) * p.rows_per_tile + row;
-            const bool row_ok = (row < p.rows_per_tile) && (grow < p.M);
+            const bool row_ok = (row < p.rows_per_tile) && (grow < p.M) && (m_tile < p.num_m_tiles);
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kMaxBN);
-            for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+            for (int c0 = chunk_par * 32; c0 < p.block_n; c0 += 64) {
                 uint32_t r[32];
                 tmem_ld32(t_row + static_cast<uint32_t>(c0), r);
                 tmem_ld_wait();
                 const int col0 = n_tile * p.block_n + c0;
                 if (col0 >= p.Cout) continue;                // warp-uniform
                 float v[32];
+                if (p.out_mode == kOutF32) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = col0 + j;
-                    v[j] = __uint_as_float(r[j]) + ((col < p.Cout) ? __ldg(p.bias + col) : 0.f);
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);       // bias is added after the transposition
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = col0 + j;
+                        v[j] = __uint_as_float(r[j]) + ((col < p.Cout) ? __ldg(p.bias + col) : 0.f);
+                    }
                 }
                 if (p.out_mode == kOutF32) {
-                    if (row_ok) {
-                        float* dst = p.out_f32 + grow * p.ld + col0;
-                        if (p.residual) {
-                            const float4* res = reinterpret_cast<const float4*>(p.residual + grow * p.ld + col0);
+                    // thread-per-row registers -> swizzled smem tile -> lane = (row % 4 group, 4 columns): every
+                    // global access below is 4 rows x 128 contiguous bytes per warp instruction
+                    float4* tile = reinterpret_cast<float4*>(epi_smem + (warp - 2) * (32 * 128));
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 rr = __ldg(res + j);
-                                v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
-                            }
+                    for (int j = 0; j < 8; ++j)
+                        tile[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
+                    const int cq = lane & 7, rsub = lane >> 3;
+                    const long long wrow0 = static_cast<long long>(m_tile) * p.rows_per_tile + q * 32;
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq * 4));
+                    const bool tile_ok = m_tile < p.num_m_tiles;
+                    float4 res[8];
+                    if (p.residual) {                        // all eight loads in flight before anything is stored
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = i * 4 + rsub;
+                            const long long g = wrow0 + rr;
+                            const bool ok = tile_ok && (q * 32 + rr < p.rows_per_tile) && (g < p.M);
+                            res[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(g) * p.ld + col0 + cq * 4))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
-                        if (p.act_silu) {
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = i * 4 + rsub;
+                        float4 o = tile[rr * 8 + (cq ^ (rr & 7))];
+                        o.x += b4.x + res[i].x; o.y += b4.y + res[i].y; o.z += b4.z + res[i].z; o.w += b4.w + res[i].w;
+                        if (p.act_silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+                        const long long g = wrow0 + rr;
+                        if (tile_ok && (q * 32 + rr < p.rows_per_tile) && (g < p.M))
+                            *reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(g) * p.ld + col0 + cq * 4) = o;
+                    }
+                    __syncwarp();
                 } else if (p.out_mode == kOutBF16) {
                     if (p.act_silu) {
 #pragma unroll
@@ -204,16 +246,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 }
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[acc]);
+            mbar_arrive_cluster(&acc_empty[acc], 0);         // the leader's MMA thread waits for both CTAs' drains
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                                      // no CTA exits while its peer may still signal it
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc_2cta(tmem_base, kTmemCols);
     }
 }
 
@@ -226,10 +269,10 @@ cudaError_t launch_conv_gemm(const ConvParams& p, int num_sms, cudaStream_t stre
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const int total = p.num_m_tiles * p.num_n_tiles;
-    if (total <= 0) return cudaSuccess;
-    const int grid = total < num_sms ? total : num_sms;
-    conv_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+    const int items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    if (items <= 0) return cudaSuccess;
+    const int pairs = items < num_sms / 2 ? items : num_sms / 2;
+    conv_gemm_kernel<<<2 * pairs, kThreads, kSmemBytes, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -29,7 +29,7 @@ enum ConvOutMode : int {
 
 struct alignas(64) ConvParams {
     CUtensorMap a_map[kConvMaxSegs];   // 4-D (C, W, H, N) bf16, box (64, W, box_h, box_n), SWIZZLE_128B
-    CUtensorMap b_map;                 // 2-D (K_total, Cout) bf16, box (64, block_n), SWIZZLE_128B
+    CUtensorMap b_map;                 // 2-D (K_total, Cout) 16-bit, box (64, block_n / 2), SWIZZLE_128B
     int num_segs;
     int seg_taps[kConvMaxSegs];        // 9 (3x3, pad 1) or 1 (pointwise)
     int seg_kblocks[kConvMaxSegs];     // Cin_seg / 64

@@ -629,7 +629,7 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     cp->block_n = pick_block_n(s.cout);
     if (cp->block_n == 0) return fail("unsupported output channel count %d", s.cout);
     cp->num_n_tiles = (s.cout + cp->block_n - 1) / cp->block_n;
-    CKI(make_map_2d(&cp->b_map, s.wpacked, s.wrows, ktot, ktot, cp->block_n));
+    CKI(make_map_2d(&cp->b_map, s.wpacked, s.wrows, ktot, ktot, cp->block_n / 2));   // each CTA of a pair fetches half
     cp->M = (int)M; cp->Cout = s.cout; cp->out_mode = s.out_mode; cp->ld = s.ld;
     cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16;
     cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t;
