@@ -9,7 +9,8 @@ run() {  # name, timeout, pytest args...
   echo "== $name: exit $?"; tail -n 25 "gpurun_out/$name.log"
 }
 run conv 300 tests/test_gpu_kernels.py -k conv_gemm
-run gn 300 tests/test_gpu_kernels.py -k groupnorm
+run gn 300 tests/test_gpu_kernels.py -k 'test_groupnorm'
+run gnfused 300 tests/test_gpu_kernels.py -k single_pass
 run attn 300 tests/test_gpu_kernels.py -k attention
 run sampler 300 tests/test_gpu_kernels.py -k sampler_step
 run unet 600 tests/test_gpu_unet.py -s

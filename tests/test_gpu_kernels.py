@@ -61,7 +61,7 @@ def test_conv_gemm(L, B, H, cin, cout, k, res, f16):
     xb = x.to(DT[f16])
     x_nhwc = xb.permute(0, 2, 3, 1).contiguous()
     out = torch.full((B, H, H, cout), float("nan"), device="cuda")
-    _check(L, L.vdt_op_conv(_p(x_nhwc), B, H, H, cin, _p(w), cout, k, _p(bias), _p(resid), _p(out), f16, None))
+    _check(L, L.vdt_op_conv(_p(x_nhwc), B, H, H, cin, _p(w), cout, k, _p(bias), _p(resid), _p(out), f16, None, None, None))
     torch.cuda.synchronize()
     ref = F.conv2d(xb.double(), w.to(DT[f16]).double(), bias.double(), padding=k // 2).permute(0, 2, 3, 1)
     if res:
@@ -100,7 +100,7 @@ def test_groupnorm(L, B, H, c1, c2, film, silu, resample, want_raw, want_res, f1
     out_raw = torch.zeros(B, H, H, C_, device="cuda", dtype=DT[f16]) if want_raw else None
     out_res = torch.zeros(B, Ho, Ho, C_, device="cuda") if want_res else None
     _check(L, L.vdt_op_groupnorm(_p(s1), c1, _p(s2), c2, B, H, H, _p(gamma), _p(beta), _p(ftab), stride, off,
-                                 int(silu), resample, _p(out_act), _p(out_raw), _p(out_res), f16, None))
+                                 int(silu), resample, _p(out_act), _p(out_raw), _p(out_res), f16, None, None, 0, None))
     torch.cuda.synchronize()
     x = torch.cat([s1, s2], dim=3) if c2 else s1
     xn = x.permute(0, 3, 1, 2).double()
@@ -121,6 +121,67 @@ def test_groupnorm(L, B, H, c1, c2, film, silu, resample, want_raw, want_res, f1
     if want_res:
         r = rs(xn).permute(0, 2, 3, 1)
         assert (out_res.double() - r).abs().max().item() <= 1e-5
+
+
+FUSED_GN_CASES = [
+    # B, H, c1, c2 (second conv output concatenated), in16, film, resample
+    (2, 32, 256, 0, False, True, 0),
+    (3, 8, 256, 0, False, False, 0),      # 64 pixels per image: two statistics slabs
+    (2, 16, 256, 256, False, False, 0),   # concat: 16 channels per group, one stats buffer per source
+    (2, 32, 256, 0, True, True, 0),       # conv1 output kept in 16 bits
+    (2, 16, 128, 0, False, False, 1),     # avg-pool
+    (2, 8, 256, 0, False, False, 2),      # upsample
+    (2, 64, 128, 0, True, False, 0),      # 4096 pixels: image split over 8 CTAs
+]
+
+
+@pytest.mark.parametrize("f16", [1, 0])
+@pytest.mark.parametrize("B,H,c1,c2,in16,film,resample", FUSED_GN_CASES)
+def test_conv_stats_then_single_pass_groupnorm(L, B, H, c1, c2, in16, film, resample, f16):
+    """conv epilogue writes partial (sum, sumsq) per 32-row slab / 4 channels; GroupNorm combines them and
+    makes one pass.  Checked against torch GroupNorm of the conv output."""
+    g = torch.Generator(device="cuda").manual_seed(H + c1 + c2 + in16)
+    cin = 64
+
+    def conv(cout):
+        x = torch.randn(B, H, H, cin, device="cuda", generator=g).to(DT[f16])
+        w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / math.sqrt(cin * 9)
+        bias = torch.randn(cout, device="cuda", generator=g)
+        out = torch.zeros(B, H, H, cout, device="cuda")
+        out16 = torch.zeros(B, H, H, cout, device="cuda", dtype=DT[f16]) if in16 else None
+        stats = torch.full((B * H * H // 32, cout // 4, 2), float("nan"), device="cuda")
+        _check(L, L.vdt_op_conv(_p(x), B, H, H, cin, _p(w), cout, 3, _p(bias), None, _p(out), f16, _p(out16), _p(stats), None))
+        torch.cuda.synchronize()
+        ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.to(DT[f16]).double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+        val = out16 if in16 else out
+        # the statistics describe the fp32 values before any 16-bit rounding
+        rs = ref.reshape(B * H * H // 32, 32, cout // 4, 4)
+        assert torch.isfinite(stats).all()
+        assert (stats[..., 0].double() - rs.sum(dim=(1, 3))).abs().max().item() <= 2e-3
+        assert (stats[..., 1].double() - (rs * rs).sum(dim=(1, 3))).abs().max().item() <= 2e-2
+        return val, stats, ref
+
+    v1, st1, r1 = conv(c1)
+    v2, st2, r2 = conv(c2) if c2 else (None, None, None)
+    C_ = c1 + c2
+    gamma = 1 + 0.2 * torch.randn(C_, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(C_, device="cuda", generator=g)
+    ftab = torch.randn(B, 2 * C_, device="cuda", generator=g) * 0.3 if film else None
+    Ho = H // 2 if resample == 1 else H * 2 if resample == 2 else H
+    out_act = torch.zeros(B, Ho, Ho, C_, device="cuda", dtype=DT[f16])
+    _check(L, L.vdt_op_groupnorm(_p(v1), c1, _p(v2), c2, B, H, H, _p(gamma), _p(beta), _p(ftab), 2 * C_, 0, 1, resample,
+                                 _p(out_act), None, None, f16, _p(st1), _p(st2), int(in16), None))
+    torch.cuda.synchronize()
+    x = torch.cat([r1, r2], dim=3) if c2 else r1
+    if in16:
+        x = v1.double()                      # the kernel normalises the rounded values with the fp32 statistics
+    y = F.group_norm(x.permute(0, 3, 1, 2), 32, gamma.double(), beta.double(), 1e-6)
+    if film:
+        y = (1 + ftab[:, C_:].double()[:, :, None, None]) * y + ftab[:, :C_].double()[:, :, None, None]
+    y = F.silu(y)
+    y = (F.avg_pool2d(y, 2) if resample == 1 else F.interpolate(y, scale_factor=2, mode="nearest") if resample == 2 else y)
+    y = y.permute(0, 2, 3, 1)
+    assert _rel(out_act, y) <= 4e-3 * EPS[f16] + (2e-3 if in16 else 0)
 
 
 ATTN_CASES = [(2, 1024, 1, 256), (3, 256, 1, 256), (3, 64, 1, 256), (2, 256, 1, 64), (2, 64, 2, 64), (1, 4096, 1, 64),

@@ -167,19 +167,12 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                 const int col0 = n_tile * p.block_n + c0;
                 if (col0 >= p.Cout) continue;                // warp-uniform
                 float v[32];
-                if (p.out_mode == kOutF32) {
+                const bool row_major = (p.out_mode == kOutF32) || (p.out_mode == kOutBF16 && col0 < p.split_col);
+                if (row_major) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);       // bias is added after the transposition
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = col0 + j;
-                        v[j] = __uint_as_float(r[j]) + ((col < p.Cout) ? __ldg(p.bias + col) : 0.f);
-                    }
-                }
-                if (p.out_mode == kOutF32) {
                     // thread-per-row registers -> swizzled smem tile -> lane = (row % 4 group, 4 columns): every
-                    // global access below is 4 rows x 128 contiguous bytes per warp instruction
+                    // global access below is 4 rows x 128 (fp32) / 64 (16-bit) contiguous bytes per warp instruction
                     float4* tile = reinterpret_cast<float4*>(epi_smem + (warp - 2) * (32 * 128));
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -203,6 +196,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
+                    float ssum = 0.f, ssq = 0.f;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int rr = i * 4 + rsub;
@@ -210,31 +204,40 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                         o.x += b4.x + res[i].x; o.y += b4.y + res[i].y; o.z += b4.z + res[i].z; o.w += b4.w + res[i].w;
                         if (p.act_silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
                         const long long g = wrow0 + rr;
-                        if (tile_ok && (q * 32 + rr < p.rows_per_tile) && (g < p.M))
-                            *reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(g) * p.ld + col0 + cq * 4) = o;
+                        if (tile_ok && (q * 32 + rr < p.rows_per_tile) && (g < p.M)) {
+                            const size_t off = static_cast<size_t>(g) * p.ld + col0 + cq * 4;
+                            if (p.out_mode == kOutF32)
+                                *reinterpret_cast<float4*>(p.out_f32 + off) = o;
+                            else
+                                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_16(o.x, o.y, p.f16), pack_16(o.z, o.w, p.f16));
+                            ssum += (o.x + o.y) + (o.z + o.w);
+                            ssq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+                        }
+                    }
+                    if (p.stats) {                           // fixed-order reduction over the warp's 32 rows
+                        ssum += __shfl_xor_sync(0xffffffffu, ssum, 8); ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
+                        ssum += __shfl_xor_sync(0xffffffffu, ssum, 16); ssq += __shfl_xor_sync(0xffffffffu, ssq, 16);
+                        if (rsub == 0 && tile_ok && wrow0 < p.M)
+                            p.stats[static_cast<size_t>(wrow0 / kStatRows) * (p.Cout / kStatCols) + (col0 >> 2) + cq] = make_float2(ssum, ssq);
                     }
                     __syncwarp();
-                } else if (p.out_mode == kOutBF16) {
+                } else if (p.out_mode == kOutBF16) {         // V third of proj_in: transposed per image (coalesced per column)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(p.bias + col0 + j);
                     if (p.act_silu) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
                     }
                     if (row_ok) {
-                        if (col0 < p.split_col) {
-                            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + grow * p.ld + col0);
+                        const long long img = grow / p.HW;
+                        const int pix = static_cast<int>(grow - img * p.HW);
+                        h16* dst = p.out_t + (img * (p.Cout - p.split_col) + (col0 - p.split_col)) * p.HW + pix;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                dst[j] = make_uint4(pack_16(v[8 * j], v[8 * j + 1], p.f16), pack_16(v[8 * j + 2], v[8 * j + 3], p.f16),
-                                                    pack_16(v[8 * j + 4], v[8 * j + 5], p.f16), pack_16(v[8 * j + 6], v[8 * j + 7], p.f16));
-                        } else {
-                            const long long img = grow / p.HW;
-                            const int pix = static_cast<int>(grow - img * p.HW);
-                            h16* dst = p.out_t + (img * (p.Cout - p.split_col) + (col0 - p.split_col)) * p.HW + pix;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.HW] = cvt_16(v[j], p.f16);
-                        }
+                        for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.HW] = cvt_16(v[j], p.f16);
                     }
                 } else {   // kOutNCHW
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + ((col0 + j < p.Cout) ? __ldg(p.bias + col0 + j) : 0.f);
                     if (row_ok) {
                         const long long img = grow / p.HW;
                         const int pix = static_cast<int>(grow - img * p.HW);

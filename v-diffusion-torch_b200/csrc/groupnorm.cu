@@ -5,11 +5,15 @@
 // (unet.py:28-30, 119-124, 127-132, 141-146; AttentionBlock.norm unet.py:52,76; out_conv unet.py:229-231)
 // and the channel concat feeding it (unet.py:315) by reading two sources.
 //
-// One CTA per sample.  Thread t owns VEC consecutive channels (always inside one group) and every
-// PPH-th pixel, so per-group statistics are private fp32 partials combined once through shared
-// memory in a fixed order (deterministic).  Pass 2 re-reads the sample (L2-resident) and writes the
-// normalised operand; optionally also the raw concat in bf16 (operand of the 1x1 skip conv) and the
-// resampled raw input in fp32 (identity-skip residual of a resampling block).
+// Statistics: normally the producing conv epilogue has already written per-(32-row slab, 4-channel)
+// partial (sum, sum of squares) next to the tensor (ConvParams::stats); this kernel combines the
+// partials of its image in a fixed order (deterministic, fp64) and is then a single streaming pass:
+// read fp32 (or 16-bit) once, write the 16-bit operand once.  Images are split over several CTAs.
+// Fallback (groups that are not a multiple of 4 channels, or a concat seam inside a group): one CTA
+// per sample makes its own statistics pass first (thread t owns VEC consecutive channels of one
+// group and every PPH-th pixel; private fp32 partials combined once through shared memory).
+// Optionally also writes the raw concat in 16 bits (operand of the 1x1 skip conv) and the resampled
+// raw input in fp32 (identity-skip residual of a resampling block).
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -30,6 +34,22 @@ __device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC]) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) v[i] = f[i];
 }
+// 16-bit source (conv1 output kept in the operand format): VEC == 4 only
+__device__ __forceinline__ void load_vec16(const h16* p, float (&v)[4], int f16) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    if (f16) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void load_vec16(const h16*, float (&)[VEC], int) {}
+
 template <int VEC>
 __device__ __forceinline__ void store_16(h16* p, const float (&v)[VEC], int f16) {
     if (VEC == 4) {
@@ -47,9 +67,43 @@ __device__ __forceinline__ void store_f32(float* p, const float (&v)[VEC]) {
     }
 }
 
-template <int VEC>
+// Combines the conv epilogue's partial statistics of one image into (mean, rstd) per group: 8 threads per
+// group, fixed summation order, fp64.
+__global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const GroupNormParams p) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int C = p.C1 + p.C2, HW = p.H * p.W, cpg = C / kGroups;
+    const int g = tid >> 3, part8 = tid & 7;
+    const int cbase = g * cpg;
+    const bool g1 = cbase < p.C1;
+    const float2* st = g1 ? p.stats1 : p.stats2;
+    const int Cs = g1 ? p.C1 : p.C2;
+    const int c4 = (g1 ? cbase : cbase - p.C1) >> 2, sub = cpg >> 2, slabs = HW / kStatRows;
+    const float2* base = st + static_cast<size_t>(b) * slabs * (Cs >> 2) + c4;
+    double ds = 0.0, dss = 0.0;
+    for (int e0 = 0; e0 < slabs * sub; e0 += 32) {           // 4 independent loads in flight per thread
+        float2 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * 8 + part8;
+            t[u] = (e < slabs * sub) ? __ldg(base + static_cast<size_t>(e / sub) * (Cs >> 2) + (e % sub)) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { ds += t[u].x; dss += t[u].y; }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, o); dss += __shfl_xor_sync(0xffffffffu, dss, o); }
+    if (part8 == 0) {
+        const double n = static_cast<double>(cpg) * HW;
+        const double mean = ds / n;
+        double var = dss / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        p.meanrstd[b * kGroups + g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(kEps))));
+    }
+}
+
+template <int VEC, bool FUSED, bool IN16>
 __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParams p, int CV, int PPH) {
-    extern __shared__ float2 part[];                 // [CV * PPH] partial (sum, sumsq); then [32] (mean, rstd)
+    extern __shared__ float2 part[];                 // [CV * PPH] partial (sum, sumsq) (fallback statistics pass)
     __shared__ float2 stat[kGroups];
     const int b = blockIdx.x;
     const int C = p.C1 + p.C2;
@@ -61,13 +115,18 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
     const int pp = active ? tid / CV : 0;
     const int c = cv * VEC;                          // first channel owned by this thread
     const bool from1 = c < p.C1;
-    const float* src = from1 ? p.src1 + static_cast<size_t>(b) * HW * p.C1 + c
+    const float* src = from1 ? static_cast<const float*>(p.src1) + static_cast<size_t>(b) * HW * p.C1 + c
                              : p.src2 + static_cast<size_t>(b) * HW * p.C2 + (c - p.C1);
+    const h16* src16 = static_cast<const h16*>(p.src1) + static_cast<size_t>(b) * HW * p.C1 + c;   // IN16 only
     const int sC = from1 ? p.C1 : p.C2;
+    auto load_px = [&](int pix, float (&v)[VEC]) {
+        if (IN16) load_vec16(src16 + static_cast<size_t>(pix) * sC, v, p.f16);
+        else load_vec<VEC>(src + static_cast<size_t>(pix) * sC, v);
+    };
 
-    // ---- pass 1: statistics
+    // ---- fallback pass 1: statistics
     float s = 0.f, ss = 0.f;
-    if (active) {
+    if (!FUSED && active) {
         int pix = pp;
         for (; pix + 3 * PPH < HW; pix += 4 * PPH) {
             float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
@@ -89,8 +148,8 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
         }
         part[tid] = make_float2(s, ss);
     }
-    __syncthreads();
-    if (tid < kGroups) {
+    if (!FUSED) __syncthreads();
+    if (!FUSED && tid < kGroups) {
         const int vpg = cpg / VEC;                   // vectors per group per pixel
         double ds = 0.0, dss = 0.0;
         for (int ph = 0; ph < PPH; ++ph)
@@ -104,11 +163,11 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
         if (var < 0.0) var = 0.0;
         stat[tid] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(kEps))));
     }
-    __syncthreads();
+    if (!FUSED) __syncthreads();
     if (!active) return;
 
     // ---- pass 2: apply
-    const float2 st = stat[c / cpg];
+    const float2 st = FUSED ? __ldg(p.meanrstd + b * kGroups + c / cpg) : stat[c / cpg];
     float ga[VEC], be[VEC], fs[VEC], fb[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -133,7 +192,7 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             const float t = x[i] * ga[i] + be[i];
-            y[i] = p.silu ? t / (1.f + expf(-t)) : t;
+            y[i] = p.silu ? __fdividef(t, 1.f + __expf(-t)) : t;     // 16-bit output: fast-math error is far below its rounding
         }
     };
 
@@ -150,7 +209,7 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             for (int d = 0; d < 4; ++d) {
                 const int pix = (2 * ho + (d >> 1)) * p.W + 2 * wo + (d & 1);
                 float x[VEC], y[VEC];
-                load_vec<VEC>(src + static_cast<size_t>(pix) * sC, x);
+                load_px(pix, x);
                 norm_act(x, y);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) { acc[i] += y[i]; racc[i] += x[i]; }
@@ -167,7 +226,7 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
         for (int pix = pp; pix < HW; pix += PPH) {
             const int h = pix / p.W, w = pix % p.W;
             float x[VEC], y[VEC];
-            load_vec<VEC>(src + static_cast<size_t>(pix) * sC, x);
+            load_px(pix, x);
             norm_act(x, y);
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
@@ -179,11 +238,13 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
     } else {
         h16* oa = p.out_act + static_cast<size_t>(b) * HW * C + c;
         h16* ow = p.out_raw ? p.out_raw + static_cast<size_t>(b) * HW * C + c : nullptr;
-        int pix = pp;
-        for (; pix + PPH < HW; pix += 2 * PPH) {
+        // FUSED: the image is split over gridDim.y CTAs
+        const int span = HW / gridDim.y, pix_end = (blockIdx.y + 1) * span;
+        int pix = blockIdx.y * span + pp;
+        for (; pix + PPH < pix_end; pix += 2 * PPH) {
             float x0[VEC], x1[VEC], y0[VEC], y1[VEC];
-            load_vec<VEC>(src + static_cast<size_t>(pix) * sC, x0);
-            load_vec<VEC>(src + static_cast<size_t>(pix + PPH) * sC, x1);
+            load_px(pix, x0);
+            load_px(pix + PPH, x1);
             norm_act(x0, y0);
             norm_act(x1, y1);
             store_16<VEC>(oa + static_cast<size_t>(pix) * C, y0, p.f16);
@@ -193,9 +254,9 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
                 store_16<VEC>(ow + static_cast<size_t>(pix + PPH) * C, x1, p.f16);
             }
         }
-        for (; pix < HW; pix += PPH) {
+        for (; pix < pix_end; pix += PPH) {
             float x0[VEC], y0[VEC];
-            load_vec<VEC>(src + static_cast<size_t>(pix) * sC, x0);
+            load_px(pix, x0);
             norm_act(x0, y0);
             store_16<VEC>(oa + static_cast<size_t>(pix) * C, y0, p.f16);
             if (ow) store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, p.f16);
@@ -213,18 +274,32 @@ cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream) {
     if (cpg % vec != 0 || p.C1 % vec != 0) return cudaErrorInvalidValue;
     const int CV = C / vec;
     if (CV > 1024) return cudaErrorInvalidValue;
-    int PPH = 1024 / CV;
     const int HW = p.H * p.W;
+    const bool fused = p.stats1 != nullptr;
+    if (fused && (vec != 4 || HW % kStatRows != 0 || (p.C2 > 0 && (p.stats2 == nullptr || p.C1 % cpg != 0)))) return cudaErrorInvalidValue;
+    if (p.in16 && (p.C2 != 0 || vec != 4 || !fused)) return cudaErrorInvalidValue;
+    int PPH = 1024 / CV;
     const int work = (p.resample == kResDown) ? HW / 4 : HW;
     if (PPH > work) PPH = work;
     if (PPH > 8) PPH = 8;                             // >= 8 pixels of work per thread at 32x32 / 256 ch
     if (PPH < 1) PPH = 1;
-    const int threads = ((CV * PPH + 31) / 32) * 32;
-    const size_t smem = static_cast<size_t>(CV) * PPH * sizeof(float2);
-    if (vec == 4)
-        groupnorm_kernel<4><<<p.B, threads, smem, stream>>>(p, CV, PPH);
-    else
-        groupnorm_kernel<2><<<p.B, threads, smem, stream>>>(p, CV, PPH);
+    int threads = ((CV * PPH + 31) / 32) * 32;
+    const size_t smem = fused ? 0 : static_cast<size_t>(CV) * PPH * sizeof(float2);
+    // split an image over several CTAs when the statistics are already known (no resampling: pixel ranges are trivial)
+    int split = 1;
+    if (fused && p.resample == kResNone)
+        while (split < 8 && (HW / (split * 2)) >= 2 * PPH * 8 && (HW % (split * 2)) == 0) split *= 2;
+    dim3 grid(p.B, split);
+    if (fused) {
+        if (p.meanrstd == nullptr) return cudaErrorInvalidValue;
+        groupnorm_finalize_kernel<<<p.B, 256, 0, stream>>>(p);
+        if (p.in16) groupnorm_kernel<4, true, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
+        else groupnorm_kernel<4, true, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
+    } else if (vec == 4) {
+        groupnorm_kernel<4, false, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
+    } else {
+        groupnorm_kernel<2, false, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
+    }
     return cudaGetLastError();
 }
 

@@ -49,7 +49,12 @@ struct alignas(64) ConvParams {
     float* out_f32;
     h16* out_bf16;
     h16* out_t;
+    // optional GroupNorm partial statistics of the row-major output (after bias/residual): for every slab of
+    // 32 consecutive rows and every 4 consecutive columns, (sum, sum of squares): stats[slab * Cout/4 + col/4]
+    float2* stats;
 };
+constexpr int kStatRows = 32;   // rows per statistics slab
+constexpr int kStatCols = 4;    // columns per statistics entry
 cudaError_t launch_conv_gemm(const ConvParams& p, int num_sms, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
@@ -59,8 +64,13 @@ cudaError_t launch_conv_gemm(const ConvParams& p, int num_sms, cudaStream_t stre
 enum Resample : int { kResNone = 0, kResDown = 1, kResUp = 2 };
 
 struct GroupNormParams {
-    const float* src1; int C1;         // fp32 [B, HW, C1]
+    const void* src1; int C1;          // fp32 (or 16-bit when in16) [B, HW, C1]
     const float* src2; int C2;         // fp32 [B, HW, C2] or null: channels C1..C1+C2 (virtual concat)
+    int in16;                          // src1 holds 16-bit values in the launch's operand format (C2 must be 0)
+    // partial statistics written by the producing conv epilogue (ConvParams::stats); when stats1 is set the
+    // kernel is a single streaming pass, otherwise it makes a statistics pass of its own
+    const float2* stats1; const float2* stats2;
+    float2* meanrstd;                  // scratch [B][32] (mean, rstd), required when stats1 is set
     int B, H, W;
     const float* gamma; const float* beta;   // [C1 + C2]
     const float* film;                 // null or fp32 table; row r holds [shift(C) | scale(C)] at film_off

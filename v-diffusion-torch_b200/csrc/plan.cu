@@ -601,6 +601,7 @@ struct ConvSpec {
     const float* bias = nullptr; const float* residual = nullptr;
     int out_mode = kOutF32; float* out_f32 = nullptr; h16* out_bf16 = nullptr; h16* out_t = nullptr;
     int ld = 0, split_col = 0, act_silu = 0, f16 = 1;
+    float2* stats = nullptr;
 };
 
 static int setup_conv(const ConvSpec& s, ConvParams* cp) {
@@ -632,7 +633,7 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     CKI(make_map_2d(&cp->b_map, s.wpacked, s.wrows, ktot, ktot, cp->block_n / 2));   // each CTA of a pair fetches half
     cp->M = (int)M; cp->Cout = s.cout; cp->out_mode = s.out_mode; cp->ld = s.ld;
     cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16;
-    cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t;
+    cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t; cp->stats = s.stats;
     if (s.out_mode != kOutNCHW && s.cout % 32 != 0) return fail("output channels must be a multiple of 32 (got %d)", s.cout);
     return 0;
 }
@@ -654,32 +655,41 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
         ex->steps.push_back({S_GN, (int)ex->gns.size() - 1});
     };
     // ---- in_conv
-    h16* patches; float* h;
+    // every fp32 stream tensor carries the partial GroupNorm statistics its producing conv wrote
+    auto stats_bytes = [&](size_t rows_px, int ch) { return (rows_px / kStatRows) * (size_t)(ch / kStatCols) * sizeof(float2); };
+    h16* patches; float* h; float2* hst;
     const size_t hw0 = (size_t)res * res;
     CKI(ex->acquire((size_t)R * hw0 * 64 * 2, (void**)&patches));
     ex->im2cols.push_back({ex->xin, patches, R / ex->rep, ex->rep, c.in_channels, res, res, p->f16});
     ex->steps.push_back({S_IM2COL, (int)ex->im2cols.size() - 1});
     CKI(ex->acquire((size_t)R * hw0 * hid * 4, (void**)&h));
+    CKI(ex->acquire(stats_bytes((size_t)R * hw0, hid), (void**)&hst));
     {
         ConvSpec s;
         s.f16 = p->f16;
         s.a1 = patches; s.c1 = 64; s.ld1 = 64; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_in; s.cout = hid; s.wrows = hid;
-        s.bias = p->W("in_conv.bias"); s.out_mode = kOutF32; s.out_f32 = h; s.ld = hid;
+        s.bias = p->W("in_conv.bias"); s.out_mode = kOutF32; s.out_f32 = h; s.ld = hid; s.stats = hst;
         CKI(add_conv(s));
     }
     ex->release(patches);
-    struct Skip { float* ptr; int ch; };
+    float2* meanrstd;                                 // (mean, rstd) scratch shared by all GroupNorms (stream-ordered)
+    CKI(ex->acquire((size_t)R * 32 * sizeof(float2), (void**)&meanrstd));
+    struct Skip { float* ptr; float2* stats; int ch; };
     std::vector<Skip> stack;
-    stack.push_back({h, hid});
+    stack.push_back({h, hst, hid});
     bool h_on_stack = true;      // h aliases the top stack entry -> must not be released when replaced
     int hch = hid;
+    auto fusable = [](int c1, int c2) {               // can a GroupNorm over concat(c1, c2) use epilogue statistics?
+        const int cpg = (c1 + c2) / 32;
+        return cpg % kStatCols == 0 && (c2 == 0 || c1 % cpg == 0);
+    };
 
     for (auto& b : p->blocks) {
         const std::string& n = b.name;
         const int HW = res * res;
         if (b.kind == 0) {
-            const float* src2 = nullptr; int c2 = 0; float* src2_buf = nullptr;
-            if (b.concat) { Skip sk = stack.back(); stack.pop_back(); src2 = sk.ptr; c2 = sk.ch; src2_buf = sk.ptr; }
+            const float* src2 = nullptr; int c2 = 0; float* src2_buf = nullptr; float2* st2 = nullptr;
+            if (b.concat) { Skip sk = stack.back(); stack.pop_back(); src2 = sk.ptr; c2 = sk.ch; src2_buf = sk.ptr; st2 = sk.stats; }
             const int cin = hch + c2;
             if (cin != b.cin) return fail("internal: channel bookkeeping mismatch at %s (%d vs %d)", n.c_str(), cin, b.cin);
             const bool skipconv = b.cin != b.cout;
@@ -692,17 +702,22 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             GroupNormParams g{};
             g.f16 = p->f16;
             g.src1 = h; g.C1 = hch; g.src2 = src2; g.C2 = c2; g.B = R; g.H = res; g.W = res;
+            if (fusable(hch, c2)) { g.stats1 = hst; g.stats2 = st2; g.meanrstd = meanrstd; }
             g.gamma = p->W(n + ".norm1.weight"); g.beta = p->W(n + ".norm1.bias");
             g.silu = 1; g.resample = b.resample; g.out_act = a1; g.out_raw = xraw; g.out_res = xres;
             add_gn(g);
-            // conv1
-            float* h1;
-            CKI(ex->acquire((size_t)R * HWo * b.cout * 4, (void**)&h1));
+            // conv1: its output only feeds norm2, so it is kept in the 16-bit operand format when norm2 can use
+            // the epilogue statistics (otherwise fp32 for the two-pass fallback)
+            const bool fuse2 = fusable(b.cout, 0);
+            void* h1; float2* h1st = nullptr;
+            CKI(ex->acquire((size_t)R * HWo * b.cout * (fuse2 ? 2 : 4), &h1));
+            if (fuse2) CKI(ex->acquire(stats_bytes((size_t)R * HWo, b.cout), (void**)&h1st));
             {
                 ConvSpec s;
                 s.f16 = p->f16;
                 s.a3 = a1; s.c3 = cin; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w1; s.cout = b.cout; s.wrows = b.cout;
-                s.bias = p->W(n + ".conv1.bias"); s.out_mode = kOutF32; s.out_f32 = h1; s.ld = b.cout;
+                s.bias = p->W(n + ".conv1.bias"); s.ld = b.cout; s.stats = h1st;
+                if (fuse2) { s.out_mode = kOutBF16; s.out_bf16 = (h16*)h1; } else { s.out_mode = kOutF32; s.out_f32 = (float*)h1; }
                 CKI(add_conv(s));
             }
             ex->release(a1);
@@ -711,15 +726,17 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire((size_t)R * HWo * b.cout * 2, (void**)&a2));
             GroupNormParams g2{};
             g2.f16 = p->f16;
-            g2.src1 = h1; g2.C1 = b.cout; g2.B = R; g2.H = ro; g2.W = ro;
+            g2.src1 = h1; g2.C1 = b.cout; g2.B = R; g2.H = ro; g2.W = ro; g2.in16 = fuse2 ? 1 : 0; g2.stats1 = h1st; g2.meanrstd = meanrstd;
             g2.gamma = p->W(n + ".norm2.weight"); g2.beta = p->W(n + ".norm2.bias");
             g2.film = film; g2.film_row = film_row; g2.film_stride = p->film_total; g2.film_off = b.film_off;
             g2.silu = 1; g2.resample = kResNone; g2.out_act = a2;
             add_gn(g2);
             ex->release(h1);
+            if (h1st) ex->release(h1st);
             // conv2 (+ fused 1x1 skip conv as extra K) + residual
-            float* hout;
+            float* hout; float2* houtst;
             CKI(ex->acquire((size_t)R * HWo * b.cout * 4, (void**)&hout));
+            CKI(ex->acquire(stats_bytes((size_t)R * HWo, b.cout), (void**)&houtst));
             {
                 ConvSpec s;
                 s.f16 = p->f16;
@@ -727,15 +744,15 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
                 if (skipconv) { s.a1 = xraw; s.c1 = cin; s.ld1 = cin; }
                 s.bias = b.bias2;
                 s.residual = skipconv ? nullptr : (b.resample != kResNone ? xres : h);
-                s.out_mode = kOutF32; s.out_f32 = hout; s.ld = b.cout;
+                s.out_mode = kOutF32; s.out_f32 = hout; s.ld = b.cout; s.stats = houtst;
                 CKI(add_conv(s));
             }
             ex->release(a2);
             if (xraw) ex->release(xraw);
             if (xres) ex->release(xres);
-            if (src2_buf) ex->release(src2_buf);
-            if (!h_on_stack) ex->release(h);
-            h = hout; hch = b.cout; h_on_stack = false; res = ro;
+            if (src2_buf) { ex->release(src2_buf); ex->release(st2); }
+            if (!h_on_stack) { ex->release(h); ex->release(hst); }
+            h = hout; hst = houtst; hch = b.cout; h_on_stack = false; res = ro;
         } else {
             int hd, nh;
             attn_dims(c, b.cin, &hd, &nh);
@@ -745,6 +762,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             GroupNormParams g{};
             g.f16 = p->f16;
             g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
+            if (fusable(hch, 0)) { g.stats1 = hst; g.meanrstd = meanrstd; }
             g.gamma = p->W(n + ".norm.weight"); g.beta = p->W(n + ".norm.bias");
             g.silu = 0; g.resample = kResNone; g.out_act = a;
             add_gn(g);
@@ -773,20 +791,22 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
                 ex->steps.push_back({S_ATTN, (int)ex->attns.size() - 1});
             }
             ex->release(qk); ex->release(vt);
-            float* hout;
+            float* hout; float2* houtst;
             CKI(ex->acquire((size_t)R * HW * b.cin * 4, (void**)&hout));
+            CKI(ex->acquire(stats_bytes((size_t)R * HW, b.cin), (void**)&houtst));
             {
                 ConvSpec s;
                 s.f16 = p->f16;
                 s.a1 = o; s.c1 = hidd; s.ld1 = hidd; s.n = R; s.h = res; s.w = res; s.wpacked = b.w2; s.cout = b.cin; s.wrows = b.cin;
                 s.bias = p->W(n + ".proj_out.bias"); s.residual = h; s.out_mode = kOutF32; s.out_f32 = hout; s.ld = b.cin;
+                s.stats = houtst;
                 CKI(add_conv(s));
             }
             ex->release(o);
-            if (!h_on_stack) ex->release(h);
-            h = hout; h_on_stack = false;
+            if (!h_on_stack) { ex->release(h); ex->release(hst); }
+            h = hout; hst = houtst; h_on_stack = false;
         }
-        if (b.push) { stack.push_back({h, hch}); h_on_stack = true; }
+        if (b.push) { stack.push_back({h, hst, hch}); h_on_stack = true; }
     }
     if (!stack.empty()) return fail("internal: skip stack not empty (%d)", (int)stack.size());
     // ---- out_conv
@@ -797,6 +817,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
         GroupNormParams g{};
         g.f16 = p->f16;
         g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
+        if (fusable(hch, 0)) { g.stats1 = hst; g.meanrstd = meanrstd; }
         g.gamma = p->W("out_conv.0.weight"); g.beta = p->W("out_conv.0.bias");
         g.silu = 1; g.resample = kResNone; g.out_act = a;
         add_gn(g);
@@ -806,7 +827,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
         s.bias = p->W("out_conv.2.bias"); s.out_mode = kOutNCHW; s.out_f32 = ex->yout; s.ld = 0;
         CKI(add_conv(s));
         ex->release(a);
-        if (!h_on_stack) ex->release(h);
+        if (!h_on_stack) { ex->release(h); ex->release(hst); }
     }
     return 0;
 }
@@ -1167,7 +1188,8 @@ extern "C" int vdt_p_sample_host(vdt_plan* p, const vdt_sampler_config* scp, con
 
 // ================================================================================================ kernel-level hooks
 extern "C" int vdt_op_conv(const void* x, int32_t batch, int32_t h, int32_t w, int32_t cin, const float* w_oihw, int32_t cout,
-                           int32_t ksize, const float* bias, const float* residual, float* out, int32_t f16, void* stream) {
+                           int32_t ksize, const float* bias, const float* residual, float* out, int32_t f16, void* out16,
+                           void* stats_out, void* stream) {
     if (ksize != 1 && ksize != 3) return fail("ksize must be 1 or 3");
     if (cin % 64) return fail("cin must be a multiple of 64");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1185,7 +1207,8 @@ extern "C" int vdt_op_conv(const void* x, int32_t batch, int32_t h, int32_t w, i
         s.f16 = f16;
         if (ksize == 3) { s.a3 = (const h16*)x; s.c3 = cin; } else { s.a1 = (const h16*)x; s.c1 = cin; s.ld1 = cin; }
         s.n = batch; s.h = h; s.w = w; s.wpacked = wp; s.cout = cout; s.wrows = wrows; s.bias = bias; s.residual = residual;
-        s.out_mode = kOutF32; s.out_f32 = out; s.ld = cout;
+        s.out_mode = kOutF32; s.out_f32 = out; s.ld = cout; s.stats = (float2*)stats_out;
+        if (out16) { s.out_mode = kOutBF16; s.out_bf16 = (h16*)out16; s.out_f32 = nullptr; }
         std::unique_ptr<ConvParams> cp(new ConvParams());
         rc = setup_conv(s, cp.get());
         if (rc == 0) {
@@ -1200,17 +1223,20 @@ extern "C" int vdt_op_conv(const void* x, int32_t batch, int32_t h, int32_t w, i
     return rc;
 }
 
-extern "C" int vdt_op_groupnorm(const float* src1, int32_t c1, const float* src2, int32_t c2, int32_t batch, int32_t h,
+extern "C" int vdt_op_groupnorm(const void* src1, int32_t c1, const float* src2, int32_t c2, int32_t batch, int32_t h,
                                 int32_t w, const float* gamma, const float* beta, const float* film, int32_t film_stride,
                                 int32_t film_off, int32_t silu, int32_t resample, void* out_act, void* out_raw, float* out_res,
-                                int32_t f16, void* stream) {
+                                int32_t f16, const void* stats1, const void* stats2, int32_t in16, void* stream) {
     GroupNormParams g{};
-    g.f16 = f16;
+    g.f16 = f16; g.stats1 = (const float2*)stats1; g.stats2 = (const float2*)stats2; g.in16 = in16;
     g.src1 = src1; g.C1 = c1; g.src2 = src2; g.C2 = c2; g.B = batch; g.H = h; g.W = w; g.gamma = gamma; g.beta = beta;
     g.film = film; g.film_row = nullptr; g.film_stride = film_stride; g.film_off = film_off; g.silu = silu; g.resample = resample;
     g.out_act = (h16*)out_act; g.out_raw = (h16*)out_raw; g.out_res = out_res;
+    float2* scratch = nullptr;
+    if (stats1) { CK(cudaMalloc(&scratch, (size_t)batch * 32 * sizeof(float2))); g.meanrstd = scratch; }
     cudaError_t e = launch_groupnorm(g, reinterpret_cast<cudaStream_t>(stream));
     ++g_launches;
+    if (scratch) { cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)); cudaFree(scratch); }
     if (e != cudaSuccess) return fail("groupnorm launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
