@@ -24,10 +24,14 @@ constexpr int kKeys = 64;                      // keys per tile = one 128-byte s
 constexpr int kThreads = 192;
 constexpr float kRescaleThreshold = 8.0f;      // log2 units
 
-struct Smem {
-    uint8_t* q; uint8_t* k[2]; uint8_t* v[2]; uint8_t* p[2];
+struct Smem {          // stage pointers are computed, not indexed (no local-memory arrays)
+    uint8_t* q; uint8_t* k0; uint8_t* v0; uint8_t* p0;
+    int k_stride, v_stride;
     uint64_t* q_full; uint64_t* k_full; uint64_t* v_full; uint64_t* kv_empty; uint64_t* s_full; uint64_t* p_full;
     uint32_t* tmem_slot;
+    __device__ __forceinline__ uint8_t* k(int s) const { return k0 + s * k_stride; }
+    __device__ __forceinline__ uint8_t* v(int s) const { return v0 + s * v_stride; }
+    __device__ __forceinline__ uint8_t* p(int s) const { return p0 + s * 16384; }
 };
 
 __host__ __device__ inline int attn_smem_bytes(int d) {
@@ -41,12 +45,9 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
     const int d = p.d, dch = d / 64;
     Smem sm;
     sm.q = base; base += dch * 16384;
-    sm.k[0] = base; base += dch * 8192;
-    sm.k[1] = base; base += dch * 8192;
-    sm.v[0] = base; base += d * 128;
-    sm.v[1] = base; base += d * 128;
-    sm.p[0] = base; base += 16384;
-    sm.p[1] = base; base += 16384;
+    sm.k0 = base; sm.k_stride = dch * 8192; base += 2 * dch * 8192;
+    sm.v0 = base; sm.v_stride = d * 128; base += 2 * d * 128;
+    sm.p0 = base; base += 2 * 16384;
     uint64_t* bars = reinterpret_cast<uint64_t*>(base);
     sm.q_full = bars; sm.k_full = bars + 1; sm.v_full = bars + 3; sm.kv_empty = bars + 5; sm.s_full = bars + 7;
     sm.p_full = bars + 8;
@@ -91,12 +92,12 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                 mbar_wait(&sm.kv_empty[s], ((j >> 1) & 1) ^ 1);
                 mbar_expect_tx(&sm.k_full[s], static_cast<uint32_t>(dch * 8192));
                 for (int c = 0; c < dch; ++c)
-                    tma_load_2d(sm.k[s] + c * 8192, &p.k_map, &sm.k_full[s], p.hid + h * d + c * 64,
+                    tma_load_2d(sm.k(s) + c * 8192, &p.k_map, &sm.k_full[s], p.hid + h * d + c * 64,
                                 static_cast<int>(krow0) + j * kKeys);
                 const int img = b0 + (j * kKeys) / N;
                 const int koff = (N >= kQRows) ? j * kKeys : (j * kKeys) % N;
                 mbar_expect_tx(&sm.v_full[s], static_cast<uint32_t>(d * 128));
-                tma_load_2d(sm.v[s], &p.vt_map, &sm.v_full[s], koff, (img * p.heads + h) * d);
+                tma_load_2d(sm.v(s), &p.vt_map, &sm.v_full[s], koff, (img * p.heads + h) * d);
             }
         }
     } else if (warp == 1) {
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                 tc_fence_after();
                 for (int kk = 0; kk < d / 16; ++kk) {
                     const uint64_t ad = umma_desc_sw128(smem_u32(sm.q + (kk >> 2) * 16384)) + 2 * (kk & 3);
-                    const uint64_t bd = umma_desc_sw128(smem_u32(sm.k[s] + (kk >> 2) * 8192)) + 2 * (kk & 3);
+                    const uint64_t bd = umma_desc_sw128(smem_u32(sm.k(s) + (kk >> 2) * 8192)) + 2 * (kk & 3);
                     umma_16(tmem_s, ad, bd, idesc_s, kk != 0);
                 }
                 umma_commit(sm.s_full);
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < kKeys / 16; ++kk) {
-                    const uint64_t ad = umma_desc_sw128(smem_u32(sm.p[s])) + 2 * kk;
-                    const uint64_t bd = umma_desc_sw128(smem_u32(sm.v[s])) + 2 * kk;
+                    const uint64_t ad = umma_desc_sw128(smem_u32(sm.p(s))) + 2 * kk;
+                    const uint64_t bd = umma_desc_sw128(smem_u32(sm.v(s))) + 2 * kk;
                     umma_16(tmem_o, ad, bd, idesc_o, (j | kk) != 0);
                 }
                 umma_commit(&sm.kv_empty[s]);             // K_j / V_j / P_j free, O updated
@@ -151,12 +152,12 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
             float sv[64];
 #pragma unroll
             for (int i = 0; i < 32; ++i) { sv[i] = __uint_as_float(r0[i]); sv[32 + i] = __uint_as_float(r1[i]); }
-            bool tile_valid = true;
-            if (N < kQRows) tile_valid = ((j * kKeys) / N) == row_img;    // kKeys <= N: a tile lies in one image
+            // N < 128: a 64-key tile belongs to one image; rows of the other image ignore it entirely
+            const bool tile_valid = (N >= kQRows) || (((j * kKeys) / N) == row_img);
             float m_tile = -INFINITY;
             if (tile_valid) {
 #pragma unroll
-                for (int i = 0; i < 64; ++i) m_tile = fmaxf(m_tile, sv[i]);
+                for (int i = 0; i < 64; i += 2) m_tile = fmaxf(m_tile, fmaxf(sv[i], sv[i + 1]));
             }
             float factor = 1.f;
             bool need = false;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                 if (m_used == -INFINITY) {
                     m_used = m_tile;                        // nothing accumulated yet for this row (O row == 0, l == 0)
                 } else if ((m_tile - m_used) * c > kRescaleThreshold) {
-                    factor = exp2f((m_used - m_tile) * c);
+                    factor = ex2_approx((m_used - m_tile) * c);
                     m_used = m_tile;
                     need = true;
                 }
@@ -184,19 +185,23 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                 tmem_st_wait();
                 l *= factor;
             }
+            // p = 2^(s*c - m*c); a row that ignores this tile writes zeros (its m may still be -inf)
             const float mc = (m_used == -INFINITY) ? 0.f : m_used * c;
-            uint8_t* prow = sm.p[j & 1] + row * 128;
+            const float cc = tile_valid ? c : 0.f;
+            const float off = tile_valid ? mc : 200.f;      // 2^-200 flushes to exactly 0
+            uint8_t* prow = sm.p(j & 1) + row * 128;
             float lsum = 0.f;
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
                 float e[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    e[i] = tile_valid ? exp2f(sv[ch * 8 + i] * c - mc) : 0.f;
+                    e[i] = ex2_approx(fmaf(sv[ch * 8 + i], cc, -off));
                     lsum += e[i];
                 }
                 *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) =
-                    make_uint4(pack_16(e[0], e[1], p.f16), pack_16(e[2], e[3], p.f16), pack_16(e[4], e[5], p.f16), pack_16(e[6], e[7], p.f16));
+                    make_uint4(pack_16_inrange(e[0], e[1], p.f16), pack_16_inrange(e[2], e[3], p.f16), pack_16_inrange(e[4], e[5], p.f16),
+                               pack_16_inrange(e[6], e[7], p.f16));   // p <= 2^8
             }
             l += lsum;
             fence_proxy_async_smem();

@@ -51,11 +51,19 @@ template <int VEC>
 __device__ __forceinline__ void load_vec16(const h16*, float (&)[VEC], int) {}
 
 template <int VEC>
-__device__ __forceinline__ void store_16(h16* p, const float (&v)[VEC], int f16) {
+__device__ __forceinline__ void store_16(h16* p, const float (&v)[VEC], int f16) {      // saturating (raw stream values)
     if (VEC == 4) {
         *reinterpret_cast<uint2*>(p) = make_uint2(pack_16(v[0], v[1], f16), pack_16(v[2], v[3], f16));
     } else {
         *reinterpret_cast<uint32_t*>(p) = pack_16(v[0], v[1], f16);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void store_16n(h16* p, const float (&v)[VEC], int f16) {     // normalised values: in range
+    if (VEC == 4) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(pack_16_inrange(v[0], v[1], f16), pack_16_inrange(v[2], v[3], f16));
+    } else {
+        *reinterpret_cast<uint32_t*>(p) = pack_16_inrange(v[0], v[1], f16);
     }
 }
 template <int VEC>
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             }
 #pragma unroll
             for (int i = 0; i < VEC; ++i) { acc[i] *= 0.25f; racc[i] *= 0.25f; }
-            store_16<VEC>(oa + static_cast<size_t>(po) * C, acc, p.f16);
+            store_16n<VEC>(oa + static_cast<size_t>(po) * C, acc, p.f16);
             if (orr) store_f32<VEC>(orr + static_cast<size_t>(po) * C, racc);
         }
     } else if (p.resample == kResUp) {
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 const size_t po = static_cast<size_t>(2 * h + (d >> 1)) * Wo + 2 * w + (d & 1);
-                store_16<VEC>(oa + po * C, y, p.f16);
+                store_16n<VEC>(oa + po * C, y, p.f16);
                 if (orr) store_f32<VEC>(orr + po * C, x);
             }
         }
@@ -241,24 +249,28 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
         // FUSED: the image is split over gridDim.y CTAs
         const int span = HW / gridDim.y, pix_end = (blockIdx.y + 1) * span;
         int pix = blockIdx.y * span + pp;
-        for (; pix + PPH < pix_end; pix += 2 * PPH) {
-            float x0[VEC], x1[VEC], y0[VEC], y1[VEC];
+        for (; pix + 3 * PPH < pix_end; pix += 4 * PPH) {     // four independent 16-byte loads in flight per thread
+            float x0[VEC], x1[VEC], x2[VEC], x3[VEC], y[VEC];
             load_px(pix, x0);
             load_px(pix + PPH, x1);
-            norm_act(x0, y0);
-            norm_act(x1, y1);
-            store_16<VEC>(oa + static_cast<size_t>(pix) * C, y0, p.f16);
-            store_16<VEC>(oa + static_cast<size_t>(pix + PPH) * C, y1, p.f16);
+            load_px(pix + 2 * PPH, x2);
+            load_px(pix + 3 * PPH, x3);
+            norm_act(x0, y); store_16n<VEC>(oa + static_cast<size_t>(pix) * C, y, p.f16);
+            norm_act(x1, y); store_16n<VEC>(oa + static_cast<size_t>(pix + PPH) * C, y, p.f16);
+            norm_act(x2, y); store_16n<VEC>(oa + static_cast<size_t>(pix + 2 * PPH) * C, y, p.f16);
+            norm_act(x3, y); store_16n<VEC>(oa + static_cast<size_t>(pix + 3 * PPH) * C, y, p.f16);
             if (ow) {
                 store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, p.f16);
                 store_16<VEC>(ow + static_cast<size_t>(pix + PPH) * C, x1, p.f16);
+                store_16<VEC>(ow + static_cast<size_t>(pix + 2 * PPH) * C, x2, p.f16);
+                store_16<VEC>(ow + static_cast<size_t>(pix + 3 * PPH) * C, x3, p.f16);
             }
         }
         for (; pix < pix_end; pix += PPH) {
             float x0[VEC], y0[VEC];
             load_px(pix, x0);
             norm_act(x0, y0);
-            store_16<VEC>(oa + static_cast<size_t>(pix) * C, y0, p.f16);
+            store_16n<VEC>(oa + static_cast<size_t>(pix) * C, y0, p.f16);
             if (ow) store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, p.f16);
         }
     }

@@ -239,11 +239,25 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mas
 }
 
 // ---- small math --------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {   // 2^x, one MUFU op (max rel. error 2^-22), flushes denormals
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 // fp32 pair -> packed 16-bit operand pair.  fp16 saturates at +-65504 instead of overflowing to inf.
 __device__ __forceinline__ uint32_t pack_16(float lo, float hi, int fp16) {
     if (fp16) {
         __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// same without the saturation, for values known to be in range (softmax probabilities, normalised activations)
+__device__ __forceinline__ uint32_t pack_16_inrange(float lo, float hi, int fp16) {
+    if (fp16) {
+        __half2 v = __floats2half2_rn(lo, hi);
         return *reinterpret_cast<uint32_t*>(&v);
     }
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
