@@ -10,9 +10,12 @@
 // Operands (written by the proj_in GEMM epilogue): QK bf16 [B*N, 2*hid] (q | k, heads contiguous,
 // unet.py:76-78) and V^T bf16 [B*hid, N], so every MMA operand is K-major.
 //
-//   warp 0     TMA producer (Q once, then 64-key K / V^T tiles through a 2-stage ring)
+//   warp 0     TMA producer for Q (once) and the 64-key K tiles (2-stage ring, slot freed when S = Q K^T retires)
+//   warp 10    TMA producer for the V^T tiles (2-stage ring, slot freed when O += P V retires)
 //   warp 1     MMA issuer
-//   warps 2-5  softmax + final normalise/store (thread = query row = TMEM lane)
+//   warps 2-9  softmax + final normalise/store: two threads per query row (= TMEM lane), each owning 32
+//              of the tile's 64 key columns (and half of O's columns); row maxima are exchanged through
+//              shared memory once per tile
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -21,13 +24,13 @@ namespace {
 
 constexpr int kQRows = 128;
 constexpr int kKeys = 64;                      // keys per tile = one 128-byte swizzle row of P / V^T
-constexpr int kThreads = 192;
+constexpr int kThreads = 64 + 256 + 32;
 constexpr float kRescaleThreshold = 8.0f;      // log2 units
 
 struct Smem {          // stage pointers are computed, not indexed (no local-memory arrays)
     uint8_t* q; uint8_t* k0; uint8_t* v0; uint8_t* p0;
     int k_stride, v_stride;
-    uint64_t* q_full; uint64_t* k_full; uint64_t* v_full; uint64_t* kv_empty; uint64_t* s_full; uint64_t* p_full;
+    uint64_t* q_full; uint64_t* k_full; uint64_t* v_full; uint64_t* k_empty; uint64_t* v_empty; uint64_t* s_full; uint64_t* p_full;
     uint32_t* tmem_slot;
     __device__ __forceinline__ uint8_t* k(int s) const { return k0 + s * k_stride; }
     __device__ __forceinline__ uint8_t* v(int s) const { return v0 + s * v_stride; }
@@ -36,12 +39,13 @@ struct Smem {          // stage pointers are computed, not indexed (no local-mem
 
 __host__ __device__ inline int attn_smem_bytes(int d) {
     // Q d/64 x 16K | K 2 x d/64 x 8K | V 2 x d*128 | P 2 x 16K | barriers | align slack
-    return (d / 64) * 16384 + 2 * (d / 64) * 8192 + 2 * d * 128 + 2 * 16384 + 256 + 1024;
+    return (d / 64) * 16384 + 2 * (d / 64) * 8192 + 2 * d * 128 + 2 * 16384 + 256 + 2048 /*row max / sum exchange*/;
 }
 
 __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled tiles need 1024-byte alignment
+    uint8_t* base = smem_raw;
+    if ((smem_u32(base) & 1023u) != 0) __trap();
     const int d = p.d, dch = d / 64;
     Smem sm;
     sm.q = base; base += dch * 16384;
@@ -49,9 +53,10 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
     sm.v0 = base; sm.v_stride = d * 128; base += 2 * d * 128;
     sm.p0 = base; base += 2 * 16384;
     uint64_t* bars = reinterpret_cast<uint64_t*>(base);
-    sm.q_full = bars; sm.k_full = bars + 1; sm.v_full = bars + 3; sm.kv_empty = bars + 5; sm.s_full = bars + 7;
-    sm.p_full = bars + 8;
-    sm.tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    sm.q_full = bars; sm.k_full = bars + 1; sm.v_full = bars + 3; sm.k_empty = bars + 5; sm.v_empty = bars + 7;
+    sm.s_full = bars + 9; sm.p_full = bars + 10;
+    sm.tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    float* xch = reinterpret_cast<float*>(base + 256);      // [2][2][128]: double-buffered row-max exchange; reused for l
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = p.N;
@@ -68,8 +73,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         mbar_init(sm.q_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&sm.k_full[s], 1); mbar_init(&sm.v_full[s], 1); mbar_init(&sm.kv_empty[s], 1);
-                                      mbar_init(&sm.p_full[s], 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.k_full[s], 1); mbar_init(&sm.v_full[s], 1); mbar_init(&sm.k_empty[s], 1);
+                                      mbar_init(&sm.v_empty[s], 1); mbar_init(&sm.p_full[s], 256); }
         mbar_init(sm.s_full, 1);
         fence_mbar_init();
         tma_prefetch_desc(&p.qk_map); tma_prefetch_desc(&p.k_map); tma_prefetch_desc(&p.vt_map);
@@ -89,11 +94,18 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                 tma_load_2d(sm.q + c * 16384, &p.qk_map, sm.q_full, h * d + c * 64, static_cast<int>(row0));
             for (int j = 0; j < nt; ++j) {
                 const int s = j & 1;
-                mbar_wait(&sm.kv_empty[s], ((j >> 1) & 1) ^ 1);
+                mbar_wait(&sm.k_empty[s], ((j >> 1) & 1) ^ 1);
                 mbar_expect_tx(&sm.k_full[s], static_cast<uint32_t>(dch * 8192));
                 for (int c = 0; c < dch; ++c)
                     tma_load_2d(sm.k(s) + c * 8192, &p.k_map, &sm.k_full[s], p.hid + h * d + c * 64,
                                 static_cast<int>(krow0) + j * kKeys);
+            }
+        }
+    } else if (warp == 10) {
+        if (lane == 0) {
+            for (int j = 0; j < nt; ++j) {
+                const int s = j & 1;
+                mbar_wait(&sm.v_empty[s], ((j >> 1) & 1) ^ 1);
                 const int img = b0 + (j * kKeys) / N;
                 const int koff = (N >= kQRows) ? j * kKeys : (j * kKeys) % N;
                 mbar_expect_tx(&sm.v_full[s], static_cast<uint32_t>(d * 128));
@@ -113,6 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                     const uint64_t bd = umma_desc_sw128(smem_u32(sm.k(s) + (kk >> 2) * 8192)) + 2 * (kk & 3);
                     umma_16(tmem_s, ad, bd, idesc_s, kk != 0);
                 }
+                umma_commit(&sm.k_empty[s]);              // K_j can be overwritten as soon as S_j has retired
                 umma_commit(sm.s_full);
             };
             mbar_wait(sm.q_full, 0);
@@ -130,35 +143,40 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                     const uint64_t bd = umma_desc_sw128(smem_u32(sm.v(s))) + 2 * kk;
                     umma_16(tmem_o, ad, bd, idesc_o, (j | kk) != 0);
                 }
-                umma_commit(&sm.kv_empty[s]);             // K_j / V_j / P_j free, O updated
+                umma_commit(&sm.v_empty[s]);              // V_j / P_j free, O updated
             }
         }
-    } else {
+    } else if (warp < 10) {
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;                   // which 32 key columns of the tile (and which half of O's columns)
         const int row = q * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
         const long long grow = row0 + row;
         const bool row_ok = grow < static_cast<long long>(p.B) * N;
         const int row_img = row / N;                        // only meaningful when N < 128
         const float c = p.scale_log2e;
+        const int dh = d >> 1;                              // O columns owned by this thread: [half*dh, half*dh + dh)
         float m_used = -INFINITY, l = 0.f;
         for (int j = 0; j < nt; ++j) {
             mbar_wait(sm.s_full, j & 1);
             tc_fence_after();
-            uint32_t r0[32], r1[32];
-            tmem_ld32(tmem_s + lane_off, r0);
-            tmem_ld32(tmem_s + lane_off + 32, r1);
+            uint32_t r0[32];
+            tmem_ld32(tmem_s + lane_off + half * 32, r0);
             tmem_ld_wait();
-            float sv[64];
+            float sv[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { sv[i] = __uint_as_float(r0[i]); sv[32 + i] = __uint_as_float(r1[i]); }
+            for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(r0[i]);
             // N < 128: a 64-key tile belongs to one image; rows of the other image ignore it entirely
             const bool tile_valid = (N >= kQRows) || (((j * kKeys) / N) == row_img);
-            float m_tile = -INFINITY;
+            float m_half = -INFINITY;
             if (tile_valid) {
 #pragma unroll
-                for (int i = 0; i < 64; i += 2) m_tile = fmaxf(m_tile, fmaxf(sv[i], sv[i + 1]));
+                for (int i = 0; i < 32; i += 2) m_half = fmaxf(m_half, fmaxf(sv[i], sv[i + 1]));
             }
+            float* xm = xch + (j & 1) * 256;
+            xm[half * 128 + row] = m_half;
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 softmax warps only
+            const float m_tile = fmaxf(m_half, xm[(half ^ 1) * 128 + row]);
             float factor = 1.f;
             bool need = false;
             if (m_tile > m_used) {
@@ -172,9 +190,9 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
             }
             if (__any_sync(0xffffffffu, need)) {
                 // O must be complete through PV_{j-1} before it is rescaled
-                mbar_wait(&sm.kv_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                mbar_wait(&sm.v_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
                 tc_fence_after();
-                for (int c0 = 0; c0 < d; c0 += 32) {
+                for (int c0 = half * dh; c0 < half * dh + dh; c0 += 32) {
                     uint32_t o[32];
                     tmem_ld32(tmem_o + lane_off + c0, o);
                     tmem_ld_wait();
@@ -192,14 +210,14 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
             uint8_t* prow = sm.p(j & 1) + row * 128;
             float lsum = 0.f;
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
+            for (int ch = 0; ch < 4; ++ch) {
                 float e[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     e[i] = ex2_approx(fmaf(sv[ch * 8 + i], cc, -off));
                     lsum += e[i];
                 }
-                *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) =
+                *reinterpret_cast<uint4*>(prow + (((half * 4 + ch) ^ (row & 7)) << 4)) =
                     make_uint4(pack_16_inrange(e[0], e[1], p.f16), pack_16_inrange(e[2], e[3], p.f16), pack_16_inrange(e[4], e[5], p.f16),
                                pack_16_inrange(e[6], e[7], p.f16));   // p <= 2^8
             }
@@ -208,11 +226,14 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
             tc_fence_before();
             mbar_arrive(&sm.p_full[j & 1]);
         }
-        // ---- final: O / l -> bf16
-        mbar_wait(&sm.kv_empty[(nt - 1) & 1], ((nt - 1) >> 1) & 1);
+        // ---- final: O / l -> 16-bit.  The two threads of a row add their partial sums.
+        xch[half * 128 + row] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l += xch[(half ^ 1) * 128 + row];
+        mbar_wait(&sm.v_empty[(nt - 1) & 1], ((nt - 1) >> 1) & 1);
         tc_fence_after();
         const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
-        for (int c0 = 0; c0 < d; c0 += 32) {
+        for (int c0 = half * dh; c0 < half * dh + dh; c0 += 32) {
             uint32_t o[32];
             tmem_ld32(tmem_o + lane_off + c0, o);
             tmem_ld_wait();
