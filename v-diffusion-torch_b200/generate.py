@@ -1,0 +1,119 @@
+"""Sampling driver: the batch loop of the reference's generate.py (generate.py:100-150) sharded over the GPUs
+of one node.  Every sample's trajectory is independent (GroupNorm is per sample, attention per image, the CFG
+pair lives inside one sample), so rank r simply owns a contiguous slice of the global batch, with its own noise,
+labels, weight replica and CUDA graphs; there is no communication inside the loop.  The only collective is the
+final gather of the images (as in Trainer.sample_fn, train_utils.py:181-183).
+
+    torchrun --nproc-per-node 8 -m v_diffusion_b200.generate --config-path cfg.json --default-config-path defaults.json \
+        --ckpt-path ckpt.pt --use-ddim --sample-timesteps 100 --w-guide 1.0 --total-size 32768 --save-path out.pt
+"""
+import argparse
+import math
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(total, rank, world):
+    """Contiguous, balanced split of `total` samples: the first total % world ranks get one extra."""
+    base, extra = divmod(total, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def gather_shards(local, total, group=None):
+    """all_gather of per-rank shards of (possibly) different length along dim 0 -> (total, ...) on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    width = math.ceil(total / world)
+    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    out = []
+    for r, part in enumerate(parts):
+        s, e = shard_bounds(total, r, world)
+        out.append(part[: e - s])
+    return torch.cat(out, dim=0)
+
+
+def sample_sharded(sample_fn, total, batch_size, seed=1234, gather=True, device=None):
+    """Runs ``sample_fn(n, generator) -> (n, C, H, W) tensor`` over this rank's slice of ``total`` samples in
+    batches of ``batch_size`` and returns the gathered (total, C, H, W) tensor (or the local shard).
+    Per-rank generator seeds are ``seed + rank`` (SURVEY §8d cfg 2)."""
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    start, end = shard_bounds(total, rank, world)
+    gen = torch.Generator(device=device if device is not None else "cpu").manual_seed(seed + rank)
+    outs = []
+    for b0 in range(start, end, batch_size):
+        n = min(batch_size, end - b0)
+        outs.append(sample_fn(n, gen))
+    local = torch.cat(outs, dim=0) if outs else None
+    if local is None:
+        raise ValueError("a rank received an empty shard: total must be >= world size")
+    return gather_shards(local, total) if gather else local
+
+
+def main():
+    from . import GaussianDiffusion, UNet, load_config, build_from_config  # noqa: F401
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config-path", required=True)
+    ap.add_argument("--default-config-path", required=True)
+    ap.add_argument("--ckpt-path", default=None, help="reference checkpoint (.pt); random init when omitted")
+    ap.add_argument("--use-ema", action="store_true")
+    ap.add_argument("--use-ddim", action="store_true")
+    ap.add_argument("--sample-timesteps", type=int, default=1024)      # generate.py:25
+    ap.add_argument("--uncond", action="store_true")
+    ap.add_argument("--w-guide", type=float, default=0.1)              # generate.py:27
+    ap.add_argument("--batch-size", type=int, default=128)
+    ap.add_argument("--total-size", type=int, default=50000)
+    ap.add_argument("--save-path", default=None, help="torch.save of the uint8 NHWC images (rank 0)")
+    ap.add_argument("--seed", type=int, default=1234)
+    args = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    state_dict, use_cfg = None, True
+    if args.ckpt_path:
+        ckpt = torch.load(args.ckpt_path, map_location="cpu")
+        state_dict = ckpt["ema"]["shadow"] if args.use_ema else ckpt["model"]            # generate.py:35-38
+        state_dict = {(k.split(".", 1)[1] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        use_cfg = "class_embed" in {k.split(".")[0] for k in state_dict}                 # generate.py:44
+    config = load_config(args.config_path, args.default_config_path)
+    if not args.ckpt_path:
+        use_cfg = bool(config.get("conditional", {}).get("use_cfg", False))
+    diffusion, model, chw = build_from_config(config, use_cfg, args.w_guide, args.sample_timesteps, args.uncond)
+    if state_dict is not None:
+        model.load_state_dict(state_dict)
+    model = model.to(device).eval()
+    num_classes = model.num_classes
+
+    def sample_fn(n, gen):
+        noise = torch.randn((n,) + chw, device=device, generator=gen)
+        if num_classes:
+            label = torch.zeros(n, dtype=torch.int64, device=device) if args.uncond else \
+                torch.randint(num_classes, (n,), device=device, generator=gen) + 1       # generate.py:132-134
+        else:
+            label = None
+        return diffusion.p_sample(model, (n,) + chw, noise=noise, label=label, device=device,
+                                  use_ddim=args.use_ddim).to(device)
+
+    x = sample_sharded(sample_fn, args.total_size, args.batch_size, seed=args.seed, device=device)
+    if (not dist.is_initialized() or dist.get_rank() == 0) and args.save_path:
+        img = (x * 127.5 + 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).cpu()   # generate.py:149
+        torch.save(img, args.save_path)
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
