@@ -72,6 +72,12 @@ def attn_case(N, d):
     print(f"attention N={N} d={d}: {ms:.3f} ms {fl / ms / 1e9 if ms else 0:.0f} TFLOP/s")
 
 
+if "--small" in sys.argv:
+    conv_case(32, 64, 256, 1, False, True)                 # in_conv-like: K = 64, fp32 out + stats
+    conv_case(16, 256, 512, 1, False, False, out16=True)   # q|k projection: K = 256, 16-bit out
+    conv_case(16, 256, 256, 1, True, True)                 # proj_out: K = 256, fp32 out + residual
+    torch.cuda.synchronize()
+    sys.exit(0)
 st, out, _ = conv_case(32, 256, 256, 3, True, True)
 gn_case(32, 256, st, out, False, False)
 st16, _, o16 = conv_case(32, 256, 256, 3, False, True, out16=True)

@@ -200,7 +200,7 @@ def test_attention(L, B, N, heads, d, f16):
     q[:, : N // 2] *= 3.0
     k[:, N // 2:] *= 2.0
     qk = torch.cat([q.reshape(B * N, hid), k.reshape(B * N, hid)], dim=1).contiguous()
-    vt = v.permute(0, 2, 3, 1).reshape(B * hid, N).contiguous()
+    vt = v.permute(0, 2, 3, 1).reshape(B * hid, N).contiguous()          # V^T [B*hid, N]
     out = torch.zeros(B * N, hid, device="cuda", dtype=DT[f16])
     _check(L, L.vdt_op_attention(_p(qk), _p(vt), _p(out), B, N, heads, d, f16, None))
     torch.cuda.synchronize()

@@ -8,7 +8,7 @@
 // row maximum grows by more than 2^8), so the TMEM round trip is rare.
 //
 // Operands (written by the proj_in GEMM epilogue): QK bf16 [B*N, 2*hid] (q | k, heads contiguous,
-// unet.py:76-78) and V^T bf16 [B*hid, N], so every MMA operand is K-major.
+// unet.py:76-78) and V^T bf16 [B*hid, N] (the v third of proj_in, stored transposed), so every MMA operand is K-major.
 //
 //   warp 0     TMA producer for Q (once) and the 64-key K tiles (2-stage ring, slot freed when S = Q K^T retires)
 //   warp 10    TMA producer for the V^T tiles (2-stage ring, slot freed when O += P V retires)
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
     if (threadIdx.x == 0) {
         mbar_init(sm.q_full, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&sm.k_full[s], 1); mbar_init(&sm.v_full[s], 1); mbar_init(&sm.k_empty[s], 1);
-                                      mbar_init(&sm.v_empty[s], 1); mbar_init(&sm.p_full[s], 256); }
+                                      mbar_init(&sm.v_empty[s], 1); mbar_init(&sm.p_full[s], 8); }   // one arrival per softmax warp
         mbar_init(sm.s_full, 1);
         fence_mbar_init();
         tma_prefetch_desc(&p.qk_map); tma_prefetch_desc(&p.k_map); tma_prefetch_desc(&p.vt_map);
@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
             l += lsum;
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(&sm.p_full[j & 1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.p_full[j & 1]);
         }
         // ---- final: O / l -> 16-bit.  The two threads of a row add their partial sums.
         xch[half * 128 + row] = l;

@@ -53,6 +53,99 @@ __device__ __forceinline__ TileCoord tile_origin(const ConvParams& p, int m_tile
     return t;
 }
 
+// Row-major epilogue of one 32-row x 32-column chunk after the smem transposition: lane = (row % 4 group rsub,
+// 4 columns cq).  Compile-time variants keep the instruction count low (the epilogue warps are issue-bound
+// otherwise); CHECK adds the per-row bounds tests needed only for ragged tiles.
+template <bool F32OUT, bool RESID, bool STATS, bool ROWBIAS, bool SILU, bool CHECK>
+__device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const float4* tile, int lane, int q, int m_tile,
+                                                  long long wrow0, int col0) {
+    const int cq = lane & 7, rsub = lane >> 3;
+    const size_t off0 = static_cast<size_t>(wrow0 + rsub) * p.ld + col0 + cq * 4;
+    const size_t step = static_cast<size_t>(4) * p.ld;
+    const bool tile_ok = m_tile < p.num_m_tiles;
+    auto valid = [&](int i) {
+        if (!CHECK) return true;
+        const int rr = i * 4 + rsub;
+        return tile_ok && (q * 32 + rr < p.rows_per_tile) && (wrow0 + rr < p.M);
+    };
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!ROWBIAS) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq * 4));
+    float4 res[8];
+    if (RESID) {                                             // all eight loads in flight before anything is stored
+        const float* rp = p.residual + off0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            res[i] = valid(i) ? ldg_nc_v4_issue(rp + i * step) : make_float4(0.f, 0.f, 0.f, 0.f);
+        compiler_fence();
+    }
+    float ssum = 0.f, ssq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + rsub;
+        float4 o = tile[rr * 8 + (cq ^ (rr & 7))];
+        if (ROWBIAS) {
+            const float br = valid(i) ? __ldg(p.bias + wrow0 + rr) : 0.f;
+            o.x += br; o.y += br; o.z += br; o.w += br;
+        } else {
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+        }
+        if (RESID) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
+        if (SILU) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+        if (valid(i)) {
+            if (F32OUT)
+                *reinterpret_cast<float4*>(p.out_f32 + off0 + i * step) = o;
+            else
+                *reinterpret_cast<uint2*>(p.out_bf16 + off0 + i * step) = make_uint2(pack_16(o.x, o.y, p.f16), pack_16(o.z, o.w, p.f16));
+            if (STATS) {
+                ssum += (o.x + o.y) + (o.z + o.w);
+                ssq = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ssq))));
+            }
+        }
+    }
+    if (STATS) {                                             // fixed-order reduction over the warp's 32 rows
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, 8); ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, 16); ssq += __shfl_xor_sync(0xffffffffu, ssq, 16);
+        if (rsub == 0 && tile_ok && wrow0 < p.M)
+            p.stats[static_cast<size_t>(wrow0 / kStatRows) * (p.Cout / kStatCols) + (col0 >> 2) + cq] = make_float2(ssum, ssq);
+    }
+}
+
+// Same with every option and bound checked at run time (ragged tiles, SiLU epilogues).
+__device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, const float4* tile, int lane, int q, int m_tile,
+                                                       long long wrow0, int col0) {
+    const int cq = lane & 7, rsub = lane >> 3;
+    const bool tile_ok = m_tile < p.num_m_tiles;
+    const float4 b4 = p.bias_per_row ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq * 4));
+    float ssum = 0.f, ssq = 0.f;
+    for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + rsub;
+        const long long g = wrow0 + rr;
+        const bool ok = tile_ok && (q * 32 + rr < p.rows_per_tile) && (g < p.M);
+        if (!ok) continue;
+        float4 o = tile[rr * 8 + (cq ^ (rr & 7))];
+        const size_t off = static_cast<size_t>(g) * p.ld + col0 + cq * 4;
+        const float br = p.bias_per_row ? __ldg(p.bias + g) : 0.f;
+        o.x += b4.x + br; o.y += b4.y + br; o.z += b4.z + br; o.w += b4.w + br;
+        if (p.residual) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+        }
+        if (p.act_silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+        if (p.out_mode == kOutF32)
+            *reinterpret_cast<float4*>(p.out_f32 + off) = o;
+        else
+            *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_16(o.x, o.y, p.f16), pack_16(o.z, o.w, p.f16));
+        ssum += (o.x + o.y) + (o.z + o.w);
+        ssq = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ssq))));
+    }
+    if (p.stats) {
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, 8); ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, 16); ssq += __shfl_xor_sync(0xffffffffu, ssq, 16);
+        if (rsub == 0 && tile_ok && wrow0 < p.M)
+            p.stats[static_cast<size_t>(wrow0 / kStatRows) * (p.Cout / kStatCols) + (col0 >> 2) + cq] = make_float2(ssum, ssq);
+    }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -73,7 +166,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     if (threadIdx.x == 0) {
         // full / acc_empty are only used in the leader CTA (rank 0); empty / acc_full in both
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 2 * 32 * kEpiWarps); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 2 * kEpiWarps); }   // one arrival per epilogue warp of both CTAs
         fence_mbar_init();
         for (int s = 0; s < p.num_segs; ++s) tma_prefetch_desc(&p.a_map[s]);
         tma_prefetch_desc(&p.b_map);
@@ -178,47 +271,20 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                     for (int j = 0; j < 8; ++j)
                         tile[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     __syncwarp();
-                    const int cq = lane & 7, rsub = lane >> 3;
                     const long long wrow0 = static_cast<long long>(m_tile) * p.rows_per_tile + q * 32;
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq * 4));
-                    const bool tile_ok = m_tile < p.num_m_tiles;
-                    float4 res[8];
-                    if (p.residual) {                        // all eight loads in flight before anything is stored
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int rr = i * 4 + rsub;
-                            const long long g = wrow0 + rr;
-                            const bool ok = tile_ok && (q * 32 + rr < p.rows_per_tile) && (g < p.M);
-                            res[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(g) * p.ld + col0 + cq * 4))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
+                    const bool f32o = p.out_mode == kOutF32, resid = p.residual != nullptr, st = p.stats != nullptr;
+                    const bool all_valid = (m_tile < p.num_m_tiles) && (q * 32 + 32 <= p.rows_per_tile) && (wrow0 + 32 <= p.M);
+                    if (!all_valid || p.act_silu) {          // ragged tile / rare variants: run-time checked generic path
+                        epilogue_rowmajor_generic(p, tile, lane, q, m_tile, wrow0, col0);
+                    } else if (f32o) {
+                        if (resid && st) epilogue_rowmajor<true, true, true, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        else if (resid) epilogue_rowmajor<true, true, false, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        else if (st) epilogue_rowmajor<true, false, true, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        else epilogue_rowmajor<true, false, false, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
                     } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    float ssum = 0.f, ssq = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rr = i * 4 + rsub;
-                        float4 o = tile[rr * 8 + (cq ^ (rr & 7))];
-                        o.x += b4.x + res[i].x; o.y += b4.y + res[i].y; o.z += b4.z + res[i].z; o.w += b4.w + res[i].w;
-                        if (p.act_silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
-                        const long long g = wrow0 + rr;
-                        if (tile_ok && (q * 32 + rr < p.rows_per_tile) && (g < p.M)) {
-                            const size_t off = static_cast<size_t>(g) * p.ld + col0 + cq * 4;
-                            if (p.out_mode == kOutF32)
-                                *reinterpret_cast<float4*>(p.out_f32 + off) = o;
-                            else
-                                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_16(o.x, o.y, p.f16), pack_16(o.z, o.w, p.f16));
-                            ssum += (o.x + o.y) + (o.z + o.w);
-                            ssq += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-                        }
-                    }
-                    if (p.stats) {                           // fixed-order reduction over the warp's 32 rows
-                        ssum += __shfl_xor_sync(0xffffffffu, ssum, 8); ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
-                        ssum += __shfl_xor_sync(0xffffffffu, ssum, 16); ssq += __shfl_xor_sync(0xffffffffu, ssq, 16);
-                        if (rsub == 0 && tile_ok && wrow0 < p.M)
-                            p.stats[static_cast<size_t>(wrow0 / kStatRows) * (p.Cout / kStatCols) + (col0 >> 2) + cq] = make_float2(ssum, ssq);
+                        if (p.bias_per_row) epilogue_rowmajor<false, false, false, true, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        else if (st) epilogue_rowmajor<false, false, true, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        else epilogue_rowmajor<false, false, false, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
                     }
                     __syncwarp();
                 } else if (p.out_mode == kOutBF16) {         // V third of proj_in: transposed per image (coalesced per column)
@@ -249,7 +315,8 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                 }
             }
             tc_fence_before();
-            mbar_arrive_cluster(&acc_empty[acc], 0);         // the leader's MMA thread waits for both CTAs' drains
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&acc_empty[acc], 0);   // the leader's MMA thread waits for both CTAs' drains
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }

@@ -43,6 +43,7 @@ struct alignas(64) ConvParams {
     int ld;                            // row stride (elements) of out_f32 / out_bf16 / residual
     int split_col, HW;
     int act_silu;
+    int bias_per_row;                  // bias indexed by output row instead of column (swapped-operand GEMMs)
     int f16;                           // operand / 16-bit output format: 1 fp16, 0 bf16
     const float* bias;                 // [Cout]
     const float* residual;             // fp32 [M, ld] or null
@@ -91,7 +92,7 @@ cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream);
 struct alignas(64) AttnParams {
     CUtensorMap qk_map;                // 2-D (2*hid, B*N) bf16, box (64, 128): q at col h*d, k at hid + h*d
     CUtensorMap k_map;                 // same tensor, box (64, 64)
-    CUtensorMap vt_map;                // 2-D (N, B*hid) bf16, box (64, d): V^T per image/head
+    CUtensorMap vt_map;                // 2-D (N, B*hid) 16-bit, box (64, d): V^T per image/head
     int B, N, heads, d, hid;
     int f16;
     float scale_log2e;                 // log2(e) / sqrt(d)

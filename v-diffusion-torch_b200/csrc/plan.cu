@@ -600,7 +600,7 @@ struct ConvSpec {
     const h16* wpacked = nullptr; int cout = 0; int wrows = 0;   // weight rows actually allocated
     const float* bias = nullptr; const float* residual = nullptr;
     int out_mode = kOutF32; float* out_f32 = nullptr; h16* out_bf16 = nullptr; h16* out_t = nullptr;
-    int ld = 0, split_col = 0, act_silu = 0, f16 = 1;
+    int ld = 0, split_col = 0, act_silu = 0, f16 = 1, bias_per_row = 0;
     float2* stats = nullptr;
 };
 
@@ -632,7 +632,7 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     cp->num_n_tiles = (s.cout + cp->block_n - 1) / cp->block_n;
     CKI(make_map_2d(&cp->b_map, s.wpacked, s.wrows, ktot, ktot, cp->block_n / 2));   // each CTA of a pair fetches half
     cp->M = (int)M; cp->Cout = s.cout; cp->out_mode = s.out_mode; cp->ld = s.ld;
-    cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16;
+    cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16; cp->bias_per_row = s.bias_per_row;
     cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t; cp->stats = s.stats;
     if (s.out_mode != kOutNCHW && s.cout % 32 != 0) return fail("output channels must be a multiple of 32 (got %d)", s.cout);
     return 0;
@@ -768,7 +768,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             add_gn(g);
             CKI(ex->acquire((size_t)R * N * 2 * hidd * 2, (void**)&qk));
             CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&vt));
-            {
+            {   // one GEMM for q | k | v: q,k row-major [R*N, 2*hid]; the v third is written transposed, V^T [R*hid, N]
                 ConvSpec s;
                 s.f16 = p->f16;
                 s.a1 = a; s.c1 = b.cin; s.ld1 = b.cin; s.n = R; s.h = res; s.w = res; s.wpacked = b.w1; s.cout = 3 * hidd;

@@ -238,6 +238,15 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mas
                  : "memory");
 }
 
+// 128-bit coherent global load.  Unlike ld.global.nc, neither nvcc nor ptxas may sink it below a later store
+// that might alias, so a batch of these issued before the first store of a loop stays a batch in flight.
+__device__ __forceinline__ float4 ldg_nc_v4_issue(const float* p) {
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
+
 // ---- small math --------------------------------------------------------------------------------
 __device__ __forceinline__ float ex2_approx(float x) {   // 2^x, one MUFU op (max rel. error 2^-22), flushes denormals
     float y;
