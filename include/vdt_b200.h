@@ -39,7 +39,10 @@ typedef struct vdt_unet_config {
     int32_t resolution;           /* H = W of the images this plan serves (DATA_INFO[...]["resolution"]) */
     int32_t max_rows;             /* UNet batch rows processed per pass; larger batches are chunked */
     int32_t operand_dtype;        /* 16-bit tensor-core operand format: 0 = fp16 (default), 1 = bf16; accumulation,
-                                     GroupNorm statistics, softmax and the residual stream are fp32 either way */
+                                     GroupNorm statistics, softmax and the residual stream are fp32 either way.
+                                     2 = split-precision validation mode: every operand is an fp16 hi/lo pair and every
+                                     product three K segments (hi*hi + lo*hi + hi*lo, ~22-bit mantissa) on the same
+                                     tcgen05 kernels; attention runs in fp32 on CUDA cores. ~3x slower. */
 } vdt_unet_config;
 
 /* GaussianDiffusion constructor + get_logsnr_schedule arguments — diffusion.py:260-291, 42-112. */

@@ -199,3 +199,36 @@ def test_on_device_noise_stream():
     b = diff.p_sample(net, tuple(noise.shape), noise=noise, label=label, device="cuda", seed=5, use_ddim=False)
     c = diff.p_sample(net, tuple(noise.shape), noise=noise, label=label, device="cuda", seed=6, use_ddim=False)
     assert torch.equal(a, b) and not torch.equal(a, c) and torch.isfinite(a).all()
+
+
+VALIDATION_MAX_ABS = 1e-3        # north-star: TF32/fp32 validation mode
+
+
+@pytest.mark.parametrize("name", ["cifar_cond", "small_cond", "small_hd64"])
+def test_validation_mode_forward(golden_dir, name):
+    """operand_dtype="fp16x3": same tcgen05 kernels, every operand an fp16 hi/lo pair (three K segments per
+    product), attention in fp32: agreement with the fp32 reference at the 1e-5 level."""
+    case = UNET_CASES[name]
+    ref = torch.from_numpy(np.load(os.path.join(golden_dir, f"unet_{name}.npz"))["out"])
+    net = _model(case["cfg"], case["seed"], operand="fp16x3")
+    x, t, y = build_inputs(case)
+    out = net(x.cuda(), t.cuda(), None if y is None else y.cuda()).cpu()
+    rel = ((out - ref).norm() / ref.norm()).item()
+    err = (out - ref).abs().max().item()
+    print(f"{name} [fp16x3]: rel-L2 {rel:.3e} max-abs {err:.3e}")
+    assert rel <= 5e-5 and err <= 2e-4
+
+
+@pytest.mark.parametrize("name", sorted(SAMPLE_CASES))
+def test_validation_mode_sampler(golden_dir, name):
+    case = SAMPLE_CASES[name]
+    ucase = UNET_CASES[case["unet"]]
+    ref = torch.from_numpy(np.load(os.path.join(golden_dir, f"sample_{name}.npz"))["out"])
+    net = _model(ucase["cfg"], ucase["seed"], operand="fp16x3")
+    diff = _diffusion(case)
+    noise, label, step_noise = build_sample_inputs(case, ucase["cfg"])
+    out = diff.p_sample(net, tuple(noise.shape), noise=noise, label=label, device="cuda", use_ddim=case["use_ddim"],
+                        step_noise=None if case["use_ddim"] else step_noise)
+    err = (out - ref).abs().max().item()
+    print(f"{name} [fp16x3]: max-abs {err:.3e}")
+    assert err <= VALIDATION_MAX_ABS

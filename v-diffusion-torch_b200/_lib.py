@@ -20,7 +20,7 @@ OUT_TYPES = {"x0": 0, "eps": 1, "both": 2, "v": 3}
 VAR_TYPES = {"fixed_small": 0, "fixed_large": 1, "fixed_medium": 2}
 SCHEDULES = {"cosine": 0, "linear": 1, "sigmoid": 2, "legacy": 3}
 COEF_STRIDE = 12
-OPERAND_DTYPES = {"fp16": 0, "bf16": 1}
+OPERAND_DTYPES = {"fp16": 0, "bf16": 1, "fp16x3": 2}
 
 
 class UNetConfig(C.Structure):

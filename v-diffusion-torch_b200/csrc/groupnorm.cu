@@ -66,6 +66,22 @@ __device__ __forceinline__ void store_16n(h16* p, const float (&v)[VEC], int f16
         *reinterpret_cast<uint32_t*>(p) = pack_16_inrange(v[0], v[1], f16);
     }
 }
+// hi/lo pair for the split-precision mode: hi = round16(v), lo = round16(v - hi)
+template <int VEC>
+__device__ __forceinline__ void store_lo(h16* p, const float (&v)[VEC], int f16) {
+    float r[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const uint16_t h = cvt_16(v[i], f16);
+        const float hf = f16 ? __half2float(*reinterpret_cast<const __half*>(&h)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h));
+        r[i] = v[i] - hf;
+    }
+    if (VEC == 4) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(pack_16(r[0], r[1], f16), pack_16(r[2], r[3], f16));
+    } else {
+        *reinterpret_cast<uint32_t*>(p) = pack_16(r[0], r[1], f16);
+    }
+}
 template <int VEC>
 __device__ __forceinline__ void store_f32(float* p, const float (&v)[VEC]) {
     if (VEC == 4) {
@@ -207,6 +223,7 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
     if (p.resample == kResDown) {
         const int Wo = p.W / 2, HWo = HW / 4;
         h16* oa = p.out_act + static_cast<size_t>(b) * HWo * C + c;
+        h16* oa_lo = p.out_act_lo ? p.out_act_lo + static_cast<size_t>(b) * HWo * C + c : nullptr;
         float* orr = p.out_res ? p.out_res + static_cast<size_t>(b) * HWo * C + c : nullptr;
         for (int po = pp; po < HWo; po += PPH) {
             const int ho = po / Wo, wo = po % Wo;
@@ -225,11 +242,13 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
 #pragma unroll
             for (int i = 0; i < VEC; ++i) { acc[i] *= 0.25f; racc[i] *= 0.25f; }
             store_16n<VEC>(oa + static_cast<size_t>(po) * C, acc, p.f16);
+            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(po) * C, acc, p.f16);
             if (orr) store_f32<VEC>(orr + static_cast<size_t>(po) * C, racc);
         }
     } else if (p.resample == kResUp) {
         const int Wo = p.W * 2;
         h16* oa = p.out_act + static_cast<size_t>(b) * HW * 4 * C + c;
+        h16* oa_lo = p.out_act_lo ? p.out_act_lo + static_cast<size_t>(b) * HW * 4 * C + c : nullptr;
         float* orr = p.out_res ? p.out_res + static_cast<size_t>(b) * HW * 4 * C + c : nullptr;
         for (int pix = pp; pix < HW; pix += PPH) {
             const int h = pix / p.W, w = pix % p.W;
@@ -240,12 +259,15 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             for (int d = 0; d < 4; ++d) {
                 const size_t po = static_cast<size_t>(2 * h + (d >> 1)) * Wo + 2 * w + (d & 1);
                 store_16n<VEC>(oa + po * C, y, p.f16);
+                if (oa_lo) store_lo<VEC>(oa_lo + po * C, y, p.f16);
                 if (orr) store_f32<VEC>(orr + po * C, x);
             }
         }
     } else {
         h16* oa = p.out_act + static_cast<size_t>(b) * HW * C + c;
+        h16* oa_lo = p.out_act_lo ? p.out_act_lo + static_cast<size_t>(b) * HW * C + c : nullptr;
         h16* ow = p.out_raw ? p.out_raw + static_cast<size_t>(b) * HW * C + c : nullptr;
+        h16* ow_lo = (p.out_raw && p.out_raw_lo) ? p.out_raw_lo + static_cast<size_t>(b) * HW * C + c : nullptr;
         // FUSED: the image is split over gridDim.y CTAs
         const int span = HW / gridDim.y, pix_end = (blockIdx.y + 1) * span;
         int pix = blockIdx.y * span + pp;
@@ -256,14 +278,22 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             load_px(pix + 2 * PPH, x2);
             load_px(pix + 3 * PPH, x3);
             norm_act(x0, y); store_16n<VEC>(oa + static_cast<size_t>(pix) * C, y, p.f16);
+            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix) * C, y, p.f16);
             norm_act(x1, y); store_16n<VEC>(oa + static_cast<size_t>(pix + PPH) * C, y, p.f16);
+            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + PPH) * C, y, p.f16);
             norm_act(x2, y); store_16n<VEC>(oa + static_cast<size_t>(pix + 2 * PPH) * C, y, p.f16);
+            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + 2 * PPH) * C, y, p.f16);
             norm_act(x3, y); store_16n<VEC>(oa + static_cast<size_t>(pix + 3 * PPH) * C, y, p.f16);
+            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + 3 * PPH) * C, y, p.f16);
             if (ow) {
                 store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, p.f16);
+                if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix) * C, x0, p.f16);
                 store_16<VEC>(ow + static_cast<size_t>(pix + PPH) * C, x1, p.f16);
+                if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix + PPH) * C, x1, p.f16);
                 store_16<VEC>(ow + static_cast<size_t>(pix + 2 * PPH) * C, x2, p.f16);
+                if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix + 2 * PPH) * C, x2, p.f16);
                 store_16<VEC>(ow + static_cast<size_t>(pix + 3 * PPH) * C, x3, p.f16);
+                if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix + 3 * PPH) * C, x3, p.f16);
             }
         }
         for (; pix < pix_end; pix += PPH) {
@@ -271,7 +301,9 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             load_px(pix, x0);
             norm_act(x0, y0);
             store_16n<VEC>(oa + static_cast<size_t>(pix) * C, y0, p.f16);
+            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix) * C, y0, p.f16);
             if (ow) store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, p.f16);
+            if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix) * C, x0, p.f16);
         }
     }
 }

@@ -18,7 +18,7 @@ typedef uint16_t h16;   // storage of a 16-bit GEMM operand: IEEE fp16 (default)
 // x `box_h` image rows x W pixels; a 3x3 tap is a shifted TMA box whose out-of-bounds part the
 // hardware zero-fills (= the conv padding).
 // ------------------------------------------------------------------------------------------------
-constexpr int kConvMaxSegs = 3;
+constexpr int kConvMaxSegs = 6;   // 3x3 body + 1x1 skip, each x3 in the split-precision validation mode
 
 enum ConvOutMode : int {
     kOutF32 = 0,        // fp32 [M, ld]            (+bias, +residual, optional SiLU)
@@ -82,6 +82,8 @@ struct GroupNormParams {
     int resample;                      // applied after norm+act (unet.py:141)
     h16* out_act;                     // 16-bit [B, H'W', C]   normalised (+FiLM, +SiLU), resampled
     h16* out_raw;                     // optional 16-bit [B, HW, C]: the un-normalised concat (skip-conv operand)
+    h16* out_act_lo;                  // split-precision mode: second halves, lo = round16(x - float(round16(x)))
+    h16* out_raw_lo;
     float* out_res;                    // optional fp32 [B, H'W', C]: resampled raw input (identity-skip residual)
 };
 cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream);
@@ -106,7 +108,13 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
 // x fp32 NCHW [B, C, H, W] (9*C <= 64) -> 16-bit patch matrix [B*rep*H*W, 64]: column (r*3+s)*C + c =
 // x[b, c, h+r-1, w+s-1] (zero outside); output image i reads input image i / rep (the CFG
 // repeat-interleave of diffusion.py:30-35, 370).
-cudaError_t launch_im2col3x3(const float* x, h16* out, int B, int rep, int C, int H, int W, int f16, cudaStream_t stream);
+cudaError_t launch_im2col3x3(const float* x, h16* out, h16* out_lo, int B, int rep, int C, int H, int W, int f16,
+                             cudaStream_t stream);
+
+// fp32 CUDA-core attention for the split-precision validation mode: qkv fp32 [B*N, 3*hid] (q | k | v, heads
+// contiguous) -> O as a 16-bit hi/lo pair [B*N, hid].  One warp per query, online softmax.
+cudaError_t launch_attention_f32(const float* qkv, h16* out_hi, h16* out_lo, int B, int N, int heads, int d, int f16,
+                                 cudaStream_t stream);
 
 // sinusoidal embedding evaluated in fp64 like functions.py:11-29 -> fp32 [rows, dim]
 cudaError_t launch_timestep_embedding(const double* t, float* out, int rows, int dim, cudaStream_t stream);

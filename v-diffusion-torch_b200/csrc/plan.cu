@@ -119,24 +119,32 @@ __device__ __forceinline__ h16 to_h16(float x, int f16) {
     __nv_bfloat16 v = __float2bfloat16(x);
     return *reinterpret_cast<h16*>(&v);
 }
+__device__ __forceinline__ float h16_to_float(h16 h, int f16) {
+    return f16 ? __half2float(*reinterpret_cast<const __half*>(&h)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h));
+}
+// part 0: round16(w); part 1: round16(w - round16(w)) (the "lo" half of the split-precision validation mode)
 __global__ void pack_conv_w_kernel(const float* __restrict__ src, h16* __restrict__ dst, int O, int I, int taps,
-                                   int ktot, int koff, int f16) {
+                                   int ktot, int koff, int f16, int part) {
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long n = (long long)O * I * taps;
     if (idx >= n) return;
     const int i = (int)(idx % I);
     const int tap = (int)((idx / I) % taps);
     const int o = (int)(idx / ((long long)I * taps));
-    dst[(long long)o * ktot + koff + tap * I + i] = to_h16(src[((long long)o * I + i) * taps + tap], f16);
+    const float w = src[((long long)o * I + i) * taps + tap];
+    const h16 hi = to_h16(w, f16);
+    dst[(long long)o * ktot + koff + tap * I + i] = part == 0 ? hi : to_h16(w - h16_to_float(hi, f16), f16);
 }
 // in_conv: [O][C][3][3] -> [O][64], column tap*C + c (matches im2col3x3), zero padded
-__global__ void pack_inconv_w_kernel(const float* __restrict__ src, h16* __restrict__ dst, int O, int C, int f16) {
+__global__ void pack_inconv_w_kernel(const float* __restrict__ src, h16* __restrict__ dst, int O, int C, int f16, int ktot,
+                                     int koff, int part) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= O * 64) return;
     const int o = idx / 64, col = idx % 64;
     float v = 0.f;
     if (col < 9 * C) { const int tap = col / C, c = col % C; v = src[((long long)o * C + c) * 9 + tap]; }
-    dst[idx] = to_h16(v, f16);
+    const h16 hi = to_h16(v, f16);
+    dst[(long long)o * ktot + koff + col] = part == 0 ? hi : to_h16(v - h16_to_float(hi, f16), f16);
 }
 __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -180,9 +188,10 @@ struct Block {
     float* bias2 = nullptr;   // conv2.bias (+ skip.bias)
 };
 
-enum StepKind { S_CONV, S_GN, S_ATTN, S_IM2COL, S_TEMB, S_LINEAR, S_CLSEMB, S_BEGIN, S_SAMPLE };
+enum StepKind { S_CONV, S_GN, S_ATTN, S_IM2COL, S_TEMB, S_LINEAR, S_CLSEMB, S_BEGIN, S_SAMPLE, S_ATTN_F32 };
 struct LinearArgs { const float *x, *W, *b; float* out; int rows, K, N, silu; };
-struct Im2colArgs { const float* x; h16* out; int B, rep, C, H, W, f16; };
+struct Im2colArgs { const float* x; h16* out; h16* out_lo; int B, rep, C, H, W, f16; };
+struct AttnF32Args { const float* qkv; h16 *hi, *lo; int B, N, heads, d, f16; };
 struct TembArgs { const double* t; float* out; int rows, dim; };
 struct ClsArgs { const float* e; const int64_t* y; const float *w, *b; int ncls; float* out; int rows, E; };
 struct BeginArgs { SamplerState* st; const float* table; double* t_rows; int nrows, T; };
@@ -203,6 +212,7 @@ struct Exec {
     std::vector<std::unique_ptr<AttnParams>> attns;
     std::vector<LinearArgs> linears;
     std::vector<Im2colArgs> im2cols;
+    std::vector<AttnF32Args> attn32s;
     std::vector<TembArgs> tembs;
     std::vector<ClsArgs> clss;
     std::vector<BeginArgs> begins;
@@ -269,6 +279,7 @@ struct vdt_plan {
     std::map<std::string, std::unique_ptr<Exec>> execs;
     bool use_graph = true;
     int f16 = 1;                          // GEMM operand format: 1 fp16 (default), 0 bf16
+    int split = 0;                        // 1: split-precision validation mode (every operand as a hi/lo fp16 pair)
     // all work runs on an internal stream (the caller's may be the legacy default stream, which
     // cannot be captured); ordering against the caller's stream is kept with two events
     cudaStream_t work = nullptr;
@@ -387,8 +398,9 @@ extern "C" int vdt_plan_create(const vdt_unet_config* cfg, vdt_plan** out) {
     p->hid = c.hid_channels;
     p->E = c.embedding_dim ? c.embedding_dim : 4 * c.hid_channels;
     p->levels = c.num_levels;
-    if (c.operand_dtype != 0 && c.operand_dtype != 1) return fail("operand_dtype must be 0 (fp16) or 1 (bf16)");
-    p->f16 = c.operand_dtype == 0;
+    if (c.operand_dtype < 0 || c.operand_dtype > 2) return fail("operand_dtype must be 0 (fp16), 1 (bf16) or 2 (fp16 x3 split)");
+    p->f16 = c.operand_dtype != 1;
+    p->split = c.operand_dtype == 2;
     const char* ng = getenv("VDT_NO_GRAPH");
     p->use_graph = !(ng && ng[0] == '1');
     int dev = 0;
@@ -481,10 +493,14 @@ static int dev_alloc(vdt_plan* p, T** out, size_t count) {
     return 0;
 }
 
-static int pack_conv(const float* src, h16* dst, int O, int I, int taps, int ktot, int koff, int f16) {
+static int pack_conv(const float* src, h16* dst, int O, int I, int taps, int ktot, int koff, int f16, int split = 0) {
     const long long n = (long long)O * I * taps;
-    pack_conv_w_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src, dst, O, I, taps, ktot, koff, f16);
-    CK(cudaGetLastError());
+    const int K = taps * I;
+    // split mode: three consecutive K segments W_hi | W_hi | W_lo, multiplied by A_hi | A_lo | A_hi
+    for (int part = 0; part < (split ? 3 : 1); ++part) {
+        pack_conv_w_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src, dst, O, I, taps, ktot, koff + part * K, f16, part == 2 ? 1 : 0);
+        CK(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -497,21 +513,25 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
     p->owned.clear();
     const vdt_unet_config& c = p->cfg;
     const int E = p->E, hid = p->hid;
-    CKI(dev_alloc(p, &p->w_in, (size_t)hid * 64));
-    pack_inconv_w_kernel<<<(hid * 64 + 255) / 256, 256>>>(p->W("in_conv.weight"), p->w_in, hid, c.in_channels, p->f16);
-    CK(cudaGetLastError());
+    const int sp = p->split, km = sp ? 3 : 1;          // K multiplier of the split mode
+    CKI(dev_alloc(p, &p->w_in, (size_t)hid * 64 * km));
+    for (int part = 0; part < km; ++part) {
+        pack_inconv_w_kernel<<<(hid * 64 + 255) / 256, 256>>>(p->W("in_conv.weight"), p->w_in, hid, c.in_channels, p->f16, 64 * km,
+                                                             64 * part, part == 2 ? 1 : 0);
+        CK(cudaGetLastError());
+    }
     CKI(dev_alloc(p, &p->w_fc_all, (size_t)p->film_total * E));
     CKI(dev_alloc(p, &p->b_fc_all, (size_t)p->film_total));
     for (auto& b : p->blocks) {
         const std::string& n = b.name;
         if (b.kind == 0) {
-            CKI(dev_alloc(p, &b.w1, (size_t)b.cout * 9 * b.cin));
-            CKI(pack_conv(p->W(n + ".conv1.weight"), b.w1, b.cout, b.cin, 9, 9 * b.cin, 0, p->f16));
+            CKI(dev_alloc(p, &b.w1, (size_t)b.cout * 9 * b.cin * km));
+            CKI(pack_conv(p->W(n + ".conv1.weight"), b.w1, b.cout, b.cin, 9, 9 * b.cin * km, 0, p->f16, sp));
             const bool skipconv = b.cin != b.cout;
-            const int k2 = 9 * b.cout + (skipconv ? b.cin : 0);
+            const int k2 = (9 * b.cout + (skipconv ? b.cin : 0)) * km;
             CKI(dev_alloc(p, &b.w2, (size_t)b.cout * k2));
-            CKI(pack_conv(p->W(n + ".conv2.weight"), b.w2, b.cout, b.cout, 9, k2, 0, p->f16));
-            if (skipconv) CKI(pack_conv(p->W(n + ".skip.weight"), b.w2, b.cout, b.cin, 1, k2, 9 * b.cout, p->f16));
+            CKI(pack_conv(p->W(n + ".conv2.weight"), b.w2, b.cout, b.cout, 9, k2, 0, p->f16, sp));
+            if (skipconv) CKI(pack_conv(p->W(n + ".skip.weight"), b.w2, b.cout, b.cin, 1, k2, 9 * b.cout * km, p->f16, sp));
             CKI(dev_alloc(p, &b.bias2, (size_t)b.cout));
             add_vec_kernel<<<(b.cout + 255) / 256, 256>>>(p->W(n + ".conv2.bias"), skipconv ? p->W(n + ".skip.bias") : nullptr,
                                                           b.bias2, b.cout);
@@ -523,16 +543,16 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
             int hd, nh;
             attn_dims(c, b.cin, &hd, &nh);
             const int hidd = hd * nh;
-            CKI(dev_alloc(p, &b.w1, (size_t)3 * hidd * b.cin));
-            CKI(pack_conv(p->W(n + ".proj_in.weight"), b.w1, 3 * hidd, b.cin, 1, b.cin, 0, p->f16));
-            CKI(dev_alloc(p, &b.w2, (size_t)b.cin * hidd));
-            CKI(pack_conv(p->W(n + ".proj_out.weight"), b.w2, b.cin, hidd, 1, hidd, 0, p->f16));
+            CKI(dev_alloc(p, &b.w1, (size_t)3 * hidd * b.cin * km));
+            CKI(pack_conv(p->W(n + ".proj_in.weight"), b.w1, 3 * hidd, b.cin, 1, b.cin * km, 0, p->f16, sp));
+            CKI(dev_alloc(p, &b.w2, (size_t)b.cin * hidd * km));
+            CKI(pack_conv(p->W(n + ".proj_out.weight"), b.w2, b.cin, hidd, 1, hidd * km, 0, p->f16, sp));
         }
     }
     const int c0 = hid * c.ch_multipliers[0];
     // out_conv weight rows are padded to 16 output channels (zero rows) so the TMA box never leaves the tensor
-    CKI(dev_alloc(p, &p->w_out, (size_t)16 * 9 * c0));
-    CKI(pack_conv(p->W("out_conv.2.weight"), p->w_out, c.out_channels, c0, 9, 9 * c0, 0, p->f16));
+    CKI(dev_alloc(p, &p->w_out, (size_t)16 * 9 * c0 * km));
+    CKI(pack_conv(p->W("out_conv.2.weight"), p->w_out, c.out_channels, c0, 9, 9 * c0 * km, 0, p->f16, sp));
     CK(cudaDeviceSynchronize());
     p->finalized = true;
     return 0;
@@ -595,6 +615,8 @@ static int conv_geom(int n, int h, int w, ConvGeom* g) {
 struct ConvSpec {
     const h16* a3 = nullptr; int c3 = 0;       // 3x3 segment: NHWC [n,h,w,c3]
     const h16* a1 = nullptr; int c1 = 0;       // pointwise segment: [n*h*w, c1] with row stride ld1
+    const h16* a3_lo = nullptr;                // split-precision mode: lo halves of the operands above
+    const h16* a1_lo = nullptr;
     int ld1 = 0;
     int n = 0, h = 0, w = 0;
     const h16* wpacked = nullptr; int cout = 0; int wrows = 0;   // weight rows actually allocated
@@ -608,21 +630,29 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     memset(cp, 0, sizeof(*cp));
     const long long M = (long long)s.n * s.h * s.w;
     int seg = 0, ktot = 0;
+    // split-precision mode: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo as three K segments over the same geometry
+    const h16* a3s[3] = {s.a3, s.a3_lo, s.a3};
+    const h16* a1s[3] = {s.a1, s.a1_lo, s.a1};
+    const int n3 = s.a3 ? (s.a3_lo ? 3 : 1) : 0, n1 = s.a1 ? (s.a1_lo ? 3 : 1) : 0;
     if (s.a3) {
         ConvGeom g;
         CKI(conv_geom(s.n, s.h, s.w, &g));
-        CKI(make_map_nhwc(&cp->a_map[seg], s.a3, s.n, s.h, s.w, s.c3, g.box_h, g.box_n));
-        cp->seg_taps[seg] = 9; cp->seg_kblocks[seg] = s.c3 / 64; ktot += 9 * s.c3; ++seg;
+        for (int k = 0; k < n3; ++k) {
+            CKI(make_map_nhwc(&cp->a_map[seg], a3s[k], s.n, s.h, s.w, s.c3, g.box_h, g.box_n));
+            cp->seg_taps[seg] = 9; cp->seg_kblocks[seg] = s.c3 / 64; ktot += 9 * s.c3; ++seg;
+        }
         cp->pointwise = 0; cp->tiles_per_image = g.tiles_per_image; cp->box_h = g.box_h; cp->box_n = g.box_n;
         cp->rows_per_tile = g.rows_per_tile; cp->num_m_tiles = g.num_m_tiles;
-        if (s.a1) {
+        for (int k = 0; k < n1; ++k) {
             // the appended pointwise segment walks the same tiles through the geometric view
-            CKI(make_map_nhwc(&cp->a_map[seg], s.a1, s.n, s.h, s.w, s.c1, g.box_h, g.box_n));
+            CKI(make_map_nhwc(&cp->a_map[seg], a1s[k], s.n, s.h, s.w, s.c1, g.box_h, g.box_n));
             cp->seg_taps[seg] = 1; cp->seg_kblocks[seg] = s.c1 / 64; ktot += s.c1; ++seg;
         }
     } else {
-        CKI(make_map_rows4d(&cp->a_map[seg], s.a1, M, s.c1, s.ld1));
-        cp->seg_taps[seg] = 1; cp->seg_kblocks[seg] = s.c1 / 64; ktot += s.c1; ++seg;
+        for (int k = 0; k < n1; ++k) {
+            CKI(make_map_rows4d(&cp->a_map[seg], a1s[k], M, s.c1, s.ld1));
+            cp->seg_taps[seg] = 1; cp->seg_kblocks[seg] = s.c1 / 64; ktot += s.c1; ++seg;
+        }
         cp->pointwise = 1; cp->tiles_per_image = 1; cp->box_h = 1; cp->box_n = 1; cp->rows_per_tile = 128;
         cp->num_m_tiles = (int)((M + 127) / 128);
     }
@@ -657,17 +687,19 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
     // ---- in_conv
     // every fp32 stream tensor carries the partial GroupNorm statistics its producing conv wrote
     auto stats_bytes = [&](size_t rows_px, int ch) { return (rows_px / kStatRows) * (size_t)(ch / kStatCols) * sizeof(float2); };
-    h16* patches; float* h; float2* hst;
+    const bool sp = p->split != 0;
+    h16* patches; h16* patches_lo = nullptr; float* h; float2* hst;
     const size_t hw0 = (size_t)res * res;
     CKI(ex->acquire((size_t)R * hw0 * 64 * 2, (void**)&patches));
-    ex->im2cols.push_back({ex->xin, patches, R / ex->rep, ex->rep, c.in_channels, res, res, p->f16});
+    if (sp) CKI(ex->acquire((size_t)R * hw0 * 64 * 2, (void**)&patches_lo));
+    ex->im2cols.push_back({ex->xin, patches, patches_lo, R / ex->rep, ex->rep, c.in_channels, res, res, p->f16});
     ex->steps.push_back({S_IM2COL, (int)ex->im2cols.size() - 1});
     CKI(ex->acquire((size_t)R * hw0 * hid * 4, (void**)&h));
     CKI(ex->acquire(stats_bytes((size_t)R * hw0, hid), (void**)&hst));
     {
         ConvSpec s;
         s.f16 = p->f16;
-        s.a1 = patches; s.c1 = 64; s.ld1 = 64; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_in; s.cout = hid; s.wrows = hid;
+        s.a1 = patches; s.a1_lo = patches_lo; s.c1 = 64; s.ld1 = 64; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_in; s.cout = hid; s.wrows = hid;
         s.bias = p->W("in_conv.bias"); s.out_mode = kOutF32; s.out_f32 = h; s.ld = hid; s.stats = hst;
         CKI(add_conv(s));
     }
@@ -695,9 +727,11 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             const bool skipconv = b.cin != b.cout;
             const int ro = b.resample == kResDown ? res / 2 : b.resample == kResUp ? res * 2 : res;
             const size_t HWo = (size_t)ro * ro;
-            h16 *a1, *xraw = nullptr; float* xres = nullptr;
+            h16 *a1, *xraw = nullptr, *a1_lo = nullptr, *xraw_lo = nullptr; float* xres = nullptr;
             CKI(ex->acquire((size_t)R * HWo * cin * 2, (void**)&a1));
+            if (sp) CKI(ex->acquire((size_t)R * HWo * cin * 2, (void**)&a1_lo));
             if (skipconv) CKI(ex->acquire((size_t)R * HW * cin * 2, (void**)&xraw));
+            if (skipconv && sp) CKI(ex->acquire((size_t)R * HW * cin * 2, (void**)&xraw_lo));
             if (b.resample != kResNone) CKI(ex->acquire((size_t)R * HWo * cin * 4, (void**)&xres));
             GroupNormParams g{};
             g.f16 = p->f16;
@@ -705,28 +739,33 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             if (fusable(hch, c2)) { g.stats1 = hst; g.stats2 = st2; g.meanrstd = meanrstd; }
             g.gamma = p->W(n + ".norm1.weight"); g.beta = p->W(n + ".norm1.bias");
             g.silu = 1; g.resample = b.resample; g.out_act = a1; g.out_raw = xraw; g.out_res = xres;
+            g.out_act_lo = a1_lo; g.out_raw_lo = xraw_lo;
             add_gn(g);
             // conv1: its output only feeds norm2, so it is kept in the 16-bit operand format when norm2 can use
             // the epilogue statistics (otherwise fp32 for the two-pass fallback)
             const bool fuse2 = fusable(b.cout, 0);
+            const bool h1_16 = fuse2 && !sp;            // split-precision mode keeps conv1's output in fp32
             void* h1; float2* h1st = nullptr;
-            CKI(ex->acquire((size_t)R * HWo * b.cout * (fuse2 ? 2 : 4), &h1));
+            CKI(ex->acquire((size_t)R * HWo * b.cout * (h1_16 ? 2 : 4), &h1));
             if (fuse2) CKI(ex->acquire(stats_bytes((size_t)R * HWo, b.cout), (void**)&h1st));
             {
                 ConvSpec s;
                 s.f16 = p->f16;
-                s.a3 = a1; s.c3 = cin; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w1; s.cout = b.cout; s.wrows = b.cout;
+                s.a3 = a1; s.a3_lo = a1_lo; s.c3 = cin; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w1; s.cout = b.cout; s.wrows = b.cout;
                 s.bias = p->W(n + ".conv1.bias"); s.ld = b.cout; s.stats = h1st;
-                if (fuse2) { s.out_mode = kOutBF16; s.out_bf16 = (h16*)h1; } else { s.out_mode = kOutF32; s.out_f32 = (float*)h1; }
+                if (h1_16) { s.out_mode = kOutBF16; s.out_bf16 = (h16*)h1; } else { s.out_mode = kOutF32; s.out_f32 = (float*)h1; }
                 CKI(add_conv(s));
             }
             ex->release(a1);
+            if (a1_lo) ex->release(a1_lo);
             // norm2 + FiLM + SiLU
-            h16* a2;
+            h16* a2; h16* a2_lo = nullptr;
             CKI(ex->acquire((size_t)R * HWo * b.cout * 2, (void**)&a2));
+            if (sp) CKI(ex->acquire((size_t)R * HWo * b.cout * 2, (void**)&a2_lo));
             GroupNormParams g2{};
             g2.f16 = p->f16;
-            g2.src1 = h1; g2.C1 = b.cout; g2.B = R; g2.H = ro; g2.W = ro; g2.in16 = fuse2 ? 1 : 0; g2.stats1 = h1st; g2.meanrstd = meanrstd;
+            g2.src1 = h1; g2.C1 = b.cout; g2.B = R; g2.H = ro; g2.W = ro; g2.in16 = h1_16 ? 1 : 0; g2.stats1 = h1st; g2.meanrstd = meanrstd;
+            g2.out_act_lo = a2_lo;
             g2.gamma = p->W(n + ".norm2.weight"); g2.beta = p->W(n + ".norm2.bias");
             g2.film = film; g2.film_row = film_row; g2.film_stride = p->film_total; g2.film_off = b.film_off;
             g2.silu = 1; g2.resample = kResNone; g2.out_act = a2;
@@ -740,14 +779,16 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             {
                 ConvSpec s;
                 s.f16 = p->f16;
-                s.a3 = a2; s.c3 = b.cout; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w2; s.cout = b.cout; s.wrows = b.cout;
-                if (skipconv) { s.a1 = xraw; s.c1 = cin; s.ld1 = cin; }
+                s.a3 = a2; s.a3_lo = a2_lo; s.c3 = b.cout; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w2; s.cout = b.cout; s.wrows = b.cout;
+                if (skipconv) { s.a1 = xraw; s.a1_lo = xraw_lo; s.c1 = cin; s.ld1 = cin; }
                 s.bias = b.bias2;
                 s.residual = skipconv ? nullptr : (b.resample != kResNone ? xres : h);
                 s.out_mode = kOutF32; s.out_f32 = hout; s.ld = b.cout; s.stats = houtst;
                 CKI(add_conv(s));
             }
             ex->release(a2);
+            if (a2_lo) ex->release(a2_lo);
+            if (xraw_lo) ex->release(xraw_lo);
             if (xraw) ex->release(xraw);
             if (xres) ex->release(xres);
             if (src2_buf) { ex->release(src2_buf); ex->release(st2); }
@@ -757,28 +798,29 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             int hd, nh;
             attn_dims(c, b.cin, &hd, &nh);
             const int hidd = hd * nh, N = HW;
-            h16 *a, *qk, *vt, *o;
+            h16 *a, *a_lo = nullptr, *qk = nullptr, *vt = nullptr, *o, *o_lo = nullptr;
             CKI(ex->acquire((size_t)R * HW * b.cin * 2, (void**)&a));
+            if (sp) CKI(ex->acquire((size_t)R * HW * b.cin * 2, (void**)&a_lo));
             GroupNormParams g{};
             g.f16 = p->f16;
             g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
             if (fusable(hch, 0)) { g.stats1 = hst; g.meanrstd = meanrstd; }
             g.gamma = p->W(n + ".norm.weight"); g.beta = p->W(n + ".norm.bias");
-            g.silu = 0; g.resample = kResNone; g.out_act = a;
+            g.silu = 0; g.resample = kResNone; g.out_act = a; g.out_act_lo = a_lo;
             add_gn(g);
-            CKI(ex->acquire((size_t)R * N * 2 * hidd * 2, (void**)&qk));
-            CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&vt));
-            {   // one GEMM for q | k | v: q,k row-major [R*N, 2*hid]; the v third is written transposed, V^T [R*hid, N]
-                ConvSpec s;
-                s.f16 = p->f16;
-                s.a1 = a; s.c1 = b.cin; s.ld1 = b.cin; s.n = R; s.h = res; s.w = res; s.wpacked = b.w1; s.cout = 3 * hidd;
-                s.wrows = 3 * hidd; s.bias = p->W(n + ".proj_in.bias"); s.out_mode = kOutBF16; s.out_bf16 = qk; s.out_t = vt;
-                s.ld = 2 * hidd; s.split_col = 2 * hidd;
-                CKI(add_conv(s));
-            }
-            ex->release(a);
             CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&o));
-            {
+            if (!sp) {
+                CKI(ex->acquire((size_t)R * N * 2 * hidd * 2, (void**)&qk));
+                CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&vt));
+                {   // one GEMM for q | k | v: q,k row-major [R*N, 2*hid]; the v third is written transposed, V^T [R*hid, N]
+                    ConvSpec s;
+                    s.f16 = p->f16;
+                    s.a1 = a; s.c1 = b.cin; s.ld1 = b.cin; s.n = R; s.h = res; s.w = res; s.wpacked = b.w1; s.cout = 3 * hidd;
+                    s.wrows = 3 * hidd; s.bias = p->W(n + ".proj_in.bias"); s.out_mode = kOutBF16; s.out_bf16 = qk; s.out_t = vt;
+                    s.ld = 2 * hidd; s.split_col = 2 * hidd;
+                    CKI(add_conv(s));
+                }
+                ex->release(a);
                 std::unique_ptr<AttnParams> ap(new AttnParams());
                 memset(ap.get(), 0, sizeof(AttnParams));
                 CKI(make_map_2d(&ap->qk_map, qk, (long long)R * N, 2 * hidd, 2 * hidd, 128));
@@ -789,20 +831,38 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
                 ap->out = o;
                 ex->attns.push_back(std::move(ap));
                 ex->steps.push_back({S_ATTN, (int)ex->attns.size() - 1});
+                ex->release(qk); ex->release(vt);
+            } else {
+                // split-precision validation mode: q | k | v in fp32, attention on CUDA cores in fp32
+                float* qkv32;
+                CKI(ex->acquire((size_t)R * N * 3 * hidd * 4, (void**)&qkv32));
+                CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&o_lo));
+                {
+                    ConvSpec s;
+                    s.f16 = p->f16;
+                    s.a1 = a; s.a1_lo = a_lo; s.c1 = b.cin; s.ld1 = b.cin; s.n = R; s.h = res; s.w = res; s.wpacked = b.w1;
+                    s.cout = 3 * hidd; s.wrows = 3 * hidd; s.bias = p->W(n + ".proj_in.bias"); s.out_mode = kOutF32; s.out_f32 = qkv32;
+                    s.ld = 3 * hidd;
+                    CKI(add_conv(s));
+                }
+                ex->release(a); ex->release(a_lo);
+                ex->attn32s.push_back({qkv32, o, o_lo, R, N, nh, hd, p->f16});
+                ex->steps.push_back({S_ATTN_F32, (int)ex->attn32s.size() - 1});
+                ex->release(qkv32);
             }
-            ex->release(qk); ex->release(vt);
             float* hout; float2* houtst;
             CKI(ex->acquire((size_t)R * HW * b.cin * 4, (void**)&hout));
             CKI(ex->acquire(stats_bytes((size_t)R * HW, b.cin), (void**)&houtst));
             {
                 ConvSpec s;
                 s.f16 = p->f16;
-                s.a1 = o; s.c1 = hidd; s.ld1 = hidd; s.n = R; s.h = res; s.w = res; s.wpacked = b.w2; s.cout = b.cin; s.wrows = b.cin;
+                s.a1 = o; s.a1_lo = o_lo; s.c1 = hidd; s.ld1 = hidd; s.n = R; s.h = res; s.w = res; s.wpacked = b.w2; s.cout = b.cin; s.wrows = b.cin;
                 s.bias = p->W(n + ".proj_out.bias"); s.residual = h; s.out_mode = kOutF32; s.out_f32 = hout; s.ld = b.cin;
                 s.stats = houtst;
                 CKI(add_conv(s));
             }
             ex->release(o);
+            if (o_lo) ex->release(o_lo);
             if (!h_on_stack) { ex->release(h); ex->release(hst); }
             h = hout; hst = houtst; h_on_stack = false;
         }
@@ -812,18 +872,19 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
     // ---- out_conv
     {
         const int HW = res * res;
-        h16* a;
+        h16* a; h16* a_lo = nullptr;
         CKI(ex->acquire((size_t)R * HW * hch * 2, (void**)&a));
+        if (sp) CKI(ex->acquire((size_t)R * HW * hch * 2, (void**)&a_lo));
         GroupNormParams g{};
         g.f16 = p->f16;
         g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
         if (fusable(hch, 0)) { g.stats1 = hst; g.meanrstd = meanrstd; }
         g.gamma = p->W("out_conv.0.weight"); g.beta = p->W("out_conv.0.bias");
-        g.silu = 1; g.resample = kResNone; g.out_act = a;
+        g.silu = 1; g.resample = kResNone; g.out_act = a; g.out_act_lo = a_lo;
         add_gn(g);
         ConvSpec s;
         s.f16 = p->f16;
-        s.a3 = a; s.c3 = hch; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_out; s.cout = c.out_channels; s.wrows = 16;
+        s.a3 = a; s.a3_lo = a_lo; s.c3 = hch; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_out; s.cout = c.out_channels; s.wrows = 16;
         s.bias = p->W("out_conv.2.bias"); s.out_mode = kOutNCHW; s.out_f32 = ex->yout; s.ld = 0;
         CKI(add_conv(s));
         ex->release(a);
@@ -864,12 +925,13 @@ static int run_steps(vdt_plan* p, Exec* ex, cudaStream_t st, std::vector<cudaEve
             case S_CONV: e = launch_conv_gemm(*ex->convs[s.idx], p->num_sms, st); break;
             case S_GN: e = launch_groupnorm(ex->gns[s.idx], st); break;
             case S_ATTN: e = launch_attention(*ex->attns[s.idx], st); break;
-            case S_IM2COL: { auto& a = ex->im2cols[s.idx]; e = launch_im2col3x3(a.x, a.out, a.B, a.rep, a.C, a.H, a.W, a.f16, st); break; }
+            case S_IM2COL: { auto& a = ex->im2cols[s.idx]; e = launch_im2col3x3(a.x, a.out, a.out_lo, a.B, a.rep, a.C, a.H, a.W, a.f16, st); break; }
             case S_TEMB: { auto& a = ex->tembs[s.idx]; e = launch_timestep_embedding(a.t, a.out, a.rows, a.dim, st); break; }
             case S_LINEAR: { auto& a = ex->linears[s.idx]; e = launch_linear_f32(a.x, a.W, a.b, a.out, a.rows, a.K, a.N, a.silu, st); break; }
             case S_CLSEMB: { auto& a = ex->clss[s.idx]; e = launch_class_embed_silu(a.e, a.y, a.w, a.b, a.ncls, a.out, a.rows, a.E, st); break; }
             case S_BEGIN: { auto& a = ex->begins[s.idx]; e = launch_sampler_begin_step(a.st, a.table, a.t_rows, a.nrows, a.T, st); break; }
             case S_SAMPLE: e = launch_sampler_step(ex->samples[s.idx], st); break;
+            case S_ATTN_F32: { auto& a = ex->attn32s[s.idx]; e = launch_attention_f32(a.qkv, a.hi, a.lo, a.B, a.N, a.heads, a.d, a.f16, st); break; }
         }
         if (e != cudaSuccess) return fail("kernel launch failed (step kind %d): %s", (int)s.kind, cudaGetErrorString(e));
     }
@@ -890,7 +952,7 @@ static int run_steps_profiled(vdt_plan* p, Exec* ex, cudaStream_t st) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
             const StepKind k = ex->steps[i].kind;
-            const int fam = k == S_CONV ? VDT_PROF_CONV : k == S_GN ? VDT_PROF_GROUPNORM : k == S_ATTN ? VDT_PROF_ATTENTION : VDT_PROF_OTHER;
+            const int fam = k == S_CONV ? VDT_PROF_CONV : k == S_GN ? VDT_PROF_GROUPNORM : (k == S_ATTN || k == S_ATTN_F32) ? VDT_PROF_ATTENTION : VDT_PROF_OTHER;
             g_prof_ms[fam] += ms; g_prof_n[fam] += 1;
         }
     }

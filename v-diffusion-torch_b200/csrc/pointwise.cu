@@ -8,8 +8,8 @@ namespace vdt {
 namespace {
 
 // ------------------------------------------------------------------------------------------ im2col
-__global__ void im2col3x3_kernel(const float* __restrict__ x, h16* __restrict__ out, int B, int rep, int C, int H,
-                                 int W, int f16) {
+__global__ void im2col3x3_kernel(const float* __restrict__ x, h16* __restrict__ out, h16* __restrict__ out_lo, int B,
+                                 int rep, int C, int H, int W, int f16) {
     const long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     const long long rows = static_cast<long long>(B) * rep * H * W;
     if (row >= rows) return;
@@ -30,6 +30,62 @@ __global__ void im2col3x3_kernel(const float* __restrict__ x, h16* __restrict__ 
     for (int j = 0; j < 8; ++j)
         dst[j] = make_uint4(pack_16(v[8 * j], v[8 * j + 1], f16), pack_16(v[8 * j + 2], v[8 * j + 3], f16),
                             pack_16(v[8 * j + 4], v[8 * j + 5], f16), pack_16(v[8 * j + 6], v[8 * j + 7], f16));
+    if (out_lo) {                                    // split-precision mode: lo = round16(v - round16(v))
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            const uint16_t h = cvt_16(v[i], f16);
+            v[i] -= f16 ? __half2float(*reinterpret_cast<const __half*>(&h)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h));
+        }
+        uint4* dl = reinterpret_cast<uint4*>(out_lo + row * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            dl[j] = make_uint4(pack_16(v[8 * j], v[8 * j + 1], f16), pack_16(v[8 * j + 2], v[8 * j + 3], f16),
+                               pack_16(v[8 * j + 4], v[8 * j + 5], f16), pack_16(v[8 * j + 6], v[8 * j + 7], f16));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ fp32 attention
+// Validation-mode attention (scaled_dot_product, unet.py:55-64) entirely in fp32 on CUDA cores: one warp per
+// query row, lane l owns features l, l+32, ...; online softmax over the keys of the same image and head.
+template <int DPL>   // features per lane = d / 32
+__global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restrict__ qkv, h16* __restrict__ out_hi,
+                                                            h16* __restrict__ out_lo, int B, int N, int heads, int f16) {
+    const int d = DPL * 32, hid = heads * d;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long qrow = (static_cast<long long>(blockIdx.x) * 8 + warp) / heads;      // global query row
+    const int h = static_cast<int>((static_cast<long long>(blockIdx.x) * 8 + warp) % heads);
+    if (qrow >= static_cast<long long>(B) * N) return;
+    const long long img = qrow / N;
+    const float* qp = qkv + qrow * 3 * hid + h * d;
+    float q[DPL], o[DPL];
+    const float scale = rsqrtf(static_cast<float>(d));
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) { q[i] = qp[lane + 32 * i] * scale; o[i] = 0.f; }
+    float m = -INFINITY, l = 0.f;
+    for (int k = 0; k < N; ++k) {
+        const float* kp = qkv + (img * N + k) * 3 * hid + hid + h * d;
+        const float* vp = kp + hid;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) s = fmaf(q[i], __ldg(kp + lane + 32 * i), s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        const float mn = fmaxf(m, s);
+        const float corr = expf(m - mn), pr = expf(s - mn);
+        l = l * corr + pr;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) o[i] = fmaf(o[i], corr, pr * __ldg(vp + lane + 32 * i));
+        m = mn;
+    }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) {
+        const float v = o[i] * inv;
+        const uint16_t hi = cvt_16(v, f16);
+        const float hf = f16 ? __half2float(*reinterpret_cast<const __half*>(&hi)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&hi));
+        out_hi[qrow * hid + h * d + lane + 32 * i] = hi;
+        out_lo[qrow * hid + h * d + lane + 32 * i] = cvt_16(v - hf, f16);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ embedding
@@ -186,11 +242,27 @@ __global__ void sampler_step_kernel(const SamplerStepParams p) {
 
 }  // namespace
 
-cudaError_t launch_im2col3x3(const float* x, h16* out, int B, int rep, int C, int H, int W, int f16, cudaStream_t stream) {
+cudaError_t launch_im2col3x3(const float* x, h16* out, h16* out_lo, int B, int rep, int C, int H, int W, int f16,
+                             cudaStream_t stream) {
     if (9 * C > 64) return cudaErrorInvalidValue;
     const long long rows = static_cast<long long>(B) * rep * H * W;
     if (rows == 0) return cudaSuccess;
-    im2col3x3_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, stream>>>(x, out, B, rep, C, H, W, f16);
+    im2col3x3_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, stream>>>(x, out, out_lo, B, rep, C, H, W, f16);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_attention_f32(const float* qkv, h16* out_hi, h16* out_lo, int B, int N, int heads, int d, int f16,
+                                 cudaStream_t stream) {
+    const long long warps = static_cast<long long>(B) * N * heads;
+    if (warps == 0) return cudaSuccess;
+    const unsigned grid = static_cast<unsigned>((warps + 7) / 8);
+    switch (d) {
+        case 64: attention_f32_kernel<2><<<grid, 256, 0, stream>>>(qkv, out_hi, out_lo, B, N, heads, f16); break;
+        case 128: attention_f32_kernel<4><<<grid, 256, 0, stream>>>(qkv, out_hi, out_lo, B, N, heads, f16); break;
+        case 192: attention_f32_kernel<6><<<grid, 256, 0, stream>>>(qkv, out_hi, out_lo, B, N, heads, f16); break;
+        case 256: attention_f32_kernel<8><<<grid, 256, 0, stream>>>(qkv, out_hi, out_lo, B, N, heads, f16); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
