@@ -113,6 +113,14 @@ def main():
     co["temb_t"] = tt.numpy()
     co["temb_256"] = get_timestep_embedding(tt, 256).numpy()
     co["temb_64"] = get_timestep_embedding(tt, 64).numpy()
+    # every schedule get_logsnr_schedule knows (diffusion.py:52-96), T = 50, default +-20 range
+    for sched in ("cosine", "linear", "sigmoid", "legacy"):
+        fn = get_logsnr_schedule(sched, -20., 20., rescale=False)
+        st = torch.arange(50, dtype=torch.float64)
+        ls_, lt_ = fn(st / 50).to(torch.float32), fn((st + 1) / 50).to(torch.float32)
+        co[f"{sched}_logsnr_s"], co[f"{sched}_logsnr_t"] = ls_.numpy(), lt_.numpy()
+        c1_, c2_, lv_ = logsnr_to_posterior(ls_, lt_, "fixed_large")
+        co[f"{sched}_c1"], co[f"{sched}_c2"], co[f"{sched}_logvar"] = c1_.numpy(), c2_.numpy(), lv_.numpy()
     np.savez_compressed(os.path.join(HERE, "coefs_T100.npz"), **co)
 
     # ---- config merge known answer (utils.py:193-201 on the shipped JSONs)

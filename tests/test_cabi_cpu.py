@@ -78,3 +78,19 @@ def test_fill_with_defaults_semantics():
     cfg = {"a": None, "b": {"c": 1, "d": None}}
     fill_with_defaults(cfg, {"a": 2, "b": {"c": 3, "d": 4, "e": 5}, "f": 6})
     assert cfg == {"a": 2, "b": {"c": 1, "d": 4, "e": 5}, "f": 6}     # utils.py:204-224 demo
+
+
+def test_all_schedules_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "coefs_T100.npz"))
+    for sched in ("cosine", "linear", "sigmoid", "legacy"):
+        d = GaussianDiffusion(get_logsnr_schedule(sched, -20., 20.), 50, "eps", "fixed_large", "snr", "mse")
+        an = d.step_coefficients(use_ddim=False).numpy()
+        np.testing.assert_allclose(an[:, 10], g[f"{sched}_logsnr_s"], rtol=2e-6, atol=1e-6)
+        np.testing.assert_allclose(an[:, 11], g[f"{sched}_logsnr_t"], rtol=2e-6, atol=1e-6)
+        np.testing.assert_allclose(an[:, 6], g[f"{sched}_c1"], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(an[:, 7], g[f"{sched}_c2"], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(an[:, 9], g[f"{sched}_logvar"], rtol=1e-5, atol=1e-6)
+        # the Python-side callable (API parity with get_logsnr_schedule's closure) agrees too
+        fn = get_logsnr_schedule(sched, -20., 20.)
+        tt = torch.arange(50, dtype=torch.float64) / 50
+        np.testing.assert_allclose(fn(tt).to(torch.float32).numpy(), g[f"{sched}_logsnr_s"], rtol=2e-6, atol=1e-6)

@@ -100,3 +100,14 @@ def test_config_merge_gives_case_configs(golden_dir):
     assert unet_config_from_json(merged["cifar10_cond"]["model"], 3, 3, num_classes=10) == CIFAR_COND
     assert unet_config_from_json(merged["cifar10_uncond"]["model"], 3, 3) == CIFAR_UNCOND
     assert unet_config_from_json(merged["celeba"]["model"], 3, 6) == CELEBA
+
+
+def test_all_schedules_known_answers(golden_dir):
+    g = _load(golden_dir, "coefs_T100.npz")
+    for sched in ("cosine", "linear", "sigmoid", "legacy"):
+        an = step_coefficients(50, use_ddim=False, var_type="fixed_large", schedule=sched)
+        np.testing.assert_allclose(an["logsnr_s"], g[f"{sched}_logsnr_s"], rtol=2e-6, atol=1e-6)
+        np.testing.assert_allclose(an["logsnr_t"], g[f"{sched}_logsnr_t"], rtol=2e-6, atol=1e-6)
+        np.testing.assert_allclose(an["c1"], g[f"{sched}_c1"], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(an["c2"], g[f"{sched}_c2"], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(an["logvar"], g[f"{sched}_logvar"], rtol=1e-5, atol=1e-6)
