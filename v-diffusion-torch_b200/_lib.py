@@ -12,7 +12,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libvdt_b200.so")
+LIB_PATH = os.environ.get("VDT_LIB", os.path.join(LIB_DIR, "libvdt_b200.so"))   # VDT_LIB: A/B-test another build
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include", "vdt_b200.h")
 
 VDT_MAX_LEVELS = 8
