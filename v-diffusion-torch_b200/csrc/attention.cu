@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
     sm.p0 = base; base += 2 * 16384;
     uint64_t* bars = reinterpret_cast<uint64_t*>(base);
     sm.q_full = bars; sm.k_full = bars + 1; sm.v_full = bars + 3; sm.k_empty = bars + 5; sm.v_empty = bars + 7;
-    sm.s_full = bars + 9; sm.p_full = bars + 10;
-    sm.tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    sm.s_full = bars + 9; sm.p_full = bars + 11;              // s_full[2], p_full[2]
+    sm.tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
     float* xch = reinterpret_cast<float*>(base + 256);      // [2][2][128]: double-buffered row-max exchange; reused for l
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,13 +69,13 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
     const int b0 = (blockIdx.x / (qtiles * p.heads)) * ipc;
     const long long row0 = static_cast<long long>(b0) * N + static_cast<long long>(qt) * kQRows;   // first query row
     const long long krow0 = static_cast<long long>(b0) * N;                                          // first key row
-    uint32_t tmem_cols = 128; while (tmem_cols < static_cast<uint32_t>(d + kKeys)) tmem_cols <<= 1;
+    uint32_t tmem_cols = 128; while (tmem_cols < static_cast<uint32_t>(d + 2 * kKeys)) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         mbar_init(sm.q_full, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&sm.k_full[s], 1); mbar_init(&sm.v_full[s], 1); mbar_init(&sm.k_empty[s], 1);
                                       mbar_init(&sm.v_empty[s], 1); mbar_init(&sm.p_full[s], 8); }   // one arrival per softmax warp
-        mbar_init(sm.s_full, 1);
+        mbar_init(&sm.s_full[0], 1); mbar_init(&sm.s_full[1], 1);
         fence_mbar_init();
         tma_prefetch_desc(&p.qk_map); tma_prefetch_desc(&p.k_map); tma_prefetch_desc(&p.vt_map);
     }
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *sm.tmem_slot;
     const uint32_t tmem_o = tmem_base;                      // columns [0, d)
-    const uint32_t tmem_s = tmem_base + static_cast<uint32_t>(d);   // columns [d, d+64)
+    const uint32_t tmem_s = tmem_base + static_cast<uint32_t>(d);   // two S buffers: columns [d, d+64) and [d+64, d+128)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -123,18 +123,19 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                 for (int kk = 0; kk < d / 16; ++kk) {
                     const uint64_t ad = umma_desc_sw128(smem_u32(sm.q + (kk >> 2) * 16384)) + 2 * (kk & 3);
                     const uint64_t bd = umma_desc_sw128(smem_u32(sm.k(s) + (kk >> 2) * 8192)) + 2 * (kk & 3);
-                    umma_16(tmem_s, ad, bd, idesc_s, kk != 0);
+                    umma_16(tmem_s + static_cast<uint32_t>(s * kKeys), ad, bd, idesc_s, kk != 0);
                 }
                 umma_commit(&sm.k_empty[s]);              // K_j can be overwritten as soon as S_j has retired
-                umma_commit(sm.s_full);
+                umma_commit(&sm.s_full[s]);
             };
             mbar_wait(sm.q_full, 0);
             issue_s(0);
+            if (nt > 1) issue_s(1);                       // S is double-buffered: S_{j+1} is ready before softmax j ends
             for (int j = 0; j < nt; ++j) {
                 const int s = j & 1;
-                mbar_wait(&sm.p_full[s], (j >> 1) & 1);   // P_j in smem, S_j consumed, O rescaled if needed
+                mbar_wait(&sm.p_full[s], (j >> 1) & 1);   // P_j in smem, S_j consumed (its buffer is free), O rescaled if needed
                 tc_fence_after();
-                if (j + 1 < nt) issue_s(j + 1);
+                if (j + 2 < nt) issue_s(j + 2);
                 mbar_wait(&sm.v_full[s], (j >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
@@ -158,10 +159,10 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
         const int dh = d >> 1;                              // O columns owned by this thread: [half*dh, half*dh + dh)
         float m_used = -INFINITY, l = 0.f;
         for (int j = 0; j < nt; ++j) {
-            mbar_wait(sm.s_full, j & 1);
+            mbar_wait(&sm.s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
             uint32_t r0[32];
-            tmem_ld32(tmem_s + lane_off + half * 32, r0);
+            tmem_ld32(tmem_s + static_cast<uint32_t>((j & 1) * kKeys) + lane_off + half * 32, r0);
             tmem_ld_wait();
             float sv[32];
 #pragma unroll

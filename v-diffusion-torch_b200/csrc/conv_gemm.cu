@@ -248,10 +248,16 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = pair; w < total_items; w += num_pairs_resident) {
             const int m_tile = (w / p.num_n_tiles) * 2 + rank, n_tile = w % p.num_n_tiles;
-            mbar_wait(&acc_full[acc], acc_phase);
-            tc_fence_after();
             const long long grow = static_cast<long long>(m_tile) * p.rows_per_tile + row;
             const bool row_ok = (row < p.rows_per_tile) && (grow < p.M) && (m_tile < p.num_m_tiles);
+            if (p.residual && row_ok) {
+                // the main loop of this tile is still running: pull this warp's residual lines (one 128-byte line
+                // per row and 32-column chunk) into L2 so the epilogue's loads below do not pay DRAM latency
+                const float* rp = p.residual + static_cast<size_t>(grow) * p.ld + n_tile * p.block_n;
+                for (int c0 = chunk_par * 32; c0 < p.block_n; c0 += 64) prefetch_l2(rp + c0);
+            }
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kMaxBN);
             for (int c0 = chunk_par * 32; c0 < p.block_n; c0 += 64) {
                 uint32_t r[32];

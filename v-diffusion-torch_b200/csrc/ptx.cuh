@@ -245,6 +245,7 @@ __device__ __forceinline__ float4 ldg_nc_v4_issue(const float* p) {
     asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 
 // ---- small math --------------------------------------------------------------------------------
