@@ -244,9 +244,19 @@ def run_b200(args, rank, world, local_rank):
     conv_tflops = fc.value * rows / (fam_ms[0] * 1e-3) / 1e12 if fam_ms[0] > 0 else 0.0
     peaks = read_peaks()
     prof_total = sum(fam_ms)
+    # DRAM bytes per conv launch from the committed `ncu` capture of this same step (profiles/), scaled by rows
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_conv_dram_traffic.json")) as f:
+            tr = json.load(f)
+        traffic = tr["avg_dram_bytes_per_conv_launch_scaled_to_rows"] * min(rows, args.max_rows) / tr["rows"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all conv/1x1 launches of a step)",
                 "achieved": conv_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": conv_tflops / peaks["tflops"],
-                "peak_source": peaks["source"] + " sustained bf16 cuBLAS", "traffic": None,
+                "peak_source": peaks["source"] + " sustained bf16 cuBLAS", "traffic": traffic,
+                "traffic_note": "avg dram__bytes_read+write per conv launch (ncu, one chunk of chunk_rows UNet rows); "
+                                "launches_per_step counts every chunk's launches",
                 "algorithmic_flop_per_launch_avg": fc.value * rows / max(1, fam_n[0]),
                 "avg_launch_ms": fam_ms[0] / max(1, fam_n[0]), "launches_per_step": int(fam_n[0]),
                 "step_share": {"conv": fam_ms[0] / prof_total, "groupnorm": fam_ms[1] / prof_total,
@@ -278,11 +288,12 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16", "data": "synthetic",
+                "dtype": net.operand_dtype, "data": "synthetic",
                 "config": {"workload": "CIFAR-10 class-conditional UNet (cifar10_cond.json), CFG w=1 batched cond/uncond "
                                        f"(2B rows), 100-step DDIM, batch {B} per GPU; step = one denoising step over the batch",
                            "batch_per_gpu": B, "rows_per_unet_call": 2 * B, "chunk_rows": args.max_rows,
                            "steps_per_image": T_STEPS, "l2": "inputs_exceed_l2", "parallelism": f"replicas x{world}",
+                           "operands": net.operand_dtype + " tensor-core operands (same tcgen05 kind::f16 rate as bf16)",
                            "accumulate": "fp32", "residual_stream": "fp32"},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
