@@ -42,6 +42,7 @@ __host__ __device__ inline int attn_smem_bytes(int d) {
     return (d / 64) * 16384 + 2 * (d / 64) * 8192 + 2 * d * 128 + 2 * 16384 + 256 + 2048 /*row max / sum exchange*/;
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128B-swizzled tiles need 1024-byte alignment
     uint8_t* base = smem_raw;
@@ -114,8 +115,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc_s = umma_idesc_16(kQRows, kKeys, p.f16);
-            const uint32_t idesc_o = umma_idesc_16(kQRows, d, p.f16);
+            const uint32_t idesc_s = umma_idesc_16(kQRows, kKeys, (F16 ? 1 : 0));
+            const uint32_t idesc_o = umma_idesc_16(kQRows, d, (F16 ? 1 : 0));
             auto issue_s = [&](int j) {
                 const int s = j & 1;
                 mbar_wait(&sm.k_full[s], (j >> 1) & 1);
@@ -219,8 +220,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                     lsum += e[i];
                 }
                 *reinterpret_cast<uint4*>(prow + (((half * 4 + ch) ^ (row & 7)) << 4)) =
-                    make_uint4(pack_16_inrange(e[0], e[1], p.f16), pack_16_inrange(e[2], e[3], p.f16), pack_16_inrange(e[4], e[5], p.f16),
-                               pack_16_inrange(e[6], e[7], p.f16));   // p <= 2^8
+                    make_uint4(pack_16_inrange(e[0], e[1], (F16 ? 1 : 0)), pack_16_inrange(e[2], e[3], (F16 ? 1 : 0)), pack_16_inrange(e[4], e[5], (F16 ? 1 : 0)),
+                               pack_16_inrange(e[6], e[7], (F16 ? 1 : 0)));   // p <= 2^8
             }
             l += lsum;
             fence_proxy_async_smem();
@@ -243,10 +244,10 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                 uint4* dst = reinterpret_cast<uint4*>(p.out + grow * p.hid + h * d + c0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    dst[i] = make_uint4(pack_16(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l, p.f16),
-                                        pack_16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l, p.f16),
-                                        pack_16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l, p.f16),
-                                        pack_16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l, p.f16));
+                    dst[i] = make_uint4(pack_16(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l, (F16 ? 1 : 0)),
+                                        pack_16(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l, (F16 ? 1 : 0)),
+                                        pack_16(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l, (F16 ? 1 : 0)),
+                                        pack_16(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l, (F16 ? 1 : 0)));
             }
         }
     }
@@ -267,7 +268,8 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
     const int smem = attn_smem_bytes(p.d);
     static int smem_set = 0;
     if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         smem_set = smem;
     }
@@ -276,7 +278,8 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
     const int groups = (p.B + ipc - 1) / ipc;
     const long long grid = static_cast<long long>(groups) * p.heads * qtiles;
     if (grid <= 0) return cudaSuccess;
-    attention_kernel<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p);
+    if (p.f16) attention_kernel<true><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p);
+    else attention_kernel<false><<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

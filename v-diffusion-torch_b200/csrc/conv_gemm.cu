@@ -56,7 +56,7 @@ __device__ __forceinline__ TileCoord tile_origin(const ConvParams& p, int m_tile
 // Row-major epilogue of one 32-row x 32-column chunk after the smem transposition: lane = (row % 4 group rsub,
 // 4 columns cq).  Compile-time variants keep the instruction count low (the epilogue warps are issue-bound
 // otherwise); CHECK adds the per-row bounds tests needed only for ragged tiles.
-template <bool F32OUT, bool RESID, bool STATS, bool ROWBIAS, bool SILU, bool CHECK>
+template <bool F16, bool F32OUT, bool RESID, bool STATS, bool ROWBIAS, bool SILU, bool CHECK>
 __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const float4* tile, int lane, int q, int m_tile,
                                                   long long wrow0, int col0) {
     const int cq = lane & 7, rsub = lane >> 3;
@@ -95,7 +95,7 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
             if (F32OUT)
                 *reinterpret_cast<float4*>(p.out_f32 + off0 + i * step) = o;
             else
-                *reinterpret_cast<uint2*>(p.out_bf16 + off0 + i * step) = make_uint2(pack_16(o.x, o.y, p.f16), pack_16(o.z, o.w, p.f16));
+                *reinterpret_cast<uint2*>(p.out_bf16 + off0 + i * step) = make_uint2(pack_16(o.x, o.y, (F16 ? 1 : 0)), pack_16(o.z, o.w, (F16 ? 1 : 0)));
             if (STATS) {
                 ssum += (o.x + o.y) + (o.z + o.w);
                 ssq = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ssq))));
@@ -146,6 +146,7 @@ __device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, cons
     }
 }
 
+template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -217,7 +218,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA)
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = umma_idesc_16(2 * kBM, p.block_n, p.f16);
+            const uint32_t idesc = umma_idesc_16(2 * kBM, p.block_n, (F16 ? 1 : 0));
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int w = pair; w < total_items; w += num_pairs_resident) {
@@ -283,14 +284,14 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                     if (!all_valid || p.act_silu) {          // ragged tile / rare variants: run-time checked generic path
                         epilogue_rowmajor_generic(p, tile, lane, q, m_tile, wrow0, col0);
                     } else if (f32o) {
-                        if (resid && st) epilogue_rowmajor<true, true, true, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
-                        else if (resid) epilogue_rowmajor<true, true, false, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
-                        else if (st) epilogue_rowmajor<true, false, true, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
-                        else epilogue_rowmajor<true, false, false, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        if (resid && st) epilogue_rowmajor<F16, true, true, true, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        else if (resid) epilogue_rowmajor<F16, true, true, false, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        else if (st) epilogue_rowmajor<F16, true, false, true, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        else epilogue_rowmajor<F16, true, false, false, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
                     } else {
-                        if (p.bias_per_row) epilogue_rowmajor<false, false, false, true, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
-                        else if (st) epilogue_rowmajor<false, false, true, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
-                        else epilogue_rowmajor<false, false, false, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        if (p.bias_per_row) epilogue_rowmajor<F16, false, false, false, true, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        else if (st) epilogue_rowmajor<F16, false, false, true, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        else epilogue_rowmajor<F16, false, false, false, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
                     }
                     __syncwarp();
                 } else if (p.out_mode == kOutBF16) {         // V third of proj_in: transposed per image (coalesced per column)
@@ -305,7 +306,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                         const int pix = static_cast<int>(grow - img * p.HW);
                         h16* dst = p.out_t + (img * (p.Cout - p.split_col) + (col0 - p.split_col)) * p.HW + pix;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.HW] = cvt_16(v[j], p.f16);
+                        for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.HW] = cvt_16(v[j], (F16 ? 1 : 0));
                     }
                 } else {   // kOutNCHW
 #pragma unroll
@@ -341,14 +342,16 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
 cudaError_t launch_conv_gemm(const ConvParams& p, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const int items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     if (items <= 0) return cudaSuccess;
     const int pairs = items < num_sms / 2 ? items : num_sms / 2;
-    conv_gemm_kernel<<<2 * pairs, kThreads, kSmemBytes, stream>>>(p);
+    if (p.f16) conv_gemm_kernel<true><<<2 * pairs, kThreads, kSmemBytes, stream>>>(p);
+    else conv_gemm_kernel<false><<<2 * pairs, kThreads, kSmemBytes, stream>>>(p);
     return cudaGetLastError();
 }
 

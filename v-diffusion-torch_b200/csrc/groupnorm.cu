@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const GroupNorm
     }
 }
 
-template <int VEC, bool FUSED, bool IN16>
+template <int VEC, bool FUSED, bool IN16, bool F16>
 __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParams p, int CV, int PPH) {
     extern __shared__ float2 part[];                 // [CV * PPH] partial (sum, sumsq) (fallback statistics pass)
     __shared__ float2 stat[kGroups];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
     const h16* src16 = static_cast<const h16*>(p.src1) + static_cast<size_t>(b) * HW * p.C1 + c;   // IN16 only
     const int sC = from1 ? p.C1 : p.C2;
     auto load_px = [&](int pix, float (&v)[VEC]) {
-        if (IN16) load_vec16(src16 + static_cast<size_t>(pix) * sC, v, p.f16);
+        if (IN16) load_vec16(src16 + static_cast<size_t>(pix) * sC, v, (F16 ? 1 : 0));
         else load_vec<VEC>(src + static_cast<size_t>(pix) * sC, v);
     };
 
@@ -241,8 +241,8 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             }
 #pragma unroll
             for (int i = 0; i < VEC; ++i) { acc[i] *= 0.25f; racc[i] *= 0.25f; }
-            store_16n<VEC>(oa + static_cast<size_t>(po) * C, acc, p.f16);
-            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(po) * C, acc, p.f16);
+            store_16n<VEC>(oa + static_cast<size_t>(po) * C, acc, (F16 ? 1 : 0));
+            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(po) * C, acc, (F16 ? 1 : 0));
             if (orr) store_f32<VEC>(orr + static_cast<size_t>(po) * C, racc);
         }
     } else if (p.resample == kResUp) {
@@ -258,8 +258,8 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 const size_t po = static_cast<size_t>(2 * h + (d >> 1)) * Wo + 2 * w + (d & 1);
-                store_16n<VEC>(oa + po * C, y, p.f16);
-                if (oa_lo) store_lo<VEC>(oa_lo + po * C, y, p.f16);
+                store_16n<VEC>(oa + po * C, y, (F16 ? 1 : 0));
+                if (oa_lo) store_lo<VEC>(oa_lo + po * C, y, (F16 ? 1 : 0));
                 if (orr) store_f32<VEC>(orr + po * C, x);
             }
         }
@@ -277,33 +277,33 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             load_px(pix + PPH, x1);
             load_px(pix + 2 * PPH, x2);
             load_px(pix + 3 * PPH, x3);
-            norm_act(x0, y); store_16n<VEC>(oa + static_cast<size_t>(pix) * C, y, p.f16);
-            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix) * C, y, p.f16);
-            norm_act(x1, y); store_16n<VEC>(oa + static_cast<size_t>(pix + PPH) * C, y, p.f16);
-            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + PPH) * C, y, p.f16);
-            norm_act(x2, y); store_16n<VEC>(oa + static_cast<size_t>(pix + 2 * PPH) * C, y, p.f16);
-            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + 2 * PPH) * C, y, p.f16);
-            norm_act(x3, y); store_16n<VEC>(oa + static_cast<size_t>(pix + 3 * PPH) * C, y, p.f16);
-            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + 3 * PPH) * C, y, p.f16);
+            norm_act(x0, y); store_16n<VEC>(oa + static_cast<size_t>(pix) * C, y, (F16 ? 1 : 0));
+            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix) * C, y, (F16 ? 1 : 0));
+            norm_act(x1, y); store_16n<VEC>(oa + static_cast<size_t>(pix + PPH) * C, y, (F16 ? 1 : 0));
+            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + PPH) * C, y, (F16 ? 1 : 0));
+            norm_act(x2, y); store_16n<VEC>(oa + static_cast<size_t>(pix + 2 * PPH) * C, y, (F16 ? 1 : 0));
+            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + 2 * PPH) * C, y, (F16 ? 1 : 0));
+            norm_act(x3, y); store_16n<VEC>(oa + static_cast<size_t>(pix + 3 * PPH) * C, y, (F16 ? 1 : 0));
+            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + 3 * PPH) * C, y, (F16 ? 1 : 0));
             if (ow) {
-                store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, p.f16);
-                if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix) * C, x0, p.f16);
-                store_16<VEC>(ow + static_cast<size_t>(pix + PPH) * C, x1, p.f16);
-                if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix + PPH) * C, x1, p.f16);
-                store_16<VEC>(ow + static_cast<size_t>(pix + 2 * PPH) * C, x2, p.f16);
-                if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix + 2 * PPH) * C, x2, p.f16);
-                store_16<VEC>(ow + static_cast<size_t>(pix + 3 * PPH) * C, x3, p.f16);
-                if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix + 3 * PPH) * C, x3, p.f16);
+                store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, (F16 ? 1 : 0));
+                if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix) * C, x0, (F16 ? 1 : 0));
+                store_16<VEC>(ow + static_cast<size_t>(pix + PPH) * C, x1, (F16 ? 1 : 0));
+                if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix + PPH) * C, x1, (F16 ? 1 : 0));
+                store_16<VEC>(ow + static_cast<size_t>(pix + 2 * PPH) * C, x2, (F16 ? 1 : 0));
+                if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix + 2 * PPH) * C, x2, (F16 ? 1 : 0));
+                store_16<VEC>(ow + static_cast<size_t>(pix + 3 * PPH) * C, x3, (F16 ? 1 : 0));
+                if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix + 3 * PPH) * C, x3, (F16 ? 1 : 0));
             }
         }
         for (; pix < pix_end; pix += PPH) {
             float x0[VEC], y0[VEC];
             load_px(pix, x0);
             norm_act(x0, y0);
-            store_16n<VEC>(oa + static_cast<size_t>(pix) * C, y0, p.f16);
-            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix) * C, y0, p.f16);
-            if (ow) store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, p.f16);
-            if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix) * C, x0, p.f16);
+            store_16n<VEC>(oa + static_cast<size_t>(pix) * C, y0, (F16 ? 1 : 0));
+            if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix) * C, y0, (F16 ? 1 : 0));
+            if (ow) store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, (F16 ? 1 : 0));
+            if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix) * C, x0, (F16 ? 1 : 0));
         }
     }
 }
@@ -334,15 +334,21 @@ cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream) {
     if (fused && p.resample == kResNone)
         while (split < 8 && (HW / (split * 2)) >= 2 * PPH * 8 && (HW % (split * 2)) == 0) split *= 2;
     dim3 grid(p.B, split);
+    // the 16-bit format is a template parameter: the kernel is issue-bound, and a run-time format flag costs a
+    // second conversion plus a select per packed pair
     if (fused) {
         if (p.meanrstd == nullptr) return cudaErrorInvalidValue;
         groupnorm_finalize_kernel<<<p.B, 256, 0, stream>>>(p);
-        if (p.in16) groupnorm_kernel<4, true, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
-        else groupnorm_kernel<4, true, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
+        if (p.in16 && p.f16) groupnorm_kernel<4, true, true, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
+        else if (p.in16) groupnorm_kernel<4, true, true, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
+        else if (p.f16) groupnorm_kernel<4, true, false, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
+        else groupnorm_kernel<4, true, false, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
     } else if (vec == 4) {
-        groupnorm_kernel<4, false, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
+        if (p.f16) groupnorm_kernel<4, false, false, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
+        else groupnorm_kernel<4, false, false, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
     } else {
-        groupnorm_kernel<2, false, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
+        if (p.f16) groupnorm_kernel<2, false, false, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
+        else groupnorm_kernel<2, false, false, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
     }
     return cudaGetLastError();
 }
