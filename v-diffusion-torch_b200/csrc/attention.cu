@@ -78,7 +78,20 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                                       mbar_init(&sm.v_empty[s], 1); mbar_init(&sm.p_full[s], 8); }   // one arrival per softmax warp
         mbar_init(&sm.s_full[0], 1); mbar_init(&sm.s_full[1], 1);
         fence_mbar_init();
-        tma_prefetch_desc(&p.qk_map); tma_prefetch_desc(&p.k_map); tma_prefetch_desc(&p.vt_map);
+        // Q and the first two K / V^T tiles are requested right away, before the TMEM allocation and the CTA-wide
+        // sync, so their L2 latency overlaps the rest of the prologue (the ring slots are trivially free)
+        mbar_expect_tx(sm.q_full, static_cast<uint32_t>(dch * 16384));
+        for (int c = 0; c < dch; ++c)
+            tma_load_2d(sm.q + c * 16384, &p.qk_map, sm.q_full, h * d + c * 64, static_cast<int>(row0));
+        for (int j = 0; j < 2 && j < nt; ++j) {
+            mbar_expect_tx(&sm.k_full[j], static_cast<uint32_t>(dch * 8192));
+            for (int c = 0; c < dch; ++c)
+                tma_load_2d(sm.k(j) + c * 8192, &p.k_map, &sm.k_full[j], p.hid + h * d + c * 64, static_cast<int>(krow0) + j * kKeys);
+            const int img = b0 + (j * kKeys) / N;
+            const int koff = (N >= kQRows) ? j * kKeys : (j * kKeys) % N;
+            mbar_expect_tx(&sm.v_full[j], static_cast<uint32_t>(d * 128));
+            tma_load_2d(sm.v(j), &p.vt_map, &sm.v_full[j], koff, (img * p.heads + h) * d);
+        }
     }
     if (warp == 1) tmem_alloc(sm.tmem_slot, tmem_cols);
     tc_fence_before();
@@ -90,10 +103,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(sm.q_full, static_cast<uint32_t>(dch * 16384));
-            for (int c = 0; c < dch; ++c)
-                tma_load_2d(sm.q + c * 16384, &p.qk_map, sm.q_full, h * d + c * 64, static_cast<int>(row0));
-            for (int j = 0; j < nt; ++j) {
+            for (int j = 2; j < nt; ++j) {
                 const int s = j & 1;
                 mbar_wait(&sm.k_empty[s], ((j >> 1) & 1) ^ 1);
                 mbar_expect_tx(&sm.k_full[s], static_cast<uint32_t>(dch * 8192));
@@ -104,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
         }
     } else if (warp == 10) {
         if (lane == 0) {
-            for (int j = 0; j < nt; ++j) {
+            for (int j = 2; j < nt; ++j) {
                 const int s = j & 1;
                 mbar_wait(&sm.v_empty[s], ((j >> 1) & 1) ^ 1);
                 const int img = b0 + (j * kKeys) / N;
