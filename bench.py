@@ -25,6 +25,18 @@ sys.path.insert(0, ROOT)
 T_STEPS = 100
 W_GUIDE = 1.0
 METRIC = "ddim_images_per_sec_cifar10_cfg_100step"
+# extra workloads (parity-test configs of BASELINE.json, measurable with --workload; the headline stays cifar10_cond)
+CELEBA_MODEL = dict(in_channels=3, hid_channels=192, ch_multipliers=[1, 2, 3, 4], num_res_blocks=3,
+                    apply_attn=[False, True, True, True], embedding_dim=768, drop_rate=0.1, head_dim=64, num_heads=1)
+WORKLOADS = {
+    # name: (model kwargs, out_channels, num_classes, resolution, model_out_type, var_type, cfg, default batch, text)
+    "cifar10_cond": None,
+    "celeba": (CELEBA_MODEL, 6, 0, 64, "both", "fixed_large", False, 1024,
+               "CelebA 64x64 UNet (celeba.json), unconditional, 100-step DDIM"),
+    "cifar10_uncond": (dict(in_channels=3, hid_channels=256, ch_multipliers=[1, 1, 1], num_res_blocks=3,
+                            apply_attn=[False, True, True], drop_rate=0.2, num_heads=1), 3, 0, 32, "x0", "fixed_large",
+                       False, 4096, "CIFAR-10 unconditional UNet (cifar10_uncond.json), 100-step DDIM"),
+}
 # cifar10_cond.json merged with defaults.json (tests/golden/merged_configs.json pins this in the CPU tests)
 CIFAR_COND_MODEL = dict(in_channels=3, hid_channels=256, ch_multipliers=[1, 1, 1], num_res_blocks=3,
                         apply_attn=[False, True, True], drop_rate=0.2, num_heads=1)
@@ -82,11 +94,17 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 7)}
 
 
-def build_model(device, seed):
+def build_model(device, seed, workload="cifar10_cond"):
     import torch
     from v_diffusion_b200 import UNet, GaussianDiffusion, get_logsnr_schedule
     torch.manual_seed(seed)
-    net = UNet(out_channels=3, num_classes=10, multitags=False, **CIFAR_COND_MODEL)
+    wl = WORKLOADS[workload]
+    if wl is None:
+        net = UNet(out_channels=3, num_classes=10, multitags=False, **CIFAR_COND_MODEL)
+        out_type, var_type = "v", "fixed_medium"
+    else:
+        net = UNet(out_channels=wl[1], num_classes=wl[2], multitags=False, **wl[0])
+        out_type, var_type = wl[4], wl[5]
     g = torch.Generator().manual_seed(seed + 7)
     with torch.no_grad():
         for name, p in net.named_parameters():
@@ -98,7 +116,7 @@ def build_model(device, seed):
             elif p.ndim == 1:
                 p.add_(0.05 * torch.randn(p.shape, generator=g))
     net = net.to(device).eval()
-    diff = GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), T_STEPS, "v", "fixed_medium", "snr_trunc",
+    diff = GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), T_STEPS, out_type, var_type, "snr_trunc",
                              "mse", intp_frac=0.3, w_guide=W_GUIDE)
     return net, diff
 
@@ -185,14 +203,17 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     L = _lib.lib()
-    B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    net, diff = build_model(device, seed=0)
+    wl = WORKLOADS[args.workload]
+    res = 32 if wl is None else wl[3]
+    use_cfg = wl is None
+    B, K, W = (args.batch if args.batch > 0 else (4096 if wl is None else wl[7])), args.steps, max(args.warmup, 3)
+    net, diff = build_model(device, seed=0, workload=args.workload)
     net.max_rows = args.max_rows
-    plan = net.plan_for(32, device)
+    plan = net.plan_for(res, device)
     sc = diff.sampler_config(use_ddim=True)
     g = torch.Generator(device=device).manual_seed(1234 + rank)      # SURVEY §8d cfg 2: per-rank seeds 1234+rank
-    noise = torch.randn(B, 3, 32, 32, device=device, generator=g)
-    label = torch.randint(10, (B,), device=device, generator=g) + 1
+    noise = torch.randn(B, 3, res, res, device=device, generator=g)
+    label = (torch.randint(10, (B,), device=device, generator=g) + 1) if use_cfg else None
     stream = torch.cuda.current_stream()
 
     def run_range(x, first, n):
@@ -240,7 +261,8 @@ def run_b200(args, rank, world, local_rank):
     L.vdt_profile_enable(0)
     fc, fa, fl = C.c_double(), C.c_double(), C.c_double()
     L.vdt_plan_flops(plan, C.byref(fc), C.byref(fa), C.byref(fl))
-    rows = 2 * B
+    rows = (2 if use_cfg else 1) * B
+    flop_per_row = fc.value + fa.value + fl.value
     conv_tflops = fc.value * rows / (fam_ms[0] * 1e-3) / 1e12 if fam_ms[0] > 0 else 0.0
     peaks = read_peaks()
     prof_total = sum(fam_ms)
@@ -249,7 +271,7 @@ def run_b200(args, rank, world, local_rank):
     try:
         with open(os.path.join(ROOT, "profiles", "r1_conv_dram_traffic.json")) as f:
             tr = json.load(f)
-        traffic = tr["avg_dram_bytes_per_conv_launch_scaled_to_rows"] * min(rows, args.max_rows) / tr["rows"]
+        traffic = tr["avg_dram_bytes_per_conv_launch_scaled_to_rows"] * min(rows, args.max_rows) / tr["rows"] if wl is None else None
     except Exception:
         traffic = None
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all conv/1x1 launches of a step)",
@@ -262,16 +284,16 @@ def run_b200(args, rank, world, local_rank):
                 "step_share": {"conv": fam_ms[0] / prof_total, "groupnorm": fam_ms[1] / prof_total,
                                "attention": fam_ms[2] / prof_total, "other": fam_ms[3] / prof_total},
                 "family_ms_per_step": {"conv": fam_ms[0], "groupnorm": fam_ms[1], "attention": fam_ms[2], "other": fam_ms[3]},
-                "unet_tflops_whole_step": FLOP_PER_ROW * rows / (ms_step * 1e-3) / 1e12,
-                "unet_frac_of_peak_whole_step": FLOP_PER_ROW * rows / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
-                "unet_frac_of_nominal_2250": FLOP_PER_ROW * rows / (ms_step * 1e-3) / 1e12 / 2250.0}
+                "unet_tflops_whole_step": flop_per_row * rows / (ms_step * 1e-3) / 1e12,
+                "unet_frac_of_peak_whole_step": flop_per_row * rows / (ms_step * 1e-3) / 1e12 / peaks["tflops"],
+                "unet_frac_of_nominal_2250": flop_per_row * rows / (ms_step * 1e-3) / 1e12 / 2250.0}
 
     # ---- end to end through the public API: host noise/labels in (pinned), CPU images out, all 100 steps
     noise_h = noise.cpu().pin_memory()
-    label_h = label.cpu().pin_memory()
+    label_h = label.cpu().pin_memory() if label is not None else None
     barrier()
     t0 = time.perf_counter()
-    imgs = diff.p_sample(net, (B, 3, 32, 32), noise=noise_h, label=label_h, device=device, use_ddim=True)
+    imgs = diff.p_sample(net, (B, 3, res, res), noise=noise_h, label=label_h, device=device, use_ddim=True)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
     if world > 1:
@@ -280,23 +302,25 @@ def run_b200(args, rank, world, local_rank):
         dist.all_gather(gathered, imgs.to(device))
     assert torch.isfinite(imgs).all()
     e2e = {"value": world * B / e2e_s.item(), "unit": "images/s",
-           "h2d_bytes_per_step": (noise_h.numel() * 4 + label_h.numel() * 8) / T_STEPS,
+           "h2d_bytes_per_step": (noise_h.numel() * 4 + (label_h.numel() * 8 if label_h is not None else 0)) / T_STEPS,
            "d2h_bytes_per_step": imgs.numel() * 4 / T_STEPS,
            "note": "one GaussianDiffusion.p_sample call = 100 denoising steps; bytes are per call / 100",
            "seconds_per_call": e2e_s.item()}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+        metric = METRIC if wl is None else f"ddim_images_per_sec_{args.workload}_100step"
+        wtext = ("CIFAR-10 class-conditional UNet (cifar10_cond.json), CFG w=1 batched cond/uncond (2B rows), 100-step DDIM"
+                 if wl is None else wl[8])
+        line = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": net.operand_dtype, "data": "synthetic",
-                "config": {"workload": "CIFAR-10 class-conditional UNet (cifar10_cond.json), CFG w=1 batched cond/uncond "
-                                       f"(2B rows), 100-step DDIM, batch {B} per GPU; step = one denoising step over the batch",
-                           "batch_per_gpu": B, "rows_per_unet_call": 2 * B, "chunk_rows": args.max_rows,
+                "config": {"workload": f"{wtext}, batch {B} per GPU; step = one denoising step over the batch",
+                           "batch_per_gpu": B, "rows_per_unet_call": rows, "chunk_rows": args.max_rows,
                            "steps_per_image": T_STEPS, "l2": "inputs_exceed_l2", "parallelism": f"replicas x{world}",
                            "operands": net.operand_dtype + " tensor-core operands (same tcgen05 kind::f16 rate as bf16)",
                            "accumulate": "fp32", "residual_stream": "fp32"},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and wl is None:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -310,7 +334,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="images per GPU (BASELINE configs[1]: 4096)")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: 4096 for cifar10_cond, BASELINE configs[1])")
+    ap.add_argument("--workload", default="cifar10_cond", choices=sorted(WORKLOADS))
     ap.add_argument("--max-rows", type=int, default=int(os.environ.get("VDT_MAX_ROWS", "1024")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
