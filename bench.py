@@ -217,7 +217,7 @@ def run_b200(args, rank, world, local_rank):
     stream = torch.cuda.current_stream()
 
     def run_range(x, first, n):
-        _lib.check(L.vdt_p_sample_range(plan, C.byref(sc), _lib.ptr(x), _lib.ptr(label), None, B, first, n,
+        _lib.check(L.vdt_p_sample_range(plan, C.byref(sc), _lib.ptr(x), _lib.ptr(label), None, B, first, n, None,
                                         C.c_void_p(stream.cuda_stream)))
 
     def barrier():

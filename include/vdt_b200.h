@@ -98,7 +98,10 @@ int vdt_p_sample(vdt_plan* plan, const vdt_sampler_config* sc, const float* nois
  * applied num_steps times.  vdt_p_sample == copy noise, range(T-1, T), copy out.  Used by bench.py to time
  * K denoising steps of the real loop. */
 int vdt_p_sample_range(vdt_plan* plan, const vdt_sampler_config* sc, float* x, const int64_t* label,
-                       const float* step_noise, int32_t batch, int32_t first_step, int32_t num_steps, void* stream);
+                       const float* step_noise, int32_t batch, int32_t first_step, int32_t num_steps,
+                       float* pred_x0 /* optional [B, C, R, R]: guided x0 prediction of the last step run
+                                         (p_sample_step(return_pred=True); used by p_sample_progressive, 416-441) */,
+                       void* stream);
 /* Same with HOST buffers (pinned or pageable); copies in/out inside the call and synchronises. */
 int vdt_p_sample_host(vdt_plan* plan, const vdt_sampler_config* sc, const float* noise, const int64_t* label,
                       const float* step_noise, float* out, int32_t batch);

@@ -134,7 +134,7 @@ def p_sample(denoise_fn: Callable, shape, noise: torch.Tensor, label: Optional[t
              T: int, model_out_type: str, w_guide: float = 0., use_ddim: bool = True,
              var_type: str = "fixed_large", intp_frac=None, step_noise: Optional[torch.Tensor] = None,
              schedule: str = "cosine", logsnr_min: float = -20., logsnr_max: float = 20.,
-             record: Optional[list] = None) -> torch.Tensor:
+             record: Optional[list] = None, pred_record: Optional[list] = None) -> torch.Tensor:
     """Reverse loop (diffusion.py:394-414 + 360-392).  ``noise``: initial x_T.
     ``step_noise``: (T, B, C, H, W) pre-drawn per-step normal draws, indexed by the step
     index ti (required for ancestral sampling so both sides inject identical noise);
@@ -161,9 +161,13 @@ def p_sample(denoise_fn: Callable, shape, noise: torch.Tensor, label: Optional[t
         mean = torch.tensor(c1) * xin + torch.tensor(c2) * x0
         if ti == 0:                                   # where(cond, mean, pred_x_0)  diffusion.py:378
             mean = x0
+        pred = x0
         if use_cfg:
             mc, mu = mean[0::2], mean[1::2]
             mean = mc + w_guide * (mc - mu)           # not re-clipped
+            pred = x0[0::2] + w_guide * (x0[0::2] - x0[1::2])       # diffusion.py:385
+        if pred_record is not None:
+            pred_record.append((ti, pred.clone()))
         if ti > 0 and not use_ddim:
             assert step_noise is not None, "ancestral sampling needs injected step noise"
             mean = mean + torch.tensor(co["std"][ti]) * step_noise[ti]

@@ -232,3 +232,25 @@ def test_validation_mode_sampler(golden_dir, name):
     err = (out - ref).abs().max().item()
     print(f"{name} [fp16x3]: max-abs {err:.3e}")
     assert err <= VALIDATION_MAX_ABS
+
+
+def test_p_sample_progressive_vs_oracle():
+    """diffusion.py:416-441: x0 previews every pred_freq steps (guided prediction of p_sample_step)."""
+    from oracle import unet_forward, make_state_dict, p_sample
+    case = SAMPLE_CASES["ddim_cfg_v"]
+    ucase = UNET_CASES[case["unet"]]
+    cfg = ucase["cfg"]
+    sd = make_state_dict(cfg, ucase["seed"])
+    net = _model(cfg, ucase["seed"])
+    diff = _diffusion(case)                                    # T = 8
+    noise, label, _ = build_sample_inputs(case, cfg)
+    x, preds = diff.p_sample_progressive(net, tuple(noise.shape), noise=noise, label=label, device="cuda", use_ddim=True,
+                                         pred_freq=3)
+    rec = []
+    ref = p_sample(lambda a, b, c: unet_forward(sd, cfg, a, b, c), tuple(noise.shape), noise, label, T=case["T"],
+                   model_out_type="v", w_guide=case["w_guide"], use_ddim=True, pred_record=rec)
+    assert (x - ref).abs().max().item() <= SAMPLE_MAX_ABS
+    want = {ti: p for ti, p in rec if (ti + 1) % 3 == 0}       # ti = 5, 2 -> preds[1], preds[0]
+    assert preds.shape[0] == 8 // 3 == 2
+    assert (preds[1] - want[5]).abs().max().item() <= 3 * SAMPLE_MAX_ABS      # guided x0 is amplified by (1 + 2w)
+    assert (preds[0] - want[2]).abs().max().item() <= 3 * SAMPLE_MAX_ABS

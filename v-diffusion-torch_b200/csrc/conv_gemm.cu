@@ -54,28 +54,20 @@ __device__ __forceinline__ TileCoord tile_origin(const ConvParams& p, int m_tile
 }
 
 // Row-major epilogue of one 32-row x 32-column chunk after the smem transposition: lane = (row % 4 group rsub,
-// 4 columns cq).  Compile-time variants keep the instruction count low (the epilogue warps are issue-bound
-// otherwise); CHECK adds the per-row bounds tests needed only for ragged tiles.
-template <bool F16, bool F32OUT, bool RESID, bool STATS, bool ROWBIAS, bool SILU, bool CHECK>
-__device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const float4* tile, int lane, int q, int m_tile,
-                                                  long long wrow0, int col0) {
+// 4 columns cq), all 32 rows valid.  Compile-time variants keep the instruction count low (the epilogue warps
+// are issue-bound otherwise); ragged tiles and SiLU epilogues take epilogue_rowmajor_generic.
+template <bool F16, bool F32OUT, bool RESID, bool STATS>
+__device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const float4* tile, int lane, long long wrow0, int col0) {
     const int cq = lane & 7, rsub = lane >> 3;
     const size_t off0 = static_cast<size_t>(wrow0 + rsub) * p.ld + col0 + cq * 4;
     const size_t step = static_cast<size_t>(4) * p.ld;
-    const bool tile_ok = m_tile < p.num_m_tiles;
-    auto valid = [&](int i) {
-        if (!CHECK) return true;
-        const int rr = i * 4 + rsub;
-        return tile_ok && (q * 32 + rr < p.rows_per_tile) && (wrow0 + rr < p.M);
-    };
-    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!ROWBIAS) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq * 4));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq * 4));
     float4 res[8];
     if (RESID) {                                             // all eight loads in flight before anything is stored
         const float* rp = p.residual + off0;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            res[i] = valid(i) ? ldg_nc_v4_issue(rp + i * step) : make_float4(0.f, 0.f, 0.f, 0.f);
+            res[i] = ldg_nc_v4_issue(rp + i * step);
         compiler_fence();
     }
     float ssum = 0.f, ssq = 0.f;
@@ -83,15 +75,9 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
     for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + rsub;
         float4 o = tile[rr * 8 + (cq ^ (rr & 7))];
-        if (ROWBIAS) {
-            const float br = valid(i) ? __ldg(p.bias + wrow0 + rr) : 0.f;
-            o.x += br; o.y += br; o.z += br; o.w += br;
-        } else {
-            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-        }
+        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
         if (RESID) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
-        if (SILU) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
-        if (valid(i)) {
+        {
             if (F32OUT)
                 *reinterpret_cast<float4*>(p.out_f32 + off0 + i * step) = o;
             else
@@ -105,7 +91,7 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
     if (STATS) {                                             // fixed-order reduction over the warp's 32 rows
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 8); ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 16); ssq += __shfl_xor_sync(0xffffffffu, ssq, 16);
-        if (rsub == 0 && tile_ok && wrow0 < p.M)
+        if (rsub == 0)
             p.stats[static_cast<size_t>(wrow0 / kStatRows) * (p.Cout / kStatCols) + (col0 >> 2) + cq] = make_float2(ssum, ssq);
     }
 }
@@ -115,7 +101,7 @@ __device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, cons
                                                        long long wrow0, int col0) {
     const int cq = lane & 7, rsub = lane >> 3;
     const bool tile_ok = m_tile < p.num_m_tiles;
-    const float4 b4 = p.bias_per_row ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq * 4));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq * 4));
     float ssum = 0.f, ssq = 0.f;
     for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + rsub;
@@ -124,8 +110,7 @@ __device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, cons
         if (!ok) continue;
         float4 o = tile[rr * 8 + (cq ^ (rr & 7))];
         const size_t off = static_cast<size_t>(g) * p.ld + col0 + cq * 4;
-        const float br = p.bias_per_row ? __ldg(p.bias + g) : 0.f;
-        o.x += b4.x + br; o.y += b4.y + br; o.z += b4.z + br; o.w += b4.w + br;
+        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
         if (p.residual) {
             const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + off));
             o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
@@ -284,14 +269,13 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                     if (!all_valid || p.act_silu) {          // ragged tile / rare variants: run-time checked generic path
                         epilogue_rowmajor_generic(p, tile, lane, q, m_tile, wrow0, col0);
                     } else if (f32o) {
-                        if (resid && st) epilogue_rowmajor<F16, true, true, true, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
-                        else if (resid) epilogue_rowmajor<F16, true, true, false, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
-                        else if (st) epilogue_rowmajor<F16, true, false, true, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
-                        else epilogue_rowmajor<F16, true, false, false, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        if (resid && st) epilogue_rowmajor<F16, true, true, true>(p, tile, lane, wrow0, col0);
+                        else if (resid) epilogue_rowmajor<F16, true, true, false>(p, tile, lane, wrow0, col0);
+                        else if (st) epilogue_rowmajor<F16, true, false, true>(p, tile, lane, wrow0, col0);
+                        else epilogue_rowmajor<F16, true, false, false>(p, tile, lane, wrow0, col0);
                     } else {
-                        if (p.bias_per_row) epilogue_rowmajor<F16, false, false, false, true, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
-                        else if (st) epilogue_rowmajor<F16, false, false, true, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
-                        else epilogue_rowmajor<F16, false, false, false, false, false, false>(p, tile, lane, q, m_tile, wrow0, col0);
+                        if (st) epilogue_rowmajor<F16, false, false, true>(p, tile, lane, wrow0, col0);
+                        else epilogue_rowmajor<F16, false, false, false>(p, tile, lane, wrow0, col0);
                     }
                     __syncwarp();
                 } else if (p.out_mode == kOutBF16) {         // V third of proj_in: transposed per image (coalesced per column)

@@ -43,7 +43,6 @@ struct alignas(64) ConvParams {
     int ld;                            // row stride (elements) of out_f32 / out_bf16 / residual
     int split_col, HW;
     int act_silu;
-    int bias_per_row;                  // bias indexed by output row instead of column (swapped-operand GEMMs)
     int f16;                           // operand / 16-bit output format: 1 fp16, 0 bf16
     const float* bias;                 // [Cout]
     const float* residual;             // fp32 [M, ld] or null
@@ -148,6 +147,8 @@ struct SamplerStepParams {
     const float* model_out;            // fp32 NCHW [B*(1+cfg), Cm, HW]; cond rows even, uncond rows odd
     const float* x_t;                  // fp32 NCHW [B, C, HW]
     float* x_s;                        // fp32 NCHW [B, C, HW]  (may alias x_t)
+    float* pred_x0;                    // optional fp32 NCHW [B, C, HW]: the (guided) x0 prediction of this step
+                                       // (p_sample_step(return_pred=True), diffusion.py:385, 392)
     const float* noise;                // injected per-step noise [T, Btotal, C, HW] or null
     long long noise_step_stride;       // elements between steps (Btotal*C*HW)
     const SamplerState* st;

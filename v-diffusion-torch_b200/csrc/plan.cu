@@ -224,6 +224,7 @@ struct Exec {
     int64_t* y_rows = nullptr;   // [emb_rows]
     int* film_row = nullptr;     // [rows] (sampler)
     SamplerState* state = nullptr;
+    float* pred = nullptr;       // sampler: (guided) x0 prediction of the last executed step [rows/rep, C, HW]
     float* coef_table = nullptr; // [T][12] (sampler)
     // sampler signature this exec was built for
     vdt_sampler_config sc{};
@@ -622,7 +623,7 @@ struct ConvSpec {
     const h16* wpacked = nullptr; int cout = 0; int wrows = 0;   // weight rows actually allocated
     const float* bias = nullptr; const float* residual = nullptr;
     int out_mode = kOutF32; float* out_f32 = nullptr; h16* out_bf16 = nullptr; h16* out_t = nullptr;
-    int ld = 0, split_col = 0, act_silu = 0, f16 = 1, bias_per_row = 0;
+    int ld = 0, split_col = 0, act_silu = 0, f16 = 1;
     float2* stats = nullptr;
 };
 
@@ -662,7 +663,7 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     cp->num_n_tiles = (s.cout + cp->block_n - 1) / cp->block_n;
     CKI(make_map_2d(&cp->b_map, s.wpacked, s.wrows, ktot, ktot, cp->block_n / 2));   // each CTA of a pair fetches half
     cp->M = (int)M; cp->Cout = s.cout; cp->out_mode = s.out_mode; cp->ld = s.ld;
-    cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16; cp->bias_per_row = s.bias_per_row;
+    cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16;
     cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t; cp->stats = s.stats;
     if (s.out_mode != kOutNCHW && s.cout % 32 != 0) return fail("output channels must be a multiple of 32 (got %d)", s.cout);
     return 0;
@@ -1145,6 +1146,7 @@ static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs,
     CKI(ex->acquire(ex->emb_rows * sizeof(int64_t), (void**)&ex->y_rows));
     CKI(ex->acquire(ex->rows * sizeof(int), (void**)&ex->film_row));
     CKI(ex->acquire(sizeof(SamplerState), (void**)&ex->state));
+    CKI(ex->acquire(imgs * HW * c.in_channels * 4, (void**)&ex->pred));
     CKI(ex->acquire((size_t)T * kCoefStride * 4, (void**)&ex->coef_table));
     iota_i64_kernel<<<(ex->emb_rows + 127) / 128, 128>>>(ex->y_rows, ex->emb_rows);
     CK(cudaGetLastError());
@@ -1158,7 +1160,7 @@ static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs,
     CKI(add_embedding_steps(p, ex.get(), film, cond_model));
     CKI(build_unet_steps(p, ex.get(), film, ex->film_row));
     SamplerStepParams sp{};
-    sp.model_out = ex->yout; sp.x_t = ex->xin; sp.x_s = ex->xin; sp.noise = step_noise; sp.noise_step_stride = noise_stride;
+    sp.model_out = ex->yout; sp.x_t = ex->xin; sp.x_s = ex->xin; sp.pred_x0 = ex->pred; sp.noise = step_noise; sp.noise_step_stride = noise_stride;
     sp.st = ex->state; sp.seed = sc.seed; sp.B = imgs; sp.C = c.in_channels; sp.HW = (int)HW; sp.cfg = cfg ? 1 : 0;
     sp.model_out_type = sc.model_out_type; sp.w = (float)sc.w_guide;
     ex->samples.push_back(sp);
@@ -1169,7 +1171,8 @@ static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs,
 }
 
 extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, float* x, const int64_t* label,
-                                  const float* step_noise, int32_t batch, int32_t first_step, int32_t num_steps, void* stream) {
+                                  const float* step_noise, int32_t batch, int32_t first_step, int32_t num_steps,
+                                  float* pred_x0, void* stream) {
     if (!p || !scp || !x) return fail("null argument");
     if (!p->finalized) return fail("plan not finalized (load every state_dict key, then vdt_plan_finalize)");
     const vdt_sampler_config& sc = *scp;
@@ -1198,6 +1201,8 @@ extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, fl
         g_launches += 2;
         for (int step = 0; step < num_steps; ++step) CKI(run_exec(p, ex, st));
         CK(cudaMemcpyAsync(x + (size_t)i0 * CHW, ex->xin, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
+        if (pred_x0 && num_steps > 0)
+            CK(cudaMemcpyAsync(pred_x0 + (size_t)i0 * CHW, ex->pred, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
     }
     return leave_work(p, user);
 }
@@ -1208,7 +1213,7 @@ extern "C" int vdt_p_sample(vdt_plan* p, const vdt_sampler_config* scp, const fl
     const size_t CHW = (size_t)p->cfg.in_channels * p->cfg.resolution * p->cfg.resolution;
     cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
     if (out != noise) CK(cudaMemcpyAsync(out, noise, (size_t)batch * CHW * 4, cudaMemcpyDeviceToDevice, user));
-    return vdt_p_sample_range(p, scp, out, label, step_noise, batch, scp->sample_timesteps - 1, scp->sample_timesteps, stream);
+    return vdt_p_sample_range(p, scp, out, label, step_noise, batch, scp->sample_timesteps - 1, scp->sample_timesteps, nullptr, stream);
 }
 
 extern "C" int vdt_p_sample_host(vdt_plan* p, const vdt_sampler_config* scp, const float* noise, const int64_t* label,
@@ -1332,7 +1337,7 @@ extern "C" int vdt_op_sampler_step(const float* model_out, const float* x_t, con
     CK(cudaMemcpy(ds, &hs, sizeof(hs), cudaMemcpyHostToDevice));
     SamplerStepParams sp{};
     sp.model_out = model_out; sp.x_t = x_t; sp.x_s = x_s; sp.noise = noise;
-    sp.noise_step_stride = 0; sp.st = ds; sp.seed = 0; sp.B = batch; sp.C = c; sp.HW = hw; sp.cfg = cfg;
+    sp.noise_step_stride = 0; sp.st = ds; sp.seed = 0; sp.pred_x0 = nullptr; sp.B = batch; sp.C = c; sp.HW = hw; sp.cfg = cfg;
     sp.model_out_type = model_out_type; sp.w = w;
     cudaError_t e = launch_sampler_step(sp, st);
     ++g_launches;

@@ -223,6 +223,7 @@ __global__ void sampler_step_kernel(const SamplerStepParams p) {
     const bool last = (step == 0);
     const float x0c = pred_x0(p.model_out_type, x, o, o2, cf);
     float mean = last ? x0c : c1 * x + c2 * x0c;                     // where(cond, mean, pred_x_0)  (diffusion.py:378)
+    float pred = x0c;
     if (p.cfg) {
         const float* mu = mo + static_cast<size_t>(Cm) * p.HW;
         const float u = mu[0];
@@ -230,7 +231,9 @@ __global__ void sampler_step_kernel(const SamplerStepParams p) {
         const float x0u = pred_x0(p.model_out_type, x, u, u2, cf);
         const float mean_u = last ? x0u : c1 * x + c2 * x0u;
         mean = mean + p.w * (mean - mean_u);                         // guided, not re-clipped (diffusion.py:384)
+        pred = x0c + p.w * (x0c - x0u);                              // diffusion.py:385
     }
+    if (p.pred_x0) p.pred_x0[i] = pred;
     if (!last && sd > 0.f) {
         float z;
         if (p.noise) z = p.noise[static_cast<long long>(step) * p.noise_step_stride + static_cast<long long>(p.st->img0) * chw + i];

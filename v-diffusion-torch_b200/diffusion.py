@@ -121,6 +121,51 @@ class GaussianDiffusion:
                                           _lib.ptr(out), B, _lib.current_stream_ptr()))
             return out.cpu()
         # generic callable: same fused update kernel, one step at a time
+        return self._p_sample_generic(denoise_fn, shape, x_t, label, step_noise, sc, device, seed, use_ddim).cpu()
+
+    @torch.no_grad()
+    def p_sample_progressive(self, denoise_fn, shape, noise=None, label=None, device="cpu", seed=None, use_ddim=False,
+                             pred_freq=50, step_noise=None):
+        """diffusion.py:416-441: returns (x_0, preds) where preds[k] is the (guided) x0 prediction made at the
+        steps ti with (ti + 1) % pred_freq == 0, ordered like the reference (index L-1 = earliest).  Fused path only."""
+        if not isinstance(denoise_fn, UNet):
+            raise TypeError("p_sample_progressive needs the v_diffusion_b200 UNet")
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("v_diffusion_b200 samples on CUDA (sm_100a) only; there is no CPU fallback")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        B, T = shape[0], self.sample_timesteps
+        gen = None if seed is None else torch.Generator(device).manual_seed(seed)
+        x = (torch.randn(shape, device=device, generator=gen) if noise is None else noise.to(device)).to(torch.float32).contiguous().clone()
+        if label is not None:
+            label = label.to(device=device, dtype=torch.int64).contiguous()
+        if step_noise is not None:
+            step_noise = step_noise.to(device=device, dtype=torch.float32).contiguous()
+        sc = self.sampler_config(use_ddim, seed)
+        plan = denoise_fn.plan_for(shape[2], device)
+        Lp = T // pred_freq
+        preds = torch.zeros((Lp, B) + tuple(shape[1:]), dtype=torch.float32)
+        pred = torch.empty_like(x)
+        lib, idx, first = _lib.lib(), Lp, T - 1
+        with torch.cuda.device(device):
+            while first >= 0:
+                # run down to (and including) the next step whose prediction is recorded: (ti + 1) % pred_freq == 0
+                stop = ((first + 1) // pred_freq) * pred_freq - 1
+                record = stop >= 0
+                if not record:
+                    stop = 0
+                _lib.check(lib.vdt_p_sample_range(plan, C.byref(sc), _lib.ptr(x), _lib.ptr(label), _lib.ptr(step_noise), B,
+                                                  first, first - stop + 1, _lib.ptr(pred), _lib.current_stream_ptr()))
+                if record and idx > 0:
+                    idx -= 1
+                    preds[idx] = pred.cpu()
+                first = stop - 1
+        return x.cpu(), preds
+
+    def _p_sample_generic(self, denoise_fn, shape, x_t, label, step_noise, sc, device, seed, use_ddim):
+        L = _lib.lib()
+        B = shape[0]
         coefs = self.step_coefficients(use_ddim)
         use_cfg = (self.w_guide > 0) and (label is not None)        # diffusion.py:368
         T = self.sample_timesteps
@@ -147,4 +192,4 @@ class GaussianDiffusion:
                                                  _lib.ptr(coefs[ti].contiguous()), float(self.w_guide),
                                                  _lib.current_stream_ptr()))
                 x_t = x_s
-        return x_t.cpu()
+        return x_t
