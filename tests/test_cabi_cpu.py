@@ -94,3 +94,34 @@ def test_all_schedules_match_reference(golden_dir):
         fn = get_logsnr_schedule(sched, -20., 20.)
         tt = torch.arange(50, dtype=torch.float64) / 50
         np.testing.assert_allclose(fn(tt).to(torch.float32).numpy(), g[f"{sched}_logsnr_s"], rtol=2e-6, atol=1e-6)
+
+
+def test_reference_checkpoint_interop(tmp_path, golden_dir):
+    """A checkpoint written in the reference's format (train_utils.py:328-348: model / ema.shadow, optionally with
+    DDP's "module." prefix) loads into the drop-in UNet built from the reference's merged config."""
+    import json
+    from oracle.unet_ref import make_state_dict
+    from tests.cases import CIFAR_COND
+    from v_diffusion_b200 import build_from_config
+    from v_diffusion_b200.generate import load_reference_checkpoint
+    sd = make_state_dict(CIFAR_COND, 3)
+    ema = {k: v * 0.5 for k, v in sd.items()}
+    path = tmp_path / "ckpt_last.pt"
+    torch.save({"model": {"module." + k: v for k, v in sd.items()}, "ema": {"decay": 0.9999, "shadow": ema, "num_updates": 7},
+                "optimizer": {}, "scheduler": {}, "epoch": 3}, path)
+    with open(os.path.join(golden_dir, "merged_configs.json")) as f:
+        merged = json.load(f)["cifar10_cond"]
+    config = {"data": {"name": "cifar10"}, "model": merged["model"], "diffusion": merged["diffusion"]}
+    for use_ema, want in ((False, sd), (True, ema)):
+        state_dict, use_cfg = load_reference_checkpoint(str(path), use_ema)
+        assert use_cfg                                                  # class_embed.* present (generate.py:44)
+        diffusion, model, chw = build_from_config(config, use_cfg, w_guide=1.0, sample_timesteps=100)
+        model.load_state_dict(state_dict)                               # strict: same 414 keys and shapes
+        assert chw == (3, 32, 32) and diffusion.model_out_type == "v" and model.num_classes == 10
+        got = model.state_dict()
+        assert all(torch.equal(got[k], want[k]) for k in want) and len(got) == len(want) == 414
+    import pytest
+    bad = dict(sd); bad.pop("in_conv.bias")
+    _, model, _ = build_from_config(config, True, 1.0, 100)
+    with pytest.raises(RuntimeError, match="in_conv.bias"):
+        model.load_state_dict(bad)

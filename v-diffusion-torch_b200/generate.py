@@ -57,6 +57,17 @@ def sample_sharded(sample_fn, total, batch_size, seed=1234, gather=True, device=
     return gather_shards(local, total) if gather else local
 
 
+def load_reference_checkpoint(path, use_ema=False):
+    """generate.py:33-44: a reference checkpoint is {"model": sd, "ema": {"shadow": sd-like, ...}, ...}; DDP
+    checkpoints carry a "module." prefix; a class-conditional model is recognised by its class_embed.* keys.
+    Returns (state_dict, use_cfg)."""
+    ckpt = torch.load(path, map_location="cpu")
+    state_dict = ckpt["ema"]["shadow"] if use_ema else ckpt["model"]
+    state_dict = {(k.split(".", 1)[1] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+    use_cfg = "class_embed" in {k.split(".")[0] for k in state_dict}
+    return state_dict, use_cfg
+
+
 def main():
     from . import GaussianDiffusion, UNet, load_config, build_from_config  # noqa: F401
     ap = argparse.ArgumentParser()
@@ -83,10 +94,7 @@ def main():
 
     state_dict, use_cfg = None, True
     if args.ckpt_path:
-        ckpt = torch.load(args.ckpt_path, map_location="cpu")
-        state_dict = ckpt["ema"]["shadow"] if args.use_ema else ckpt["model"]            # generate.py:35-38
-        state_dict = {(k.split(".", 1)[1] if k.startswith("module.") else k): v for k, v in state_dict.items()}
-        use_cfg = "class_embed" in {k.split(".")[0] for k in state_dict}                 # generate.py:44
+        state_dict, use_cfg = load_reference_checkpoint(args.ckpt_path, args.use_ema)
     config = load_config(args.config_path, args.default_config_path)
     if not args.ckpt_path:
         use_cfg = bool(config.get("conditional", {}).get("use_cfg", False))
