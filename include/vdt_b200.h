@@ -35,7 +35,7 @@ typedef struct vdt_unet_config {
     int32_t head_dim;
     int32_t num_heads;
     int32_t num_classes;
-    int32_t multitags;            /* not supported yet: must be 0 */
+    int32_t multitags;            /* 1: labels are fp32 multi-hot [B, num_classes] (CelebA attributes, unet.py:209-210, 290-294) */
     int32_t resolution;           /* H = W of the images this plan serves (DATA_INFO[...]["resolution"]) */
     int32_t max_rows;             /* UNet batch rows processed per pass; larger batches are chunked */
     int32_t operand_dtype;        /* 16-bit tensor-core operand format: 0 = fp16 (default), 1 = bf16; accumulation,
@@ -82,28 +82,28 @@ int vdt_plan_load_weight(vdt_plan* plan, const char* key, const float* data, int
 /* After all keys are loaded: pack bf16 GEMM operands.  Fails listing the first missing key. */
 int vdt_plan_finalize(vdt_plan* plan);
 
-/* UNet.forward(x, t, y) — unet.py:286-322.  x fp32 NCHW [B, in, R, R]; t fp64 [B]; y int64 [B] or NULL;
- * out fp32 NCHW [B, out, R, R]. */
-int vdt_unet_forward(vdt_plan* plan, const float* x, const double* t, const int64_t* y, float* out, int32_t batch,
+/* UNet.forward(x, t, y) — unet.py:286-322.  x fp32 NCHW [B, in, R, R]; t fp64 [B]; y NULL, int64 [B] class ids
+ * (0 = none), or fp32 multi-hot [B, num_classes] when the plan was created with multitags; out fp32 NCHW [B, out, R, R]. */
+int vdt_unet_forward(vdt_plan* plan, const float* x, const double* t, const void* y, float* out, int32_t batch,
                      void* stream);
 
 /* GaussianDiffusion.p_sample(denoise_fn=UNet, shape, noise, label, use_ddim) — diffusion.py:394-414,
  * with p_sample_step (360-392) and p_mean_var (317-356) fused into one kernel per step and the step
- * captured as a CUDA graph.  noise fp32 [B, C, R, R] (x_T); label int64 [B] or NULL; step_noise NULL or
+ * captured as a CUDA graph.  noise fp32 [B, C, R, R] (x_T); label NULL, int64 [B], or fp32 multi-hot [B, num_classes] (multitags); step_noise NULL or
  * fp32 [T, B, C, R, R] (the per-step normal draws of diffusion.py:389, indexed by step); out fp32 [B, C, R, R]. */
-int vdt_p_sample(vdt_plan* plan, const vdt_sampler_config* sc, const float* noise, const int64_t* label,
+int vdt_p_sample(vdt_plan* plan, const vdt_sampler_config* sc, const float* noise, const void* label,
                  const float* step_noise, float* out, int32_t batch, void* stream);
 /* A slice of the same loop, in place on x (fp32 [B, C, R, R]): runs `num_steps` consecutive steps starting
  * at step index `first_step` (T-1 is the first step of a trajectory) — p_sample_step (diffusion.py:360-392)
  * applied num_steps times.  vdt_p_sample == copy noise, range(T-1, T), copy out.  Used by bench.py to time
  * K denoising steps of the real loop. */
-int vdt_p_sample_range(vdt_plan* plan, const vdt_sampler_config* sc, float* x, const int64_t* label,
+int vdt_p_sample_range(vdt_plan* plan, const vdt_sampler_config* sc, float* x, const void* label,
                        const float* step_noise, int32_t batch, int32_t first_step, int32_t num_steps,
                        float* pred_x0 /* optional [B, C, R, R]: guided x0 prediction of the last step run
                                          (p_sample_step(return_pred=True); used by p_sample_progressive, 416-441) */,
                        void* stream);
 /* Same with HOST buffers (pinned or pageable); copies in/out inside the call and synchronises. */
-int vdt_p_sample_host(vdt_plan* plan, const vdt_sampler_config* sc, const float* noise, const int64_t* label,
+int vdt_p_sample_host(vdt_plan* plan, const vdt_sampler_config* sc, const float* noise, const void* label,
                       const float* step_noise, float* out, int32_t batch);
 
 /* logsnr schedule + posterior coefficients — diffusion.py:42-112, 126-203 (host, fp64 with the reference's

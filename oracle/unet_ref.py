@@ -150,7 +150,7 @@ def make_state_dict(cfg: dict, seed: int = 0, residual_gain: float = 1.0) -> Dic
             if k.endswith("conv2.weight") or k.endswith("proj_out.weight"):
                 w = w * residual_gain
             sd[k] = w
-        elif ".norm" in k and k.endswith("weight") or k == "out_conv.0.weight":
+        elif (".norm" in k and k.endswith("weight")) or k == "out_conv.0.weight":
             sd[k] = 1.0 + 0.1 * torch.randn(shp, generator=g)
         else:
             sd[k] = 0.1 * torch.randn(shp, generator=g)

@@ -53,6 +53,11 @@ SAMPLE_CASES = {
     "ancestral_both": dict(unet="small_hd64", seed=24, B=2, res=32, T=5, model_out_type="both", w_guide=0.0,
                            use_ddim=False, var_type="fixed_large", labels=None),
 }
+# multitag (multi-hot) class conditioning as used by the reference's conditional CelebA checkpoints
+UNET_CASES["small_multitag"] = dict(cfg=_cfg(mult=(1, 2), nrb=1, attn=(False, True), num_classes=40, multitags=True),
+                                    seed=15, B=3, res=16, labels="multihot", trace=[])
+SAMPLE_CASES["ddim_cfg_multitag"] = dict(unet="small_multitag", seed=25, B=3, res=16, T=6, model_out_type="v", w_guide=1.0,
+                                         use_ddim=True, var_type="fixed_large", labels="multihot")
 UNET_CASES["small_hd64_x0"] = dict(cfg=_cfg(out_channels=3, mult=(1, 1, 2), nrb=1, attn=(False, True, True),
                                             embedding_dim=192, head_dim=64, num_heads=1),
                                    seed=14, B=2, res=32, labels=None, trace=[])
@@ -64,8 +69,18 @@ def build_inputs(case):
     cfg = case["cfg"]
     x = torch.randn(case["B"], cfg["in_channels"], case["res"], case["res"], generator=g)
     t = torch.rand(case["B"], generator=g, dtype=torch.float64) * 0.98 + 0.01
-    y = torch.tensor(case["labels"], dtype=torch.int64) if case["labels"] is not None else None
+    y = _labels(case, cfg, g)
     return x, t, y
+
+
+def _labels(case, cfg, g):
+    if case["labels"] is None:
+        return None
+    if case["labels"] == "multihot":        # ~5 of 40 attributes set per image; first row all zero (clamp(min=1) path)
+        y = (torch.rand(case["B"], cfg["num_classes"], generator=g) < 0.12).float()
+        y[0] = 0
+        return y
+    return torch.tensor(case["labels"], dtype=torch.int64)
 
 
 def build_sample_inputs(case, cfg):
@@ -75,7 +90,7 @@ def build_sample_inputs(case, cfg):
     g0 = torch.Generator().manual_seed(case["seed"] + 2000)
     shape = (case["B"], cfg["in_channels"], case["res"], case["res"])
     noise = torch.randn(shape, generator=g0)
-    label = torch.tensor(case["labels"], dtype=torch.int64) if case["labels"] is not None else None
+    label = _labels(case, cfg, g0)
     g = torch.Generator().manual_seed(case["seed"])
     step_noise = torch.empty((case["T"],) + shape)
     for ti in reversed(range(case["T"])):

@@ -21,7 +21,7 @@ def _model(cfg, seed, operand="fp16"):
     from v_diffusion_b200 import UNet
     net = UNet(cfg["in_channels"], cfg["hid_channels"], cfg["out_channels"], cfg["ch_multipliers"],
                cfg["num_res_blocks"], cfg["apply_attn"], embedding_dim=cfg["embedding_dim"], head_dim=cfg["head_dim"],
-               num_heads=cfg["num_heads"], num_classes=cfg["num_classes"])
+               num_heads=cfg["num_heads"], num_classes=cfg["num_classes"], multitags=cfg["multitags"])
     net.load_state_dict(make_state_dict(cfg, seed), strict=True)
     net.operand_dtype = operand
     return net.cuda().eval()

@@ -129,6 +129,11 @@ cudaError_t launch_linear_f32(const float* x, const float* W, const float* b, fl
 cudaError_t launch_class_embed_silu(const float* e, const int64_t* y, const float* w_cls, const float* b_cls,
                                     int num_classes, float* out, int rows, int E, cudaStream_t stream);
 
+// multitag labels (unet.py:290-294): y fp32 multi-hot [rows, num_classes]; e[r, :] = SiLU(e[r, :] + W (y[r] /
+// sqrt(max(nnz(y[r]), 1))) + b) with W the stock nn.Linear weight [E, num_classes] (y == nullptr: SiLU only)
+cudaError_t launch_class_embed_multitag_silu(const float* e, const float* y, const float* w_cls, const float* b_cls,
+                                             int num_classes, float* out, int rows, int E, cudaStream_t stream);
+
 // Per-step device-side sampler state: everything that changes from step to step lives here so one
 // captured CUDA graph can be replayed for every step.
 struct SamplerState {

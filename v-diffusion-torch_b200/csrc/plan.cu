@@ -157,6 +157,13 @@ __global__ void film_rows_kernel(const int64_t* __restrict__ label, int* __restr
     if (label != nullptr && !(rep == 2 && (i & 1))) r = (int)label[i / rep];   // odd rows: y = 0 (diffusion.py:372)
     film_row[i] = r;
 }
+// multitag labels of a chunk -> per-UNet-row multi-hot rows with the CFG interleave (odd rows: all zero, diffusion.py:372)
+__global__ void multitag_rows_kernel(const float* __restrict__ label, float* __restrict__ y_rows, int rows, int rep, int ncls) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * ncls) return;
+    const int r = i / ncls, k = i % ncls;
+    y_rows[i] = (rep == 2 && (r & 1)) ? 0.f : label[(size_t)(r / rep) * ncls + k];
+}
 __global__ void sampler_init_state_kernel(SamplerState* st, int next_step, int img0) {
     if (threadIdx.x == 0 && blockIdx.x == 0) { st->next_step = next_step; st->step = next_step; st->img0 = img0; st->pad = 0; }
 }
@@ -193,7 +200,7 @@ struct LinearArgs { const float *x, *W, *b; float* out; int rows, K, N, silu; };
 struct Im2colArgs { const float* x; h16* out; h16* out_lo; int B, rep, C, H, W, f16; };
 struct AttnF32Args { const float* qkv; h16 *hi, *lo; int B, N, heads, d, f16; };
 struct TembArgs { const double* t; float* out; int rows, dim; };
-struct ClsArgs { const float* e; const int64_t* y; const float *w, *b; int ncls; float* out; int rows, E; };
+struct ClsArgs { const float* e; const int64_t* y; const float* y_multi; const float *w, *b; int ncls; float* out; int rows, E; };
 struct BeginArgs { SamplerState* st; const float* table; double* t_rows; int nrows, T; };
 
 struct Step { StepKind kind; int idx; };
@@ -222,6 +229,7 @@ struct Exec {
     float* yout = nullptr;       // fp32 NCHW [rows, Cout, HW]
     double* t_rows = nullptr;    // [emb_rows]
     int64_t* y_rows = nullptr;   // [emb_rows]
+    float* y_multi = nullptr;    // multitag labels: fp32 multi-hot [emb_rows, num_classes]
     int* film_row = nullptr;     // [rows] (sampler)
     SamplerState* state = nullptr;
     float* pred = nullptr;       // sampler: (guided) x0 prediction of the last executed step [rows/rep, C, HW]
@@ -383,7 +391,6 @@ extern "C" int vdt_plan_create(const vdt_unet_config* cfg, vdt_plan** out) {
     if (!cfg || !out) return fail("null argument");
     const vdt_unet_config& c = *cfg;
     if (c.num_levels < 1 || c.num_levels > VDT_MAX_LEVELS) return fail("num_levels out of range");
-    if (c.multitags) return fail("multitags (multi-hot labels) is not supported yet");
     if (c.hid_channels % 64 != 0) return fail("hid_channels must be a multiple of 64 (got %d)", c.hid_channels);
     if (9 * c.in_channels > 64) return fail("in_channels must be <= 7");
     if (c.out_channels > 16) return fail("out_channels must be <= 16");
@@ -418,8 +425,9 @@ extern "C" int vdt_plan_create(const vdt_unet_config* cfg, vdt_plan** out) {
     add_weight(p.get(), "time_embed.2.weight", {E, E});
     add_weight(p.get(), "time_embed.2.bias", {E});
     if (c.num_classes > 0) {
-        add_weight(p.get(), "class_embed.1.weight", {E, c.num_classes});
-        add_weight(p.get(), "class_embed.1.bias", {E});
+        // OneHot + Linear (keys class_embed.1.*) or, for multitag data, a stock nn.Linear (keys class_embed.*)
+        add_weight(p.get(), c.multitags ? "class_embed.weight" : "class_embed.1.weight", {E, c.num_classes});
+        add_weight(p.get(), c.multitags ? "class_embed.bias" : "class_embed.1.bias", {E});
     }
     add_weight(p.get(), "in_conv.weight", {hid, c.in_channels, 3, 3});
     add_weight(p.get(), "in_conv.bias", {hid});
@@ -908,8 +916,10 @@ static int add_embedding_steps(vdt_plan* p, Exec* ex, float* film, bool has_y) {
     ex->linears.push_back({e1, p->W("time_embed.2.weight"), p->W("time_embed.2.bias"), e2, ER, E, E, 0});
     ex->steps.push_back({S_LINEAR, (int)ex->linears.size() - 1});
     const bool cls = p->cfg.num_classes > 0 && has_y;
-    ex->clss.push_back({e2, cls ? ex->y_rows : nullptr, cls ? p->W("class_embed.1.weight") : nullptr,
-                        cls ? p->W("class_embed.1.bias") : nullptr, p->cfg.num_classes, act, ER, E});
+    const bool mt = p->cfg.multitags != 0;
+    ex->clss.push_back({e2, (cls && !mt) ? ex->y_rows : nullptr, (cls && mt) ? ex->y_multi : nullptr,
+                        cls ? p->W(mt ? "class_embed.weight" : "class_embed.1.weight") : nullptr,
+                        cls ? p->W(mt ? "class_embed.bias" : "class_embed.1.bias") : nullptr, p->cfg.num_classes, act, ER, E});
     ex->steps.push_back({S_CLSEMB, (int)ex->clss.size() - 1});
     ex->linears.push_back({act, p->w_fc_all, p->b_fc_all, film, ER, E, p->film_total, 0});
     ex->steps.push_back({S_LINEAR, (int)ex->linears.size() - 1});
@@ -929,7 +939,12 @@ static int run_steps(vdt_plan* p, Exec* ex, cudaStream_t st, std::vector<cudaEve
             case S_IM2COL: { auto& a = ex->im2cols[s.idx]; e = launch_im2col3x3(a.x, a.out, a.out_lo, a.B, a.rep, a.C, a.H, a.W, a.f16, st); break; }
             case S_TEMB: { auto& a = ex->tembs[s.idx]; e = launch_timestep_embedding(a.t, a.out, a.rows, a.dim, st); break; }
             case S_LINEAR: { auto& a = ex->linears[s.idx]; e = launch_linear_f32(a.x, a.W, a.b, a.out, a.rows, a.K, a.N, a.silu, st); break; }
-            case S_CLSEMB: { auto& a = ex->clss[s.idx]; e = launch_class_embed_silu(a.e, a.y, a.w, a.b, a.ncls, a.out, a.rows, a.E, st); break; }
+            case S_CLSEMB: {
+                auto& a = ex->clss[s.idx];
+                e = a.y_multi ? launch_class_embed_multitag_silu(a.e, a.y_multi, a.w, a.b, a.ncls, a.out, a.rows, a.E, st)
+                              : launch_class_embed_silu(a.e, a.y, a.w, a.b, a.ncls, a.out, a.rows, a.E, st);
+                break;
+            }
             case S_BEGIN: { auto& a = ex->begins[s.idx]; e = launch_sampler_begin_step(a.st, a.table, a.t_rows, a.nrows, a.T, st); break; }
             case S_SAMPLE: e = launch_sampler_step(ex->samples[s.idx], st); break;
             case S_ATTN_F32: { auto& a = ex->attn32s[s.idx]; e = launch_attention_f32(a.qkv, a.hi, a.lo, a.B, a.N, a.heads, a.d, a.f16, st); break; }
@@ -1005,6 +1020,7 @@ static int get_forward_exec(vdt_plan* p, int rows, bool has_y, Exec** out) {
     CKI(ex->acquire(rows * HW * c.out_channels * 4, (void**)&ex->yout));
     CKI(ex->acquire(rows * sizeof(double), (void**)&ex->t_rows));
     CKI(ex->acquire(rows * sizeof(int64_t), (void**)&ex->y_rows));
+    if (c.multitags && c.num_classes > 0) CKI(ex->acquire((size_t)rows * c.num_classes * 4, (void**)&ex->y_multi));
     float* film;
     CKI(ex->acquire((size_t)rows * p->film_total * 4, (void**)&film));
     CKI(add_embedding_steps(p, ex.get(), film, has_y));
@@ -1014,7 +1030,7 @@ static int get_forward_exec(vdt_plan* p, int rows, bool has_y, Exec** out) {
     return 0;
 }
 
-extern "C" int vdt_unet_forward(vdt_plan* p, const float* x, const double* t, const int64_t* y, float* out, int32_t batch,
+extern "C" int vdt_unet_forward(vdt_plan* p, const float* x, const double* t, const void* y, float* out, int32_t batch,
                                 void* stream) {
     if (!p || !x || !t || !out) return fail("null argument");
     if (!p->finalized) return fail("plan not finalized (load every state_dict key, then vdt_plan_finalize)");
@@ -1029,7 +1045,11 @@ extern "C" int vdt_unet_forward(vdt_plan* p, const float* x, const double* t, co
         CKI(get_forward_exec(p, rows, y != nullptr, &ex));
         CK(cudaMemcpyAsync(ex->xin, x + (size_t)b0 * c.in_channels * HW, rows * HW * c.in_channels * 4, cudaMemcpyDeviceToDevice, st));
         CK(cudaMemcpyAsync(ex->t_rows, t + b0, rows * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        if (y) CK(cudaMemcpyAsync(ex->y_rows, y + b0, rows * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        if (y && c.multitags)
+            CK(cudaMemcpyAsync(ex->y_multi, static_cast<const float*>(y) + (size_t)b0 * c.num_classes,
+                               (size_t)rows * c.num_classes * 4, cudaMemcpyDeviceToDevice, st));
+        else if (y)
+            CK(cudaMemcpyAsync(ex->y_rows, static_cast<const int64_t*>(y) + b0, rows * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
         CKI(run_exec(p, ex, st));
         CK(cudaMemcpyAsync(out + (size_t)b0 * c.out_channels * HW, ex->yout, rows * HW * c.out_channels * 4, cudaMemcpyDeviceToDevice, st));
     }
@@ -1139,7 +1159,9 @@ static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs,
     const int T = sc.sample_timesteps;
     ex->rows = imgs * rep; ex->rep = rep; ex->sampler = true; ex->has_y = has_label; ex->sc = sc;
     const bool cond_model = c.num_classes > 0 && has_label;
-    ex->emb_rows = cond_model ? c.num_classes + 1 : 1;
+    const bool mt = cond_model && c.multitags;           // multi-hot labels: every UNet row has its own embedding row
+    ex->emb_rows = mt ? ex->rows : cond_model ? c.num_classes + 1 : 1;
+    if (mt) CKI(ex->acquire((size_t)ex->rows * c.num_classes * 4, (void**)&ex->y_multi));
     CKI(ex->acquire(imgs * HW * c.in_channels * 4, (void**)&ex->xin));
     CKI(ex->acquire((size_t)ex->rows * HW * c.out_channels * 4, (void**)&ex->yout));
     CKI(ex->acquire(ex->emb_rows * sizeof(double), (void**)&ex->t_rows));
@@ -1158,7 +1180,7 @@ static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs,
     ex->begins.push_back({ex->state, ex->coef_table, ex->t_rows, ex->emb_rows, T});
     ex->steps.push_back({S_BEGIN, 0});
     CKI(add_embedding_steps(p, ex.get(), film, cond_model));
-    CKI(build_unet_steps(p, ex.get(), film, ex->film_row));
+    CKI(build_unet_steps(p, ex.get(), film, mt ? nullptr : ex->film_row));
     SamplerStepParams sp{};
     sp.model_out = ex->yout; sp.x_t = ex->xin; sp.x_s = ex->xin; sp.pred_x0 = ex->pred; sp.noise = step_noise; sp.noise_step_stride = noise_stride;
     sp.st = ex->state; sp.seed = sc.seed; sp.B = imgs; sp.C = c.in_channels; sp.HW = (int)HW; sp.cfg = cfg ? 1 : 0;
@@ -1170,7 +1192,7 @@ static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs,
     return 0;
 }
 
-extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, float* x, const int64_t* label,
+extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, float* x, const void* label,
                                   const float* step_noise, int32_t batch, int32_t first_step, int32_t num_steps,
                                   float* pred_x0, void* stream) {
     if (!p || !scp || !x) return fail("null argument");
@@ -1186,7 +1208,8 @@ extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, fl
     const vdt_unet_config& c = p->cfg;
     const size_t CHW = (size_t)c.in_channels * c.resolution * c.resolution;
     const bool cfg = sc.w_guide > 0.0 && label != nullptr;
-    const int64_t* row_label = c.num_classes > 0 ? label : nullptr;   // an unconditional UNet ignores y (unet.py:289)
+    const bool mt = c.multitags && c.num_classes > 0 && label != nullptr;
+    const int64_t* row_label = (c.num_classes > 0 && !mt) ? static_cast<const int64_t*>(label) : nullptr;   // an unconditional UNet ignores y (unet.py:289)
     const int rep = cfg ? 2 : 1;
     const int chunk = std::max(1, c.max_rows / rep);
     for (int i0 = 0; i0 < batch; i0 += chunk) {
@@ -1194,7 +1217,13 @@ extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, fl
         Exec* ex;
         CKI(get_sampler_exec(p, sc, imgs, label != nullptr, step_noise, (long long)batch * (long long)CHW, &ex));
         CK(cudaMemcpyAsync(ex->xin, x + (size_t)i0 * CHW, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
-        film_rows_kernel<<<(ex->rows + 127) / 128, 128, 0, st>>>(row_label ? row_label + i0 : nullptr, ex->film_row, ex->rows, rep);
+        if (mt) {
+            const int n = ex->rows * c.num_classes;
+            multitag_rows_kernel<<<(n + 127) / 128, 128, 0, st>>>(static_cast<const float*>(label) + (size_t)i0 * c.num_classes,
+                                                                ex->y_multi, ex->rows, rep, c.num_classes);
+        } else {
+            film_rows_kernel<<<(ex->rows + 127) / 128, 128, 0, st>>>(row_label ? row_label + i0 : nullptr, ex->film_row, ex->rows, rep);
+        }
         CK(cudaGetLastError());
         sampler_init_state_kernel<<<1, 32, 0, st>>>(ex->state, first_step, i0);
         CK(cudaGetLastError());
@@ -1207,7 +1236,7 @@ extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, fl
     return leave_work(p, user);
 }
 
-extern "C" int vdt_p_sample(vdt_plan* p, const vdt_sampler_config* scp, const float* noise, const int64_t* label,
+extern "C" int vdt_p_sample(vdt_plan* p, const vdt_sampler_config* scp, const float* noise, const void* label,
                             const float* step_noise, float* out, int32_t batch, void* stream) {
     if (!p || !scp || !noise || !out) return fail("null argument");
     const size_t CHW = (size_t)p->cfg.in_channels * p->cfg.resolution * p->cfg.resolution;
@@ -1216,14 +1245,15 @@ extern "C" int vdt_p_sample(vdt_plan* p, const vdt_sampler_config* scp, const fl
     return vdt_p_sample_range(p, scp, out, label, step_noise, batch, scp->sample_timesteps - 1, scp->sample_timesteps, nullptr, stream);
 }
 
-extern "C" int vdt_p_sample_host(vdt_plan* p, const vdt_sampler_config* scp, const float* noise, const int64_t* label,
+extern "C" int vdt_p_sample_host(vdt_plan* p, const vdt_sampler_config* scp, const float* noise, const void* label,
                                  const float* step_noise, float* out, int32_t batch) {
     if (!p || !scp || !noise || !out) return fail("null argument");
     const vdt_unet_config& c = p->cfg;
     const size_t CHW = (size_t)c.in_channels * c.resolution * c.resolution;
     const size_t n = (size_t)batch * CHW;
     float *d_noise = nullptr, *d_out = nullptr, *d_sn = nullptr;
-    int64_t* d_label = nullptr;
+    void* d_label = nullptr;
+    const size_t label_bytes = (c.multitags && c.num_classes > 0) ? (size_t)batch * c.num_classes * 4 : (size_t)batch * sizeof(int64_t);
     int rc = 0;
     cudaStream_t st = nullptr;
     auto cleanup = [&]() { cudaFree(d_noise); cudaFree(d_out); cudaFree(d_sn); cudaFree(d_label); };
@@ -1236,8 +1266,8 @@ extern "C" int vdt_p_sample_host(vdt_plan* p, const vdt_sampler_config* scp, con
     CKH(cudaMalloc(&d_out, n * 4));
     CKH(cudaMemcpyAsync(d_noise, noise, n * 4, cudaMemcpyHostToDevice, st));
     if (label) {
-        CKH(cudaMalloc(&d_label, batch * sizeof(int64_t)));
-        CKH(cudaMemcpyAsync(d_label, label, batch * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CKH(cudaMalloc(&d_label, label_bytes));
+        CKH(cudaMemcpyAsync(d_label, label, label_bytes, cudaMemcpyHostToDevice, st));
     }
     if (step_noise) {
         CKH(cudaMalloc(&d_sn, n * 4 * scp->sample_timesteps));

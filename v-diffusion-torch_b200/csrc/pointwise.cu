@@ -159,6 +159,26 @@ __global__ void class_embed_silu_kernel(const float* __restrict__ e, const int64
     out[idx] = v / (1.f + expf(-v));
 }
 
+__global__ void class_embed_multitag_silu_kernel(const float* __restrict__ e, const float* __restrict__ y,
+                                                 const float* __restrict__ w_cls, const float* __restrict__ b_cls,
+                                                 int num_classes, float* __restrict__ out, int rows, int E) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * E) return;
+    const int r = idx / E, j = idx % E;
+    float v = e[idx];
+    if (y != nullptr) {
+        const float* yr = y + static_cast<size_t>(r) * num_classes;
+        float nnz = 0.f, s = 0.f;
+        for (int k = 0; k < num_classes; ++k) {
+            const float yk = yr[k];
+            nnz += (yk != 0.f) ? 1.f : 0.f;
+            s = fmaf(w_cls[static_cast<size_t>(j) * num_classes + k], yk, s);
+        }
+        v += s / sqrtf(fmaxf(nnz, 1.f)) + b_cls[j];
+    }
+    out[idx] = v / (1.f + expf(-v));
+}
+
 // ------------------------------------------------------------------------------------------ sampler
 __global__ void sampler_begin_step_kernel(SamplerState* st, const float* __restrict__ coef_table, double* t_rows,
                                           int nrows, int T) {
@@ -291,6 +311,14 @@ cudaError_t launch_class_embed_silu(const float* e, const int64_t* y, const floa
     const int n = rows * E;
     if (n == 0) return cudaSuccess;
     class_embed_silu_kernel<<<(n + 255) / 256, 256, 0, stream>>>(e, y, w_cls, b_cls, num_classes, out, rows, E);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_class_embed_multitag_silu(const float* e, const float* y, const float* w_cls, const float* b_cls,
+                                             int num_classes, float* out, int rows, int E, cudaStream_t stream) {
+    const int n = rows * E;
+    if (n == 0) return cudaSuccess;
+    class_embed_multitag_silu_kernel<<<(n + 255) / 256, 256, 0, stream>>>(e, y, w_cls, b_cls, num_classes, out, rows, E);
     return cudaGetLastError();
 }
 

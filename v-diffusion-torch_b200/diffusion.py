@@ -107,8 +107,9 @@ class GaussianDiffusion:
         else:
             x_t = noise.to(device)
         x_t = x_t.to(torch.float32).contiguous()
+        multitags = bool(getattr(denoise_fn, "multitags", False))
         if label is not None:
-            label = label.to(device=device, dtype=torch.int64).contiguous()
+            label = label.to(device=device, dtype=torch.float32 if multitags else torch.int64).contiguous()
         if step_noise is not None:
             step_noise = step_noise.to(device=device, dtype=torch.float32).contiguous()
         sc = self.sampler_config(use_ddim, seed)
@@ -177,7 +178,7 @@ class GaussianDiffusion:
                 t = torch.full((B,), (ti + 1) / T, dtype=torch.float64, device=device)
                 if use_cfg:
                     xin, tin = x_t.repeat_interleave(2, dim=0), t.repeat_interleave(2)
-                    yin = label.repeat_interleave(2)
+                    yin = label.repeat_interleave(2, dim=0)
                     yin[1::2] = 0
                 else:
                     xin, tin, yin = x_t, t, label

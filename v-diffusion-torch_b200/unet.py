@@ -75,8 +75,6 @@ class UNet(nn.Module):
         super().__init__()
         if not resample_with_res:
             raise NotImplementedError("resample_with_res=False is not used by any reference config")
-        if multitags and num_classes > 0:
-            raise NotImplementedError("multitags (CelebA multi-hot labels) is a later row (SURVEY §8f)")
         self.in_channels, self.hid_channels, self.out_channels = in_channels, hid_channels, out_channels
         self.embedding_dim = embedding_dim or 4 * hid_channels
         self.levels = levels = len(ch_multipliers)
@@ -94,7 +92,10 @@ class UNet(nn.Module):
 
         self.time_embed = nn.ModuleList([_Affine((E, hid)), _Slot(), _Affine((E, E))])
         if num_classes > 0:
-            self.class_embed = nn.ModuleList([_Slot(), _Affine((E, num_classes))])
+            if multitags:
+                self.class_embed = nn.Linear(num_classes, E)          # stock nn.Linear and init (unet.py:209-210)
+            else:
+                self.class_embed = nn.ModuleList([_Slot(), _Affine((E, num_classes))])
         self.in_conv = _Affine((hid, in_channels, 3, 3))
         chs = [hid * m for m in ch_multipliers]
 
@@ -199,9 +200,15 @@ class UNet(nn.Module):
         if t.numel() != B:
             raise ValueError("t must have one entry per batch row")
         if self.num_classes and y is not None:
-            y = y.to(device=dev, dtype=torch.int64).contiguous()      # OneHot casts to long (modules.py:191-192)
-            if y.numel() != B:
-                raise ValueError("y must have one entry per batch row")
+            if self.multitags:
+                assert y.ndim == 2                                     # unet.py:291
+                y = y.to(device=dev, dtype=torch.float32).contiguous()
+                if tuple(y.shape) != (B, self.num_classes):
+                    raise ValueError(f"multitag y must have shape ({B}, {self.num_classes})")
+            else:
+                y = y.to(device=dev, dtype=torch.int64).contiguous()  # OneHot casts to long (modules.py:191-192)
+                if y.numel() != B:
+                    raise ValueError("y must have one entry per batch row")
         else:
             y = None
         out = torch.empty((B, self.out_channels, x.shape[2], x.shape[3]), device=dev, dtype=torch.float32)
