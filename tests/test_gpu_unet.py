@@ -254,3 +254,41 @@ def test_p_sample_progressive_vs_oracle():
     assert preds.shape[0] == 8 // 3 == 2
     assert (preds[1] - want[5]).abs().max().item() <= 3 * SAMPLE_MAX_ABS      # guided x0 is amplified by (1 + 2w)
     assert (preds[0] - want[2]).abs().max().item() <= 3 * SAMPLE_MAX_ABS
+
+
+def test_full_size_chunk_properties():
+    """Size-independent properties on the real CIFAR-10 conditional network at a batch that spans full 1024-row
+    chunks (BASELINE configs[1] geometry): a sample's trajectory does not depend on its batch neighbours, its
+    chunk, or the chunk size, and the run is deterministic."""
+    from tests.cases import CIFAR_COND
+    from v_diffusion_b200 import GaussianDiffusion, get_logsnr_schedule
+    net = _model(CIFAR_COND, 13)
+    diff = GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), 100, "v", "fixed_medium", "snr_trunc", "mse",
+                             intp_frac=0.3, w_guide=1.0)
+    g = torch.Generator().manual_seed(77)
+    B = 520                                                # 512 images (one full 1024-row chunk) + 8
+    noise = torch.randn(B, 3, 32, 32, generator=g)
+    label = torch.randint(0, 11, (B,), generator=g)
+    # only the first 2 of the 100 steps are run: the property is per step
+    import ctypes as C
+    from v_diffusion_b200 import _lib
+    sc = diff.sampler_config(use_ddim=True)
+
+    def run(n_idx, max_rows):
+        net.max_rows = max_rows
+        plan = net.plan_for(32, torch.device("cuda", 0))
+        x = noise[n_idx].cuda().contiguous().clone()
+        y = label[n_idx].cuda().contiguous()
+        _lib.check(_lib.lib().vdt_p_sample_range(plan, C.byref(sc), _lib.ptr(x), _lib.ptr(y), None, x.shape[0], 99, 2, None, None))
+        torch.cuda.synchronize()
+        return x.cpu()
+
+    full = run(torch.arange(B), 1024)
+    again = run(torch.arange(B), 1024)
+    assert torch.equal(full, again)                        # deterministic (fixed-order statistics, no atomics)
+    pick = torch.tensor([0, 255, 511, 512, 519])
+    alone = run(pick, 1024)
+    assert (alone - full[pick]).abs().max().item() <= 1e-5
+    small_chunks = run(torch.arange(B), 128)
+    assert (small_chunks - full).abs().max().item() <= 1e-5
+    assert torch.isfinite(full).all() and (full - noise).abs().max().item() > 1e-3
