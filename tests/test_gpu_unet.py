@@ -292,3 +292,40 @@ def test_full_size_chunk_properties():
     small_chunks = run(torch.arange(B), 128)
     assert (small_chunks - full).abs().max().item() <= 1e-5
     assert torch.isfinite(full).all() and (full - noise).abs().max().item() > 1e-3
+
+
+def test_c_abi_host_entry_point_matches_python_api():
+    """vdt_p_sample_host (host buffers in, host buffer out, copies inside the call) == GaussianDiffusion.p_sample."""
+    import ctypes as C
+    from v_diffusion_b200 import _lib
+    case = SAMPLE_CASES["ancestral_cfg_v"]
+    ucase = UNET_CASES[case["unet"]]
+    net = _model(ucase["cfg"], ucase["seed"])
+    diff = _diffusion(case)
+    noise, label, step_noise = build_sample_inputs(case, ucase["cfg"])
+    ref = diff.p_sample(net, tuple(noise.shape), noise=noise, label=label, device="cuda", use_ddim=False, step_noise=step_noise)
+    plan = net.plan_for(noise.shape[2], torch.device("cuda", 0))
+    sc = diff.sampler_config(use_ddim=False)
+    out = torch.empty_like(noise)
+    noise_h, label_h, sn_h = noise.contiguous(), label.contiguous(), step_noise.contiguous()
+    rc = _lib.lib().vdt_p_sample_host(plan, C.byref(sc), _lib.ptr(noise_h), _lib.ptr(label_h), _lib.ptr(sn_h), _lib.ptr(out),
+                                      noise.shape[0])
+    assert rc == 0, _lib.lib().vdt_last_error()
+    assert torch.equal(out, ref)
+    # error path: a plan that is not finalized refuses to run and says why
+    from v_diffusion_b200 import UNet
+    cfg = ucase["cfg"]
+    blank = UNet(cfg["in_channels"], cfg["hid_channels"], cfg["out_channels"], cfg["ch_multipliers"], cfg["num_res_blocks"],
+                 cfg["apply_attn"], num_classes=cfg["num_classes"]).cuda().eval()
+    handle = C.c_void_p()
+    ucfg = _lib.UNetConfig()
+    ucfg.in_channels, ucfg.hid_channels, ucfg.out_channels, ucfg.num_levels = 3, 64, 3, 2
+    ucfg.ch_multipliers[0], ucfg.ch_multipliers[1] = 1, 2
+    ucfg.apply_attn[1] = 1
+    ucfg.num_res_blocks, ucfg.num_heads, ucfg.resolution, ucfg.max_rows = 1, 1, 16, 8
+    assert _lib.lib().vdt_plan_create(C.byref(ucfg), C.byref(handle)) == 0
+    assert _lib.lib().vdt_plan_finalize(handle) != 0 and b"missing key" in _lib.lib().vdt_last_error()
+    rc = _lib.lib().vdt_p_sample_host(handle, C.byref(sc), _lib.ptr(noise_h), None, None, _lib.ptr(out), noise.shape[0])
+    assert rc != 0 and b"not finalized" in _lib.lib().vdt_last_error()
+    _lib.lib().vdt_plan_destroy(handle)
+    del blank
