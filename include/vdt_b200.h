@@ -128,17 +128,17 @@ int vdt_profile_read(double* ms4, uint64_t* launches4);
 /* ---- kernel-level entry points (used by the parity tests; device pointers) ------------------------- */
 /* f16: 1 = fp16 operands, 0 = bf16.  conv2d(k x k, pad k/2) on 16-bit NHWC input with fp32 OIHW weights -> fp32 NHWC
  * (+bias, +residual), or 16-bit NHWC when out16 is given.  stats_out (optional): GroupNorm partial statistics,
- * float2 (sum, sum of squares) per (slab of 32 rows, 4 columns): [rows/32][cout/4]. */
+ * float2 (sum, sum of squares) per (slab of 32 rows, stat_cols = 4 or 2 columns): [rows/32][cout/stat_cols]. */
 int vdt_op_conv(const void* x_16_nhwc, int32_t batch, int32_t h, int32_t w, int32_t cin, const float* w_oihw,
                 int32_t cout, int32_t ksize, const float* bias, const float* residual, float* out_nhwc, int32_t f16,
-                void* out16, void* stats_out, void* stream);
+                void* out16, void* stats_out, int32_t stat_cols, void* stream);
 /* GroupNorm(32, 1e-6) [+FiLM] [+SiLU] [+resample 0 none / 1 avgpool2 / 2 nearest x2] over concat(src1, src2).
  * stats1/stats2 (optional): partial statistics from vdt_op_conv for src1/src2 -> single-pass kernel;
  * in16: src1 is 16-bit (needs stats1). */
 int vdt_op_groupnorm(const void* src1, int32_t c1, const float* src2, int32_t c2, int32_t batch, int32_t h, int32_t w,
                      const float* gamma, const float* beta, const float* film, int32_t film_stride, int32_t film_off,
                      int32_t silu, int32_t resample, void* out_act_16, void* out_raw_16, float* out_res,
-                     int32_t f16, const void* stats1, const void* stats2, int32_t in16, void* stream);
+                     int32_t f16, const void* stats1, const void* stats2, int32_t stat_cols, int32_t in16, void* stream);
 /* attention on qk 16-bit [B*N, 2*hid], v^T 16-bit [B*hid, N] -> 16-bit [B*N, hid] */
 int vdt_op_attention(const void* qk_16, const void* vt_16, void* out_16, int32_t batch, int32_t n, int32_t heads,
                      int32_t d, int32_t f16, void* stream);

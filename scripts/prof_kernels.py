@@ -46,7 +46,7 @@ def conv_case(H, cin, cout, k, resid, stats, out16=False):
     out = torch.empty(R, H, H, cout, device=dev)
     o16 = torch.empty(R, H, H, cout, device=dev, dtype=torch.float16) if out16 else None
     st = torch.empty(R * H * H // 32, cout // 4, 2, device=dev) if stats else None
-    ms = timed(lambda: L.vdt_op_conv(p(x), R, H, H, cin, p(w), cout, k, p(b), p(res), p(out), 1, p(o16), p(st), None), 5)
+    ms = timed(lambda: L.vdt_op_conv(p(x), R, H, H, cin, p(w), cout, k, p(b), p(res), p(out), 1, p(o16), p(st), 4, None), 5)
     fl = 2.0 * R * H * H * cout * cin * k * k
     print(f"conv {k}x{k} {cin}->{cout} @{H}x{H} rows={R} resid={resid} stats={stats} out16={out16}: {ms:.3f} ms "
           f"{fl / ms / 1e9 if ms else 0:.0f} TFLOP/s (includes weight pack + sync of the hook)")
@@ -58,7 +58,7 @@ def gn_case(H, c, st, src, in16, film):
     ftab = torch.randn(R, 2 * c, device=dev, generator=g) * 0.1 if film else None
     oa = torch.empty(R, H, H, c, device=dev, dtype=torch.float16)
     ms = timed(lambda: L.vdt_op_groupnorm(p(src), c, None, 0, R, H, H, p(gamma), p(beta), p(ftab), 2 * c, 0, 1, 0, p(oa),
-                                          None, None, 1, p(st), None, int(in16), None), 5)
+                                          None, None, 1, p(st), None, 4, int(in16), None), 5)
     byts = R * H * H * c * ((2 if in16 else 4) + 2)
     print(f"groupnorm fused C={c} @{H}x{H} in16={in16}: {ms:.3f} ms {byts / ms / 1e6 if ms else 0:.0f} GB/s (hook allocs scratch)")
 

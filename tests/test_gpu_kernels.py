@@ -61,7 +61,7 @@ def test_conv_gemm(L, B, H, cin, cout, k, res, f16):
     xb = x.to(DT[f16])
     x_nhwc = xb.permute(0, 2, 3, 1).contiguous()
     out = torch.full((B, H, H, cout), float("nan"), device="cuda")
-    _check(L, L.vdt_op_conv(_p(x_nhwc), B, H, H, cin, _p(w), cout, k, _p(bias), _p(resid), _p(out), f16, None, None, None))
+    _check(L, L.vdt_op_conv(_p(x_nhwc), B, H, H, cin, _p(w), cout, k, _p(bias), _p(resid), _p(out), f16, None, None, 4, None))
     torch.cuda.synchronize()
     ref = F.conv2d(xb.double(), w.to(DT[f16]).double(), bias.double(), padding=k // 2).permute(0, 2, 3, 1)
     if res:
@@ -100,7 +100,7 @@ def test_groupnorm(L, B, H, c1, c2, film, silu, resample, want_raw, want_res, f1
     out_raw = torch.zeros(B, H, H, C_, device="cuda", dtype=DT[f16]) if want_raw else None
     out_res = torch.zeros(B, Ho, Ho, C_, device="cuda") if want_res else None
     _check(L, L.vdt_op_groupnorm(_p(s1), c1, _p(s2), c2, B, H, H, _p(gamma), _p(beta), _p(ftab), stride, off,
-                                 int(silu), resample, _p(out_act), _p(out_raw), _p(out_res), f16, None, None, 0, None))
+                                 int(silu), resample, _p(out_act), _p(out_raw), _p(out_res), f16, None, None, 4, 0, None))
     torch.cuda.synchronize()
     x = torch.cat([s1, s2], dim=3) if c2 else s1
     xn = x.permute(0, 3, 1, 2).double()
@@ -132,6 +132,10 @@ FUSED_GN_CASES = [
     (2, 16, 128, 0, False, False, 1),     # avg-pool
     (2, 8, 256, 0, False, False, 2),      # upsample
     (2, 64, 128, 0, True, False, 0),      # 4096 pixels: image split over 8 CTAs
+    (2, 16, 192, 0, False, True, 0),      # 6 channels per group -> 2-column statistics entries, VEC = 2
+    (2, 16, 192, 0, True, False, 0),      # same with a 16-bit input
+    (2, 16, 128, 64, False, False, 0),    # concat 128 + 64: 6-channel groups straddling the seam
+    (2, 8, 64, 0, False, False, 0),       # 2 channels per group
 ]
 
 
@@ -142,6 +146,7 @@ def test_conv_stats_then_single_pass_groupnorm(L, B, H, c1, c2, in16, film, resa
     makes one pass.  Checked against torch GroupNorm of the conv output."""
     g = torch.Generator(device="cuda").manual_seed(H + c1 + c2 + in16)
     cin = 64
+    sc = 4 if ((c1 + c2) // 32) % 4 == 0 else 2          # columns per statistics entry
 
     def conv(cout):
         x = torch.randn(B, H, H, cin, device="cuda", generator=g).to(DT[f16])
@@ -149,13 +154,13 @@ def test_conv_stats_then_single_pass_groupnorm(L, B, H, c1, c2, in16, film, resa
         bias = torch.randn(cout, device="cuda", generator=g)
         out = torch.zeros(B, H, H, cout, device="cuda")
         out16 = torch.zeros(B, H, H, cout, device="cuda", dtype=DT[f16]) if in16 else None
-        stats = torch.full((B * H * H // 32, cout // 4, 2), float("nan"), device="cuda")
-        _check(L, L.vdt_op_conv(_p(x), B, H, H, cin, _p(w), cout, 3, _p(bias), None, _p(out), f16, _p(out16), _p(stats), None))
+        stats = torch.full((B * H * H // 32, cout // sc, 2), float("nan"), device="cuda")
+        _check(L, L.vdt_op_conv(_p(x), B, H, H, cin, _p(w), cout, 3, _p(bias), None, _p(out), f16, _p(out16), _p(stats), sc, None))
         torch.cuda.synchronize()
         ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.to(DT[f16]).double(), bias.double(), padding=1).permute(0, 2, 3, 1)
         val = out16 if in16 else out
         # the statistics describe the fp32 values before any 16-bit rounding
-        rs = ref.reshape(B * H * H // 32, 32, cout // 4, 4)
+        rs = ref.reshape(B * H * H // 32, 32, cout // sc, sc)
         assert torch.isfinite(stats).all()
         assert (stats[..., 0].double() - rs.sum(dim=(1, 3))).abs().max().item() <= 2e-3
         assert (stats[..., 1].double() - (rs * rs).sum(dim=(1, 3))).abs().max().item() <= 2e-2
@@ -170,7 +175,7 @@ def test_conv_stats_then_single_pass_groupnorm(L, B, H, c1, c2, in16, film, resa
     Ho = H // 2 if resample == 1 else H * 2 if resample == 2 else H
     out_act = torch.zeros(B, Ho, Ho, C_, device="cuda", dtype=DT[f16])
     _check(L, L.vdt_op_groupnorm(_p(v1), c1, _p(v2), c2, B, H, H, _p(gamma), _p(beta), _p(ftab), 2 * C_, 0, 1, resample,
-                                 _p(out_act), None, None, f16, _p(st1), _p(st2), int(in16), None))
+                                 _p(out_act), None, None, f16, _p(st1), _p(st2), sc, int(in16), None))
     torch.cuda.synchronize()
     x = torch.cat([r1, r2], dim=3) if c2 else r1
     if in16:

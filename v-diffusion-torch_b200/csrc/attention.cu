@@ -215,6 +215,9 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
                 tmem_st_wait();
                 l *= factor;
             }
+            // P_j goes into the buffer PV_{j-2} read: S_j was issued before PV_{j-2}, so s_full alone does not
+            // order this tile's stores after that MMA's operand reads (a late V_{j-2} tile delays it arbitrarily)
+            if (j >= 2) mbar_wait(&sm.v_empty[j & 1], ((j - 2) >> 1) & 1);
             // p = 2^(s*c - m*c); a row that ignores this tile writes zeros (its m may still be -inf)
             const float mc = (m_used == -INFINITY) ? 0.f : m_used * c;
             const float cc = tile_valid ? c : 0.f;

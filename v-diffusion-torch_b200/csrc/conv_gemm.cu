@@ -56,7 +56,7 @@ __device__ __forceinline__ TileCoord tile_origin(const ConvParams& p, int m_tile
 // Row-major epilogue of one 32-row x 32-column chunk after the smem transposition: lane = (row % 4 group rsub,
 // 4 columns cq), all 32 rows valid.  Compile-time variants keep the instruction count low (the epilogue warps
 // are issue-bound otherwise); ragged tiles and SiLU epilogues take epilogue_rowmajor_generic.
-template <bool F16, bool F32OUT, bool RESID, bool STATS>
+template <bool F16, bool F32OUT, bool RESID, int STATS>   // STATS: 0 none, 4 / 2 = columns per statistics entry
 __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const float4* tile, int lane, long long wrow0, int col0) {
     const int cq = lane & 7, rsub = lane >> 3;
     const size_t off0 = static_cast<size_t>(wrow0 + rsub) * p.ld + col0 + cq * 4;
@@ -70,7 +70,7 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
             res[i] = ldg_nc_v4_issue(rp + i * step);
         compiler_fence();
     }
-    float ssum = 0.f, ssq = 0.f;
+    float ssum = 0.f, ssq = 0.f, ssum1 = 0.f, ssq1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + rsub;
@@ -82,17 +82,31 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
                 *reinterpret_cast<float4*>(p.out_f32 + off0 + i * step) = o;
             else
                 *reinterpret_cast<uint2*>(p.out_bf16 + off0 + i * step) = make_uint2(pack_16(o.x, o.y, (F16 ? 1 : 0)), pack_16(o.z, o.w, (F16 ? 1 : 0)));
-            if (STATS) {
+            if (STATS == 4) {
                 ssum += (o.x + o.y) + (o.z + o.w);
                 ssq = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ssq))));
+            } else if (STATS == 2) {
+                ssum += o.x + o.y; ssq = fmaf(o.x, o.x, fmaf(o.y, o.y, ssq));
+                ssum1 += o.z + o.w; ssq1 = fmaf(o.z, o.z, fmaf(o.w, o.w, ssq1));
             }
         }
     }
     if (STATS) {                                             // fixed-order reduction over the warp's 32 rows
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 8); ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 16); ssq += __shfl_xor_sync(0xffffffffu, ssq, 16);
-        if (rsub == 0)
-            p.stats[static_cast<size_t>(wrow0 / kStatRows) * (p.Cout / kStatCols) + (col0 >> 2) + cq] = make_float2(ssum, ssq);
+        if (STATS == 2) {
+            ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, 8); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, 8);
+            ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, 16); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, 16);
+        }
+        if (rsub == 0) {
+            float2* st = p.stats + static_cast<size_t>(wrow0 / kStatRows) * (p.Cout / (STATS ? STATS : 1));
+            if (STATS == 4) {
+                st[(col0 >> 2) + cq] = make_float2(ssum, ssq);
+            } else {
+                st[(col0 >> 1) + cq * 2] = make_float2(ssum, ssq);
+                st[(col0 >> 1) + cq * 2 + 1] = make_float2(ssum1, ssq1);
+            }
+        }
     }
 }
 
@@ -102,7 +116,7 @@ __device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, cons
     const int cq = lane & 7, rsub = lane >> 3;
     const bool tile_ok = m_tile < p.num_m_tiles;
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq * 4));
-    float ssum = 0.f, ssq = 0.f;
+    float ssum = 0.f, ssq = 0.f, ssum1 = 0.f, ssq1 = 0.f;   // (x, y) and (z, w) halves; merged for 4-column entries
     for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + rsub;
         const long long g = wrow0 + rr;
@@ -120,14 +134,23 @@ __device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, cons
             *reinterpret_cast<float4*>(p.out_f32 + off) = o;
         else
             *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_16(o.x, o.y, p.f16), pack_16(o.z, o.w, p.f16));
-        ssum += (o.x + o.y) + (o.z + o.w);
-        ssq = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ssq))));
+        ssum += o.x + o.y; ssq = fmaf(o.x, o.x, fmaf(o.y, o.y, ssq));
+        ssum1 += o.z + o.w; ssq1 = fmaf(o.z, o.z, fmaf(o.w, o.w, ssq1));
     }
     if (p.stats) {
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 8); ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 16); ssq += __shfl_xor_sync(0xffffffffu, ssq, 16);
-        if (rsub == 0 && tile_ok && wrow0 < p.M)
-            p.stats[static_cast<size_t>(wrow0 / kStatRows) * (p.Cout / kStatCols) + (col0 >> 2) + cq] = make_float2(ssum, ssq);
+        ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, 8); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, 8);
+        ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, 16); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, 16);
+        if (rsub == 0 && tile_ok && wrow0 < p.M) {
+            float2* st = p.stats + static_cast<size_t>(wrow0 / kStatRows) * (p.Cout / p.stat_cols);
+            if (p.stat_cols == 4) {
+                st[(col0 >> 2) + cq] = make_float2(ssum + ssum1, ssq + ssq1);
+            } else {
+                st[(col0 >> 1) + cq * 2] = make_float2(ssum, ssq);
+                st[(col0 >> 1) + cq * 2 + 1] = make_float2(ssum1, ssq1);
+            }
+        }
     }
 }
 
@@ -269,13 +292,16 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                     if (!all_valid || p.act_silu) {          // ragged tile / rare variants: run-time checked generic path
                         epilogue_rowmajor_generic(p, tile, lane, q, m_tile, wrow0, col0);
                     } else if (f32o) {
-                        if (resid && st) epilogue_rowmajor<F16, true, true, true>(p, tile, lane, wrow0, col0);
-                        else if (resid) epilogue_rowmajor<F16, true, true, false>(p, tile, lane, wrow0, col0);
-                        else if (st) epilogue_rowmajor<F16, true, false, true>(p, tile, lane, wrow0, col0);
-                        else epilogue_rowmajor<F16, true, false, false>(p, tile, lane, wrow0, col0);
+                        if (resid && st && p.stat_cols == 4) epilogue_rowmajor<F16, true, true, 4>(p, tile, lane, wrow0, col0);
+                        else if (resid && st) epilogue_rowmajor<F16, true, true, 2>(p, tile, lane, wrow0, col0);
+                        else if (resid) epilogue_rowmajor<F16, true, true, 0>(p, tile, lane, wrow0, col0);
+                        else if (st && p.stat_cols == 4) epilogue_rowmajor<F16, true, false, 4>(p, tile, lane, wrow0, col0);
+                        else if (st) epilogue_rowmajor<F16, true, false, 2>(p, tile, lane, wrow0, col0);
+                        else epilogue_rowmajor<F16, true, false, 0>(p, tile, lane, wrow0, col0);
                     } else {
-                        if (st) epilogue_rowmajor<F16, false, false, true>(p, tile, lane, wrow0, col0);
-                        else epilogue_rowmajor<F16, false, false, false>(p, tile, lane, wrow0, col0);
+                        if (st && p.stat_cols == 4) epilogue_rowmajor<F16, false, false, 4>(p, tile, lane, wrow0, col0);
+                        else if (st) epilogue_rowmajor<F16, false, false, 2>(p, tile, lane, wrow0, col0);
+                        else epilogue_rowmajor<F16, false, false, 0>(p, tile, lane, wrow0, col0);
                     }
                     __syncwarp();
                 } else if (p.out_mode == kOutBF16) {         // V third of proj_in: transposed per image (coalesced per column)

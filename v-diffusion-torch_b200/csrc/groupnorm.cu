@@ -47,8 +47,11 @@ __device__ __forceinline__ void load_vec16(const h16* p, float (&v)[4], int f16)
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
     }
 }
-template <int VEC>
-__device__ __forceinline__ void load_vec16(const h16*, float (&)[VEC], int) {}
+__device__ __forceinline__ void load_vec16(const h16* p, float (&v)[2], int f16) {
+    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+    const float2 a = f16 ? __half22float2(*reinterpret_cast<const __half2*>(&t)) : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t));
+    v[0] = a.x; v[1] = a.y;
+}
 
 template <int VEC>
 __device__ __forceinline__ void store_16(h16* p, const float (&v)[VEC], int f16) {      // saturating (raw stream values)
@@ -92,27 +95,42 @@ __device__ __forceinline__ void store_f32(float* p, const float (&v)[VEC]) {
 }
 
 // Combines the conv epilogue's partial statistics of one image into (mean, rstd) per group: 8 threads per
-// group, fixed summation order, fp64.
+// group, fixed summation order, fp64.  Works for any even channels-per-group and for groups that straddle the
+// seam of a channel concat.
 __global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const GroupNormParams p) {
     const int b = blockIdx.x, tid = threadIdx.x;
     const int C = p.C1 + p.C2, HW = p.H * p.W, cpg = C / kGroups;
     const int g = tid >> 3, part8 = tid & 7;
-    const int cbase = g * cpg;
-    const bool g1 = cbase < p.C1;
-    const float2* st = g1 ? p.stats1 : p.stats2;
-    const int Cs = g1 ? p.C1 : p.C2;
-    const int c4 = (g1 ? cbase : cbase - p.C1) >> 2, sub = cpg >> 2, slabs = HW / kStatRows;
-    const float2* base = st + static_cast<size_t>(b) * slabs * (Cs >> 2) + c4;
+    // entries of stat_cols channels; a group may straddle the concat seam, so each entry picks its source
+    const int sc = p.stat_cols, sub = cpg / sc, slabs = HW / kStatRows;
+    const int e1 = p.C1 / sc, e2 = p.C2 / sc;              // entries per slab in source 1 / 2
+    const float2* s1 = p.stats1 + static_cast<size_t>(b) * slabs * e1;
+    const float2* s2 = p.stats2 ? p.stats2 + static_cast<size_t>(b) * slabs * e2 : nullptr;
     double ds = 0.0, dss = 0.0;
-    for (int e0 = 0; e0 < slabs * sub; e0 += 32) {           // 4 independent loads in flight per thread
-        float2 t[4];
+    const int ent0 = g * sub;                                // first entry of this group over the concatenated channels
+    if (ent0 + sub <= e1 || ent0 >= e1) {
+        // the whole group lies in one source (always the case without a concat): plain strided walk
+        const bool in1 = ent0 < e1;
+        const int es = in1 ? e1 : e2;
+        const float2* base = (in1 ? s1 : s2) + (in1 ? ent0 : ent0 - e1);
+        for (int e0 = 0; e0 < slabs * sub; e0 += 32) {       // 4 independent loads in flight per thread
+            float2 t[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int e = e0 + u * 8 + part8;
-            t[u] = (e < slabs * sub) ? __ldg(base + static_cast<size_t>(e / sub) * (Cs >> 2) + (e % sub)) : make_float2(0.f, 0.f);
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 8 + part8;
+                t[u] = (e < slabs * sub) ? __ldg(base + static_cast<size_t>(e / sub) * es + (e % sub)) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { ds += t[u].x; dss += t[u].y; }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { ds += t[u].x; dss += t[u].y; }
+    } else {
+        // the group straddles the concat seam: every entry picks its source
+        for (int e = part8; e < slabs * sub; e += 8) {
+            const int slab = e / sub, ent = ent0 + (e % sub);
+            const float2 t = (ent < e1) ? __ldg(s1 + static_cast<size_t>(slab) * e1 + ent)
+                                        : __ldg(s2 + static_cast<size_t>(slab) * e2 + (ent - e1));
+            ds += t.x; dss += t.y;
+        }
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, o); dss += __shfl_xor_sync(0xffffffffu, dss, o); }
@@ -320,8 +338,9 @@ cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream) {
     if (CV > 1024) return cudaErrorInvalidValue;
     const int HW = p.H * p.W;
     const bool fused = p.stats1 != nullptr;
-    if (fused && (vec != 4 || HW % kStatRows != 0 || (p.C2 > 0 && (p.stats2 == nullptr || p.C1 % cpg != 0)))) return cudaErrorInvalidValue;
-    if (p.in16 && (p.C2 != 0 || vec != 4 || !fused)) return cudaErrorInvalidValue;
+    if (fused && (HW % kStatRows != 0 || (p.stat_cols != 2 && p.stat_cols != 4) || cpg % p.stat_cols != 0 ||
+                  p.C1 % p.stat_cols != 0 || (p.C2 > 0 && p.stats2 == nullptr))) return cudaErrorInvalidValue;
+    if (p.in16 && (p.C2 != 0 || !fused)) return cudaErrorInvalidValue;
     int PPH = 1024 / CV;
     const int work = (p.resample == kResDown) ? HW / 4 : HW;
     if (PPH > work) PPH = work;
@@ -339,10 +358,17 @@ cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream) {
     if (fused) {
         if (p.meanrstd == nullptr) return cudaErrorInvalidValue;
         groupnorm_finalize_kernel<<<p.B, 256, 0, stream>>>(p);
-        if (p.in16 && p.f16) groupnorm_kernel<4, true, true, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
-        else if (p.in16) groupnorm_kernel<4, true, true, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
-        else if (p.f16) groupnorm_kernel<4, true, false, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
-        else groupnorm_kernel<4, true, false, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
+        if (vec == 4) {
+            if (p.in16 && p.f16) groupnorm_kernel<4, true, true, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
+            else if (p.in16) groupnorm_kernel<4, true, true, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
+            else if (p.f16) groupnorm_kernel<4, true, false, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
+            else groupnorm_kernel<4, true, false, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
+        } else {
+            if (p.in16 && p.f16) groupnorm_kernel<2, true, true, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
+            else if (p.in16) groupnorm_kernel<2, true, true, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
+            else if (p.f16) groupnorm_kernel<2, true, false, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
+            else groupnorm_kernel<2, true, false, false><<<grid, threads, smem, stream>>>(p, CV, PPH);
+        }
     } else if (vec == 4) {
         if (p.f16) groupnorm_kernel<4, false, false, true><<<grid, threads, smem, stream>>>(p, CV, PPH);
         else groupnorm_kernel<4, false, false, false><<<grid, threads, smem, stream>>>(p, CV, PPH);

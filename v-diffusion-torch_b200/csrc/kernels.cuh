@@ -50,11 +50,12 @@ struct alignas(64) ConvParams {
     h16* out_bf16;
     h16* out_t;
     // optional GroupNorm partial statistics of the row-major output (after bias/residual): for every slab of
-    // 32 consecutive rows and every 4 consecutive columns, (sum, sum of squares): stats[slab * Cout/4 + col/4]
+    // 32 consecutive rows and every stat_cols (4 or 2) consecutive columns, (sum, sum of squares):
+    // stats[slab * Cout/stat_cols + col/stat_cols]
     float2* stats;
+    int stat_cols;
 };
 constexpr int kStatRows = 32;   // rows per statistics slab
-constexpr int kStatCols = 4;    // columns per statistics entry
 cudaError_t launch_conv_gemm(const ConvParams& p, int num_sms, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
@@ -70,6 +71,7 @@ struct GroupNormParams {
     // partial statistics written by the producing conv epilogue (ConvParams::stats); when stats1 is set the
     // kernel is a single streaming pass, otherwise it makes a statistics pass of its own
     const float2* stats1; const float2* stats2;
+    int stat_cols;                     // columns per statistics entry (4, or 2 when groups are not a multiple of 4 channels)
     float2* meanrstd;                  // scratch [B][32] (mean, rstd), required when stats1 is set
     int B, H, W;
     const float* gamma; const float* beta;   // [C1 + C2]

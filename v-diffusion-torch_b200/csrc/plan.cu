@@ -289,6 +289,7 @@ struct vdt_plan {
     bool use_graph = true;
     int f16 = 1;                          // GEMM operand format: 1 fp16 (default), 0 bf16
     int split = 0;                        // 1: split-precision validation mode (every operand as a hi/lo fp16 pair)
+    int stat_cols = 4;                    // columns per GroupNorm statistics entry: 4, or 2 when some group is not a multiple of 4 channels
     // all work runs on an internal stream (the caller's may be the legacy default stream, which
     // cannot be captured); ordering against the caller's stream is kept with two events
     cudaStream_t work = nullptr;
@@ -458,6 +459,9 @@ extern "C" int vdt_plan_create(const vdt_unet_config* cfg, vdt_plan** out) {
         }
     }
     p->film_total = film;
+    for (auto& b : p->blocks)
+        if ((b.cin / 32) % 4 != 0 || (b.cout / 32) % 4 != 0) p->stat_cols = 2;
+    if (((hid * c.ch_multipliers[0]) / 32) % 4 != 0) p->stat_cols = 2;
     const int c0 = hid * c.ch_multipliers[0];
     add_weight(p.get(), "out_conv.0.weight", {c0}); add_weight(p.get(), "out_conv.0.bias", {c0});
     add_weight(p.get(), "out_conv.2.weight", {c.out_channels, c0, 3, 3}); add_weight(p.get(), "out_conv.2.bias", {c.out_channels});
@@ -633,6 +637,7 @@ struct ConvSpec {
     int out_mode = kOutF32; float* out_f32 = nullptr; h16* out_bf16 = nullptr; h16* out_t = nullptr;
     int ld = 0, split_col = 0, act_silu = 0, f16 = 1;
     float2* stats = nullptr;
+    int stat_cols = 4;
 };
 
 static int setup_conv(const ConvSpec& s, ConvParams* cp) {
@@ -672,7 +677,8 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     CKI(make_map_2d(&cp->b_map, s.wpacked, s.wrows, ktot, ktot, cp->block_n / 2));   // each CTA of a pair fetches half
     cp->M = (int)M; cp->Cout = s.cout; cp->out_mode = s.out_mode; cp->ld = s.ld;
     cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16;
-    cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t; cp->stats = s.stats;
+    cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t; cp->stat_cols = s.stat_cols;
+    cp->stats = ((s.h * s.w) % kStatRows == 0) ? s.stats : nullptr;   // statistics slabs never span two images
     if (s.out_mode != kOutNCHW && s.cout % 32 != 0) return fail("output channels must be a multiple of 32 (got %d)", s.cout);
     return 0;
 }
@@ -695,7 +701,8 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
     };
     // ---- in_conv
     // every fp32 stream tensor carries the partial GroupNorm statistics its producing conv wrote
-    auto stats_bytes = [&](size_t rows_px, int ch) { return (rows_px / kStatRows) * (size_t)(ch / kStatCols) * sizeof(float2); };
+    const int scols = p->stat_cols;
+    auto stats_bytes = [&](size_t rows_px, int ch) { return (rows_px / kStatRows + 1) * (size_t)(ch / scols) * sizeof(float2); };
     const bool sp = p->split != 0;
     h16* patches; h16* patches_lo = nullptr; float* h; float2* hst;
     const size_t hw0 = (size_t)res * res;
@@ -707,7 +714,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
     CKI(ex->acquire(stats_bytes((size_t)R * hw0, hid), (void**)&hst));
     {
         ConvSpec s;
-        s.f16 = p->f16;
+        s.f16 = p->f16; s.stat_cols = p->stat_cols;
         s.a1 = patches; s.a1_lo = patches_lo; s.c1 = 64; s.ld1 = 64; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_in; s.cout = hid; s.wrows = hid;
         s.bias = p->W("in_conv.bias"); s.out_mode = kOutF32; s.out_f32 = h; s.ld = hid; s.stats = hst;
         CKI(add_conv(s));
@@ -720,9 +727,10 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
     stack.push_back({h, hst, hid});
     bool h_on_stack = true;      // h aliases the top stack entry -> must not be released when replaced
     int hch = hid;
-    auto fusable = [](int c1, int c2) {               // can a GroupNorm over concat(c1, c2) use epilogue statistics?
+    auto fusable = [scols](int c1, int c2, int hw) {  // can a GroupNorm over concat(c1, c2) use epilogue statistics?
         const int cpg = (c1 + c2) / 32;
-        return cpg % kStatCols == 0 && (c2 == 0 || c1 % cpg == 0);
+        // groups may straddle the concat seam (finalize handles it); an image must be whole statistics slabs
+        return cpg % scols == 0 && c1 % scols == 0 && hw % kStatRows == 0;
     };
 
     for (auto& b : p->blocks) {
@@ -743,23 +751,24 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             if (skipconv && sp) CKI(ex->acquire((size_t)R * HW * cin * 2, (void**)&xraw_lo));
             if (b.resample != kResNone) CKI(ex->acquire((size_t)R * HWo * cin * 4, (void**)&xres));
             GroupNormParams g{};
-            g.f16 = p->f16;
+            g.f16 = p->f16; g.stat_cols = p->stat_cols;
             g.src1 = h; g.C1 = hch; g.src2 = src2; g.C2 = c2; g.B = R; g.H = res; g.W = res;
-            if (fusable(hch, c2)) { g.stats1 = hst; g.stats2 = st2; g.meanrstd = meanrstd; }
+            if (fusable(hch, c2, HW)) { g.stats1 = hst; g.stats2 = st2; g.meanrstd = meanrstd; }
             g.gamma = p->W(n + ".norm1.weight"); g.beta = p->W(n + ".norm1.bias");
             g.silu = 1; g.resample = b.resample; g.out_act = a1; g.out_raw = xraw; g.out_res = xres;
             g.out_act_lo = a1_lo; g.out_raw_lo = xraw_lo;
             add_gn(g);
             // conv1: its output only feeds norm2, so it is kept in the 16-bit operand format when norm2 can use
             // the epilogue statistics (otherwise fp32 for the two-pass fallback)
-            const bool fuse2 = fusable(b.cout, 0);
-            const bool h1_16 = fuse2 && !sp;            // split-precision mode keeps conv1's output in fp32
+            const bool fuse2 = fusable(b.cout, 0, (int)HWo);
+            // (split-precision mode keeps every stream tensor fp32)
+            const bool h1_16 = fuse2 && !sp;
             void* h1; float2* h1st = nullptr;
             CKI(ex->acquire((size_t)R * HWo * b.cout * (h1_16 ? 2 : 4), &h1));
             if (fuse2) CKI(ex->acquire(stats_bytes((size_t)R * HWo, b.cout), (void**)&h1st));
             {
                 ConvSpec s;
-                s.f16 = p->f16;
+                s.f16 = p->f16; s.stat_cols = p->stat_cols;
                 s.a3 = a1; s.a3_lo = a1_lo; s.c3 = cin; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w1; s.cout = b.cout; s.wrows = b.cout;
                 s.bias = p->W(n + ".conv1.bias"); s.ld = b.cout; s.stats = h1st;
                 if (h1_16) { s.out_mode = kOutBF16; s.out_bf16 = (h16*)h1; } else { s.out_mode = kOutF32; s.out_f32 = (float*)h1; }
@@ -772,7 +781,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire((size_t)R * HWo * b.cout * 2, (void**)&a2));
             if (sp) CKI(ex->acquire((size_t)R * HWo * b.cout * 2, (void**)&a2_lo));
             GroupNormParams g2{};
-            g2.f16 = p->f16;
+            g2.f16 = p->f16; g2.stat_cols = p->stat_cols;
             g2.src1 = h1; g2.C1 = b.cout; g2.B = R; g2.H = ro; g2.W = ro; g2.in16 = h1_16 ? 1 : 0; g2.stats1 = h1st; g2.meanrstd = meanrstd;
             g2.out_act_lo = a2_lo;
             g2.gamma = p->W(n + ".norm2.weight"); g2.beta = p->W(n + ".norm2.bias");
@@ -787,7 +796,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire(stats_bytes((size_t)R * HWo, b.cout), (void**)&houtst));
             {
                 ConvSpec s;
-                s.f16 = p->f16;
+                s.f16 = p->f16; s.stat_cols = p->stat_cols;
                 s.a3 = a2; s.a3_lo = a2_lo; s.c3 = b.cout; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w2; s.cout = b.cout; s.wrows = b.cout;
                 if (skipconv) { s.a1 = xraw; s.a1_lo = xraw_lo; s.c1 = cin; s.ld1 = cin; }
                 s.bias = b.bias2;
@@ -811,9 +820,9 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire((size_t)R * HW * b.cin * 2, (void**)&a));
             if (sp) CKI(ex->acquire((size_t)R * HW * b.cin * 2, (void**)&a_lo));
             GroupNormParams g{};
-            g.f16 = p->f16;
+            g.f16 = p->f16; g.stat_cols = p->stat_cols;
             g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
-            if (fusable(hch, 0)) { g.stats1 = hst; g.meanrstd = meanrstd; }
+            if (fusable(hch, 0, HW)) { g.stats1 = hst; g.meanrstd = meanrstd; }
             g.gamma = p->W(n + ".norm.weight"); g.beta = p->W(n + ".norm.bias");
             g.silu = 0; g.resample = kResNone; g.out_act = a; g.out_act_lo = a_lo;
             add_gn(g);
@@ -823,7 +832,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
                 CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&vt));
                 {   // one GEMM for q | k | v: q,k row-major [R*N, 2*hid]; the v third is written transposed, V^T [R*hid, N]
                     ConvSpec s;
-                    s.f16 = p->f16;
+                    s.f16 = p->f16; s.stat_cols = p->stat_cols;
                     s.a1 = a; s.c1 = b.cin; s.ld1 = b.cin; s.n = R; s.h = res; s.w = res; s.wpacked = b.w1; s.cout = 3 * hidd;
                     s.wrows = 3 * hidd; s.bias = p->W(n + ".proj_in.bias"); s.out_mode = kOutBF16; s.out_bf16 = qk; s.out_t = vt;
                     s.ld = 2 * hidd; s.split_col = 2 * hidd;
@@ -848,7 +857,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
                 CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&o_lo));
                 {
                     ConvSpec s;
-                    s.f16 = p->f16;
+                    s.f16 = p->f16; s.stat_cols = p->stat_cols;
                     s.a1 = a; s.a1_lo = a_lo; s.c1 = b.cin; s.ld1 = b.cin; s.n = R; s.h = res; s.w = res; s.wpacked = b.w1;
                     s.cout = 3 * hidd; s.wrows = 3 * hidd; s.bias = p->W(n + ".proj_in.bias"); s.out_mode = kOutF32; s.out_f32 = qkv32;
                     s.ld = 3 * hidd;
@@ -864,7 +873,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire(stats_bytes((size_t)R * HW, b.cin), (void**)&houtst));
             {
                 ConvSpec s;
-                s.f16 = p->f16;
+                s.f16 = p->f16; s.stat_cols = p->stat_cols;
                 s.a1 = o; s.a1_lo = o_lo; s.c1 = hidd; s.ld1 = hidd; s.n = R; s.h = res; s.w = res; s.wpacked = b.w2; s.cout = b.cin; s.wrows = b.cin;
                 s.bias = p->W(n + ".proj_out.bias"); s.residual = h; s.out_mode = kOutF32; s.out_f32 = hout; s.ld = b.cin;
                 s.stats = houtst;
@@ -885,14 +894,14 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
         CKI(ex->acquire((size_t)R * HW * hch * 2, (void**)&a));
         if (sp) CKI(ex->acquire((size_t)R * HW * hch * 2, (void**)&a_lo));
         GroupNormParams g{};
-        g.f16 = p->f16;
+        g.f16 = p->f16; g.stat_cols = p->stat_cols;
         g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
-        if (fusable(hch, 0)) { g.stats1 = hst; g.meanrstd = meanrstd; }
+        if (fusable(hch, 0, HW)) { g.stats1 = hst; g.meanrstd = meanrstd; }
         g.gamma = p->W("out_conv.0.weight"); g.beta = p->W("out_conv.0.bias");
         g.silu = 1; g.resample = kResNone; g.out_act = a; g.out_act_lo = a_lo;
         add_gn(g);
         ConvSpec s;
-        s.f16 = p->f16;
+        s.f16 = p->f16; s.stat_cols = p->stat_cols;
         s.a3 = a; s.a3_lo = a_lo; s.c3 = hch; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_out; s.cout = c.out_channels; s.wrows = 16;
         s.bias = p->W("out_conv.2.bias"); s.out_mode = kOutNCHW; s.out_f32 = ex->yout; s.ld = 0;
         CKI(add_conv(s));
@@ -1286,7 +1295,7 @@ extern "C" int vdt_p_sample_host(vdt_plan* p, const vdt_sampler_config* scp, con
 // ================================================================================================ kernel-level hooks
 extern "C" int vdt_op_conv(const void* x, int32_t batch, int32_t h, int32_t w, int32_t cin, const float* w_oihw, int32_t cout,
                            int32_t ksize, const float* bias, const float* residual, float* out, int32_t f16, void* out16,
-                           void* stats_out, void* stream) {
+                           void* stats_out, int32_t stat_cols, void* stream) {
     if (ksize != 1 && ksize != 3) return fail("ksize must be 1 or 3");
     if (cin % 64) return fail("cin must be a multiple of 64");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1304,7 +1313,7 @@ extern "C" int vdt_op_conv(const void* x, int32_t batch, int32_t h, int32_t w, i
         s.f16 = f16;
         if (ksize == 3) { s.a3 = (const h16*)x; s.c3 = cin; } else { s.a1 = (const h16*)x; s.c1 = cin; s.ld1 = cin; }
         s.n = batch; s.h = h; s.w = w; s.wpacked = wp; s.cout = cout; s.wrows = wrows; s.bias = bias; s.residual = residual;
-        s.out_mode = kOutF32; s.out_f32 = out; s.ld = cout; s.stats = (float2*)stats_out;
+        s.out_mode = kOutF32; s.out_f32 = out; s.ld = cout; s.stats = (float2*)stats_out; s.stat_cols = stat_cols == 2 ? 2 : 4;
         if (out16) { s.out_mode = kOutBF16; s.out_bf16 = (h16*)out16; s.out_f32 = nullptr; }
         std::unique_ptr<ConvParams> cp(new ConvParams());
         rc = setup_conv(s, cp.get());
@@ -1323,9 +1332,9 @@ extern "C" int vdt_op_conv(const void* x, int32_t batch, int32_t h, int32_t w, i
 extern "C" int vdt_op_groupnorm(const void* src1, int32_t c1, const float* src2, int32_t c2, int32_t batch, int32_t h,
                                 int32_t w, const float* gamma, const float* beta, const float* film, int32_t film_stride,
                                 int32_t film_off, int32_t silu, int32_t resample, void* out_act, void* out_raw, float* out_res,
-                                int32_t f16, const void* stats1, const void* stats2, int32_t in16, void* stream) {
+                                int32_t f16, const void* stats1, const void* stats2, int32_t stat_cols, int32_t in16, void* stream) {
     GroupNormParams g{};
-    g.f16 = f16; g.stats1 = (const float2*)stats1; g.stats2 = (const float2*)stats2; g.in16 = in16;
+    g.f16 = f16; g.stats1 = (const float2*)stats1; g.stats2 = (const float2*)stats2; g.in16 = in16; g.stat_cols = stat_cols == 2 ? 2 : 4;
     g.src1 = src1; g.C1 = c1; g.src2 = src2; g.C2 = c2; g.B = batch; g.H = h; g.W = w; g.gamma = gamma; g.beta = beta;
     g.film = film; g.film_row = nullptr; g.film_stride = film_stride; g.film_off = film_off; g.silu = silu; g.resample = resample;
     g.out_act = (h16*)out_act; g.out_raw = (h16*)out_raw; g.out_res = out_res;
