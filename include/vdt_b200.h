@@ -55,7 +55,7 @@ typedef struct vdt_sampler_config {
     int32_t model_var_type;       /* VDT_VAR_* */
     int32_t logsnr_schedule;      /* VDT_SCHED_* */
     int32_t use_ddim;             /* p_sample(..., use_ddim=) */
-    int32_t reserved;
+    int32_t x0eps_coef;           /* GaussianDiffusion(x0eps_coef=): posterior mean as c1*eps + c2*x0 (diffusion.py:137-140, 335-343) */
     double intp_frac;
     double logsnr_min, logsnr_max;
     double w_guide;
@@ -107,8 +107,10 @@ int vdt_p_sample_host(vdt_plan* plan, const vdt_sampler_config* sc, const float*
                       const float* step_noise, float* out, int32_t batch);
 
 /* logsnr schedule + posterior coefficients — diffusion.py:42-112, 126-203 (host, fp64 with the reference's
- * fp32 rounding points).  out: [T][12] floats: alpha_t, sigma_t, rsqrt(sigmoid l_t), exp(-l_t/2), sigmoid(l_t),
- * sigmoid(-l_t), c1, c2, std, logvar, logsnr_s, logsnr_t. */
+ * fp32 rounding points).  out: [T][16] floats: alpha_t, sigma_t, rsqrt(sigmoid l_t), exp(-l_t/2), sigmoid(l_t),
+ * sigmoid(-l_t), c1, c2, std, logvar, logsnr_s, logsnr_t, rsqrt(sigmoid -l_t), exp(l_t/2), x0eps_coef (0/1), 0.
+ * With x0eps_coef and DDIM, c1/c2 are the LOGARITHMS 0.5*logsigmoid(-+l_s): the reference only exponentiates
+ * them for eta != 0 (diffusion.py:180-182 vs 199) and p_sample always runs eta = 0; reproduced as is. */
 int vdt_step_coefficients(const vdt_sampler_config* sc, float* out);
 
 /* Counters: kernels launched by this library since process start (graph replays count their nodes). */

@@ -59,13 +59,18 @@ def _log1mexp(x):
 
 
 def step_coefficients(T: int, use_ddim: bool, var_type: str = "fixed_large", intp_frac=None,
-                      schedule: str = "cosine", logsnr_min: float = -20., logsnr_max: float = 20.):
+                      schedule: str = "cosine", logsnr_min: float = -20., logsnr_max: float = 20.,
+                      x0eps_coef: bool = False):
     """Per-step fp32 scalars for step index i = 0..T-1 (the loop visits T-1 .. 0).
 
     Returns dict of float32 arrays of length T: ``logsnr_s, logsnr_t, alpha_t, sigma_t
     (fp32 math on the fp32 log-SNR: diffusion.py:233-234), c1, c2, logvar, std``
     (std = exp(0.5 logvar) in fp32, 0 for DDIM) and fp64 ``t_model`` = (i+1)/T, the time
-    fed to the network (diffusion.py:364, 374)."""
+    fed to the network (diffusion.py:364, 374).
+
+    ``x0eps_coef`` (diffusion.py:137-140, 180-182): the posterior mean is written as c1 * eps + c2 * x0.  The
+    reference's DDIM branch returns the two coefficients as LOGARITHMS (the ``.exp_()`` at diffusion.py:199 is
+    only reached for eta != 0); that is restated as is."""
     i = np.arange(T, dtype=np.float64)
     s, t = i / T, (i + 1) / T
     ls32 = logsnr_schedule(s, schedule, logsnr_min, logsnr_max).astype(np.float32)
@@ -73,14 +78,22 @@ def step_coefficients(T: int, use_ddim: bool, var_type: str = "fixed_large", int
     ls, lt = ls32.astype(np.float64), lt32.astype(np.float64)
     logr = lt - ls
     if use_ddim:                                     # eta = 0 branch, diffusion.py:178-187
-        c1 = np.exp(0.5 * (_logsigmoid(-ls) - _logsigmoid(-lt)))
-        c2 = np.exp(_log1mexp(0.5 * logr) + 0.5 * _logsigmoid(ls))
+        if x0eps_coef:                               # diffusion.py:180-182 (not exponentiated, see docstring)
+            c1 = 0.5 * _logsigmoid(-ls)
+            c2 = 0.5 * _logsigmoid(ls)
+        else:
+            c1 = np.exp(0.5 * (_logsigmoid(-ls) - _logsigmoid(-lt)))
+            c2 = np.exp(_log1mexp(0.5 * logr) + 0.5 * _logsigmoid(ls))
         logvar = np.full(T, -np.inf)
     else:                                            # diffusion.py:133-161
         log_alpha_st = 0.5 * (_logsigmoid(ls) - _logsigmoid(lt))
         l1mr = _log1mexp(logr)
-        c1 = np.exp(logr + log_alpha_st)
-        c2 = np.exp(l1mr + 0.5 * _logsigmoid(ls))
+        if x0eps_coef:                               # diffusion.py:137-140
+            c1 = np.exp(0.5 * (_logsigmoid(ls) - lt) + logr)
+            c2 = np.sqrt(1.0 / (1.0 + np.exp(-ls)))
+        else:
+            c1 = np.exp(logr + log_alpha_st)
+            c2 = np.exp(l1mr + 0.5 * _logsigmoid(ls))
         if var_type == "fixed_large":
             logvar = l1mr + _logsigmoid(-lt)
         elif var_type == "fixed_small":
@@ -134,13 +147,14 @@ def p_sample(denoise_fn: Callable, shape, noise: torch.Tensor, label: Optional[t
              T: int, model_out_type: str, w_guide: float = 0., use_ddim: bool = True,
              var_type: str = "fixed_large", intp_frac=None, step_noise: Optional[torch.Tensor] = None,
              schedule: str = "cosine", logsnr_min: float = -20., logsnr_max: float = 20.,
-             record: Optional[list] = None, pred_record: Optional[list] = None) -> torch.Tensor:
+             record: Optional[list] = None, pred_record: Optional[list] = None,
+             x0eps_coef: bool = False) -> torch.Tensor:
     """Reverse loop (diffusion.py:394-414 + 360-392).  ``noise``: initial x_T.
     ``step_noise``: (T, B, C, H, W) pre-drawn per-step normal draws, indexed by the step
     index ti (required for ancestral sampling so both sides inject identical noise);
     DDIM multiplies them by exp(-inf)=0.  ``record`` collects (ti, model_out)."""
     B = shape[0]
-    co = step_coefficients(T, use_ddim, var_type, intp_frac, schedule, logsnr_min, logsnr_max)
+    co = step_coefficients(T, use_ddim, var_type, intp_frac, schedule, logsnr_min, logsnr_max, x0eps_coef)
     x_t = noise.clone().float()
     use_cfg = (w_guide > 0) and (label is not None)
     for ti in reversed(range(T)):
@@ -158,7 +172,10 @@ def p_sample(denoise_fn: Callable, shape, noise: torch.Tensor, label: Optional[t
         if record is not None:
             record.append((ti, out.clone()))
         x0 = _pred_x0(xin, out, lt, model_out_type).clamp(-1., 1.)
-        mean = torch.tensor(c1) * xin + torch.tensor(c2) * x0
+        xt_or_eps = xin
+        if x0eps_coef:                                # eps re-derived from the clipped x0 (diffusion.py:335-343, 222-223)
+            xt_or_eps = xin * torch.sigmoid(-lt).rsqrt() - x0 * (lt * 0.5).exp()
+        mean = torch.tensor(c1) * xt_or_eps + torch.tensor(c2) * x0
         if ti == 0:                                   # where(cond, mean, pred_x_0)  diffusion.py:378
             mean = x0
         pred = x0

@@ -49,6 +49,14 @@ SAMPLE_CASES = {
     # BASELINE configs[3] in miniature: ancestral, CFG w=3, injected per-step noise
     "ancestral_cfg_v": dict(unet="small_cond", seed=23, B=2, res=16, T=10, model_out_type="v", w_guide=3.0,
                             use_ddim=False, var_type="fixed_medium", intp_frac=0.3, labels=[4, 9]),
+    # x0eps_coef=True (diffusion.py:137-140, 335-343): posterior mean written in (eps, x0), eps re-derived from the
+    # clipped x0.  (v-prediction: an eps-prediction network at logsnr_min = -20 amplifies any rounding by e^10 before
+    # the clip -- the reference under its own TF32 numerics moves by 0.5 on such a fixture.)
+    "ancestral_x0eps": dict(unet="small_cond", seed=25, B=2, res=16, T=6, model_out_type="v", w_guide=0.5,
+                            use_ddim=False, var_type="fixed_small", labels=[3, 8], x0eps_coef=True),
+    # same under DDIM: the reference hands back LOG coefficients there (diffusion.py:180-182) -- reproduced as is
+    "ddim_x0eps": dict(unet="small_cond", seed=26, B=2, res=16, T=5, model_out_type="v", w_guide=0.0,
+                       use_ddim=True, var_type="fixed_small", labels=[1, 6], x0eps_coef=True),
     # CelebA-style "both" output (2C channels), ancestral fixed_large
     "ancestral_both": dict(unet="small_hd64", seed=24, B=2, res=32, T=5, model_out_type="both", w_guide=0.0,
                            use_ddim=False, var_type="fixed_large", labels=None),

@@ -79,7 +79,7 @@ def main():
         diff = GaussianDiffusion(
             logsnr_fn=logsnr_fn, sample_timesteps=case["T"], model_out_type=case["model_out_type"],
             model_var_type=case["var_type"], reweight_type="snr_trunc", loss_type="mse",
-            intp_frac=case.get("intp_frac"), w_guide=case["w_guide"])
+            intp_frac=case.get("intp_frac"), w_guide=case["w_guide"], x0eps_coef=case.get("x0eps_coef", False))
         outs = []
 
         def rec(x, t, y):
@@ -107,6 +107,12 @@ def main():
         c1, c2, lv = logsnr_to_posterior(ls, lt, vt, intp_frac=0.3)
         co[f"{vt}_c1"], co[f"{vt}_c2"], co[f"{vt}_logvar"] = (
             c1.flatten().numpy(), c2.flatten().numpy(), lv.flatten().numpy())
+    # x0eps_coef=True variants (diffusion.py:137-140, 180-182; the DDIM pair comes back un-exponentiated)
+    c1, c2, _ = logsnr_to_posterior_ddim(ls, lt, eta=0., x0eps_coef=True)
+    co["x0eps_ddim_c1"], co["x0eps_ddim_c2"] = c1.flatten().numpy(), c2.flatten().numpy()
+    c1, c2, lv = logsnr_to_posterior(ls, lt, "fixed_small", x0eps_coef=True)
+    co["x0eps_small_c1"], co["x0eps_small_c2"], co["x0eps_small_logvar"] = (
+        c1.flatten().numpy(), c2.flatten().numpy(), lv.flatten().numpy())
     co["alpha_t"] = torch.sigmoid(lt).sqrt().flatten().numpy()
     co["sigma_t"] = torch.sigmoid(-lt).sqrt().flatten().numpy()
     tt = torch.tensor([0.37, 0.01, 1.0, 0.5], dtype=torch.float64)

@@ -44,7 +44,7 @@ def run(case, tf32):
     diff = mg.GaussianDiffusion(
         logsnr_fn=mg.get_logsnr_schedule("cosine", -20., 20., rescale=False), sample_timesteps=case["T"],
         model_out_type=case["model_out_type"], model_var_type=case["var_type"], reweight_type="snr_trunc",
-        loss_type="mse", intp_frac=case.get("intp_frac"), w_guide=case["w_guide"])
+        loss_type="mse", intp_frac=case.get("intp_frac"), w_guide=case["w_guide"], x0eps_coef=case.get("x0eps_coef", False))
     F.conv2d = conv2d_tf32 if tf32 else _conv2d
     torch.conv2d, saved = (conv2d_tf32 if tf32 else torch.conv2d), torch.conv2d
     try:

@@ -44,6 +44,20 @@ def test_step_coefficients_match_reference(golden_dir):
         np.testing.assert_allclose(an[:, 7], g[f"{vt}_c2"], rtol=2e-6, atol=1e-10)
         np.testing.assert_allclose(an[:, 9], g[f"{vt}_logvar"], rtol=2e-6, atol=1e-7)
         np.testing.assert_allclose(an[:, 8], np.exp(0.5 * g[f"{vt}_logvar"]), rtol=1e-5)
+    # x0eps_coef=True: posterior mean in (eps, x0) (diffusion.py:137-140); the DDIM pair is returned by the reference
+    # as logarithms (180-182 never reach the .exp_() of line 199) and is reproduced as such
+    x = GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), 100, "eps", "fixed_small", "snr_trunc", "mse",
+                          x0eps_coef=True)
+    xd, xa = x.step_coefficients(use_ddim=True).numpy(), x.step_coefficients(use_ddim=False).numpy()
+    np.testing.assert_allclose(xd[:, 6], g["x0eps_ddim_c1"], rtol=2e-6, atol=1e-10)
+    np.testing.assert_allclose(xd[:, 7], g["x0eps_ddim_c2"], rtol=2e-6, atol=1e-10)
+    np.testing.assert_allclose(xa[:, 6], g["x0eps_small_c1"], rtol=2e-6, atol=1e-10)
+    np.testing.assert_allclose(xa[:, 7], g["x0eps_small_c2"], rtol=2e-6, atol=1e-10)
+    np.testing.assert_allclose(xa[:, 9], g["x0eps_small_logvar"], rtol=2e-6, atol=1e-7)
+    lt = g["logsnr_t"].astype(np.float64)
+    np.testing.assert_allclose(xa[:, 12], np.sqrt(1.0 + np.exp(lt)), rtol=2e-6)      # rsqrt(sigmoid(-l_t))
+    np.testing.assert_allclose(xa[:, 13], np.exp(0.5 * lt), rtol=2e-6)
+    assert np.all(xa[:, 14] == 1) and np.all(dd[:, 14] == 0)
 
 
 def test_error_behaviour_mirrors_reference():

@@ -33,7 +33,7 @@ def _diffusion(case):
     from v_diffusion_b200 import GaussianDiffusion, get_logsnr_schedule
     return GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), case["T"], case["model_out_type"],
                              case["var_type"], "snr_trunc", "mse", intp_frac=case.get("intp_frac"),
-                             w_guide=case["w_guide"])
+                             w_guide=case["w_guide"], x0eps_coef=case.get("x0eps_coef", False))
 
 
 @pytest.mark.parametrize("name", sorted(UNET_CASES))

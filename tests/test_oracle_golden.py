@@ -52,7 +52,7 @@ def test_sampler_matches_reference(golden_dir, name):
     out = p_sample(lambda x, t, y: unet_forward(sd, cfg, x, t, y), tuple(noise.shape), noise, label,
                    T=case["T"], model_out_type=case["model_out_type"], w_guide=case["w_guide"],
                    use_ddim=case["use_ddim"], var_type=case["var_type"], intp_frac=case.get("intp_frac"),
-                   step_noise=step_noise, record=rec)
+                   step_noise=step_noise, record=rec, x0eps_coef=case.get("x0eps_coef", False))
     ref = torch.from_numpy(g["out"])
     assert (out - ref).abs().max().item() <= 5e-4
     mo = torch.from_numpy(g["model_out"])
@@ -78,6 +78,15 @@ def test_step_coefficients_known_answers(golden_dir):
         np.testing.assert_allclose(an["c1"], g[f"{vt}_c1"], rtol=2e-7, atol=1e-12)
         np.testing.assert_allclose(an["c2"], g[f"{vt}_c2"], rtol=2e-7, atol=1e-12)
         np.testing.assert_allclose(an["logvar"], g[f"{vt}_logvar"], rtol=2e-7, atol=1e-9)
+    # x0eps_coef=True (diffusion.py:137-140); the DDIM pair is the un-exponentiated one the reference returns (180-182)
+    xd = step_coefficients(100, use_ddim=True, x0eps_coef=True)
+    np.testing.assert_allclose(xd["c1"], g["x0eps_ddim_c1"], rtol=2e-7, atol=1e-12)
+    np.testing.assert_allclose(xd["c2"], g["x0eps_ddim_c2"], rtol=2e-7, atol=1e-12)
+    assert np.all(xd["c1"] < 0) and np.all(xd["c2"] < 0)
+    xa = step_coefficients(100, use_ddim=False, var_type="fixed_small", x0eps_coef=True)
+    np.testing.assert_allclose(xa["c1"], g["x0eps_small_c1"], rtol=2e-7, atol=1e-12)
+    np.testing.assert_allclose(xa["c2"], g["x0eps_small_c2"], rtol=2e-7, atol=1e-12)
+    np.testing.assert_allclose(xa["logvar"], g["x0eps_small_logvar"], rtol=2e-7, atol=1e-9)
     # SURVEY §10.2 table (values printed by the reference)
     assert abs(dd["c1"][50] - 0.984656036) < 1e-7 and abs(dd["c2"][50] - 0.021871394) < 1e-7
     assert abs(dd["alpha_t"][1] - 0.999505162) < 1e-7 and abs(dd["sigma_t"][1] - 0.031454321) < 1e-7

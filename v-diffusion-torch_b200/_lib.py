@@ -19,7 +19,7 @@ VDT_MAX_LEVELS = 8
 OUT_TYPES = {"x0": 0, "eps": 1, "both": 2, "v": 3}
 VAR_TYPES = {"fixed_small": 0, "fixed_large": 1, "fixed_medium": 2}
 SCHEDULES = {"cosine": 0, "linear": 1, "sigmoid": 2, "legacy": 3}
-COEF_STRIDE = 12
+COEF_STRIDE = 16
 OPERAND_DTYPES = {"fp16": 0, "bf16": 1, "fp16x3": 2}
 
 
@@ -34,7 +34,7 @@ class UNetConfig(C.Structure):
 
 class SamplerConfig(C.Structure):
     _fields_ = [("sample_timesteps", C.c_int32), ("model_out_type", C.c_int32), ("model_var_type", C.c_int32),
-                ("logsnr_schedule", C.c_int32), ("use_ddim", C.c_int32), ("reserved", C.c_int32),
+                ("logsnr_schedule", C.c_int32), ("use_ddim", C.c_int32), ("x0eps_coef", C.c_int32),
                 ("intp_frac", C.c_double), ("logsnr_min", C.c_double), ("logsnr_max", C.c_double),
                 ("w_guide", C.c_double), ("seed", C.c_uint64)]
 

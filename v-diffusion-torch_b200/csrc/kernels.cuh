@@ -143,9 +143,9 @@ struct SamplerState {
     int step;                          // step index of the step in flight
     int img0;                          // first image of the current chunk (offset into injected noise)
     int pad;
-    float coef[12];                    // alpha_t, sigma_t, rsqrt_sig, exp_half_neg, sig_pos, sig_neg, c1, c2, std, 0...
+    float coef[16];                    // one row of vdt_step_coefficients (include/vdt_b200.h)
 };
-constexpr int kCoefStride = 12;
+constexpr int kCoefStride = 16;
 // single-thread kernel: st->step = st->next_step--, copies the coefficient row, writes t_rows[r] = (step+1)/T
 cudaError_t launch_sampler_begin_step(SamplerState* st, const float* coef_table, double* t_rows, int nrows, int T,
                                       cudaStream_t stream);
@@ -164,6 +164,7 @@ struct SamplerStepParams {
     int cfg;                           // 1: classifier-free guidance pair per sample
     int model_out_type;                // 0 x0, 1 eps, 2 both, 3 v
     float w;
+    int x0eps;                         // posterior mean = c1 * eps + c2 * x0, eps re-derived from the clipped x0
 };
 cudaError_t launch_sampler_step(const SamplerStepParams& p, cudaStream_t stream);
 

@@ -1115,13 +1115,23 @@ extern "C" int vdt_step_coefficients(const vdt_sampler_config* scp, float* out) 
         if (!(logr < 0.0)) return fail("log-SNR schedule is not strictly decreasing at step %d", i);   // assert, diffusion.py:119
         double c1, c2, logvar;
         if (sc.use_ddim) {
-            c1 = std::exp(0.5 * (logsigmoid_d(-ls) - logsigmoid_d(-lt)));
-            c2 = std::exp(log1mexp_d(0.5 * logr) + 0.5 * logsigmoid_d(ls));
+            if (sc.x0eps_coef) {                     // diffusion.py:180-182: returned un-exponentiated for eta = 0
+                c1 = 0.5 * logsigmoid_d(-ls);
+                c2 = 0.5 * logsigmoid_d(ls);
+            } else {
+                c1 = std::exp(0.5 * (logsigmoid_d(-ls) - logsigmoid_d(-lt)));
+                c2 = std::exp(log1mexp_d(0.5 * logr) + 0.5 * logsigmoid_d(ls));
+            }
             logvar = -INFINITY;
         } else {
             const double l1mr = log1mexp_d(logr);
-            c1 = std::exp(logr + 0.5 * (logsigmoid_d(ls) - logsigmoid_d(lt)));
-            c2 = std::exp(l1mr + 0.5 * logsigmoid_d(ls));
+            if (sc.x0eps_coef) {                     // diffusion.py:137-140
+                c1 = std::exp(0.5 * (logsigmoid_d(ls) - lt) + logr);
+                c2 = std::sqrt(1.0 / (1.0 + std::exp(-ls)));
+            } else {
+                c1 = std::exp(logr + 0.5 * (logsigmoid_d(ls) - logsigmoid_d(lt)));
+                c2 = std::exp(l1mr + 0.5 * logsigmoid_d(ls));
+            }
             const double lo = l1mr + logsigmoid_d(-ls), hi = l1mr + logsigmoid_d(-lt);
             if (sc.model_var_type == VDT_VAR_FIXED_LARGE) logvar = hi;
             else if (sc.model_var_type == VDT_VAR_FIXED_SMALL) logvar = lo;
@@ -1143,6 +1153,10 @@ extern "C" int vdt_step_coefficients(const vdt_sampler_config* scp, float* out) 
         o[9] = lv32;
         o[10] = ls32;
         o[11] = lt32;
+        o[12] = 1.0f / std::sqrt(sig_neg);           // pred_eps_from_x0 (diffusion.py:222-223)
+        o[13] = std::exp(0.5f * lt32);
+        o[14] = sc.x0eps_coef ? 1.0f : 0.0f;         // lets vdt_op_sampler_step pick the (eps, x0) form from the row alone
+        o[15] = 0.0f;
     }
     return 0;
 }
@@ -1152,9 +1166,9 @@ static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs,
                             long long noise_stride, Exec** out) {
     const bool cfg = sc.w_guide > 0.0 && has_label;            // diffusion.py:368
     const int rep = cfg ? 2 : 1;
-    char key[160];
-    snprintf(key, sizeof(key), "smp:%d:%d:%d:%d:%d:%d:%d:%.17g:%.17g:%.17g:%.17g:%llu:%p:%lld", imgs, (int)has_label,
-             sc.sample_timesteps, sc.model_out_type, sc.model_var_type, sc.logsnr_schedule, sc.use_ddim, sc.intp_frac,
+    char key[192];
+    snprintf(key, sizeof(key), "smp:%d:%d:%d:%d:%d:%d:%d:%d:%.17g:%.17g:%.17g:%.17g:%llu:%p:%lld", imgs, (int)has_label,
+             sc.sample_timesteps, sc.model_out_type, sc.model_var_type, sc.logsnr_schedule, sc.use_ddim, sc.x0eps_coef, sc.intp_frac,
              sc.logsnr_min, sc.logsnr_max, sc.w_guide, (unsigned long long)sc.seed, (const void*)step_noise, noise_stride);
     auto it = p->execs.find(key);
     if (it != p->execs.end()) { *out = it->second.get(); return 0; }
@@ -1179,11 +1193,13 @@ static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs,
     CKI(ex->acquire(sizeof(SamplerState), (void**)&ex->state));
     CKI(ex->acquire(imgs * HW * c.in_channels * 4, (void**)&ex->pred));
     CKI(ex->acquire((size_t)T * kCoefStride * 4, (void**)&ex->coef_table));
-    iota_i64_kernel<<<(ex->emb_rows + 127) / 128, 128>>>(ex->y_rows, ex->emb_rows);
+    // on the plan's own stream: the legacy default stream does not order against a non-blocking stream
+    iota_i64_kernel<<<(ex->emb_rows + 127) / 128, 128, 0, p->work>>>(ex->y_rows, ex->emb_rows);
     CK(cudaGetLastError());
     std::vector<float> coefs((size_t)T * kCoefStride);
     CKI(vdt_step_coefficients(&sc, coefs.data()));
-    CK(cudaMemcpy(ex->coef_table, coefs.data(), coefs.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(ex->coef_table, coefs.data(), coefs.size() * 4, cudaMemcpyHostToDevice, p->work));
+    CK(cudaStreamSynchronize(p->work));              // `coefs` is a host temporary
     float* film;
     CKI(ex->acquire((size_t)ex->emb_rows * p->film_total * 4, (void**)&film));
     ex->begins.push_back({ex->state, ex->coef_table, ex->t_rows, ex->emb_rows, T});
@@ -1193,7 +1209,7 @@ static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs,
     SamplerStepParams sp{};
     sp.model_out = ex->yout; sp.x_t = ex->xin; sp.x_s = ex->xin; sp.pred_x0 = ex->pred; sp.noise = step_noise; sp.noise_step_stride = noise_stride;
     sp.st = ex->state; sp.seed = sc.seed; sp.B = imgs; sp.C = c.in_channels; sp.HW = (int)HW; sp.cfg = cfg ? 1 : 0;
-    sp.model_out_type = sc.model_out_type; sp.w = (float)sc.w_guide;
+    sp.model_out_type = sc.model_out_type; sp.w = (float)sc.w_guide; sp.x0eps = sc.x0eps_coef ? 1 : 0;
     ex->samples.push_back(sp);
     ex->steps.push_back({S_SAMPLE, 0});
     *out = ex.get();
@@ -1377,7 +1393,7 @@ extern "C" int vdt_op_sampler_step(const float* model_out, const float* x_t, con
     SamplerStepParams sp{};
     sp.model_out = model_out; sp.x_t = x_t; sp.x_s = x_s; sp.noise = noise;
     sp.noise_step_stride = 0; sp.st = ds; sp.seed = 0; sp.pred_x0 = nullptr; sp.B = batch; sp.C = c; sp.HW = hw; sp.cfg = cfg;
-    sp.model_out_type = model_out_type; sp.w = w;
+    sp.model_out_type = model_out_type; sp.w = w; sp.x0eps = coef_host[14] != 0.0f ? 1 : 0;
     cudaError_t e = launch_sampler_step(sp, st);
     ++g_launches;
     cudaError_t e2 = cudaStreamSynchronize(st);

@@ -242,14 +242,17 @@ __global__ void sampler_step_kernel(const SamplerStepParams p) {
     const float c1 = cf[6], c2 = cf[7], sd = cf[8];
     const bool last = (step == 0);
     const float x0c = pred_x0(p.model_out_type, x, o, o2, cf);
-    float mean = last ? x0c : c1 * x + c2 * x0c;                     // where(cond, mean, pred_x_0)  (diffusion.py:378)
+    // x0eps_coef: the mean's first argument is eps re-derived from the clipped x0 (diffusion.py:335-343, 222-223)
+    const float a_c = p.x0eps ? x * cf[12] - x0c * cf[13] : x;
+    float mean = last ? x0c : c1 * a_c + c2 * x0c;                   // where(cond, mean, pred_x_0)  (diffusion.py:378)
     float pred = x0c;
     if (p.cfg) {
         const float* mu = mo + static_cast<size_t>(Cm) * p.HW;
         const float u = mu[0];
         const float u2 = (p.model_out_type == 2) ? mu[second] : 0.f;
         const float x0u = pred_x0(p.model_out_type, x, u, u2, cf);
-        const float mean_u = last ? x0u : c1 * x + c2 * x0u;
+        const float a_u = p.x0eps ? x * cf[12] - x0u * cf[13] : x;
+        const float mean_u = last ? x0u : c1 * a_u + c2 * x0u;
         mean = mean + p.w * (mean - mean_u);                         // guided, not re-clipped (diffusion.py:384)
         pred = x0c + p.w * (x0c - x0u);                              // diffusion.py:385
     }

@@ -54,8 +54,6 @@ class GaussianDiffusion:
                  intp_frac=None, w_guide=0.1, p_uncond=0.1, x0eps_coef=False):
         if not isinstance(logsnr_fn, LogSNRSchedule):
             raise TypeError("logsnr_fn must come from v_diffusion_b200.get_logsnr_schedule")
-        if x0eps_coef:
-            raise NotImplementedError("x0eps_coef=True is not used by any reference config (defaults.json:52)")
         if model_out_type not in _lib.OUT_TYPES:
             raise NotImplementedError(model_out_type)               # diffusion.py:253-257
         self.logsnr_fn = logsnr_fn
@@ -76,6 +74,7 @@ class GaussianDiffusion:
         sc.model_var_type = _lib.VAR_TYPES.get(self.model_var_type, 1)
         sc.logsnr_schedule = _lib.SCHEDULES[self.logsnr_fn.schedule]
         sc.use_ddim = int(bool(use_ddim))
+        sc.x0eps_coef = int(bool(self.x0eps_coef))                  # diffusion.py:137-140, 180-182, 335-343
         sc.intp_frac = float(self.intp_frac or 0.)
         sc.logsnr_min, sc.logsnr_max = self.logsnr_fn.logsnr_min, self.logsnr_fn.logsnr_max
         sc.w_guide = float(self.w_guide)
@@ -83,7 +82,7 @@ class GaussianDiffusion:
         return sc
 
     def step_coefficients(self, use_ddim):
-        """[T, 12] fp32 host table (include/vdt_b200.h: vdt_step_coefficients)."""
+        """[T, 16] fp32 host table (include/vdt_b200.h: vdt_step_coefficients)."""
         sc = self.sampler_config(use_ddim)
         out = torch.empty((self.sample_timesteps, _lib.COEF_STRIDE), dtype=torch.float32)
         _lib.check(_lib.lib().vdt_step_coefficients(C.byref(sc), _lib.ptr(out)))
