@@ -121,48 +121,15 @@ def build_model(device, seed, workload="cifar10_cond"):
     return net, diff
 
 
-def cpu_baseline(seconds_budget=20.0):
-    """Oracle port (oracle/unet_ref.py, plain PyTorch fp32 on the host cores) on a bounded sample of the same
-    workload: B=2 images -> 4 UNet rows per denoising step, a few steps, scaled by 100 steps / image."""
+def oracle_trajectory(sd, cfg, x_t, label, n_warm, n_steps, budget_s=None):
+    """First n_warm + n_steps denoising steps (from step index T-1 down) of the CIFAR-10 cond CFG DDIM trajectory
+    on the host CPU with the oracle port (test infrastructure, pinned to the reference by tests/golden).
+    Returns (x after the last step, seconds per timed step, timed steps)."""
     import torch
-    from oracle import unet_forward, make_state_dict
-    from oracle.unet_ref import unet_config_from_json
-    torch.set_num_threads(os.cpu_count())
-    cfg = unet_config_from_json(CIFAR_COND_MODEL, 3, 3, num_classes=10)
-    sd = make_state_dict(cfg, 0)
-    B = 2
-    x = torch.randn(2 * B, 3, 32, 32)
-    t = torch.full((2 * B,), 0.5, dtype=torch.float64)
-    y = torch.tensor([3, 0, 7, 0])
-    unet_forward(sd, cfg, x, t, y)                        # warm-up
-    n, t0 = 0, time.perf_counter()
-    while n < 2 or (time.perf_counter() - t0 < seconds_budget and n < 16):
-        unet_forward(sd, cfg, x, t, y)
-        n += 1
-    dt = (time.perf_counter() - t0) / n
-    return {"value": B / (dt * T_STEPS), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"oracle UNet forward on {2 * B} rows (B={B} images, CFG pair) x {n} denoising steps, "
-                      f"{dt:.3f} s/step, scaled by {T_STEPS} steps per image"}
-
-
-def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is a Python/PyTorch
-    repo that cannot travel to the GPU box, so this times the oracle port (pinned to the reference by
-    tests/golden) with all host threads, same metric/config, on a bounded sample per step."""
-    if rank != 0:
-        return
-    import torch
-    from oracle import unet_forward, make_state_dict
-    from oracle.unet_ref import unet_config_from_json
+    from oracle import unet_forward
     from oracle.diffusion_ref import step_coefficients, _pred_x0
-    torch.set_num_threads(os.cpu_count())
-    cfg = unet_config_from_json(CIFAR_COND_MODEL, 3, 3, num_classes=10)
-    sd = make_state_dict(cfg, 0)
-    B = 2
-    g = torch.Generator().manual_seed(1234)
-    x_t = torch.randn(B, 3, 32, 32, generator=g)
-    label = torch.randint(10, (B,), generator=g) + 1
     co = step_coefficients(T_STEPS, use_ddim=True)
+    B = x_t.shape[0]
 
     def step(x_t, ti):
         xin = x_t.repeat_interleave(2, dim=0)
@@ -173,12 +140,59 @@ def run_reference(args, rank):
         mean = float(co["c1"][ti]) * xin + float(co["c2"][ti]) * x0
         return mean[0::2] + W_GUIDE * (mean[0::2] - mean[1::2])
     ti = T_STEPS - 1
-    for _ in range(args.warmup):
-        x_t = step(x_t, ti); ti = max(ti - 1, 1)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        x_t = step(x_t, ti); ti = max(ti - 1, 1)
-    dt = (time.perf_counter() - t0) / args.steps
+    for _ in range(n_warm):
+        x_t = step(x_t, ti); ti -= 1
+    n, t0 = 0, time.perf_counter()
+    while n < n_steps and (budget_s is None or n < 2 or time.perf_counter() - t0 < budget_s):
+        x_t = step(x_t, ti); ti -= 1; n += 1
+    return x_t, (time.perf_counter() - t0) / max(n, 1), n
+
+
+def cpu_baseline(net, diff, noise2, label2, device, seconds_budget=20.0):
+    """Oracle port on the host cores on a bounded sample of the same workload: the FIRST denoising steps of the
+    bench's own trajectory for its first two images (4 UNet rows per step), on the bench's own weights, scaled by
+    100 steps / image.  The same steps are then run through the CUDA path and compared (`parity`)."""
+    import ctypes as C
+    import torch
+    from oracle.unet_ref import unet_config_from_json
+    from v_diffusion_b200 import _lib
+    torch.set_num_threads(os.cpu_count())
+    cfg = unet_config_from_json(CIFAR_COND_MODEL, 3, 3, num_classes=10)
+    sd = {k: v.detach().cpu().float() for k, v in net.state_dict().items()}
+    B = noise2.shape[0]
+    x_cpu, dt, n = oracle_trajectory(sd, cfg, noise2.clone(), label2, 1, 16, seconds_budget)
+    steps = n + 1
+    x = noise2.to(device).contiguous().clone()
+    y = label2.to(device).contiguous()
+    sc = diff.sampler_config(use_ddim=True)
+    plan = net.plan_for(noise2.shape[2], device)
+    _lib.check(_lib.lib().vdt_p_sample_range(plan, C.byref(sc), _lib.ptr(x), _lib.ptr(y), None, B, T_STEPS - 1, steps,
+                                             None, _lib.current_stream_ptr()))
+    torch.cuda.synchronize()
+    err = (x.cpu() - x_cpu).abs().max().item()
+    return {"value": B / (dt * T_STEPS), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"first {steps} denoising steps of the bench trajectory for its first {B} images "
+                      f"({2 * B} UNet rows per step, CFG pair), {n} timed at {dt:.3f} s/step, scaled by {T_STEPS} steps per image",
+            "parity": {"steps": steps, "images": B, "max_abs_vs_cuda_path": err}}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is a Python/PyTorch
+    repo that cannot travel to the GPU box, so this times the oracle port (pinned to the reference by
+    tests/golden) with all host threads, same metric/config, on a bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import make_state_dict
+    from oracle.unet_ref import unet_config_from_json
+    torch.set_num_threads(os.cpu_count())
+    cfg = unet_config_from_json(CIFAR_COND_MODEL, 3, 3, num_classes=10)
+    sd = make_state_dict(cfg, 0)
+    B = 2
+    g = torch.Generator().manual_seed(1234)
+    x_t = torch.randn(B, 3, 32, 32, generator=g)
+    label = torch.randint(10, (B,), generator=g) + 1
+    _, dt, _ = oracle_trajectory(sd, cfg, x_t, label, args.warmup, args.steps)
     val = B / (dt * T_STEPS)
     line = {"metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -313,11 +327,17 @@ def run_b200(args, rank, world, local_rank):
         gathered = [torch.empty_like(noise) for _ in range(world)]   # the only collective: final image gather
         dist.all_gather(gathered, imgs.to(device))
     assert torch.isfinite(imgs).all()
+    # outside every timed region: three images of the full-size run recomputed on their own (size-independent
+    # property: a sample's trajectory does not depend on its batch or chunk; expected difference 0)
+    pick = torch.tensor([0, B // 2, B - 1])
+    alone = diff.p_sample(net, (3, 3, res, res), noise=noise_h[pick], label=None if label_h is None else label_h[pick],
+                          device=device, use_ddim=True)
+    selfcheck = (alone - imgs[pick]).abs().max().item()
     e2e = {"value": world * B / e2e_s.item(), "unit": "images/s",
            "h2d_bytes_per_step": (noise_h.numel() * 4 + (label_h.numel() * 8 if label_h is not None else 0)) / T_STEPS,
            "d2h_bytes_per_step": imgs.numel() * 4 / T_STEPS,
            "note": "one GaussianDiffusion.p_sample call = 100 denoising steps; bytes are per call / 100",
-           "seconds_per_call": e2e_s.item()}
+           "seconds_per_call": e2e_s.item(), "selfcheck_max_abs_3_images_recomputed_alone": selfcheck}
 
     if rank == 0:
         metric = METRIC if wl is None else f"ddim_images_per_sec_{args.workload}_100step"
@@ -333,7 +353,7 @@ def run_b200(args, rank, world, local_rank):
                            "accumulate": "fp32", "residual_stream": "fp32"},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline and wl is None:
-            line["cpu_baseline"] = cpu_baseline()
+            line["cpu_baseline"] = cpu_baseline(net, diff, noise_h[:2].clone(), label_h[:2].clone(), device)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
