@@ -141,10 +141,10 @@ def oracle_trajectory(sd, cfg, x_t, label, n_warm, n_steps, budget_s=None):
         return mean[0::2] + W_GUIDE * (mean[0::2] - mean[1::2])
     ti = T_STEPS - 1
     for _ in range(n_warm):
-        x_t = step(x_t, ti); ti -= 1
+        x_t = step(x_t, ti); ti = max(ti - 1, 1)       # (a run longer than the trajectory keeps timing step 1)
     n, t0 = 0, time.perf_counter()
     while n < n_steps and (budget_s is None or n < 2 or time.perf_counter() - t0 < budget_s):
-        x_t = step(x_t, ti); ti -= 1; n += 1
+        x_t = step(x_t, ti); ti = max(ti - 1, 1); n += 1
     return x_t, (time.perf_counter() - t0) / max(n, 1), n
 
 
