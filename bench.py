@@ -36,7 +36,23 @@ WORKLOADS = {
     "cifar10_uncond": (dict(in_channels=3, hid_channels=256, ch_multipliers=[1, 1, 1], num_res_blocks=3,
                             apply_attn=[False, True, True], drop_rate=0.2, num_heads=1), 3, 0, 32, "x0", "fixed_large",
                        False, 4096, "CIFAR-10 unconditional UNet (cifar10_uncond.json), 100-step DDIM"),
+    # BASELINE configs[3]: defaults.json model block with in_channels=1, 10 classes, 28x28 (28 -> 14 -> 7), CFG w=3,
+    # 1000-step ancestral sampling with on-device noise: small images, launch-bound, one CUDA graph per step
+    "mnist28": (dict(in_channels=1, hid_channels=256, ch_multipliers=[1, 1, 1], num_res_blocks=3,
+                     apply_attn=[False, True, True], drop_rate=0.2, num_heads=1), 1, 10, 28, "v", "fixed_medium",
+                True, 256, "MNIST 28x28 conditional UNet (defaults.json model, 1 channel), CFG w=3, 1000-step ancestral sampling",
+                1000, 3.0, False),
 }
+
+
+def workload_params(name):
+    """(T, w_guide, use_ddim, in_channels) of a workload; the 100-step DDIM workloads use w = 1."""
+    wl = WORKLOADS[name]
+    if wl is None or len(wl) < 12:
+        return T_STEPS, W_GUIDE, True, 3
+    return wl[9], wl[10], wl[11], wl[0]["in_channels"]
+
+
 # cifar10_cond.json merged with defaults.json (tests/golden/merged_configs.json pins this in the CPU tests)
 CIFAR_COND_MODEL = dict(in_channels=3, hid_channels=256, ch_multipliers=[1, 1, 1], num_res_blocks=3,
                         apply_attn=[False, True, True], drop_rate=0.2, num_heads=1)
@@ -116,8 +132,9 @@ def build_model(device, seed, workload="cifar10_cond"):
             elif p.ndim == 1:
                 p.add_(0.05 * torch.randn(p.shape, generator=g))
     net = net.to(device).eval()
-    diff = GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), T_STEPS, out_type, var_type, "snr_trunc",
-                             "mse", intp_frac=0.3, w_guide=W_GUIDE)
+    T, w, _, _ = workload_params(workload)
+    diff = GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), T, out_type, var_type, "snr_trunc",
+                             "mse", intp_frac=0.3, w_guide=w)
     return net, diff
 
 
@@ -231,14 +248,15 @@ def run_b200(args, rank, world, local_rank):
     L = _lib.lib()
     wl = WORKLOADS[args.workload]
     res = 32 if wl is None else wl[3]
-    use_cfg = wl is None
+    use_cfg = wl is None or bool(wl[6])
+    T, w_guide, use_ddim, in_ch = workload_params(args.workload)
     B, K, W = (args.batch if args.batch > 0 else (4096 if wl is None else wl[7])), args.steps, max(args.warmup, 3)
     net, diff = build_model(device, seed=0, workload=args.workload)
     net.max_rows = args.max_rows
     plan = net.plan_for(res, device)
-    sc = diff.sampler_config(use_ddim=True)
+    sc = diff.sampler_config(use_ddim=use_ddim, seed=1234 + rank)
     g = torch.Generator(device=device).manual_seed(1234 + rank)      # SURVEY §8d cfg 2: per-rank seeds 1234+rank
-    noise = torch.randn(B, 3, res, res, device=device, generator=g)
+    noise = torch.randn(B, in_ch, res, res, device=device, generator=g)
     label = (torch.randint(10, (B,), device=device, generator=g) + 1) if use_cfg else None
     stream = torch.cuda.current_stream()
 
@@ -253,7 +271,7 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     x = noise.clone()
-    run_range(x, T_STEPS - 1, W)                                      # warm-up (eager pass + graph capture)
+    run_range(x, T - 1, W)                                      # warm-up (eager pass + graph capture)
     barrier()
     x = noise.clone()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -261,12 +279,12 @@ def run_b200(args, rank, world, local_rank):
     with ClockSampler(local_rank) as clocks:
         barrier()
         ev0.record(stream)
-        done, first = 0, T_STEPS - 1
+        done, first = 0, T - 1
         while done < K:                                               # K may exceed one trajectory
             n = min(K - done, first + 1)
             run_range(x, first, n)
             done += n
-            first = T_STEPS - 1 if first - n < 0 else first - n
+            first = T - 1 if first - n < 0 else first - n
         ev1.record(stream)
         barrier()
     launches = L.vdt_kernel_launches() - n0
@@ -275,12 +293,12 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = ms.item()
     ms_step = ms_total / K
-    value = world * B / (ms_step * 1e-3 * T_STEPS)
+    value = world * B / (ms_step * 1e-3 * T)
 
     # ---- per-kernel-family timing of the same step (CUDA events around every launch, on the launching stream)
     L.vdt_profile_enable(1)
     xs = noise.clone()
-    run_range(xs, T_STEPS - 1, 1)
+    run_range(xs, T - 1, 1)
     torch.cuda.synchronize()
     fam_ms, fam_n = (C.c_double * 4)(), (C.c_uint64 * 4)()
     L.vdt_profile_read(fam_ms, fam_n)
@@ -319,7 +337,8 @@ def run_b200(args, rank, world, local_rank):
     label_h = label.cpu().pin_memory() if label is not None else None
     barrier()
     t0 = time.perf_counter()
-    imgs = diff.p_sample(net, (B, 3, res, res), noise=noise_h, label=label_h, device=device, use_ddim=True)
+    imgs = diff.p_sample(net, (B, in_ch, res, res), noise=noise_h, label=label_h, device=device, seed=1234 + rank,
+                         use_ddim=use_ddim)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
     if world > 1:
@@ -330,17 +349,21 @@ def run_b200(args, rank, world, local_rank):
     # outside every timed region: three images of the full-size run recomputed on their own (size-independent
     # property: a sample's trajectory does not depend on its batch or chunk; expected difference 0)
     pick = torch.tensor([0, B // 2, B - 1])
-    alone = diff.p_sample(net, (3, 3, res, res), noise=noise_h[pick], label=None if label_h is None else label_h[pick],
-                          device=device, use_ddim=True)
-    selfcheck = (alone - imgs[pick]).abs().max().item()
+    if use_ddim:
+        alone = diff.p_sample(net, (3, in_ch, res, res), noise=noise_h[pick], label=None if label_h is None else label_h[pick],
+                              device=device, use_ddim=True)
+        selfcheck = (alone - imgs[pick]).abs().max().item()
+    else:
+        selfcheck = None      # on-device ancestral noise is indexed by batch position: a sub-batch draws other noise
     e2e = {"value": world * B / e2e_s.item(), "unit": "images/s",
-           "h2d_bytes_per_step": (noise_h.numel() * 4 + (label_h.numel() * 8 if label_h is not None else 0)) / T_STEPS,
-           "d2h_bytes_per_step": imgs.numel() * 4 / T_STEPS,
-           "note": "one GaussianDiffusion.p_sample call = 100 denoising steps; bytes are per call / 100",
+           "h2d_bytes_per_step": (noise_h.numel() * 4 + (label_h.numel() * 8 if label_h is not None else 0)) / T,
+           "d2h_bytes_per_step": imgs.numel() * 4 / T,
+           "note": f"one GaussianDiffusion.p_sample call = {T} denoising steps; bytes are per call / {T}",
            "seconds_per_call": e2e_s.item(), "selfcheck_max_abs_3_images_recomputed_alone": selfcheck}
 
     if rank == 0:
-        metric = METRIC if wl is None else f"ddim_images_per_sec_{args.workload}_100step"
+        metric = METRIC if wl is None else (f"ddim_images_per_sec_{args.workload}_100step" if use_ddim else
+                                             f"ancestral_images_per_sec_{args.workload}_{T}step")
         wtext = ("CIFAR-10 class-conditional UNet (cifar10_cond.json), CFG w=1 batched cond/uncond (2B rows), 100-step DDIM"
                  if wl is None else wl[8])
         line = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -348,7 +371,7 @@ def run_b200(args, rank, world, local_rank):
                 "dtype": net.operand_dtype, "data": "synthetic",
                 "config": {"workload": f"{wtext}, batch {B} per GPU; step = one denoising step over the batch",
                            "batch_per_gpu": B, "rows_per_unet_call": rows, "chunk_rows": args.max_rows,
-                           "steps_per_image": T_STEPS, "l2": "inputs_exceed_l2", "parallelism": f"replicas x{world}",
+                           "steps_per_image": T, "l2": "inputs_exceed_l2", "parallelism": f"replicas x{world}",
                            "operands": net.operand_dtype + " tensor-core operands (same tcgen05 kind::f16 rate as bf16)",
                            "accumulate": "fp32", "residual_stream": "fp32"},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}

@@ -61,6 +61,12 @@ SAMPLE_CASES = {
     "ancestral_both": dict(unet="small_hd64", seed=24, B=2, res=32, T=5, model_out_type="both", w_guide=0.0,
                            use_ddim=False, var_type="fixed_large", labels=None),
 }
+# BASELINE configs[3] geometry: 1-channel 28x28 conditional UNet, 28 -> 14 -> 7, attention at 14x14 and 7x7 (N = 196 / 49)
+# and in the attention-bearing upsampling block at 28x28 (N = 784)
+UNET_CASES["mnist28"] = dict(cfg=_cfg(in_channels=1, out_channels=1, mult=(1, 2, 2), nrb=1, attn=(False, True, True),
+                                      num_classes=10), seed=16, B=3, res=28, labels=[2, 0, 9], trace=[])
+SAMPLE_CASES["ancestral_mnist28"] = dict(unet="mnist28", seed=27, B=2, res=28, T=8, model_out_type="v", w_guide=3.0,
+                                         use_ddim=False, var_type="fixed_medium", intp_frac=0.3, labels=[5, 10])
 # multitag (multi-hot) class conditioning as used by the reference's conditional CelebA checkpoints
 UNET_CASES["small_multitag"] = dict(cfg=_cfg(mult=(1, 2), nrb=1, attn=(False, True), num_classes=40, multitags=True),
                                     seed=15, B=3, res=16, labels="multihot", trace=[])

@@ -47,6 +47,11 @@ CONV_CASES = [
     (3, 8, 256, 768, 1, False),      # three N tiles
     (2, 16, 128, 384, 1, False),     # N tile of 192
     (2, 64, 192, 192, 3, True),      # CelebA-style 64x64, 2 image rows per tile
+    (3, 28, 64, 64, 3, True),        # MNIST 28x28: 4 image rows = 112 of the tile's 128 rows
+    (3, 14, 128, 64, 3, False),      # 14x14: 7 image rows = 98 rows per tile
+    (3, 7, 64, 128, 3, True),        # 7x7: two whole images = 98 rows per tile, odd image count
+    (3, 14, 64, 192, 1, False),      # pointwise over 588 rows (ragged last tile)
+    (5, 4, 64, 64, 3, False),        # 4x4: eight images per tile
 ]
 
 
@@ -81,6 +86,9 @@ GN_CASES = [
     (2, 8, 64, 0, False, True, 2, False, True),       # nearest upsample
     (2, 16, 128, 0, False, False, 0, False, False),   # attention norm: no activation
     (2, 16, 576, 0, False, True, 0, False, False),    # 18 channels per group
+    (3, 28, 64, 0, True, True, 1, False, True),       # MNIST 28x28 -> 14x14 avg-pool
+    (3, 14, 64, 64, False, True, 0, True, False),     # 14x14 concat
+    (3, 7, 128, 0, False, True, 2, False, True),      # 7x7 -> 14x14 nearest upsample
 ]
 
 
@@ -190,7 +198,9 @@ def test_conv_stats_then_single_pass_groupnorm(L, B, H, c1, c2, in16, film, resa
 
 
 ATTN_CASES = [(2, 1024, 1, 256), (3, 256, 1, 256), (3, 64, 1, 256), (2, 256, 1, 64), (2, 64, 2, 64), (1, 4096, 1, 64),
-              (2, 128, 1, 128)]
+              (2, 128, 1, 128),
+              # MNIST 28x28 -> 14x14 -> 7x7: N = 784 / 196 / 49, ragged last key tile and query tile
+              (2, 784, 1, 256), (3, 196, 1, 256), (3, 49, 1, 256), (2, 196, 2, 64), (3, 16, 1, 64)]
 
 
 @pytest.mark.parametrize("f16", [1, 0])
@@ -205,7 +215,9 @@ def test_attention(L, B, N, heads, d, f16):
     q[:, : N // 2] *= 3.0
     k[:, N // 2:] *= 2.0
     qk = torch.cat([q.reshape(B * N, hid), k.reshape(B * N, hid)], dim=1).contiguous()
-    vt = v.permute(0, 2, 3, 1).reshape(B * hid, N).contiguous()          # V^T [B*hid, N]
+    Np = (N + 7) // 8 * 8                                                 # row pitch of V^T: 16-byte multiples for TMA
+    vt = torch.full((B * hid, Np), float("nan"), device="cuda", dtype=DT[f16])   # the pad is never read
+    vt[:, :N] = v.permute(0, 2, 3, 1).reshape(B * hid, N)                # V^T [B*hid, N]
     out = torch.zeros(B * N, hid, device="cuda", dtype=DT[f16])
     _check(L, L.vdt_op_attention(_p(qk), _p(vt), _p(out), B, N, heads, d, f16, None))
     torch.cuda.synchronize()

@@ -74,27 +74,27 @@ def test_unet_forward_vs_oracle_on_this_box():
     assert ((out_n - ref_n).norm() / ref_n.norm()).item() <= REL_L2
 
 
-def test_three_level_16px_network_vs_oracle_and_4x4_limit():
-    """Three levels from 32x32 reach 8x8 (the smallest feature map of every reference config; odd batch -> ragged
-    GEMM tiles at each level).  The same network at 16x16 would bottom out at 4x4, which the conv kernel does not
-    tile: the plan must refuse loudly instead of computing something else."""
+def test_three_level_network_down_to_4x4_vs_oracle():
+    """Three levels from 16x16 bottom out at 4x4 with attention over N = 64 and N = 16 tokens: 16 pixels per image is
+    less than one 32-row statistics slab (two-pass GroupNorm there), eight images share one GEMM tile, and the
+    attention key tile is ragged (16 of 64 keys).  Odd batch -> ragged GEMM tiles at every level."""
     from oracle import unet_forward, make_state_dict
-    cfg = _cfg_case(mult=(1, 2, 2), nrb=1, attn=(False, True, False), num_classes=5)
+    cfg = _cfg_case(mult=(1, 2, 2), nrb=1, attn=(False, True, True), num_classes=5)
     g = torch.Generator().manual_seed(123)
     B = 3
-    x = torch.randn(B, 3, 32, 32, generator=g)
+    x = torch.randn(B, 3, 16, 16, generator=g)
     t = torch.rand(B, generator=g, dtype=torch.float64)
     y = torch.tensor([0, 2, 5])
     net = _model(cfg, 31)
     out = net(x.cuda(), t.cuda(), y.cuda()).cpu()
     ref = unet_forward(make_state_dict(cfg, 31), cfg, x, t, y)
     rel = ((out - ref).norm() / ref.norm()).item()
-    print(f"three-level network: rel-L2 {rel:.3e}")
+    print(f"16 -> 8 -> 4 network: rel-L2 {rel:.3e}")
     assert rel <= REL_L2
-    out1 = net(x[1:2].cuda(), t[1:2].cuda(), y[1:2].cuda()).cpu()
+    out1 = net(x[1:2].cuda(), t[1:2].cuda(), y[1:2].cuda()).cpu()      # a single image: M = 16 rows at the lowest level
     assert (out1 - out[1:2]).abs().max().item() <= 1e-5
-    with pytest.raises(RuntimeError, match="feature-map size 4"):
-        net(x[:, :, :16, :16].contiguous().cuda(), t.cuda(), y.cuda())
+    with pytest.raises(RuntimeError, match="feature-map size 2"):       # 8 -> 4 -> 2 is refused, loudly
+        net(x[:, :, :8, :8].contiguous().cuda(), t.cuda(), y.cuda())
 
 
 @pytest.mark.parametrize("name", sorted(SAMPLE_CASES))

@@ -61,9 +61,13 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = p.N;
-    const int ipc = (N >= kQRows) ? 1 : kQRows / N;        // images per CTA
-    const int qtiles = (N >= kQRows) ? N / kQRows : 1;
-    const int nt = (N >= kQRows) ? N / kKeys : kQRows / kKeys;
+    // packed: N == 64 puts two images into one CTA (each 64-key tile belongs to one of them).  Otherwise one image
+    // per CTA with ceil(N / 128) query tiles and ceil(N / 64) key tiles; rows / keys past the image's N are loaded
+    // (they belong to the next image or are zero-filled by TMA) and masked: keys to -inf, query rows at the store.
+    const bool packed = (2 * N == kQRows);
+    const int ipc = packed ? 2 : 1;                         // images per CTA
+    const int qtiles = packed ? 1 : (N + kQRows - 1) / kQRows;
+    const int nt = packed ? 2 : (N + kKeys - 1) / kKeys;
     // blockIdx.x -> (image group, head, q tile)
     const int qt = blockIdx.x % qtiles;
     const int h = (blockIdx.x / qtiles) % p.heads;
@@ -87,8 +91,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
             mbar_expect_tx(&sm.k_full[j], static_cast<uint32_t>(dch * 8192));
             for (int c = 0; c < dch; ++c)
                 tma_load_2d(sm.k(j) + c * 8192, &p.k_map, &sm.k_full[j], p.hid + h * d + c * 64, static_cast<int>(krow0) + j * kKeys);
-            const int img = b0 + (j * kKeys) / N;
-            const int koff = (N >= kQRows) ? j * kKeys : (j * kKeys) % N;
+            const int img = packed ? b0 + j : b0;
+            const int koff = packed ? 0 : j * kKeys;
             mbar_expect_tx(&sm.v_full[j], static_cast<uint32_t>(d * 128));
             tma_load_2d(sm.v(j), &p.vt_map, &sm.v_full[j], koff, (img * p.heads + h) * d);
         }
@@ -117,8 +121,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
             for (int j = 2; j < nt; ++j) {
                 const int s = j & 1;
                 mbar_wait(&sm.v_empty[s], ((j >> 1) & 1) ^ 1);
-                const int img = b0 + (j * kKeys) / N;
-                const int koff = (N >= kQRows) ? j * kKeys : (j * kKeys) % N;
+                const int img = packed ? b0 + j : b0;
+                const int koff = packed ? 0 : j * kKeys;
                 mbar_expect_tx(&sm.v_full[s], static_cast<uint32_t>(d * 128));
                 tma_load_2d(sm.v(s), &p.vt_map, &sm.v_full[s], koff, (img * p.heads + h) * d);
             }
@@ -164,8 +168,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
         const int row = q * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
         const long long grow = row0 + row;
-        const bool row_ok = grow < static_cast<long long>(p.B) * N;
-        const int row_img = row / N;                        // only meaningful when N < 128
+        const bool row_ok = (grow < static_cast<long long>(p.B) * N) && (packed || qt * kQRows + row < N);
+        const int row_img = row / N;                        // only meaningful when packed
         const float c = p.scale_log2e;
         const int dh = d >> 1;                              // O columns owned by this thread: [half*dh, half*dh + dh)
         float m_used = -INFINITY, l = 0.f;
@@ -178,8 +182,14 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
             float sv[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(r0[i]);
-            // N < 128: a 64-key tile belongs to one image; rows of the other image ignore it entirely
-            const bool tile_valid = (N >= kQRows) || (((j * kKeys) / N) == row_img);
+            // packed: a 64-key tile belongs to one image; rows of the other image ignore it entirely
+            const bool tile_valid = !packed || (j == row_img);
+            if (!packed && (j + 1) * kKeys > N) {           // ragged last key tile (warp-uniform): keys >= N drop out
+                const int first_bad = N - j * kKeys - half * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i >= first_bad) sv[i] = -INFINITY;
+            }
             float m_half = -INFINITY;
             if (tile_valid) {
 #pragma unroll
@@ -242,7 +252,10 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.p_full[j & 1]);
         }
-        // ---- final: O / l -> 16-bit.  The two threads of a row add their partial sums.
+        // ---- final: O / l -> 16-bit.  The two threads of a row add their partial sums.  (The barrier keeps a fast
+        // thread from overwriting a row maximum of the last tile that its partner has not read yet: with an odd
+        // number of key tiles that exchange used this same buffer.)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         xch[half * 128 + row] = l;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         l += xch[(half ^ 1) * 128 + row];
@@ -276,8 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
 }  // namespace
 
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
-    if (p.d % 64 != 0 || p.d > 256 || p.N % kKeys != 0 || p.N < kKeys) return cudaErrorInvalidValue;
-    if (p.N > kQRows && p.N % kQRows != 0) return cudaErrorInvalidValue;
+    if (p.d % 64 != 0 || p.d > 256 || p.N < 1) return cudaErrorInvalidValue;
     const int smem = attn_smem_bytes(p.d);
     static int smem_set = 0;
     if (smem > smem_set) {
@@ -286,8 +298,9 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         smem_set = smem;
     }
-    const int ipc = (p.N >= kQRows) ? 1 : kQRows / p.N;
-    const int qtiles = (p.N >= kQRows) ? p.N / kQRows : 1;
+    const bool packed = (2 * p.N == kQRows);
+    const int ipc = packed ? 2 : 1;
+    const int qtiles = packed ? 1 : (p.N + kQRows - 1) / kQRows;
     const int groups = (p.B + ipc - 1) / ipc;
     const long long grid = static_cast<long long>(groups) * p.heads * qtiles;
     if (grid <= 0) return cudaSuccess;

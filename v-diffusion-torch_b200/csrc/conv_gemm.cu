@@ -314,9 +314,9 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                     if (row_ok) {
                         const long long img = grow / p.HW;
                         const int pix = static_cast<int>(grow - img * p.HW);
-                        h16* dst = p.out_t + (img * (p.Cout - p.split_col) + (col0 - p.split_col)) * p.HW + pix;
+                        h16* dst = p.out_t + (img * (p.Cout - p.split_col) + (col0 - p.split_col)) * p.ld_t + pix;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.HW] = cvt_16(v[j], (F16 ? 1 : 0));
+                        for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.ld_t] = cvt_16(v[j], (F16 ? 1 : 0));
                     }
                 } else {   // kOutNCHW
 #pragma unroll

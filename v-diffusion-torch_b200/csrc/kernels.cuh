@@ -23,7 +23,7 @@ constexpr int kConvMaxSegs = 6;   // 3x3 body + 1x1 skip, each x3 in the split-p
 enum ConvOutMode : int {
     kOutF32 = 0,        // fp32 [M, ld]            (+bias, +residual, optional SiLU)
     kOutBF16 = 1,       // 16-bit [M, ld] for columns < split_col; columns >= split_col are written
-                        // transposed per image: out_t[(img * (Cout - split_col) + col - split_col) * HW + pix]
+                        // transposed per image: out_t[(img * (Cout - split_col) + col - split_col) * ld_t + pix]
     kOutNCHW = 2,       // fp32 [img, Cout, HW]    (network output, Cout may be tiny)
 };
 
@@ -54,6 +54,7 @@ struct alignas(64) ConvParams {
     // stats[slab * Cout/stat_cols + col/stat_cols]
     float2* stats;
     int stat_cols;
+    int ld_t;                          // row pitch (elements) of out_t: HW rounded up to 8 (TMA needs 16-byte pitches)
 };
 constexpr int kStatRows = 32;   // rows per statistics slab
 cudaError_t launch_conv_gemm(const ConvParams& p, int num_sms, cudaStream_t stream);
@@ -95,7 +96,7 @@ cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream);
 struct alignas(64) AttnParams {
     CUtensorMap qk_map;                // 2-D (2*hid, B*N) bf16, box (64, 128): q at col h*d, k at hid + h*d
     CUtensorMap k_map;                 // same tensor, box (64, 64)
-    CUtensorMap vt_map;                // 2-D (N, B*hid) 16-bit, box (64, d): V^T per image/head
+    CUtensorMap vt_map;                // 2-D (N, B*hid) 16-bit with row pitch round_up(N, 8), box (64, d): V^T per image/head
     int B, N, heads, d, hid;
     int f16;
     float scale_log2e;                 // log2(e) / sqrt(d)

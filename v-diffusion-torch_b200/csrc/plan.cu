@@ -398,10 +398,8 @@ extern "C" int vdt_plan_create(const vdt_unet_config* cfg, vdt_plan** out) {
     if (c.max_rows < 1) return fail("max_rows must be >= 1");
     const int minres = c.resolution >> (c.num_levels - 1);
     if ((minres << (c.num_levels - 1)) != c.resolution) return fail("resolution must be divisible by 2^(levels-1)");
-    for (int i = 0, r = c.resolution; i < c.num_levels; ++i, r /= 2) {
-        const bool pow2 = (r & (r - 1)) == 0;
-        if (!pow2 || r < 8 || r > 128) return fail("unsupported feature-map size %d (need a power of two in [8, 128])", r);
-    }
+    for (int i = 0, r = c.resolution; i < c.num_levels; ++i, r /= 2)
+        if (r < 4 || r > 128) return fail("unsupported feature-map size %d (need 4 <= size <= 128)", r);
     std::unique_ptr<vdt_plan> p(new vdt_plan());
     p->cfg = c;
     p->hid = c.hid_channels;
@@ -451,8 +449,6 @@ extern "C" int vdt_plan_create(const vdt_unet_config* cfg, vdt_plan** out) {
             int hd, nh;
             attn_dims(c, b.cin, &hd, &nh);
             if (hd % 64 || hd > 256) return fail("head_dim must be a multiple of 64 and <= 256 (got %d)", hd);
-            const int tokens = b.res_in * b.res_in;
-            if (tokens % 64) return fail("attention needs a multiple of 64 tokens (got %d)", tokens);
             add_weight(p.get(), n + ".norm.weight", {b.cin}); add_weight(p.get(), n + ".norm.bias", {b.cin});
             add_weight(p.get(), n + ".proj_in.weight", {3 * hd * nh, b.cin, 1, 1}); add_weight(p.get(), n + ".proj_in.bias", {3 * hd * nh});
             add_weight(p.get(), n + ".proj_out.weight", {b.cin, hd * nh, 1, 1}); add_weight(p.get(), n + ".proj_out.bias", {b.cin});
@@ -612,13 +608,19 @@ static int pick_block_n(int cout) {
 
 struct ConvGeom { int box_h, box_n, tiles_per_image, rows_per_tile, num_m_tiles; };
 static int conv_geom(int n, int h, int w, ConvGeom* g) {
-    if (w > 128 || 128 % w != 0) return fail("unsupported feature-map width %d", w);
-    if (w * h >= 128) {
-        g->box_h = 128 / w; g->box_n = 1;
-        if (h % g->box_h) return fail("unsupported feature-map height %d", h);
-        g->tiles_per_image = h / g->box_h; g->rows_per_tile = 128; g->num_m_tiles = n * g->tiles_per_image;
+    // One M tile = one TMA box of whole image rows: box_h rows of one image (box_h | h, box_h * w <= 128), or
+    // box_n whole images when an image has at most 64 pixels.  Widths that do not divide 128 (28, 14, 7: MNIST)
+    // leave the tail of the 128-row tile unused (rows_per_tile < 128; those accumulator rows are never stored).
+    if (w < 1 || h < 1 || w > 128) return fail("unsupported feature-map width %d", w);
+    if (2 * w * h > 128) {
+        int bh = 0;
+        for (int d = 1; d <= h; ++d)
+            if (h % d == 0 && d * w <= 128) bh = d;
+        if (bh == 0) return fail("unsupported feature-map size %dx%d", h, w);
+        g->box_h = bh; g->box_n = 1;
+        g->tiles_per_image = h / bh; g->rows_per_tile = bh * w; g->num_m_tiles = n * g->tiles_per_image;
     } else {
-        g->box_h = h; g->box_n = 128 / (w * h); g->tiles_per_image = 1; g->rows_per_tile = 128;
+        g->box_h = h; g->box_n = 128 / (w * h); g->tiles_per_image = 1; g->rows_per_tile = g->box_n * w * h;
         g->num_m_tiles = (n + g->box_n - 1) / g->box_n;
     }
     return 0;
@@ -679,6 +681,7 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16;
     cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t; cp->stat_cols = s.stat_cols;
     cp->stats = ((s.h * s.w) % kStatRows == 0) ? s.stats : nullptr;   // statistics slabs never span two images
+    cp->ld_t = (s.h * s.w + 7) & ~7;
     if (s.out_mode != kOutNCHW && s.cout % 32 != 0) return fail("output channels must be a multiple of 32 (got %d)", s.cout);
     return 0;
 }
@@ -829,7 +832,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&o));
             if (!sp) {
                 CKI(ex->acquire((size_t)R * N * 2 * hidd * 2, (void**)&qk));
-                CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&vt));
+                CKI(ex->acquire((size_t)R * ((N + 7) & ~7) * hidd * 2, (void**)&vt));
                 {   // one GEMM for q | k | v: q,k row-major [R*N, 2*hid]; the v third is written transposed, V^T [R*hid, N]
                     ConvSpec s;
                     s.f16 = p->f16; s.stat_cols = p->stat_cols;
@@ -843,7 +846,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
                 memset(ap.get(), 0, sizeof(AttnParams));
                 CKI(make_map_2d(&ap->qk_map, qk, (long long)R * N, 2 * hidd, 2 * hidd, 128));
                 CKI(make_map_2d(&ap->k_map, qk, (long long)R * N, 2 * hidd, 2 * hidd, 64));
-                CKI(make_map_2d(&ap->vt_map, vt, (long long)R * hidd, N, N, hd));
+                CKI(make_map_2d(&ap->vt_map, vt, (long long)R * hidd, N, (N + 7) & ~7, hd));   // columns >= N are zero-filled by TMA
                 ap->B = R; ap->N = N; ap->heads = nh; ap->d = hd; ap->hid = hidd; ap->f16 = p->f16;
                 ap->scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)hd));
                 ap->out = o;
@@ -1370,7 +1373,7 @@ extern "C" int vdt_op_attention(const void* qk, const void* vt, void* out, int32
     memset(ap.get(), 0, sizeof(AttnParams));
     CKI(make_map_2d(&ap->qk_map, qk, (long long)batch * n, 2 * hid, 2 * hid, 128));
     CKI(make_map_2d(&ap->k_map, qk, (long long)batch * n, 2 * hid, 2 * hid, 64));
-    CKI(make_map_2d(&ap->vt_map, vt, (long long)batch * hid, n, n, d));
+    CKI(make_map_2d(&ap->vt_map, vt, (long long)batch * hid, n, (n + 7) & ~7, d));
     ap->B = batch; ap->N = n; ap->heads = heads; ap->d = d; ap->hid = hid; ap->f16 = f16;
     ap->scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)d));
     ap->out = (h16*)out;
