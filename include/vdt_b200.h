@@ -134,6 +134,11 @@ int vdt_profile_read(double* ms4, uint64_t* launches4);
 int vdt_op_conv(const void* x_16_nhwc, int32_t batch, int32_t h, int32_t w, int32_t cin, const float* w_oihw,
                 int32_t cout, int32_t ksize, const float* bias, const float* residual, float* out_nhwc, int32_t f16,
                 void* out16, void* stats_out, int32_t stat_cols, void* stream);
+/* Rows of the statistics table vdt_op_conv writes per image: stats_out is [batch * slabs (+ 4 rows of slack: the last
+ * M tile always writes its four quarters)][cout / stat_cols] (sum, sumsq)
+ * float2, one slab per 32-row quarter of an M tile of the conv kernel's image-aligned tiling; 0 = this feature-map size
+ * has no such layout (the GroupNorm then makes its own statistics pass). */
+int vdt_stat_slabs_per_image(int32_t h, int32_t w);
 /* GroupNorm(32, 1e-6) [+FiLM] [+SiLU] [+resample 0 none / 1 avgpool2 / 2 nearest x2] over concat(src1, src2).
  * stats1/stats2 (optional): partial statistics from vdt_op_conv for src1/src2 -> single-pass kernel;
  * in16: src1 is 16-bit (needs stats1). */

@@ -144,6 +144,9 @@ FUSED_GN_CASES = [
     (2, 16, 192, 0, True, False, 0),      # same with a 16-bit input
     (2, 16, 128, 64, False, False, 0),    # concat 128 + 64: 6-channel groups straddling the seam
     (2, 8, 64, 0, False, False, 0),       # 2 channels per group
+    (3, 28, 64, 0, False, True, 0),       # MNIST 28x28: tiles of 112 rows, the fourth slab of every tile half empty
+    (3, 14, 128, 64, False, False, 0),    # 14x14: tiles of 98 rows (slab 3 holds 2 rows), concat seam inside a group
+    (2, 28, 128, 0, True, False, 1),      # 28x28 -> 14x14 avg-pool from a 16-bit input
 ]
 
 
@@ -162,16 +165,24 @@ def test_conv_stats_then_single_pass_groupnorm(L, B, H, c1, c2, in16, film, resa
         bias = torch.randn(cout, device="cuda", generator=g)
         out = torch.zeros(B, H, H, cout, device="cuda")
         out16 = torch.zeros(B, H, H, cout, device="cuda", dtype=DT[f16]) if in16 else None
-        stats = torch.full((B * H * H // 32, cout // sc, 2), float("nan"), device="cuda")
+        slabs = L.vdt_stat_slabs_per_image(H, H)             # 32-row quarters of the conv kernel's image-aligned M tiles
+        assert slabs > 0
+        stats = torch.full((B * slabs + 4, cout // sc, 2), float("nan"), device="cuda")   # + one tile of slack
         _check(L, L.vdt_op_conv(_p(x), B, H, H, cin, _p(w), cout, 3, _p(bias), None, _p(out), f16, _p(out16), _p(stats), sc, None))
         torch.cuda.synchronize()
         ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.to(DT[f16]).double(), bias.double(), padding=1).permute(0, 2, 3, 1)
         val = out16 if in16 else out
         # the statistics describe the fp32 values before any 16-bit rounding
-        rs = ref.reshape(B * H * H // 32, 32, cout // sc, sc)
+        stats = stats[:B * slabs]
         assert torch.isfinite(stats).all()
-        assert (stats[..., 0].double() - rs.sum(dim=(1, 3))).abs().max().item() <= 2e-3
-        assert (stats[..., 1].double() - (rs * rs).sum(dim=(1, 3))).abs().max().item() <= 2e-2
+        if (H * H) % 128 == 0 or 2 * H * H <= 128:           # full tiles: slab = 32 consecutive pixels
+            rs = ref.reshape(B * H * H // 32, 32, cout // sc, sc)
+            assert (stats[..., 0].double() - rs.sum(dim=(1, 3))).abs().max().item() <= 2e-3
+            assert (stats[..., 1].double() - (rs * rs).sum(dim=(1, 3))).abs().max().item() <= 2e-2
+        ri = ref.reshape(B, H * H, cout // sc, sc)           # any geometry: an image's slabs add up to its totals
+        tot = stats.reshape(B, slabs, cout // sc, 2).double().sum(dim=1)
+        assert (tot[..., 0] - ri.sum(dim=(1, 3))).abs().max().item() <= 2e-2
+        assert (tot[..., 1] - (ri * ri).sum(dim=(1, 3))).abs().max().item() <= 2e-1
         return val, stats, ref
 
     v1, st1, r1 = conv(c1)
@@ -195,6 +206,19 @@ def test_conv_stats_then_single_pass_groupnorm(L, B, H, c1, c2, in16, film, resa
     y = (F.avg_pool2d(y, 2) if resample == 1 else F.interpolate(y, scale_factor=2, mode="nearest") if resample == 2 else y)
     y = y.permute(0, 2, 3, 1)
     assert _rel(out_act, y) <= 4e-3 * EPS[f16] + (2e-3 if in16 else 0)
+
+
+def test_statistics_layout_exists_only_for_image_aligned_slabs(L):
+    assert L.vdt_stat_slabs_per_image(32, 32) == 32 and L.vdt_stat_slabs_per_image(8, 8) == 2
+    assert L.vdt_stat_slabs_per_image(28, 28) == 28 and L.vdt_stat_slabs_per_image(14, 14) == 8
+    assert L.vdt_stat_slabs_per_image(7, 7) == 0 and L.vdt_stat_slabs_per_image(4, 4) == 0
+    x = torch.zeros(2, 7, 7, 64, device="cuda", dtype=torch.float16)
+    w = torch.zeros(64, 64, 3, 3, device="cuda")
+    b = torch.zeros(64, device="cuda")
+    out = torch.zeros(2, 7, 7, 64, device="cuda")
+    st = torch.zeros(64, 16, 2, device="cuda")
+    rc = L.vdt_op_conv(_p(x), 2, 7, 7, 64, _p(w), 64, 3, _p(b), None, _p(out), 1, None, _p(st), 4, None)
+    assert rc != 0 and b"statistics layout" in L.vdt_last_error()
 
 
 ATTN_CASES = [(2, 1024, 1, 256), (3, 256, 1, 256), (3, 64, 1, 256), (2, 256, 1, 64), (2, 64, 2, 64), (1, 4096, 1, 64),

@@ -57,7 +57,7 @@ __device__ __forceinline__ TileCoord tile_origin(const ConvParams& p, int m_tile
 // 4 columns cq), all 32 rows valid.  Compile-time variants keep the instruction count low (the epilogue warps
 // are issue-bound otherwise); ragged tiles and SiLU epilogues take epilogue_rowmajor_generic.
 template <bool F16, bool F32OUT, bool RESID, int STATS>   // STATS: 0 none, 4 / 2 = columns per statistics entry
-__device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const float4* tile, int lane, long long wrow0, int col0) {
+__device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const float4* tile, int lane, long long wrow0, int col0, int slab) {
     const int cq = lane & 7, rsub = lane >> 3;
     const size_t off0 = static_cast<size_t>(wrow0 + rsub) * p.ld + col0 + cq * 4;
     const size_t step = static_cast<size_t>(4) * p.ld;
@@ -99,7 +99,7 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
             ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, 16); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, 16);
         }
         if (rsub == 0) {
-            float2* st = p.stats + static_cast<size_t>(wrow0 / kStatRows) * (p.Cout / (STATS ? STATS : 1));
+            float2* st = p.stats + static_cast<size_t>(slab) * (p.Cout / (STATS ? STATS : 1));
             if (STATS == 4) {
                 st[(col0 >> 2) + cq] = make_float2(ssum, ssq);
             } else {
@@ -142,8 +142,8 @@ __device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, cons
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 16); ssq += __shfl_xor_sync(0xffffffffu, ssq, 16);
         ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, 8); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, 8);
         ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, 16); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, 16);
-        if (rsub == 0 && tile_ok && wrow0 < p.M) {
-            float2* st = p.stats + static_cast<size_t>(wrow0 / kStatRows) * (p.Cout / p.stat_cols);
+        if (rsub == 0 && tile_ok) {                          // a quarter without valid rows still writes its zeros
+            float2* st = p.stats + static_cast<size_t>(m_tile * 4 + q) * (p.Cout / p.stat_cols);
             if (p.stat_cols == 4) {
                 st[(col0 >> 2) + cq] = make_float2(ssum + ssum1, ssq + ssq1);
             } else {
@@ -292,16 +292,16 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                     if (!all_valid || p.act_silu) {          // ragged tile / rare variants: run-time checked generic path
                         epilogue_rowmajor_generic(p, tile, lane, q, m_tile, wrow0, col0);
                     } else if (f32o) {
-                        if (resid && st && p.stat_cols == 4) epilogue_rowmajor<F16, true, true, 4>(p, tile, lane, wrow0, col0);
-                        else if (resid && st) epilogue_rowmajor<F16, true, true, 2>(p, tile, lane, wrow0, col0);
-                        else if (resid) epilogue_rowmajor<F16, true, true, 0>(p, tile, lane, wrow0, col0);
-                        else if (st && p.stat_cols == 4) epilogue_rowmajor<F16, true, false, 4>(p, tile, lane, wrow0, col0);
-                        else if (st) epilogue_rowmajor<F16, true, false, 2>(p, tile, lane, wrow0, col0);
-                        else epilogue_rowmajor<F16, true, false, 0>(p, tile, lane, wrow0, col0);
+                        if (resid && st && p.stat_cols == 4) epilogue_rowmajor<F16, true, true, 4>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
+                        else if (resid && st) epilogue_rowmajor<F16, true, true, 2>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
+                        else if (resid) epilogue_rowmajor<F16, true, true, 0>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
+                        else if (st && p.stat_cols == 4) epilogue_rowmajor<F16, true, false, 4>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
+                        else if (st) epilogue_rowmajor<F16, true, false, 2>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
+                        else epilogue_rowmajor<F16, true, false, 0>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
                     } else {
-                        if (st && p.stat_cols == 4) epilogue_rowmajor<F16, false, false, 4>(p, tile, lane, wrow0, col0);
-                        else if (st) epilogue_rowmajor<F16, false, false, 2>(p, tile, lane, wrow0, col0);
-                        else epilogue_rowmajor<F16, false, false, 0>(p, tile, lane, wrow0, col0);
+                        if (st && p.stat_cols == 4) epilogue_rowmajor<F16, false, false, 4>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
+                        else if (st) epilogue_rowmajor<F16, false, false, 2>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
+                        else epilogue_rowmajor<F16, false, false, 0>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
                     }
                     __syncwarp();
                 } else if (p.out_mode == kOutBF16) {         // V third of proj_in: transposed per image (coalesced per column)

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const GroupNorm
     const int C = p.C1 + p.C2, HW = p.H * p.W, cpg = C / kGroups;
     const int g = tid >> 3, part8 = tid & 7;
     // entries of stat_cols channels; a group may straddle the concat seam, so each entry picks its source
-    const int sc = p.stat_cols, sub = cpg / sc, slabs = HW / kStatRows;
+    const int sc = p.stat_cols, sub = cpg / sc, slabs = p.stat_slabs;
     const int e1 = p.C1 / sc, e2 = p.C2 / sc;              // entries per slab in source 1 / 2
     const float2* s1 = p.stats1 + static_cast<size_t>(b) * slabs * e1;
     const float2* s2 = p.stats2 ? p.stats2 + static_cast<size_t>(b) * slabs * e2 : nullptr;
@@ -338,7 +338,7 @@ cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream) {
     if (CV > 1024) return cudaErrorInvalidValue;
     const int HW = p.H * p.W;
     const bool fused = p.stats1 != nullptr;
-    if (fused && (HW % kStatRows != 0 || (p.stat_cols != 2 && p.stat_cols != 4) || cpg % p.stat_cols != 0 ||
+    if (fused && (p.stat_slabs != stat_slabs_per_image(p.H, p.W) || p.stat_slabs <= 0 || (p.stat_cols != 2 && p.stat_cols != 4) || cpg % p.stat_cols != 0 ||
                   p.C1 % p.stat_cols != 0 || (p.C2 > 0 && p.stats2 == nullptr))) return cudaErrorInvalidValue;
     if (p.in16 && (p.C2 != 0 || !fused)) return cudaErrorInvalidValue;
     int PPH = 1024 / CV;

@@ -51,12 +51,25 @@ struct alignas(64) ConvParams {
     h16* out_t;
     // optional GroupNorm partial statistics of the row-major output (after bias/residual): for every slab of
     // 32 consecutive rows and every stat_cols (4 or 2) consecutive columns, (sum, sum of squares):
-    // stats[slab * Cout/stat_cols + col/stat_cols]
+    // stats[slab * Cout/stat_cols + col/stat_cols], slab = m_tile * 4 + (row in tile) / 32
     float2* stats;
     int stat_cols;
     int ld_t;                          // row pitch (elements) of out_t: HW rounded up to 8 (TMA needs 16-byte pitches)
 };
-constexpr int kStatRows = 32;   // rows per statistics slab
+constexpr int kStatRows = 32;   // rows per statistics slab: one epilogue warp's quarter of an M tile (slab = m_tile * 4 + quarter)
+// Statistics slabs per image for an h x w feature map under the conv kernel's tiling, 0 when a slab could mix two
+// images: whole-image-row tiles (one image per tile) give 4 slabs per tile, partly or entirely empty when the tile
+// uses fewer than 128 rows; several images per tile need images of 32 or 64 pixels.
+inline int stat_slabs_per_image(int h, int w) {
+    if (w < 1 || h < 1 || w > 128) return 0;
+    if (2 * w * h > 128) {
+        int bh = 0;
+        for (int d = 1; d <= h; ++d)
+            if (h % d == 0 && d * w <= 128) bh = d;
+        return bh ? 4 * (h / bh) : 0;
+    }
+    return ((w * h) % kStatRows == 0 && 128 % (w * h) == 0) ? (w * h) / kStatRows : 0;
+}
 cudaError_t launch_conv_gemm(const ConvParams& p, int num_sms, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
@@ -73,6 +86,7 @@ struct GroupNormParams {
     // kernel is a single streaming pass, otherwise it makes a statistics pass of its own
     const float2* stats1; const float2* stats2;
     int stat_cols;                     // columns per statistics entry (4, or 2 when groups are not a multiple of 4 channels)
+    int stat_slabs;                    // statistics slabs per image = stat_slabs_per_image(H, W)
     float2* meanrstd;                  // scratch [B][32] (mean, rstd), required when stats1 is set
     int B, H, W;
     const float* gamma; const float* beta;   // [C1 + C2]

@@ -567,6 +567,8 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
     return 0;
 }
 
+extern "C" int vdt_stat_slabs_per_image(int32_t h, int32_t w) { return stat_slabs_per_image(h, w); }
+
 extern "C" int vdt_plan_flops(const vdt_plan* p, double* conv, double* attn, double* linear) {
     if (!p) return fail("null plan");
     const vdt_unet_config& c = p->cfg;
@@ -650,6 +652,11 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     const h16* a3s[3] = {s.a3, s.a3_lo, s.a3};
     const h16* a1s[3] = {s.a1, s.a1_lo, s.a1};
     const int n3 = s.a3 ? (s.a3_lo ? 3 : 1) : 0, n1 = s.a1 ? (s.a1_lo ? 3 : 1) : 0;
+    // GroupNorm statistics slabs (kernels.cuh: stat_slabs_per_image): flat 128-row tiles produce the same slab
+    // layout as the image-aligned tiles only when an image is whole tiles (or two / four whole images are one tile)
+    const int slabs = stat_slabs_per_image(s.h, s.w);
+    const bool flat_ok = ((s.h * s.w) % 128 == 0) || (2 * s.h * s.w <= 128 && slabs > 0);
+    const bool geo_pointwise = !s.a3 && s.stats && slabs > 0 && !flat_ok && s.ld1 == s.c1;
     if (s.a3) {
         ConvGeom g;
         CKI(conv_geom(s.n, s.h, s.w, &g));
@@ -664,6 +671,17 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
             CKI(make_map_nhwc(&cp->a_map[seg], a1s[k], s.n, s.h, s.w, s.c1, g.box_h, g.box_n));
             cp->seg_taps[seg] = 1; cp->seg_kblocks[seg] = s.c1 / 64; ktot += s.c1; ++seg;
         }
+    } else if (geo_pointwise) {
+        // a pointwise GEMM that must write GroupNorm statistics for images that are not whole 128-row tiles walks
+        // the image-aligned tiles of the 3x3 path (one tap) so that no statistics slab mixes two images
+        ConvGeom g;
+        CKI(conv_geom(s.n, s.h, s.w, &g));
+        for (int k = 0; k < n1; ++k) {
+            CKI(make_map_nhwc(&cp->a_map[seg], a1s[k], s.n, s.h, s.w, s.c1, g.box_h, g.box_n));
+            cp->seg_taps[seg] = 1; cp->seg_kblocks[seg] = s.c1 / 64; ktot += s.c1; ++seg;
+        }
+        cp->pointwise = 0; cp->tiles_per_image = g.tiles_per_image; cp->box_h = g.box_h; cp->box_n = g.box_n;
+        cp->rows_per_tile = g.rows_per_tile; cp->num_m_tiles = g.num_m_tiles;
     } else {
         for (int k = 0; k < n1; ++k) {
             CKI(make_map_rows4d(&cp->a_map[seg], a1s[k], M, s.c1, s.ld1));
@@ -680,7 +698,7 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     cp->M = (int)M; cp->Cout = s.cout; cp->out_mode = s.out_mode; cp->ld = s.ld;
     cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16;
     cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t; cp->stat_cols = s.stat_cols;
-    cp->stats = ((s.h * s.w) % kStatRows == 0) ? s.stats : nullptr;   // statistics slabs never span two images
+    cp->stats = (slabs > 0 && (s.a3 || flat_ok || geo_pointwise)) ? s.stats : nullptr;   // statistics slabs never span two images
     cp->ld_t = (s.h * s.w + 7) & ~7;
     if (s.out_mode != kOutNCHW && s.cout % 32 != 0) return fail("output channels must be a multiple of 32 (got %d)", s.cout);
     return 0;
@@ -705,7 +723,9 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
     // ---- in_conv
     // every fp32 stream tensor carries the partial GroupNorm statistics its producing conv wrote
     const int scols = p->stat_cols;
-    auto stats_bytes = [&](size_t rows_px, int ch) { return (rows_px / kStatRows + 1) * (size_t)(ch / scols) * sizeof(float2); };
+    auto stats_bytes = [&](size_t imgs, int r, int ch) {    // imgs images at r x r
+        return ((size_t)imgs * stat_slabs_per_image(r, r) + 4) * (size_t)(ch / scols) * sizeof(float2);
+    };
     const bool sp = p->split != 0;
     h16* patches; h16* patches_lo = nullptr; float* h; float2* hst;
     const size_t hw0 = (size_t)res * res;
@@ -714,7 +734,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
     ex->im2cols.push_back({ex->xin, patches, patches_lo, R / ex->rep, ex->rep, c.in_channels, res, res, p->f16});
     ex->steps.push_back({S_IM2COL, (int)ex->im2cols.size() - 1});
     CKI(ex->acquire((size_t)R * hw0 * hid * 4, (void**)&h));
-    CKI(ex->acquire(stats_bytes((size_t)R * hw0, hid), (void**)&hst));
+    CKI(ex->acquire(stats_bytes(R, res, hid), (void**)&hst));
     {
         ConvSpec s;
         s.f16 = p->f16; s.stat_cols = p->stat_cols;
@@ -730,10 +750,10 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
     stack.push_back({h, hst, hid});
     bool h_on_stack = true;      // h aliases the top stack entry -> must not be released when replaced
     int hch = hid;
-    auto fusable = [scols](int c1, int c2, int hw) {  // can a GroupNorm over concat(c1, c2) use epilogue statistics?
+    auto fusable = [scols](int c1, int c2, int r) {   // can a GroupNorm over concat(c1, c2) at r x r use epilogue statistics?
         const int cpg = (c1 + c2) / 32;
-        // groups may straddle the concat seam (finalize handles it); an image must be whole statistics slabs
-        return cpg % scols == 0 && c1 % scols == 0 && hw % kStatRows == 0;
+        // groups may straddle the concat seam (finalize handles it); no statistics slab may mix two images
+        return cpg % scols == 0 && c1 % scols == 0 && stat_slabs_per_image(r, r) > 0;
     };
 
     for (auto& b : p->blocks) {
@@ -756,19 +776,19 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             GroupNormParams g{};
             g.f16 = p->f16; g.stat_cols = p->stat_cols;
             g.src1 = h; g.C1 = hch; g.src2 = src2; g.C2 = c2; g.B = R; g.H = res; g.W = res;
-            if (fusable(hch, c2, HW)) { g.stats1 = hst; g.stats2 = st2; g.meanrstd = meanrstd; }
+            if (fusable(hch, c2, res)) { g.stats1 = hst; g.stats2 = st2; g.meanrstd = meanrstd; g.stat_slabs = stat_slabs_per_image(res, res); }
             g.gamma = p->W(n + ".norm1.weight"); g.beta = p->W(n + ".norm1.bias");
             g.silu = 1; g.resample = b.resample; g.out_act = a1; g.out_raw = xraw; g.out_res = xres;
             g.out_act_lo = a1_lo; g.out_raw_lo = xraw_lo;
             add_gn(g);
             // conv1: its output only feeds norm2, so it is kept in the 16-bit operand format when norm2 can use
             // the epilogue statistics (otherwise fp32 for the two-pass fallback)
-            const bool fuse2 = fusable(b.cout, 0, (int)HWo);
+            const bool fuse2 = fusable(b.cout, 0, ro);
             // (split-precision mode keeps every stream tensor fp32)
             const bool h1_16 = fuse2 && !sp;
             void* h1; float2* h1st = nullptr;
             CKI(ex->acquire((size_t)R * HWo * b.cout * (h1_16 ? 2 : 4), &h1));
-            if (fuse2) CKI(ex->acquire(stats_bytes((size_t)R * HWo, b.cout), (void**)&h1st));
+            if (fuse2) CKI(ex->acquire(stats_bytes(R, ro, b.cout), (void**)&h1st));
             {
                 ConvSpec s;
                 s.f16 = p->f16; s.stat_cols = p->stat_cols;
@@ -785,7 +805,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             if (sp) CKI(ex->acquire((size_t)R * HWo * b.cout * 2, (void**)&a2_lo));
             GroupNormParams g2{};
             g2.f16 = p->f16; g2.stat_cols = p->stat_cols;
-            g2.src1 = h1; g2.C1 = b.cout; g2.B = R; g2.H = ro; g2.W = ro; g2.in16 = h1_16 ? 1 : 0; g2.stats1 = h1st; g2.meanrstd = meanrstd;
+            g2.src1 = h1; g2.C1 = b.cout; g2.B = R; g2.H = ro; g2.W = ro; g2.in16 = h1_16 ? 1 : 0; g2.stats1 = h1st; g2.meanrstd = meanrstd; g2.stat_slabs = stat_slabs_per_image(ro, ro);
             g2.out_act_lo = a2_lo;
             g2.gamma = p->W(n + ".norm2.weight"); g2.beta = p->W(n + ".norm2.bias");
             g2.film = film; g2.film_row = film_row; g2.film_stride = p->film_total; g2.film_off = b.film_off;
@@ -796,7 +816,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             // conv2 (+ fused 1x1 skip conv as extra K) + residual
             float* hout; float2* houtst;
             CKI(ex->acquire((size_t)R * HWo * b.cout * 4, (void**)&hout));
-            CKI(ex->acquire(stats_bytes((size_t)R * HWo, b.cout), (void**)&houtst));
+            CKI(ex->acquire(stats_bytes(R, ro, b.cout), (void**)&houtst));
             {
                 ConvSpec s;
                 s.f16 = p->f16; s.stat_cols = p->stat_cols;
@@ -825,7 +845,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             GroupNormParams g{};
             g.f16 = p->f16; g.stat_cols = p->stat_cols;
             g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
-            if (fusable(hch, 0, HW)) { g.stats1 = hst; g.meanrstd = meanrstd; }
+            if (fusable(hch, 0, res)) { g.stats1 = hst; g.meanrstd = meanrstd; g.stat_slabs = stat_slabs_per_image(res, res); }
             g.gamma = p->W(n + ".norm.weight"); g.beta = p->W(n + ".norm.bias");
             g.silu = 0; g.resample = kResNone; g.out_act = a; g.out_act_lo = a_lo;
             add_gn(g);
@@ -873,7 +893,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             }
             float* hout; float2* houtst;
             CKI(ex->acquire((size_t)R * HW * b.cin * 4, (void**)&hout));
-            CKI(ex->acquire(stats_bytes((size_t)R * HW, b.cin), (void**)&houtst));
+            CKI(ex->acquire(stats_bytes(R, res, b.cin), (void**)&houtst));
             {
                 ConvSpec s;
                 s.f16 = p->f16; s.stat_cols = p->stat_cols;
@@ -899,7 +919,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
         GroupNormParams g{};
         g.f16 = p->f16; g.stat_cols = p->stat_cols;
         g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
-        if (fusable(hch, 0, HW)) { g.stats1 = hst; g.meanrstd = meanrstd; }
+        if (fusable(hch, 0, res)) { g.stats1 = hst; g.meanrstd = meanrstd; g.stat_slabs = stat_slabs_per_image(res, res); }
         g.gamma = p->W("out_conv.0.weight"); g.beta = p->W("out_conv.0.bias");
         g.silu = 1; g.resample = kResNone; g.out_act = a; g.out_act_lo = a_lo;
         add_gn(g);
@@ -1336,6 +1356,7 @@ extern "C" int vdt_op_conv(const void* x, int32_t batch, int32_t h, int32_t w, i
         if (out16) { s.out_mode = kOutBF16; s.out_bf16 = (h16*)out16; s.out_f32 = nullptr; }
         std::unique_ptr<ConvParams> cp(new ConvParams());
         rc = setup_conv(s, cp.get());
+        if (rc == 0 && stats_out && !cp->stats) rc = fail("no conv-epilogue statistics layout for %dx%d feature maps", h, w);
         if (rc == 0) {
             cudaError_t e = launch_conv_gemm(*cp, nsm, st);
             ++g_launches;
@@ -1354,6 +1375,8 @@ extern "C" int vdt_op_groupnorm(const void* src1, int32_t c1, const float* src2,
                                 int32_t f16, const void* stats1, const void* stats2, int32_t stat_cols, int32_t in16, void* stream) {
     GroupNormParams g{};
     g.f16 = f16; g.stats1 = (const float2*)stats1; g.stats2 = (const float2*)stats2; g.in16 = in16; g.stat_cols = stat_cols == 2 ? 2 : 4;
+    g.stat_slabs = stat_slabs_per_image(h, w);
+    if (stats1 && g.stat_slabs <= 0) return fail("no conv-epilogue statistics layout for %dx%d feature maps", h, w);
     g.src1 = src1; g.C1 = c1; g.src2 = src2; g.C2 = c2; g.B = batch; g.H = h; g.W = w; g.gamma = gamma; g.beta = beta;
     g.film = film; g.film_row = nullptr; g.film_stride = film_stride; g.film_off = film_off; g.silu = silu; g.resample = resample;
     g.out_act = (h16*)out_act; g.out_raw = (h16*)out_raw; g.out_res = out_res;
