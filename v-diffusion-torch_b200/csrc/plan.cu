@@ -233,7 +233,7 @@ struct Exec {
     int* film_row = nullptr;     // [rows] (sampler)
     SamplerState* state = nullptr;
     float* pred = nullptr;       // sampler: (guided) x0 prediction of the last executed step [rows/rep, C, HW]
-    float* coef_table = nullptr; // [T][12] (sampler)
+    float* coef_table = nullptr; // [T][kCoefStride] (sampler)
     // sampler signature this exec was built for
     vdt_sampler_config sc{};
     int rep = 1;
@@ -517,6 +517,7 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
     if (!p) return fail("null plan");
     for (auto& w : p->weights)
         if (!w.loaded) return fail("missing key in state_dict: %s", w.name.c_str());
+    if (p->work) CK(cudaStreamSynchronize(p->work));        // re-finalize after re-loading a key: nothing may still run
     p->execs.clear();
     for (void* q : p->owned) cudaFree(q);
     p->owned.clear();
@@ -1043,7 +1044,10 @@ static int get_forward_exec(vdt_plan* p, int rows, bool has_y, Exec** out) {
     snprintf(key, sizeof(key), "fwd:%d:%d", rows, (int)has_y);
     auto it = p->execs.find(key);
     if (it != p->execs.end()) { *out = it->second.get(); return 0; }
-    if (p->execs.size() >= 4) p->execs.clear();
+    if (p->execs.size() >= 4) {                          // evict everything; queued work may still use the old buffers / graphs
+        if (p->work) CK(cudaStreamSynchronize(p->work));
+        p->execs.clear();
+    }
     std::unique_ptr<Exec> ex(new Exec());
     const vdt_unet_config& c = p->cfg;
     const size_t HW = (size_t)c.resolution * c.resolution;
@@ -1195,7 +1199,10 @@ static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs,
              sc.logsnr_min, sc.logsnr_max, sc.w_guide, (unsigned long long)sc.seed, (const void*)step_noise, noise_stride);
     auto it = p->execs.find(key);
     if (it != p->execs.end()) { *out = it->second.get(); return 0; }
-    if (p->execs.size() >= 4) p->execs.clear();
+    if (p->execs.size() >= 4) {                          // evict everything; queued work may still use the old buffers / graphs
+        if (p->work) CK(cudaStreamSynchronize(p->work));
+        p->execs.clear();
+    }
     const vdt_unet_config& c = p->cfg;
     const int Cm = sc.model_out_type == VDT_OUT_BOTH ? 2 * c.in_channels : c.in_channels;
     if (Cm != c.out_channels)
