@@ -1009,6 +1009,19 @@ static int run_steps_profiled(vdt_plan* p, Exec* ex, cudaStream_t st) {
     return rc;
 }
 
+// Measurement aid (VDT_IDLE_US=n): one thread sleeps n microseconds at the end of every step.  Tells a power-capped
+// step (the governor hands the idle time back as clock, throughput barely moves) from a time-bound one.
+__global__ void idle_kernel(unsigned long long ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do { __nanosleep(1000); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
+}
+static long long idle_us() {
+    static long long v = -1;
+    if (v < 0) { const char* e = getenv("VDT_IDLE_US"); v = e ? atoll(e) : 0; }
+    return v;
+}
+
 // Run the exec's step list, through a CUDA graph when enabled.
 static int run_exec(vdt_plan* p, Exec* ex, cudaStream_t st) {
     if (g_profile) { g_launches += ex->steps.size(); return run_steps_profiled(p, ex, st); }
@@ -1034,9 +1047,11 @@ static int run_exec(vdt_plan* p, Exec* ex, cudaStream_t st) {
     g_launches += ex->steps.size();
     if (ex->graph) {
         CK(cudaGraphLaunch(ex->graph, st));
-        return 0;
+    } else {
+        CKI(run_steps(p, ex, st));
     }
-    return run_steps(p, ex, st);
+    if (idle_us() > 0) idle_kernel<<<1, 1, 0, st>>>((unsigned long long)idle_us() * 1000ull);
+    return 0;
 }
 
 static int get_forward_exec(vdt_plan* p, int rows, bool has_y, Exec** out) {

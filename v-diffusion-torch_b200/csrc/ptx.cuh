@@ -257,9 +257,10 @@ __device__ __forceinline__ float ex2_approx(float x) {   // 2^x, one MUFU op (ma
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 // fp32 pair -> packed 16-bit operand pair.  fp16 saturates at +-65504 instead of overflowing to inf.
 __device__ __forceinline__ uint32_t pack_16(float lo, float hi, int fp16) {
-    if (fp16) {
-        __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
-        return *reinterpret_cast<uint32_t*>(&v);
+    if (fp16) {                                      // one F2FP.SATFINITE.F16.F32.PACK_AB: overflow clamps to +-65504
+        uint32_t r;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+        return r;
     }
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -275,8 +276,9 @@ __device__ __forceinline__ uint32_t pack_16_inrange(float lo, float hi, int fp16
 }
 __device__ __forceinline__ uint16_t cvt_16(float x, int fp16) {
     if (fp16) {
-        __half v = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
-        return *reinterpret_cast<uint16_t*>(&v);
+        uint16_t r;
+        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+        return r;
     }
     __nv_bfloat16 v = __float2bfloat16(x);
     return *reinterpret_cast<uint16_t*>(&v);
