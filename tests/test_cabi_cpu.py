@@ -139,3 +139,14 @@ def test_reference_checkpoint_interop(tmp_path, golden_dir):
     _, model, _ = build_from_config(config, True, 1.0, 100)
     with pytest.raises(RuntimeError, match="in_conv.bias"):
         model.load_state_dict(bad)
+
+
+def test_statistics_slab_layout_follows_the_conv_tiling():
+    """Host logic: GroupNorm statistics slabs per image = 4 per image-aligned M tile (include/vdt_b200.h)."""
+    L = _lib.lib()
+    want = {32: 32, 16: 8, 64: 128, 128: 512,      # whole 128-row tiles: HW / 32
+            28: 28, 14: 8,                          # ragged tiles of 112 / 98 rows: 4 slabs per tile
+            8: 2,                                   # two images per tile, 64 pixels each
+            7: 0, 4: 0}                             # a slab would mix two images -> no layout, two-pass GroupNorm
+    for r, n in want.items():
+        assert L.vdt_stat_slabs_per_image(r, r) == n, r
