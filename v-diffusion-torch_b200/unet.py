@@ -164,6 +164,9 @@ class UNet(nn.Module):
             with torch.cuda.device(device):
                 _lib.check(L.vdt_plan_create(C.byref(cfg), C.byref(handle)))
             ent = {"handle": handle, "sig": None}
+            while len(self._plans) >= 4:                       # a plan owns packed weights + workspace: keep a few
+                old_key = next(iter(self._plans))
+                L.vdt_plan_destroy(self._plans.pop(old_key)["handle"])
             self._plans[key] = ent
         if ent["sig"] != sig:
             with torch.cuda.device(device):
