@@ -120,3 +120,15 @@ def test_all_schedules_known_answers(golden_dir):
         np.testing.assert_allclose(an["c1"], g[f"{sched}_c1"], rtol=1e-5, atol=1e-9)
         np.testing.assert_allclose(an["c2"], g[f"{sched}_c2"], rtol=1e-5, atol=1e-9)
         np.testing.assert_allclose(an["logvar"], g[f"{sched}_logvar"], rtol=1e-5, atol=1e-6)
+
+
+def test_tf32_calibration_covers_every_sampler_fixture(golden_dir):
+    """tests/golden/make_tf32_dev.py: the GPU sampler test reads one entry per fixture (deviation of the unmodified
+    reference under its own default GPU numerics); every w <= 1 fixture must sit well under the flat 2e-2 bar."""
+    with open(os.path.join(golden_dir, "ref_tf32_deviation.json")) as f:
+        dev = json.load(f)
+    assert set(dev) == set(SAMPLE_CASES)
+    for name, d in dev.items():
+        assert d["w_guide"] == SAMPLE_CASES[name]["w_guide"] and d["T"] == SAMPLE_CASES[name]["T"]
+        if d["w_guide"] <= 1.0:
+            assert 3.0 * d["max_abs"] <= 2e-2, name           # only the w = 3 fixtures get a calibrated bar
