@@ -56,6 +56,9 @@ typedef struct vdt_sampler_config {
     int32_t logsnr_schedule;      /* VDT_SCHED_* */
     int32_t use_ddim;             /* p_sample(..., use_ddim=) */
     int32_t x0eps_coef;           /* GaussianDiffusion(x0eps_coef=): posterior mean as c1*eps + c2*x0 (diffusion.py:137-140, 335-343) */
+    int32_t t_fp32;               /* 1: the step tensor is fp32 as in p_sample_progressive (diffusion.py:421): s, t are fp32
+                                     quotients and the timestep embedding is evaluated in fp32; 0: fp64 as in p_sample (:399) */
+    int32_t reserved;             /* 0 */
     double intp_frac;
     double logsnr_min, logsnr_max;
     double w_guide;
@@ -106,12 +109,23 @@ int vdt_p_sample_range(vdt_plan* plan, const vdt_sampler_config* sc, float* x, c
 int vdt_p_sample_host(vdt_plan* plan, const vdt_sampler_config* sc, const float* noise, const void* label,
                       const float* step_noise, float* out, int32_t batch);
 
+/* The tail of generate.py's batch loop (generate.py:149): fp32 NCHW samples -> uint8 NHWC pixels,
+ * (x * 127.5 + 127.5).clamp(0, 255).to(uint8).permute(0, 2, 3, 1).  x fp32 [B, C, HW], out uint8 [B, HW, C]; device pointers. */
+int vdt_images_to_uint8(const float* x_nchw, uint8_t* out_nhwc, int32_t batch, int32_t c, int32_t hw, void* stream);
+
 /* logsnr schedule + posterior coefficients — diffusion.py:42-112, 126-203 (host, fp64 with the reference's
  * fp32 rounding points).  out: [T][16] floats: alpha_t, sigma_t, rsqrt(sigmoid l_t), exp(-l_t/2), sigmoid(l_t),
  * sigmoid(-l_t), c1, c2, std, logvar, logsnr_s, logsnr_t, rsqrt(sigmoid -l_t), exp(l_t/2), x0eps_coef (0/1), 0.
  * With x0eps_coef and DDIM, c1/c2 are the LOGARITHMS 0.5*logsigmoid(-+l_s): the reference only exponentiates
  * them for eta != 0 (diffusion.py:180-182 vs 199) and p_sample always runs eta = 0; reproduced as is. */
 int vdt_step_coefficients(const vdt_sampler_config* sc, float* out);
+
+/* fp16 range monitor.  With fp16 operands (operand_dtype 0 / 2) every conversion of an unbounded value -- the raw
+ * residual stream copied as the skip conv's operand, conv1 / q / k / v outputs kept in 16 bits -- saturates at +-65504
+ * instead of overflowing to inf.  This returns how many (warp, 32x32-chunk) / thread events clamped a value since the
+ * plan was finalized (or since the last call with reset != 0).  Non-zero means the checkpoint's activations leave the
+ * fp16 range: use operand_dtype = 1 (bf16, fp32 exponent range) for it.  Synchronises the plan's stream. */
+int vdt_plan_saturations(vdt_plan* plan, uint64_t* count, int reset);
 
 /* Counters: kernels launched by this library since process start (graph replays count their nodes). */
 uint64_t vdt_kernel_launches(void);

@@ -60,8 +60,13 @@ def _log1mexp(x):
 
 def step_coefficients(T: int, use_ddim: bool, var_type: str = "fixed_large", intp_frac=None,
                       schedule: str = "cosine", logsnr_min: float = -20., logsnr_max: float = 20.,
-                      x0eps_coef: bool = False):
+                      x0eps_coef: bool = False, t_fp32: bool = False):
     """Per-step fp32 scalars for step index i = 0..T-1 (the loop visits T-1 .. 0).
+
+    ``t_fp32``: the step tensor is fp32 as in p_sample_progressive (diffusion.py:421, ``t = torch.empty(B)``): s and t
+    are fp32 quotients (the schedule upcasts them, diffusion.py:101) and ``t_model`` is an fp32 array, so the network's
+    sinusoidal embedding is evaluated in fp32 (functions.py:20-25).  p_sample itself carries fp64 (diffusion.py:399).
+
 
     Returns dict of float32 arrays of length T: ``logsnr_s, logsnr_t, alpha_t, sigma_t
     (fp32 math on the fp32 log-SNR: diffusion.py:233-234), c1, c2, logvar, std``
@@ -71,8 +76,15 @@ def step_coefficients(T: int, use_ddim: bool, var_type: str = "fixed_large", int
     ``x0eps_coef`` (diffusion.py:137-140, 180-182): the posterior mean is written as c1 * eps + c2 * x0.  The
     reference's DDIM branch returns the two coefficients as LOGARITHMS (the ``.exp_()`` at diffusion.py:199 is
     only reached for eta != 0); that is restated as is."""
-    i = np.arange(T, dtype=np.float64)
-    s, t = i / T, (i + 1) / T
+    if t_fp32:
+        i32 = np.arange(T, dtype=np.float32)
+        s, t = i32 / np.float32(T), (i32 + np.float32(1)) / np.float32(T)      # fp32 divisions (diffusion.py:363-364)
+        t_model = t.copy()
+        s, t = s.astype(np.float64), t.astype(np.float64)
+    else:
+        i = np.arange(T, dtype=np.float64)
+        s, t = i / T, (i + 1) / T
+        t_model = t
     ls32 = logsnr_schedule(s, schedule, logsnr_min, logsnr_max).astype(np.float32)
     lt32 = logsnr_schedule(t, schedule, logsnr_min, logsnr_max).astype(np.float32)
     ls, lt = ls32.astype(np.float64), lt32.astype(np.float64)
@@ -110,7 +122,7 @@ def step_coefficients(T: int, use_ddim: bool, var_type: str = "fixed_large", int
     std = torch.exp(0.5 * torch.from_numpy(logvar32)).numpy()
     return dict(logsnr_s=ls32, logsnr_t=lt32, alpha_t=alpha, sigma_t=sigma,
                 c1=c1.astype(np.float32), c2=c2.astype(np.float32), logvar=logvar32, std=std,
-                t_model=t)
+                t_model=t_model)
 
 
 # ----------------------------------------------------------------------------- embedding
@@ -148,19 +160,20 @@ def p_sample(denoise_fn: Callable, shape, noise: torch.Tensor, label: Optional[t
              var_type: str = "fixed_large", intp_frac=None, step_noise: Optional[torch.Tensor] = None,
              schedule: str = "cosine", logsnr_min: float = -20., logsnr_max: float = 20.,
              record: Optional[list] = None, pred_record: Optional[list] = None,
-             x0eps_coef: bool = False) -> torch.Tensor:
-    """Reverse loop (diffusion.py:394-414 + 360-392).  ``noise``: initial x_T.
+             x0eps_coef: bool = False, t_fp32: bool = False) -> torch.Tensor:
+    """Reverse loop (diffusion.py:394-414 + 360-392; with ``t_fp32`` and ``pred_record`` the loop of
+    p_sample_progressive, 416-441).  ``noise``: initial x_T.
     ``step_noise``: (T, B, C, H, W) pre-drawn per-step normal draws, indexed by the step
     index ti (required for ancestral sampling so both sides inject identical noise);
     DDIM multiplies them by exp(-inf)=0.  ``record`` collects (ti, model_out)."""
     B = shape[0]
-    co = step_coefficients(T, use_ddim, var_type, intp_frac, schedule, logsnr_min, logsnr_max, x0eps_coef)
+    co = step_coefficients(T, use_ddim, var_type, intp_frac, schedule, logsnr_min, logsnr_max, x0eps_coef, t_fp32)
     x_t = noise.clone().float()
     use_cfg = (w_guide > 0) and (label is not None)
     for ti in reversed(range(T)):
         lt = torch.tensor(co["logsnr_t"][ti])
         c1, c2 = float(co["c1"][ti]), float(co["c2"][ti])
-        t = torch.full((B,), co["t_model"][ti], dtype=torch.float64)
+        t = torch.full((B,), float(co["t_model"][ti]), dtype=torch.float32 if t_fp32 else torch.float64)
         if use_cfg:                                   # rows 2i cond, 2i+1 uncond (diffusion.py:368-372)
             xin = x_t.repeat_interleave(2, dim=0)
             tin = t.repeat_interleave(2)

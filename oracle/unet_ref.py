@@ -169,6 +169,26 @@ def dezero_(sd: Dict[str, torch.Tensor], seed: int = 7) -> Dict[str, torch.Tenso
     return sd
 
 
+# Optional numerics model of the CUDA path (test / calibration aid, off by default): ``operand_round`` of
+# unet_forward names a 16-bit format ("fp16" | "bf16"); every tensor the CUDA path holds in that format -- GEMM operands
+# (normalised activations, packed weights, the raw concat feeding the 1x1 skip conv), conv1's output, q / k / v,
+# the softmax probabilities and the attention output -- is rounded to it here, everything else stays fp32.
+_ROUND = {"fp16": torch.float16, "bf16": torch.bfloat16}
+_round_dtype = None
+
+
+def _q(x):
+    if _round_dtype is None:
+        return x
+    if _round_dtype == torch.float16:
+        x = x.clamp(-65504.0, 65504.0)                                # the CUDA conversions saturate
+    return x.to(_round_dtype).float()
+
+
+def _conv(x, w, b, padding=0):
+    return F.conv2d(_q(x), _q(w), b, padding=padding)
+
+
 def _gn(x, sd, prefix):
     return F.group_norm(x, GN_GROUPS, sd[prefix + ".weight"], sd[prefix + ".bias"], GN_EPS)
 
@@ -185,13 +205,13 @@ def _res_block(x, emb_act, sd, op):
     n = op["name"]
     skip = _resample(x, op["resample"])                             # unet.py:138
     if op["cin"] != op["cout"]:
-        skip = F.conv2d(skip, sd[n + ".skip.weight"], sd[n + ".skip.bias"])
+        skip = _conv(skip, sd[n + ".skip.weight"], sd[n + ".skip.bias"])
     h = _resample(F.silu(_gn(x, sd, n + ".norm1")), op["resample"])  # unet.py:141 norm->act->resample
-    h = F.conv2d(h, sd[n + ".conv1.weight"], sd[n + ".conv1.bias"], padding=1)
+    h = _q(_conv(h, sd[n + ".conv1.weight"], sd[n + ".conv1.bias"], padding=1))    # kept in 16 bits on the CUDA path
     film = F.linear(emb_act, sd[n + ".fc.weight"], sd[n + ".fc.bias"])[:, :, None, None]
     shift, scale = film.chunk(2, dim=1)                             # unet.py:145 (shift first)
     h = (1 + scale) * _gn(h, sd, n + ".norm2") + shift
-    h = F.conv2d(F.silu(h), sd[n + ".conv2.weight"], sd[n + ".conv2.bias"], padding=1)
+    h = _conv(F.silu(h), sd[n + ".conv2.weight"], sd[n + ".conv2.bias"], padding=1)
     return h + skip
 
 
@@ -199,12 +219,16 @@ def _attn_block(x, sd, op, cfg):
     n = op["name"]
     B, C, H, W = x.shape
     hd, nh = _attn_dims(C, cfg["head_dim"], cfg["num_heads"])
-    qkv = F.conv2d(_gn(x, sd, n + ".norm"), sd[n + ".proj_in.weight"], sd[n + ".proj_in.bias"])
+    qkv = _q(_conv(_gn(x, sd, n + ".norm"), sd[n + ".proj_in.weight"], sd[n + ".proj_in.bias"]))
     q, k, v = qkv.reshape(B, 3 * nh, hd, H * W).chunk(3, dim=1)     # unet.py:76-78: all-q | all-k | all-v
     w = torch.einsum("bncq,bnck->bnqk", q, k) / math.sqrt(hd)       # unet.py:58-60
-    w = torch.softmax(w, dim=-1)
-    o = torch.einsum("bnqk,bnck->bncq", w, v).reshape(B, nh * hd, H, W)
-    o = F.conv2d(o, sd[n + ".proj_out.weight"], sd[n + ".proj_out.bias"])
+    if _round_dtype is None:
+        w = torch.softmax(w, dim=-1)
+    else:                                                           # un-normalised probabilities are rounded, the sum is fp32
+        e = torch.exp(w - w.amax(dim=-1, keepdim=True))
+        w = _q(e) / e.sum(dim=-1, keepdim=True)
+    o = _q(torch.einsum("bnqk,bnck->bncq", w, v).reshape(B, nh * hd, H, W))
+    o = _conv(o, sd[n + ".proj_out.weight"], sd[n + ".proj_out.bias"])
     return o + x
 
 
@@ -228,13 +252,23 @@ def embedding(sd: Dict[str, torch.Tensor], cfg: dict, t: torch.Tensor, y: Option
 
 @torch.no_grad()
 def unet_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, t: torch.Tensor,
-                 y: Optional[torch.Tensor] = None, trace: Optional[dict] = None) -> torch.Tensor:
+                 y: Optional[torch.Tensor] = None, trace: Optional[dict] = None,
+                 operand_round: Optional[str] = None) -> torch.Tensor:
     """fp32 NCHW in, fp32 NCHW out.  ``t`` may be fp64 (sampler) — the sinusoid is
     evaluated in t's dtype (functions.py:20-25).  ``trace`` (optional dict) receives
     the output of every block keyed by its state_dict prefix, for layer-wise checks."""
+    global _round_dtype
+    _round_dtype = _ROUND[operand_round] if operand_round else None
+    try:
+        return _unet_forward(sd, cfg, x, t, y, trace)
+    finally:
+        _round_dtype = None
+
+
+def _unet_forward(sd, cfg, x, t, y, trace):
     x = x.float()
     emb_act = F.silu(embedding(sd, cfg, t, y))                      # unet.py:142: fc(act(t_emb))
-    hs = [F.conv2d(x, sd["in_conv.weight"], sd["in_conv.bias"], padding=1)]
+    hs = [_conv(x, sd["in_conv.weight"], sd["in_conv.bias"], padding=1)]
     if trace is not None:
         trace["in_conv"] = hs[0]
     h = hs[0]
@@ -248,4 +282,4 @@ def unet_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, t: tor
             hs.append(h)
     assert len(hs) == 0, len(hs)
     h = F.silu(_gn(h, sd, "out_conv.0"))
-    return F.conv2d(h, sd["out_conv.2.weight"], sd["out_conv.2.bias"], padding=1)
+    return _conv(h, sd["out_conv.2.weight"], sd["out_conv.2.bias"], padding=1)

@@ -46,8 +46,10 @@ SAMPLE_CASES = {
     # BASELINE configs[0] in miniature: x0-prediction, unconditional, DDIM
     "ddim_x0_uncond": dict(unet="small_hd64_x0", seed=22, B=3, res=32, T=6, model_out_type="x0",
                            w_guide=0.0, use_ddim=True, var_type="fixed_large", labels=None),
-    # BASELINE configs[3] in miniature: ancestral, CFG w=3, injected per-step noise
-    "ancestral_cfg_v": dict(unet="small_cond", seed=23, B=2, res=16, T=10, model_out_type="v", w_guide=3.0,
+    # BASELINE configs[3] in miniature: ancestral, CFG w=3, injected per-step noise.  64 steps: a w=3 ancestral
+    # trajectory of 10 coarse steps on a random-weight network is chaotic (round 1: unrelated kernel changes moved its
+    # final-sample error between 1.9e-2 and 3.0e-2 while every per-step error stayed put), so it pinned nothing
+    "ancestral_cfg_v": dict(unet="small_cond", seed=23, B=2, res=16, T=64, model_out_type="v", w_guide=3.0,
                             use_ddim=False, var_type="fixed_medium", intp_frac=0.3, labels=[4, 9]),
     # x0eps_coef=True (diffusion.py:137-140, 335-343): posterior mean written in (eps, x0), eps re-derived from the
     # clipped x0.  (v-prediction: an eps-prediction network at logsnr_min = -20 amplifies any rounding by e^10 before
@@ -65,7 +67,7 @@ SAMPLE_CASES = {
 # and in the attention-bearing upsampling block at 28x28 (N = 784)
 UNET_CASES["mnist28"] = dict(cfg=_cfg(in_channels=1, out_channels=1, mult=(1, 2, 2), nrb=1, attn=(False, True, True),
                                       num_classes=10), seed=16, B=3, res=28, labels=[2, 0, 9], trace=[])
-SAMPLE_CASES["ancestral_mnist28"] = dict(unet="mnist28", seed=27, B=2, res=28, T=8, model_out_type="v", w_guide=3.0,
+SAMPLE_CASES["ancestral_mnist28"] = dict(unet="mnist28", seed=27, B=2, res=28, T=64, model_out_type="v", w_guide=3.0,
                                          use_ddim=False, var_type="fixed_medium", intp_frac=0.3, labels=[5, 10])
 # multitag (multi-hot) class conditioning as used by the reference's conditional CelebA checkpoints
 UNET_CASES["small_multitag"] = dict(cfg=_cfg(mult=(1, 2), nrb=1, attn=(False, True), num_classes=40, multitags=True),
@@ -110,3 +112,47 @@ def build_sample_inputs(case, cfg):
     for ti in reversed(range(case["T"])):
         step_noise[ti] = torch.empty(shape).normal_(generator=g)
     return noise, label, step_noise
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Full-length trajectories of the real CIFAR-10 networks (BASELINE configs[0] and configs[1]), SURVEY §8d recipe:
+# the network is the reference's own random initialisation under torch.manual_seed(init_seed) -- this package's UNet
+# constructor consumes the RNG exactly like the reference's (checked bit for bit in make_golden.py), so the GPU box can
+# rebuild the weights without the reference -- with every all-zero matrix "de-zeroed" (oracle.dezero_, generator seed 7).
+FULL_CASES = {
+    # configs[0]: cifar10_uncond.json, x0-prediction, fixed_large, 10-step DDIM, batch 16
+    "cifar10_uncond_ddim10": dict(cfg=CIFAR_UNCOND, init_seed=0, dezero_seed=7, B=16, T=10, model_out_type="x0",
+                                  var_type="fixed_large", intp_frac=None, w_guide=0.0, use_ddim=True, noise_seed=1234,
+                                  labelled=False, keep_rows=16),
+    # configs[1] at B=8: cifar10_cond.json, v-prediction, CFG w=1 (16 UNet rows per step), 100-step DDIM
+    "cifar10_cond_cfg_ddim100": dict(cfg=CIFAR_COND, init_seed=0, dezero_seed=7, B=8, T=100, model_out_type="v",
+                                     var_type="fixed_medium", intp_frac=0.3, w_guide=1.0, use_ddim=True, noise_seed=1234,
+                                     labelled=True, keep_rows=4),
+}
+
+
+def build_full_inputs(case):
+    """noise = randn(B, 3, 32, 32) from Generator().manual_seed(noise_seed); labels = randint(10) + 1 from the same
+    generator afterwards (generate.py:134)."""
+    g = torch.Generator().manual_seed(case["noise_seed"])
+    noise = torch.randn(case["B"], 3, 32, 32, generator=g)
+    label = (torch.randint(10, (case["B"],), generator=g) + 1) if case["labelled"] else None
+    return noise, label
+
+
+def full_state_dict(case, unet_cls):
+    """State dict of ``unet_cls`` (the reference's UNet or this package's) initialised under manual_seed(init_seed)
+    and de-zeroed.  Restores the global RNG state afterwards."""
+    from oracle.unet_ref import dezero_
+    cfg = case["cfg"]
+    state = torch.get_rng_state()
+    try:
+        torch.manual_seed(case["init_seed"])
+        net = unet_cls(cfg["in_channels"], cfg["hid_channels"], cfg["out_channels"], cfg["ch_multipliers"],
+                       cfg["num_res_blocks"], cfg["apply_attn"], embedding_dim=cfg["embedding_dim"], drop_rate=0.2,
+                       head_dim=cfg["head_dim"], num_heads=cfg["num_heads"], num_classes=cfg["num_classes"],
+                       multitags=cfg["multitags"])
+    finally:
+        torch.set_rng_state(state)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    return dezero_(sd, case["dezero_seed"]), net

@@ -32,7 +32,8 @@ from v_diffusion.diffusion import logsnr_to_posterior, logsnr_to_posterior_ddim 
 from v_diffusion.functions import get_timestep_embedding  # noqa: E402
 
 from oracle.unet_ref import make_state_dict, state_dict_shapes  # noqa: E402
-from tests.cases import UNET_CASES, SAMPLE_CASES, build_inputs, build_sample_inputs  # noqa: E402
+from tests.cases import (UNET_CASES, SAMPLE_CASES, FULL_CASES, build_inputs, build_sample_inputs,  # noqa: E402
+                         build_full_inputs, full_state_dict)
 
 torch.set_num_threads(os.cpu_count())
 
@@ -93,6 +94,53 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"sample_{name}.npz"), out=x.numpy(),
                             model_out=torch.stack(outs).numpy())
         print(name, tuple(x.shape), float(x.abs().mean()), float(x.abs().max()))
+
+    # ---- p_sample_progressive (diffusion.py:416-441): fp32 step tensor (:421), x0 previews every pred_freq steps
+    for name, pred_freq in (("ddim_cfg_v", 3), ("ancestral_cfg_v", 16)):
+        case = SAMPLE_CASES[name]
+        cfg = UNET_CASES[case["unet"]]["cfg"]
+        net = ref_unet(cfg, UNET_CASES[case["unet"]]["seed"])
+        noise, label, step_noise = build_sample_inputs(case, cfg)
+        diff = GaussianDiffusion(
+            logsnr_fn=get_logsnr_schedule("cosine", -20., 20., rescale=False), sample_timesteps=case["T"],
+            model_out_type=case["model_out_type"], model_var_type=case["var_type"], reweight_type="snr_trunc",
+            loss_type="mse", intp_frac=case.get("intp_frac"), w_guide=case["w_guide"])
+        x, preds = diff.p_sample_progressive(net, shape=tuple(noise.shape), noise=noise, label=label, device="cpu",
+                                             seed=case["seed"], use_ddim=case["use_ddim"], pred_freq=pred_freq)
+        np.savez_compressed(os.path.join(HERE, f"progressive_{name}.npz"), out=x.numpy(), preds=preds.numpy(),
+                            pred_freq=np.int64(pred_freq))
+        print("progressive", name, tuple(x.shape), tuple(preds.shape), float(x.abs().max()))
+
+    # ---- full-length trajectories of the real CIFAR-10 networks (BASELINE configs[0], configs[1] at B=8)
+    from v_diffusion_b200.unet import UNet as OurUNet
+    for name, case in FULL_CASES.items():
+        cfg = case["cfg"]
+        sd, net = full_state_dict(case, UNet)
+        sd_ours, _ = full_state_dict(case, OurUNet)
+        assert list(sd) == list(sd_ours) and all(torch.equal(sd[k], sd_ours[k]) for k in sd), \
+            "this package's UNet constructor no longer reproduces the reference's initialisation"
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        noise, label = build_full_inputs(case)
+        diff = GaussianDiffusion(
+            logsnr_fn=get_logsnr_schedule("cosine", -20., 20., rescale=False), sample_timesteps=case["T"],
+            model_out_type=case["model_out_type"], model_var_type=case["var_type"], reweight_type="snr_trunc",
+            loss_type="mse", intp_frac=case["intp_frac"], w_guide=case["w_guide"])
+        outs = []
+        keep = case["keep_rows"]
+
+        def rec(x, t, y):
+            o = net(x, t, y)
+            outs.append(o[:keep].clone())
+            return o
+        import time
+        t0 = time.time()
+        x = diff.p_sample(rec, shape=tuple(noise.shape), noise=noise, label=label, device="cpu",
+                          seed=case["noise_seed"], use_ddim=case["use_ddim"])
+        mo = torch.stack(outs)
+        np.savez_compressed(os.path.join(HERE, f"full_{name}.npz"), out=x.numpy(), model_out=mo.numpy())
+        print("full", name, tuple(x.shape), tuple(mo.shape), float(x.abs().mean()), float(x.abs().max()),
+              f"{time.time() - t0:.1f}s")
 
     # ---- coefficient known answers (T = 100, cosine +-20) straight from the reference functions
     T = 100

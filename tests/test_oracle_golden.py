@@ -9,7 +9,8 @@ import torch
 
 from oracle import unet_forward, make_state_dict, step_coefficients, p_sample, timestep_embedding
 from oracle.unet_ref import unet_config_from_json
-from tests.cases import UNET_CASES, SAMPLE_CASES, CIFAR_COND, CIFAR_UNCOND, CELEBA, build_inputs, build_sample_inputs
+from tests.cases import (UNET_CASES, SAMPLE_CASES, FULL_CASES, CIFAR_COND, CIFAR_UNCOND, CELEBA, build_inputs,
+                         build_sample_inputs, build_full_inputs, full_state_dict)
 
 
 def _load(golden_dir, name):
@@ -61,6 +62,69 @@ def test_sampler_matches_reference(golden_dir, name):
         assert ti == case["T"] - 1 - i
         rel = (o - mo[i]).norm() / mo[i].norm()
         assert rel.item() <= 1e-4
+
+
+@pytest.mark.parametrize("name,pred_freq", [("ddim_cfg_v", 3), ("ancestral_cfg_v", 16)])
+def test_progressive_matches_reference(golden_dir, name, pred_freq):
+    """p_sample_progressive (diffusion.py:416-441) feeds an fp32 step tensor (:421): fp32 s / t, fp32 sinusoid."""
+    case = SAMPLE_CASES[name]
+    ucase = UNET_CASES[case["unet"]]
+    cfg = ucase["cfg"]
+    g = _load(golden_dir, f"progressive_{name}.npz")
+    assert int(g["pred_freq"]) == pred_freq
+    sd = make_state_dict(cfg, ucase["seed"])
+    noise, label, step_noise = build_sample_inputs(case, cfg)
+    rec = []
+    out = p_sample(lambda x, t, y: unet_forward(sd, cfg, x, t, y), tuple(noise.shape), noise, label,
+                   T=case["T"], model_out_type=case["model_out_type"], w_guide=case["w_guide"],
+                   use_ddim=case["use_ddim"], var_type=case["var_type"], intp_frac=case.get("intp_frac"),
+                   step_noise=step_noise, pred_record=rec, t_fp32=True)
+    assert (out - torch.from_numpy(g["out"])).abs().max().item() <= 5e-4
+    preds = torch.from_numpy(g["preds"])
+    want = [p for ti, p in rec if (ti + 1) % pred_freq == 0]       # loop order: ti descending -> preds index descending
+    assert len(want) == preds.shape[0] == case["T"] // pred_freq
+    for k, p in enumerate(want):
+        assert (p - preds[preds.shape[0] - 1 - k]).abs().max().item() <= 5e-4
+
+
+def test_full_trajectory_configs0_matches_reference(golden_dir):
+    """BASELINE configs[0] exactly as SURVEY §8d specifies it: cifar10_uncond.json network initialised under
+    manual_seed(0) and de-zeroed (seed 7), x0 / fixed_large, 10-step DDIM, batch 16, noise from Generator(1234).
+    Also proves that this package's UNet constructor reproduces the reference's initialisation bit for bit (the
+    fixture was generated with the reference's own module)."""
+    from v_diffusion_b200 import UNet
+    case = FULL_CASES["cifar10_uncond_ddim10"]
+    g = _load(golden_dir, "full_cifar10_uncond_ddim10.npz")
+    sd, _ = full_state_dict(case, UNet)
+    noise, label = build_full_inputs(case)
+    rec = []
+    out = p_sample(lambda x, t, y: unet_forward(sd, case["cfg"], x, t, y), tuple(noise.shape), noise, label,
+                   T=case["T"], model_out_type=case["model_out_type"], w_guide=case["w_guide"], use_ddim=True,
+                   var_type=case["var_type"], record=rec)
+    assert (out - torch.from_numpy(g["out"])).abs().max().item() <= 5e-4
+    mo = torch.from_numpy(g["model_out"])
+    for i, (ti, o) in enumerate(rec):
+        assert ((o - mo[i]).norm() / mo[i].norm()).item() <= 1e-4
+
+
+def test_full_trajectory_configs1_matches_reference(golden_dir):
+    """BASELINE configs[1] at reduced batch: cifar10_cond.json network, v-prediction, CFG w = 1, all 100 DDIM steps.
+    The fixture holds 8 images; trajectories are independent per sample, so the oracle replays the first two
+    (4 UNet rows per step) to keep the CPU suite short."""
+    from v_diffusion_b200 import UNet
+    case = FULL_CASES["cifar10_cond_cfg_ddim100"]
+    g = _load(golden_dir, "full_cifar10_cond_cfg_ddim100.npz")
+    sd, _ = full_state_dict(case, UNet)
+    noise, label = build_full_inputs(case)
+    rec = []
+    out = p_sample(lambda x, t, y: unet_forward(sd, case["cfg"], x, t, y), (2, 3, 32, 32), noise[:2], label[:2],
+                   T=case["T"], model_out_type="v", w_guide=1.0, use_ddim=True, var_type="fixed_medium", intp_frac=0.3,
+                   record=rec)
+    assert (out - torch.from_numpy(g["out"])[:2]).abs().max().item() <= 1e-3
+    mo = torch.from_numpy(g["model_out"])                       # (100, 4, 3, 32, 32): rows of the first two images
+    assert len(rec) == 100
+    for i, (ti, o) in enumerate(rec):
+        assert ((o - mo[i]).norm() / mo[i].norm()).item() <= 2e-4, ti
 
 
 def test_step_coefficients_known_answers(golden_dir):
@@ -123,12 +187,34 @@ def test_all_schedules_known_answers(golden_dir):
 
 
 def test_tf32_calibration_covers_every_sampler_fixture(golden_dir):
-    """tests/golden/make_tf32_dev.py: the GPU sampler test reads one entry per fixture (deviation of the unmodified
-    reference under its own default GPU numerics); every w <= 1 fixture must sit well under the flat 2e-2 bar."""
+    """tests/golden/make_tf32_dev.py: deviation of the unmodified reference under its own default GPU numerics (TF32
+    convolutions) per sampler fixture.  Reported next to the CUDA path's error in the GPU tests; the bar itself is the
+    flat north-star 2e-2 on every fixture, so every fixture must leave room under it."""
     with open(os.path.join(golden_dir, "ref_tf32_deviation.json")) as f:
         dev = json.load(f)
     assert set(dev) == set(SAMPLE_CASES)
     for name, d in dev.items():
         assert d["w_guide"] == SAMPLE_CASES[name]["w_guide"] and d["T"] == SAMPLE_CASES[name]["T"]
-        if d["w_guide"] <= 1.0:
-            assert 3.0 * d["max_abs"] <= 2e-2, name           # only the w = 3 fixtures get a calibrated bar
+        assert d["max_abs"] <= 1.5e-2, name
+
+
+@pytest.mark.parametrize("name", ["ddim_cfg_v", "ancestral_cfg_v"])
+def test_numerics_model_of_the_cuda_path(golden_dir, name):
+    """oracle.unet_forward(operand_round=...) rounds every tensor the CUDA path keeps in 16 bits.  With fp16 it must
+    stay inside the production bar on the fixtures (this is what the GPU tests then measure for real); with bf16 it
+    does not -- the reason fp16 is the shipped operand format."""
+    case = SAMPLE_CASES[name]
+    ucase = UNET_CASES[case["unet"]]
+    cfg = ucase["cfg"]
+    ref = torch.from_numpy(_load(golden_dir, f"sample_{name}.npz")["out"])
+    sd = make_state_dict(cfg, ucase["seed"])
+    noise, label, step_noise = build_sample_inputs(case, cfg)
+    err = {}
+    for mode in ("fp16", "bf16"):
+        out = p_sample(lambda x, t, y: unet_forward(sd, cfg, x, t, y, operand_round=mode), tuple(noise.shape), noise, label,
+                       T=case["T"], model_out_type=case["model_out_type"], w_guide=case["w_guide"],
+                       use_ddim=case["use_ddim"], var_type=case["var_type"], intp_frac=case.get("intp_frac"),
+                       step_noise=step_noise)
+        err[mode] = (out - ref).abs().max().item()
+    print(name, err)
+    assert err["fp16"] <= 2e-2 and err["bf16"] > err["fp16"]

@@ -16,6 +16,8 @@
 //   warps 2-9  softmax + final normalise/store: two threads per query row (= TMEM lane), each owning 32
 //              of the tile's 64 key columns (and half of O's columns); row maxima are exchanged through
 //              shared memory once per tile
+#include <atomic>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -291,12 +293,17 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
     if (p.d % 64 != 0 || p.d > 256 || p.N < 1) return cudaErrorInvalidValue;
     const int smem = attn_smem_bytes(p.d);
-    static int smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    // cudaFuncSetAttribute is per device: the configured size is tracked per device ordinal
+    static std::atomic<int> smem_set[kMaxDevices];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (smem > smem_set[dev].load(std::memory_order_acquire)) {
+        e = cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        smem_set = smem;
+        smem_set[dev].store(smem, std::memory_order_release);
     }
     const bool packed = (2 * p.N == kQRows);
     const int ipc = packed ? 2 : 1;

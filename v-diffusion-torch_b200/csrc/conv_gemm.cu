@@ -17,6 +17,8 @@
 //                               double-buffered in TMEM (2 x 256 columns per CTA)
 //   warps 2-9  epilogue (both CTAs): tcgen05.ld -> registers -> smem transposition -> coalesced global
 //                               stores (+bias, +residual), overlapping the next tile's main loop
+#include <atomic>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -71,6 +73,7 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
         compiler_fence();
     }
     float ssum = 0.f, ssq = 0.f, ssum1 = 0.f, ssq1 = 0.f;
+    float amax = 0.f;                                        // fp16 16-bit outputs: largest magnitude converted
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + rsub;
@@ -80,8 +83,10 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
         {
             if (F32OUT)
                 *reinterpret_cast<float4*>(p.out_f32 + off0 + i * step) = o;
-            else
+            else {
                 *reinterpret_cast<uint2*>(p.out_bf16 + off0 + i * step) = make_uint2(pack_16(o.x, o.y, (F16 ? 1 : 0)), pack_16(o.z, o.w, (F16 ? 1 : 0)));
+                if (F16) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+            }
             if (STATS == 4) {
                 ssum += (o.x + o.y) + (o.z + o.w);
                 ssq = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, ssq))));
@@ -90,6 +95,9 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
                 ssum1 += o.z + o.w; ssq1 = fmaf(o.z, o.z, fmaf(o.w, o.w, ssq1));
             }
         }
+    }
+    if (F16 && !F32OUT && p.sat_count != nullptr) {         // the saturating pack clamped something: count the event
+        if (__any_sync(0xffffffffu, amax > 65504.f) && lane == 0) atomicAdd(p.sat_count, 1ull);
     }
     if (STATS) {                                             // fixed-order reduction over the warp's 32 rows
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 8); ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
@@ -132,8 +140,11 @@ __device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, cons
         if (p.act_silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
         if (p.out_mode == kOutF32)
             *reinterpret_cast<float4*>(p.out_f32 + off) = o;
-        else
+        else {
             *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_16(o.x, o.y, p.f16), pack_16(o.z, o.w, p.f16));
+            if (p.f16 && p.sat_count != nullptr && fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))) > 65504.f)
+                atomicAdd(p.sat_count, 1ull);
+        }
         ssum += o.x + o.y; ssq = fmaf(o.x, o.x, fmaf(o.y, o.y, ssq));
         ssum1 += o.z + o.w; ssq1 = fmaf(o.z, o.z, fmaf(o.w, o.w, ssq1));
     }
@@ -350,12 +361,17 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
 }  // namespace
 
 cudaError_t launch_conv_gemm(const ConvParams& p, int num_sms, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    // cudaFuncSetAttribute is per device: one flag per device ordinal (a process may drive several GPUs)
+    static std::atomic<bool> attr_set[kMaxDevices];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (!attr_set[dev].load(std::memory_order_acquire)) {
+        e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set[dev].store(true, std::memory_order_release);
     }
     const int items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     if (items <= 0) return cudaSuccess;

@@ -181,9 +181,17 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
                              : p.src2 + static_cast<size_t>(b) * HW * p.C2 + (c - p.C1);
     const h16* src16 = static_cast<const h16*>(p.src1) + static_cast<size_t>(b) * HW * p.C1 + c;   // IN16 only
     const int sC = from1 ? p.C1 : p.C2;
+    float amax = 0.f;                                // fp16 range events seen by this thread (see GroupNormParams::sat_count)
     auto load_px = [&](int pix, float (&v)[VEC]) {
-        if (IN16) load_vec16(src16 + static_cast<size_t>(pix) * sC, v, (F16 ? 1 : 0));
-        else load_vec<VEC>(src + static_cast<size_t>(pix) * sC, v);
+        if (IN16) {
+            load_vec16(src16 + static_cast<size_t>(pix) * sC, v, (F16 ? 1 : 0));
+            if (F16) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) amax = fmaxf(amax, fabsf(v[i]));
+            }
+        } else {
+            load_vec<VEC>(src + static_cast<size_t>(pix) * sC, v);
+        }
     };
 
     // ---- fallback pass 1: statistics
@@ -322,6 +330,10 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
                 for (int u = 0; u < 8; ++u) {
                     float x[VEC], y[VEC];
                     unpack16(r[u], x, (F16 ? 1 : 0));
+                    if (F16) {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) amax = fmaxf(amax, fabsf(x[i]));
+                    }
                     norm_act(x, y);
                     store_16n<VEC>(oa + static_cast<size_t>(pix + u * PPH) * C, y, (F16 ? 1 : 0));
                 }
@@ -342,6 +354,10 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             norm_act(x3, y); store_16n<VEC>(oa + static_cast<size_t>(pix + 3 * PPH) * C, y, (F16 ? 1 : 0));
             if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + 3 * PPH) * C, y, (F16 ? 1 : 0));
             if (ow) {
+                if (F16) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(x0[i]), fabsf(x1[i]))), fmaxf(fabsf(x2[i]), fabsf(x3[i])));
+                }
                 store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, (F16 ? 1 : 0));
                 if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix) * C, x0, (F16 ? 1 : 0));
                 store_16<VEC>(ow + static_cast<size_t>(pix + PPH) * C, x1, (F16 ? 1 : 0));
@@ -358,10 +374,19 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             norm_act(x0, y0);
             store_16n<VEC>(oa + static_cast<size_t>(pix) * C, y0, (F16 ? 1 : 0));
             if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix) * C, y0, (F16 ? 1 : 0));
-            if (ow) store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, (F16 ? 1 : 0));
+            if (ow) {
+                if (F16) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) amax = fmaxf(amax, fabsf(x0[i]));
+                }
+                store_16<VEC>(ow + static_cast<size_t>(pix) * C, x0, (F16 ? 1 : 0));
+            }
             if (ow_lo) store_lo<VEC>(ow_lo + static_cast<size_t>(pix) * C, x0, (F16 ? 1 : 0));
         }
     }
+    // a 16-bit input that sits at the fp16 maximum was clamped by the conv epilogue that wrote it; a raw stream value
+    // above it was clamped by out_raw's conversion just now
+    if (F16 && p.sat_count != nullptr && amax >= 65504.f) atomicAdd(p.sat_count, 1ull);
 }
 
 }  // namespace

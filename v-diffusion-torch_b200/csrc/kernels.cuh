@@ -9,6 +9,7 @@
 
 namespace vdt {
 
+constexpr int kMaxDevices = 64;   // per-device launch state (function attributes) is indexed by device ordinal
 typedef uint16_t h16;   // storage of a 16-bit GEMM operand: IEEE fp16 (default) or bf16, per the launch's `f16` flag
 
 // ------------------------------------------------------------------------------------------------
@@ -55,6 +56,9 @@ struct alignas(64) ConvParams {
     float2* stats;
     int stat_cols;
     int ld_t;                          // row pitch (elements) of out_t: HW rounded up to 8 (TMA needs 16-byte pitches)
+    // optional device counter of fp16 range events: incremented (once per warp and 32x32 chunk) when a value written in
+    // the fp16 operand format had |x| > 65504 and was clamped by the saturating conversion
+    unsigned long long* sat_count;
 };
 constexpr int kStatRows = 32;   // rows per statistics slab: one epilogue warp's quarter of an M tile (slab = m_tile * 4 + quarter)
 // Statistics slabs per image for an h x w feature map under the conv kernel's tiling, 0 when a slab could mix two
@@ -101,6 +105,8 @@ struct GroupNormParams {
     h16* out_act_lo;                  // split-precision mode: second halves, lo = round16(x - float(round16(x)))
     h16* out_raw_lo;
     float* out_res;                    // optional fp32 [B, H'W', C]: resampled raw input (identity-skip residual)
+    unsigned long long* sat_count;     // optional device counter of fp16 range events (see ConvParams::sat_count): raw
+                                       // stream values clamped by out_raw's conversion, saturated 16-bit inputs read
 };
 cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream);
 
@@ -133,7 +139,9 @@ cudaError_t launch_attention_f32(const float* qkv, h16* out_hi, h16* out_lo, int
                                  cudaStream_t stream);
 
 // sinusoidal embedding evaluated in fp64 like functions.py:11-29 -> fp32 [rows, dim]
-cudaError_t launch_timestep_embedding(const double* t, float* out, int rows, int dim, cudaStream_t stream);
+// fp32_flag (optional device int): non-zero -> the arithmetic runs in fp32 like the reference's when it is handed an
+// fp32 t (functions.py:20-25 computes in the dtype of `timesteps`; p_sample_progressive passes fp32, diffusion.py:421)
+cudaError_t launch_timestep_embedding(const double* t, float* out, int rows, int dim, const int* fp32_flag, cudaStream_t stream);
 
 // out[r, n] = act( sum_k x[r, k] * W[n, k] + b[n] )   fp32 CUDA-core path for the embedding MLP
 // (time_embed, fc of every ResidualBlock: unet.py:201-205, 122, 142); rows are few (one per distinct
@@ -151,13 +159,21 @@ cudaError_t launch_class_embed_silu(const float* e, const int64_t* y, const floa
 cudaError_t launch_class_embed_multitag_silu(const float* e, const float* y, const float* w_cls, const float* b_cls,
                                              int num_classes, float* out, int rows, int E, cudaStream_t stream);
 
-// Per-step device-side sampler state: everything that changes from step to step lives here so one
-// captured CUDA graph can be replayed for every step.
+// generate.py:149: fp32 NCHW images in [-1, 1] -> uint8 NHWC, (x * 127.5 + 127.5).clamp(0, 255) truncated
+cudaError_t launch_images_to_uint8(const float* x, uint8_t* out, int B, int C, int HW, cudaStream_t stream);
+
+// Per-step device-side sampler state: everything that changes from step to step -- and everything that changes from
+// call to call (noise tensor, seed) -- lives here, so one captured CUDA graph is replayed for every step of every call.
 struct SamplerState {
     int next_step;                     // step index the next begin_step will consume (T-1 .. 0)
     int step;                          // step index of the step in flight
     int img0;                          // first image of the current chunk (offset into injected noise)
-    int pad;
+    int t_fp32;                        // 1: t = (step+1)/T and the sinusoidal embedding are evaluated in fp32, as
+                                       // p_sample_progressive does (diffusion.py:421: `t = torch.empty(B)`)
+    const float* noise;                // injected per-step noise [T, Btotal, C, HW] or null
+    long long noise_step_stride;       // elements between steps (Btotal*C*HW)
+    unsigned long long seed;           // on-device Philox noise when `noise` is null and std > 0
+    unsigned long long pad;
     float coef[16];                    // one row of vdt_step_coefficients (include/vdt_b200.h)
 };
 constexpr int kCoefStride = 16;
@@ -171,10 +187,7 @@ struct SamplerStepParams {
     float* x_s;                        // fp32 NCHW [B, C, HW]  (may alias x_t)
     float* pred_x0;                    // optional fp32 NCHW [B, C, HW]: the (guided) x0 prediction of this step
                                        // (p_sample_step(return_pred=True), diffusion.py:385, 392)
-    const float* noise;                // injected per-step noise [T, Btotal, C, HW] or null
-    long long noise_step_stride;       // elements between steps (Btotal*C*HW)
-    const SamplerState* st;
-    unsigned long long seed;           // on-device Philox noise when `noise` is null and std > 0
+    const SamplerState* st;            // step index, coefficient row, injected noise / seed of this call
     int B, C, HW;
     int cfg;                           // 1: classifier-free guidance pair per sample
     int model_out_type;                // 0 x0, 1 eps, 2 both, 3 v

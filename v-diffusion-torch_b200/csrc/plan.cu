@@ -7,8 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -20,7 +22,7 @@ using namespace vdt;
 
 // ================================================================================================ errors
 static thread_local char g_err[1024] = "";
-static uint64_t g_launches = 0;
+static std::atomic<uint64_t> g_launches{0};
 
 static int fail(const char* fmt, ...) {
     va_list ap;
@@ -40,11 +42,14 @@ static int fail(const char* fmt, ...) {
         if (_r != 0) return _r;         \
     } while (0)
 
-static bool g_profile = false;
+// process-wide profiling switch and accumulators (several plans / host threads may run at once)
+static std::atomic<bool> g_profile{false};
+static std::mutex g_prof_mu;
 static double g_prof_ms[VDT_PROF_FAMILIES] = {0, 0, 0, 0};
 static uint64_t g_prof_n[VDT_PROF_FAMILIES] = {0, 0, 0, 0};
-extern "C" int vdt_profile_enable(int on) { g_profile = on != 0; return 0; }
+extern "C" int vdt_profile_enable(int on) { g_profile.store(on != 0); return 0; }
 extern "C" int vdt_profile_read(double* ms4, uint64_t* n4) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (int i = 0; i < VDT_PROF_FAMILIES; ++i) {
         if (ms4) ms4[i] = g_prof_ms[i];
         if (n4) n4[i] = g_prof_n[i];
@@ -55,7 +60,7 @@ extern "C" int vdt_profile_read(double* ms4, uint64_t* n4) {
 
 extern "C" const char* vdt_last_error(void) { return g_err; }
 extern "C" int vdt_version(void) { return 1; }
-extern "C" uint64_t vdt_kernel_launches(void) { return g_launches; }
+extern "C" uint64_t vdt_kernel_launches(void) { return g_launches.load(); }
 
 // ================================================================================================ tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -150,12 +155,14 @@ __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
 }
-__global__ void film_rows_kernel(const int64_t* __restrict__ label, int* __restrict__ film_row, int rows, int rep) {
+// The Python shim rejects labels outside [0, num_classes] (F.one_hot raises in the reference, modules.py:191-196); a
+// C caller's out-of-range label is clamped here so that it can never index outside the FiLM table.
+__global__ void film_rows_kernel(const int64_t* __restrict__ label, int* __restrict__ film_row, int rows, int rep, int ncls) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
-    int r = 0;
-    if (label != nullptr && !(rep == 2 && (i & 1))) r = (int)label[i / rep];   // odd rows: y = 0 (diffusion.py:372)
-    film_row[i] = r;
+    long long r = 0;
+    if (label != nullptr && !(rep == 2 && (i & 1))) r = label[i / rep];   // odd rows: y = 0 (diffusion.py:372)
+    film_row[i] = (int)(r < 0 ? 0 : r > ncls ? ncls : r);
 }
 // multitag labels of a chunk -> per-UNet-row multi-hot rows with the CFG interleave (odd rows: all zero, diffusion.py:372)
 __global__ void multitag_rows_kernel(const float* __restrict__ label, float* __restrict__ y_rows, int rows, int rep, int ncls) {
@@ -164,8 +171,12 @@ __global__ void multitag_rows_kernel(const float* __restrict__ label, float* __r
     const int r = i / ncls, k = i % ncls;
     y_rows[i] = (rep == 2 && (r & 1)) ? 0.f : label[(size_t)(r / rep) * ncls + k];
 }
-__global__ void sampler_init_state_kernel(SamplerState* st, int next_step, int img0) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { st->next_step = next_step; st->step = next_step; st->img0 = img0; st->pad = 0; }
+__global__ void sampler_init_state_kernel(SamplerState* st, int next_step, int img0, int t_fp32, const float* noise,
+                                          long long noise_stride, unsigned long long seed) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        st->next_step = next_step; st->step = next_step; st->img0 = img0; st->t_fp32 = t_fp32;
+        st->noise = noise; st->noise_step_stride = noise_stride; st->seed = seed; st->pad = 0;
+    }
 }
 __global__ void iota_i64_kernel(int64_t* p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,7 +210,7 @@ enum StepKind { S_CONV, S_GN, S_ATTN, S_IM2COL, S_TEMB, S_LINEAR, S_CLSEMB, S_BE
 struct LinearArgs { const float *x, *W, *b; float* out; int rows, K, N, silu; };
 struct Im2colArgs { const float* x; h16* out; h16* out_lo; int B, rep, C, H, W, f16; };
 struct AttnF32Args { const float* qkv; h16 *hi, *lo; int B, N, heads, d, f16; };
-struct TembArgs { const double* t; float* out; int rows, dim; };
+struct TembArgs { const double* t; float* out; int rows, dim; const int* fp32_flag; };
 struct ClsArgs { const float* e; const int64_t* y; const float* y_multi; const float *w, *b; int ncls; float* out; int rows, E; };
 struct BeginArgs { SamplerState* st; const float* table; double* t_rows; int nrows, T; };
 
@@ -237,7 +248,7 @@ struct Exec {
     // sampler signature this exec was built for
     vdt_sampler_config sc{};
     int rep = 1;
-    const float* noise_ptr = nullptr; long long noise_stride = 0;
+    uint64_t last_use = 0;       // LRU stamp of the plan's exec cache
     cudaGraphExec_t graph = nullptr;
     bool graph_failed = false;
     int runs = 0;
@@ -286,6 +297,8 @@ struct vdt_plan {
     float* b_fc_all = nullptr;            // [film_total]
     std::vector<void*> owned;
     std::map<std::string, std::unique_ptr<Exec>> execs;
+    uint64_t use_clock = 0;
+    unsigned long long* sat_count = nullptr;  // device counter: fp16 operand packs that hit +-65504 (saturated)
     bool use_graph = true;
     int f16 = 1;                          // GEMM operand format: 1 fp16 (default), 0 bf16
     int split = 0;                        // 1: split-precision validation mode (every operand as a hi/lo fp16 pair)
@@ -524,6 +537,7 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
     const vdt_unet_config& c = p->cfg;
     const int E = p->E, hid = p->hid;
     const int sp = p->split, km = sp ? 3 : 1;          // K multiplier of the split mode
+    CKI(dev_alloc(p, &p->sat_count, 1));
     CKI(dev_alloc(p, &p->w_in, (size_t)hid * 64 * km));
     for (int part = 0; part < km; ++part) {
         pack_inconv_w_kernel<<<(hid * 64 + 255) / 256, 256>>>(p->W("in_conv.weight"), p->w_in, hid, c.in_channels, p->f16, 64 * km,
@@ -569,6 +583,18 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
 }
 
 extern "C" int vdt_stat_slabs_per_image(int32_t h, int32_t w) { return stat_slabs_per_image(h, w); }
+
+extern "C" int vdt_plan_saturations(vdt_plan* p, uint64_t* count, int reset) {
+    if (!p || !count) return fail("null argument");
+    *count = 0;
+    if (!p->sat_count) return 0;                        // not finalized yet: nothing has run
+    if (p->work) CK(cudaStreamSynchronize(p->work));
+    unsigned long long v = 0;
+    CK(cudaMemcpy(&v, p->sat_count, sizeof(v), cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(p->sat_count, 0, sizeof(v)));
+    *count = v;
+    return 0;
+}
 
 extern "C" int vdt_plan_flops(const vdt_plan* p, double* conv, double* attn, double* linear) {
     if (!p) return fail("null plan");
@@ -643,6 +669,7 @@ struct ConvSpec {
     int ld = 0, split_col = 0, act_silu = 0, f16 = 1;
     float2* stats = nullptr;
     int stat_cols = 4;
+    unsigned long long* sat_count = nullptr;
 };
 
 static int setup_conv(const ConvSpec& s, ConvParams* cp) {
@@ -701,6 +728,7 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t; cp->stat_cols = s.stat_cols;
     cp->stats = (slabs > 0 && (s.a3 || flat_ok || geo_pointwise)) ? s.stats : nullptr;   // statistics slabs never span two images
     cp->ld_t = (s.h * s.w + 7) & ~7;
+    cp->sat_count = s.sat_count;
     if (s.out_mode != kOutNCHW && s.cout % 32 != 0) return fail("output channels must be a multiple of 32 (got %d)", s.cout);
     return 0;
 }
@@ -738,7 +766,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
     CKI(ex->acquire(stats_bytes(R, res, hid), (void**)&hst));
     {
         ConvSpec s;
-        s.f16 = p->f16; s.stat_cols = p->stat_cols;
+        s.f16 = p->f16; s.stat_cols = p->stat_cols; s.sat_count = p->sat_count;
         s.a1 = patches; s.a1_lo = patches_lo; s.c1 = 64; s.ld1 = 64; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_in; s.cout = hid; s.wrows = hid;
         s.bias = p->W("in_conv.bias"); s.out_mode = kOutF32; s.out_f32 = h; s.ld = hid; s.stats = hst;
         CKI(add_conv(s));
@@ -775,7 +803,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             if (skipconv && sp) CKI(ex->acquire((size_t)R * HW * cin * 2, (void**)&xraw_lo));
             if (b.resample != kResNone) CKI(ex->acquire((size_t)R * HWo * cin * 4, (void**)&xres));
             GroupNormParams g{};
-            g.f16 = p->f16; g.stat_cols = p->stat_cols;
+            g.f16 = p->f16; g.stat_cols = p->stat_cols; g.sat_count = p->sat_count;
             g.src1 = h; g.C1 = hch; g.src2 = src2; g.C2 = c2; g.B = R; g.H = res; g.W = res;
             if (fusable(hch, c2, res)) { g.stats1 = hst; g.stats2 = st2; g.meanrstd = meanrstd; g.stat_slabs = stat_slabs_per_image(res, res); }
             g.gamma = p->W(n + ".norm1.weight"); g.beta = p->W(n + ".norm1.bias");
@@ -792,7 +820,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             if (fuse2) CKI(ex->acquire(stats_bytes(R, ro, b.cout), (void**)&h1st));
             {
                 ConvSpec s;
-                s.f16 = p->f16; s.stat_cols = p->stat_cols;
+                s.f16 = p->f16; s.stat_cols = p->stat_cols; s.sat_count = p->sat_count;
                 s.a3 = a1; s.a3_lo = a1_lo; s.c3 = cin; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w1; s.cout = b.cout; s.wrows = b.cout;
                 s.bias = p->W(n + ".conv1.bias"); s.ld = b.cout; s.stats = h1st;
                 if (h1_16) { s.out_mode = kOutBF16; s.out_bf16 = (h16*)h1; } else { s.out_mode = kOutF32; s.out_f32 = (float*)h1; }
@@ -805,7 +833,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire((size_t)R * HWo * b.cout * 2, (void**)&a2));
             if (sp) CKI(ex->acquire((size_t)R * HWo * b.cout * 2, (void**)&a2_lo));
             GroupNormParams g2{};
-            g2.f16 = p->f16; g2.stat_cols = p->stat_cols;
+            g2.f16 = p->f16; g2.stat_cols = p->stat_cols; g2.sat_count = p->sat_count;
             g2.src1 = h1; g2.C1 = b.cout; g2.B = R; g2.H = ro; g2.W = ro; g2.in16 = h1_16 ? 1 : 0; g2.stats1 = h1st; g2.meanrstd = meanrstd; g2.stat_slabs = stat_slabs_per_image(ro, ro);
             g2.out_act_lo = a2_lo;
             g2.gamma = p->W(n + ".norm2.weight"); g2.beta = p->W(n + ".norm2.bias");
@@ -820,7 +848,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire(stats_bytes(R, ro, b.cout), (void**)&houtst));
             {
                 ConvSpec s;
-                s.f16 = p->f16; s.stat_cols = p->stat_cols;
+                s.f16 = p->f16; s.stat_cols = p->stat_cols; s.sat_count = p->sat_count;
                 s.a3 = a2; s.a3_lo = a2_lo; s.c3 = b.cout; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w2; s.cout = b.cout; s.wrows = b.cout;
                 if (skipconv) { s.a1 = xraw; s.a1_lo = xraw_lo; s.c1 = cin; s.ld1 = cin; }
                 s.bias = b.bias2;
@@ -844,7 +872,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire((size_t)R * HW * b.cin * 2, (void**)&a));
             if (sp) CKI(ex->acquire((size_t)R * HW * b.cin * 2, (void**)&a_lo));
             GroupNormParams g{};
-            g.f16 = p->f16; g.stat_cols = p->stat_cols;
+            g.f16 = p->f16; g.stat_cols = p->stat_cols; g.sat_count = p->sat_count;
             g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
             if (fusable(hch, 0, res)) { g.stats1 = hst; g.meanrstd = meanrstd; g.stat_slabs = stat_slabs_per_image(res, res); }
             g.gamma = p->W(n + ".norm.weight"); g.beta = p->W(n + ".norm.bias");
@@ -856,7 +884,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
                 CKI(ex->acquire((size_t)R * ((N + 7) & ~7) * hidd * 2, (void**)&vt));
                 {   // one GEMM for q | k | v: q,k row-major [R*N, 2*hid]; the v third is written transposed, V^T [R*hid, N]
                     ConvSpec s;
-                    s.f16 = p->f16; s.stat_cols = p->stat_cols;
+                    s.f16 = p->f16; s.stat_cols = p->stat_cols; s.sat_count = p->sat_count;
                     s.a1 = a; s.c1 = b.cin; s.ld1 = b.cin; s.n = R; s.h = res; s.w = res; s.wpacked = b.w1; s.cout = 3 * hidd;
                     s.wrows = 3 * hidd; s.bias = p->W(n + ".proj_in.bias"); s.out_mode = kOutBF16; s.out_bf16 = qk; s.out_t = vt;
                     s.ld = 2 * hidd; s.split_col = 2 * hidd;
@@ -881,7 +909,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
                 CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&o_lo));
                 {
                     ConvSpec s;
-                    s.f16 = p->f16; s.stat_cols = p->stat_cols;
+                    s.f16 = p->f16; s.stat_cols = p->stat_cols; s.sat_count = p->sat_count;
                     s.a1 = a; s.a1_lo = a_lo; s.c1 = b.cin; s.ld1 = b.cin; s.n = R; s.h = res; s.w = res; s.wpacked = b.w1;
                     s.cout = 3 * hidd; s.wrows = 3 * hidd; s.bias = p->W(n + ".proj_in.bias"); s.out_mode = kOutF32; s.out_f32 = qkv32;
                     s.ld = 3 * hidd;
@@ -897,7 +925,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             CKI(ex->acquire(stats_bytes(R, res, b.cin), (void**)&houtst));
             {
                 ConvSpec s;
-                s.f16 = p->f16; s.stat_cols = p->stat_cols;
+                s.f16 = p->f16; s.stat_cols = p->stat_cols; s.sat_count = p->sat_count;
                 s.a1 = o; s.a1_lo = o_lo; s.c1 = hidd; s.ld1 = hidd; s.n = R; s.h = res; s.w = res; s.wpacked = b.w2; s.cout = b.cin; s.wrows = b.cin;
                 s.bias = p->W(n + ".proj_out.bias"); s.residual = h; s.out_mode = kOutF32; s.out_f32 = hout; s.ld = b.cin;
                 s.stats = houtst;
@@ -918,14 +946,14 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
         CKI(ex->acquire((size_t)R * HW * hch * 2, (void**)&a));
         if (sp) CKI(ex->acquire((size_t)R * HW * hch * 2, (void**)&a_lo));
         GroupNormParams g{};
-        g.f16 = p->f16; g.stat_cols = p->stat_cols;
+        g.f16 = p->f16; g.stat_cols = p->stat_cols; g.sat_count = p->sat_count;
         g.src1 = h; g.C1 = hch; g.B = R; g.H = res; g.W = res;
         if (fusable(hch, 0, res)) { g.stats1 = hst; g.meanrstd = meanrstd; g.stat_slabs = stat_slabs_per_image(res, res); }
         g.gamma = p->W("out_conv.0.weight"); g.beta = p->W("out_conv.0.bias");
         g.silu = 1; g.resample = kResNone; g.out_act = a; g.out_act_lo = a_lo;
         add_gn(g);
         ConvSpec s;
-        s.f16 = p->f16; s.stat_cols = p->stat_cols;
+        s.f16 = p->f16; s.stat_cols = p->stat_cols; s.sat_count = p->sat_count;
         s.a3 = a; s.a3_lo = a_lo; s.c3 = hch; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_out; s.cout = c.out_channels; s.wrows = 16;
         s.bias = p->W("out_conv.2.bias"); s.out_mode = kOutNCHW; s.out_f32 = ex->yout; s.ld = 0;
         CKI(add_conv(s));
@@ -942,7 +970,7 @@ static int add_embedding_steps(vdt_plan* p, Exec* ex, float* film, bool has_y) {
     CKI(ex->acquire((size_t)ER * E * 4, (void**)&e1));
     CKI(ex->acquire((size_t)ER * E * 4, (void**)&e2));
     CKI(ex->acquire((size_t)ER * E * 4, (void**)&act));
-    ex->tembs.push_back({ex->t_rows, temb, ER, hid});
+    ex->tembs.push_back({ex->t_rows, temb, ER, hid, ex->state ? &ex->state->t_fp32 : nullptr});
     ex->steps.push_back({S_TEMB, (int)ex->tembs.size() - 1});
     ex->linears.push_back({temb, p->W("time_embed.0.weight"), p->W("time_embed.0.bias"), e1, ER, hid, E, 1});
     ex->steps.push_back({S_LINEAR, (int)ex->linears.size() - 1});
@@ -970,7 +998,7 @@ static int run_steps(vdt_plan* p, Exec* ex, cudaStream_t st, std::vector<cudaEve
             case S_GN: e = launch_groupnorm(ex->gns[s.idx], st); break;
             case S_ATTN: e = launch_attention(*ex->attns[s.idx], st); break;
             case S_IM2COL: { auto& a = ex->im2cols[s.idx]; e = launch_im2col3x3(a.x, a.out, a.out_lo, a.B, a.rep, a.C, a.H, a.W, a.f16, st); break; }
-            case S_TEMB: { auto& a = ex->tembs[s.idx]; e = launch_timestep_embedding(a.t, a.out, a.rows, a.dim, st); break; }
+            case S_TEMB: { auto& a = ex->tembs[s.idx]; e = launch_timestep_embedding(a.t, a.out, a.rows, a.dim, a.fp32_flag, st); break; }
             case S_LINEAR: { auto& a = ex->linears[s.idx]; e = launch_linear_f32(a.x, a.W, a.b, a.out, a.rows, a.K, a.N, a.silu, st); break; }
             case S_CLSEMB: {
                 auto& a = ex->clss[s.idx];
@@ -997,6 +1025,7 @@ static int run_steps_profiled(vdt_plan* p, Exec* ex, cudaStream_t st) {
         if (e != cudaSuccess) rc = fail("profiled step failed: %s", cudaGetErrorString(e));
     }
     if (rc == 0) {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
         for (size_t i = 0; i < ex->steps.size(); ++i) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
@@ -1024,7 +1053,7 @@ static long long idle_us() {
 
 // Run the exec's step list, through a CUDA graph when enabled.
 static int run_exec(vdt_plan* p, Exec* ex, cudaStream_t st) {
-    if (g_profile) { g_launches += ex->steps.size(); return run_steps_profiled(p, ex, st); }
+    if (g_profile.load()) { g_launches += ex->steps.size(); return run_steps_profiled(p, ex, st); }
     // first run is eager (sets function attributes, surfaces launch errors); the second run captures
     if (p->use_graph && !ex->graph && !ex->graph_failed && ex->runs++ >= 1) {
         cudaGraph_t g = nullptr;
@@ -1054,16 +1083,35 @@ static int run_exec(vdt_plan* p, Exec* ex, cudaStream_t st) {
     return 0;
 }
 
+// The plan keeps a handful of execs (workspace + captured graph per batch size / sampler signature).  A miss on a full
+// cache evicts the least recently used entry only; queued work may still use its buffers, hence the stream sync.
+constexpr size_t kMaxExecs = 4;
+static int exec_cache_lookup(vdt_plan* p, const std::string& key, Exec** out) {
+    auto it = p->execs.find(key);
+    if (it == p->execs.end()) { *out = nullptr; return 0; }
+    it->second->last_use = ++p->use_clock;
+    *out = it->second.get();
+    return 0;
+}
+static int exec_cache_make_room(vdt_plan* p) {
+    while (p->execs.size() >= kMaxExecs) {
+        auto victim = p->execs.begin();
+        for (auto it = p->execs.begin(); it != p->execs.end(); ++it)
+            if (it->second->last_use < victim->second->last_use) victim = it;
+        if (p->work) CK(cudaStreamSynchronize(p->work));
+        p->execs.erase(victim);
+    }
+    return 0;
+}
+
 static int get_forward_exec(vdt_plan* p, int rows, bool has_y, Exec** out) {
     char key[64];
     snprintf(key, sizeof(key), "fwd:%d:%d", rows, (int)has_y);
-    auto it = p->execs.find(key);
-    if (it != p->execs.end()) { *out = it->second.get(); return 0; }
-    if (p->execs.size() >= 4) {                          // evict everything; queued work may still use the old buffers / graphs
-        if (p->work) CK(cudaStreamSynchronize(p->work));
-        p->execs.clear();
-    }
+    CKI(exec_cache_lookup(p, key, out));
+    if (*out) return 0;
+    CKI(exec_cache_make_room(p));
     std::unique_ptr<Exec> ex(new Exec());
+    ex->last_use = ++p->use_clock;
     const vdt_unet_config& c = p->cfg;
     const size_t HW = (size_t)c.resolution * c.resolution;
     ex->rows = rows; ex->emb_rows = rows; ex->sampler = false; ex->has_y = has_y; ex->rep = 1;
@@ -1149,8 +1197,12 @@ extern "C" int vdt_step_coefficients(const vdt_sampler_config* scp, float* out) 
     if (T < 1) return fail("sample_timesteps must be >= 1");
     for (int i = 0; i < T; ++i) {
         double ls_d, lt_d;
-        CKI(logsnr_d(sc, (double)i / (double)T, &ls_d));
-        CKI(logsnr_d(sc, (double)(i + 1) / (double)T, &lt_d));
+        // s = step / T, t = (step + 1) / T: fp64 tensors in p_sample (diffusion.py:399), fp32 in p_sample_progressive
+        // (diffusion.py:421), where the schedule then sees the fp32-rounded quotients (`_t = t.to(float64)`, :101)
+        const double s_in = sc.t_fp32 ? (double)((float)i / (float)T) : (double)i / (double)T;
+        const double t_in = sc.t_fp32 ? (double)((float)(i + 1) / (float)T) : (double)(i + 1) / (double)T;
+        CKI(logsnr_d(sc, s_in, &ls_d));
+        CKI(logsnr_d(sc, t_in, &lt_d));
         const float ls32 = (float)ls_d, lt32 = (float)lt_d;     // broadcast_to casts to x.dtype (diffusion.py:23-26)
         const double ls = ls32, lt = lt32;                      // re-upcast inside the posterior (131, 171)
         const double logr = lt - ls;
@@ -1204,25 +1256,25 @@ extern "C" int vdt_step_coefficients(const vdt_sampler_config* scp, float* out) 
 }
 
 // ================================================================================================ sampler
-static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs, bool has_label, const float* step_noise,
-                            long long noise_stride, Exec** out) {
+static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs, bool has_label, Exec** out) {
     const bool cfg = sc.w_guide > 0.0 && has_label;            // diffusion.py:368
     const int rep = cfg ? 2 : 1;
+    // the key holds what shapes the workspace, the coefficient table and the kernel parameters baked into the graph;
+    // per-call values (seed, injected-noise tensor, fp32-t mode of p_sample_progressive) live in the device-side
+    // SamplerState and are rewritten before every call
     char key[192];
-    snprintf(key, sizeof(key), "smp:%d:%d:%d:%d:%d:%d:%d:%d:%.17g:%.17g:%.17g:%.17g:%llu:%p:%lld", imgs, (int)has_label,
-             sc.sample_timesteps, sc.model_out_type, sc.model_var_type, sc.logsnr_schedule, sc.use_ddim, sc.x0eps_coef, sc.intp_frac,
-             sc.logsnr_min, sc.logsnr_max, sc.w_guide, (unsigned long long)sc.seed, (const void*)step_noise, noise_stride);
-    auto it = p->execs.find(key);
-    if (it != p->execs.end()) { *out = it->second.get(); return 0; }
-    if (p->execs.size() >= 4) {                          // evict everything; queued work may still use the old buffers / graphs
-        if (p->work) CK(cudaStreamSynchronize(p->work));
-        p->execs.clear();
-    }
+    snprintf(key, sizeof(key), "smp:%d:%d:%d:%d:%d:%d:%d:%d:%d:%.17g:%.17g:%.17g:%.17g", imgs, (int)has_label,
+             sc.sample_timesteps, sc.model_out_type, sc.model_var_type, sc.logsnr_schedule, sc.use_ddim, sc.x0eps_coef, sc.t_fp32,
+             sc.intp_frac, sc.logsnr_min, sc.logsnr_max, sc.w_guide);
+    CKI(exec_cache_lookup(p, key, out));
+    if (*out) return 0;
+    CKI(exec_cache_make_room(p));
     const vdt_unet_config& c = p->cfg;
     const int Cm = sc.model_out_type == VDT_OUT_BOTH ? 2 * c.in_channels : c.in_channels;
     if (Cm != c.out_channels)
         return fail("model_out_type needs %d output channels but the UNet has %d", Cm, c.out_channels);
     std::unique_ptr<Exec> ex(new Exec());
+    ex->last_use = ++p->use_clock;
     const size_t HW = (size_t)c.resolution * c.resolution;
     const int T = sc.sample_timesteps;
     ex->rows = imgs * rep; ex->rep = rep; ex->sampler = true; ex->has_y = has_label; ex->sc = sc;
@@ -1252,8 +1304,8 @@ static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs,
     CKI(add_embedding_steps(p, ex.get(), film, cond_model));
     CKI(build_unet_steps(p, ex.get(), film, mt ? nullptr : ex->film_row));
     SamplerStepParams sp{};
-    sp.model_out = ex->yout; sp.x_t = ex->xin; sp.x_s = ex->xin; sp.pred_x0 = ex->pred; sp.noise = step_noise; sp.noise_step_stride = noise_stride;
-    sp.st = ex->state; sp.seed = sc.seed; sp.B = imgs; sp.C = c.in_channels; sp.HW = (int)HW; sp.cfg = cfg ? 1 : 0;
+    sp.model_out = ex->yout; sp.x_t = ex->xin; sp.x_s = ex->xin; sp.pred_x0 = ex->pred;
+    sp.st = ex->state; sp.B = imgs; sp.C = c.in_channels; sp.HW = (int)HW; sp.cfg = cfg ? 1 : 0;
     sp.model_out_type = sc.model_out_type; sp.w = (float)sc.w_guide; sp.x0eps = sc.x0eps_coef ? 1 : 0;
     ex->samples.push_back(sp);
     ex->steps.push_back({S_SAMPLE, 0});
@@ -1285,17 +1337,19 @@ extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, fl
     for (int i0 = 0; i0 < batch; i0 += chunk) {
         const int imgs = std::min(chunk, batch - i0);
         Exec* ex;
-        CKI(get_sampler_exec(p, sc, imgs, label != nullptr, step_noise, (long long)batch * (long long)CHW, &ex));
+        CKI(get_sampler_exec(p, sc, imgs, label != nullptr, &ex));
         CK(cudaMemcpyAsync(ex->xin, x + (size_t)i0 * CHW, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
         if (mt) {
             const int n = ex->rows * c.num_classes;
             multitag_rows_kernel<<<(n + 127) / 128, 128, 0, st>>>(static_cast<const float*>(label) + (size_t)i0 * c.num_classes,
                                                                 ex->y_multi, ex->rows, rep, c.num_classes);
         } else {
-            film_rows_kernel<<<(ex->rows + 127) / 128, 128, 0, st>>>(row_label ? row_label + i0 : nullptr, ex->film_row, ex->rows, rep);
+            film_rows_kernel<<<(ex->rows + 127) / 128, 128, 0, st>>>(row_label ? row_label + i0 : nullptr, ex->film_row, ex->rows, rep,
+                                                                     c.num_classes);
         }
         CK(cudaGetLastError());
-        sampler_init_state_kernel<<<1, 32, 0, st>>>(ex->state, first_step, i0);
+        sampler_init_state_kernel<<<1, 32, 0, st>>>(ex->state, first_step, i0, sc.t_fp32 ? 1 : 0, step_noise,
+                                                    (long long)batch * (long long)CHW, (unsigned long long)sc.seed);
         CK(cudaGetLastError());
         g_launches += 2;
         for (int step = 0; step < num_steps; ++step) CKI(run_exec(p, ex, st));
@@ -1428,19 +1482,28 @@ extern "C" int vdt_op_attention(const void* qk, const void* vt, void* out, int32
     return 0;
 }
 
+extern "C" int vdt_images_to_uint8(const float* x, uint8_t* out, int32_t batch, int32_t c, int32_t hw, void* stream) {
+    if (!x || !out) return fail("null argument");
+    if (batch < 0 || c < 1 || hw < 1) return fail("bad image shape (%d, %d, %d)", batch, c, hw);
+    cudaError_t e = launch_images_to_uint8(x, out, batch, c, hw, reinterpret_cast<cudaStream_t>(stream));
+    ++g_launches;
+    if (e != cudaSuccess) return fail("images_to_uint8 launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int vdt_op_sampler_step(const float* model_out, const float* x_t, const float* noise, float* x_s, int32_t batch,
                                    int32_t c, int32_t hw, int32_t cfg, int32_t model_out_type, int32_t step,
                                    const float* coef_host, float w, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     SamplerState hs{};
-    hs.next_step = step - 1; hs.step = step; hs.img0 = 0;
+    hs.next_step = step - 1; hs.step = step; hs.img0 = 0; hs.noise = noise; hs.noise_step_stride = 0; hs.seed = 0;
     for (int i = 0; i < kCoefStride; ++i) hs.coef[i] = coef_host[i];
     SamplerState* ds = nullptr;
     CK(cudaMalloc(&ds, sizeof(SamplerState)));
     CK(cudaMemcpy(ds, &hs, sizeof(hs), cudaMemcpyHostToDevice));
     SamplerStepParams sp{};
-    sp.model_out = model_out; sp.x_t = x_t; sp.x_s = x_s; sp.noise = noise;
-    sp.noise_step_stride = 0; sp.st = ds; sp.seed = 0; sp.pred_x0 = nullptr; sp.B = batch; sp.C = c; sp.HW = hw; sp.cfg = cfg;
+    sp.model_out = model_out; sp.x_t = x_t; sp.x_s = x_s;
+    sp.st = ds; sp.pred_x0 = nullptr; sp.B = batch; sp.C = c; sp.HW = hw; sp.cfg = cfg;
     sp.model_out_type = model_out_type; sp.w = w; sp.x0eps = coef_host[14] != 0.0f ? 1 : 0;
     cudaError_t e = launch_sampler_step(sp, st);
     ++g_launches;

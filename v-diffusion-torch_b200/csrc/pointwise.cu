@@ -89,15 +89,26 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------ embedding
-__global__ void timestep_embedding_kernel(const double* __restrict__ t, float* __restrict__ out, int rows, int dim) {
+__global__ void timestep_embedding_kernel(const double* __restrict__ t, float* __restrict__ out, int rows, int dim,
+                                          const int* __restrict__ fp32_flag) {
     const int half = dim / 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * half) return;
     const int r = idx / half, k = idx % half;
     const double c = log(10000.0) / static_cast<double>(half - 1);
-    const double ang = (1000.0 * t[r]) * exp(-static_cast<double>(k) * c);
-    out[static_cast<size_t>(r) * dim + k] = static_cast<float>(sin(ang));
-    out[static_cast<size_t>(r) * dim + half + k] = static_cast<float>(cos(ang));
+    float sn, cs;
+    if (fp32_flag != nullptr && *fp32_flag != 0) {
+        // fp32 `timesteps` (p_sample_progressive, diffusion.py:421): every op of functions.py:20-25 rounds to fp32
+        const float ts = __fmul_rn(1000.0f, static_cast<float>(t[r]));
+        const float fr = expf(__fmul_rn(-static_cast<float>(k), static_cast<float>(c)));
+        const float ang = __fmul_rn(ts, fr);
+        sn = sinf(ang); cs = cosf(ang);
+    } else {
+        const double ang = (1000.0 * t[r]) * exp(-static_cast<double>(k) * c);
+        sn = static_cast<float>(sin(ang)); cs = static_cast<float>(cos(ang));
+    }
+    out[static_cast<size_t>(r) * dim + k] = sn;
+    out[static_cast<size_t>(r) * dim + half + k] = cs;
     if ((dim & 1) && k == 0) out[static_cast<size_t>(r) * dim + dim - 1] = 0.f;
 }
 
@@ -187,13 +198,16 @@ __global__ void sampler_begin_step_kernel(SamplerState* st, const float* __restr
         st->step = step;
         st->next_step = step - 1;
         for (int i = 0; i < kCoefStride; ++i) st->coef[i] = coef_table[step * kCoefStride + i];
-        const double t = static_cast<double>(step + 1) / static_cast<double>(T);   // diffusion.py:364
+        // t = (step + 1) / T: fp64 in p_sample (diffusion.py:399, 364), fp32 in p_sample_progressive (diffusion.py:421)
+        const double t = st->t_fp32 ? static_cast<double>(__fdiv_rn(static_cast<float>(step + 1), static_cast<float>(T)))
+                                    : static_cast<double>(step + 1) / static_cast<double>(T);
         for (int r = 0; r < nrows; ++r) t_rows[r] = t;
     }
 }
 
 // Philox4x32-10 counter RNG + Box-Muller for on-device ancestral noise (used only when no noise
-// tensor is injected; the stream is this library's own, not torch's).
+// tensor is injected; the stream is this library's own, not torch's).  One counter value yields the four
+// normals of elements 4q .. 4q+3.
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
@@ -204,15 +218,17 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     }
     return ctr;
 }
-__device__ __forceinline__ float philox_normal(unsigned long long seed, uint32_t step, unsigned long long idx) {
-    const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(idx >> 1), static_cast<uint32_t>(idx >> 33), step, 0u),
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, uint32_t step, unsigned long long quad) {
+    const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(quad), static_cast<uint32_t>(quad >> 32), step, 0u),
                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
-    const float u1 = (static_cast<float>(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float u2 = (static_cast<float>(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float rad = sqrtf(-2.0f * logf(u1));
-    float sn, cs;
-    sincosf(6.283185307179586f * u2, &sn, &cs);
-    return (idx & 1) ? rad * sn : rad * cs;
+    const float k = 1.0f / 16777216.0f;
+    const float u1 = (static_cast<float>(r.x >> 8) + 0.5f) * k, u2 = (static_cast<float>(r.y >> 8) + 0.5f) * k;
+    const float u3 = (static_cast<float>(r.z >> 8) + 0.5f) * k, u4 = (static_cast<float>(r.w >> 8) + 0.5f) * k;
+    const float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
+    float sa, ca, sb, cb;
+    sincosf(6.283185307179586f * u2, &sa, &ca);
+    sincosf(6.283185307179586f * u4, &sb, &cb);
+    return make_float4(ra * ca, ra * sa, rb * cb, rb * sb);
 }
 
 __device__ __forceinline__ float pred_x0(int type, float x, float o, float o2, const float* cf) {
@@ -224,49 +240,121 @@ __device__ __forceinline__ float pred_x0(int type, float x, float o, float o2, c
     return fminf(fmaxf(x0, -1.f), 1.f);                              // clip_denoised (diffusion.py:327)
 }
 
-__global__ void sampler_step_kernel(const SamplerStepParams p) {
+template <int VEC> struct SVec;
+template <> struct SVec<4> { typedef float4 type; };
+template <> struct SVec<1> { typedef float type; };
+
+// One thread owns VEC (4 or 1) consecutive elements of one image: every tensor is read / written once with 16-byte
+// (VEC = 4) fully coalesced accesses; the per-step scalars come from the device-side SamplerState.
+template <int VEC>
+__global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerStepParams p) {
+    typedef typename SVec<VEC>::type vec_t;
     const long long n = static_cast<long long>(p.B) * p.C * p.HW;
-    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * VEC;
     if (i >= n) return;
-    const float* cf = p.st->coef;
-    const int step = p.st->step;
+    const SamplerState* st = p.st;
+    float cf[kCoefStride];
+#pragma unroll
+    for (int k = 0; k < kCoefStride; k += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(st->coef + k);
+        cf[k] = c4.x; cf[k + 1] = c4.y; cf[k + 2] = c4.z; cf[k + 3] = c4.w;
+    }
+    const int step = st->step;
     const int chw = p.C * p.HW;
     const int b = static_cast<int>(i / chw), e = static_cast<int>(i % chw);
     const int Cm = (p.model_out_type == 2) ? 2 * p.C : p.C;
     const int rep = 1 + p.cfg;
-    const float x = p.x_t[i];
     const float* mo = p.model_out + static_cast<size_t>(b) * rep * Cm * p.HW + e;
     const size_t second = static_cast<size_t>(p.C) * p.HW;           // "both": eps half follows the x0 half
-    const float o = mo[0];
-    const float o2 = (p.model_out_type == 2) ? mo[second] : 0.f;
+    float x[VEC], o[VEC], o2[VEC], u[VEC], u2[VEC], out[VEC], pr[VEC];
+    auto ldv = [](const float* q, float (&v)[VEC]) {
+        const vec_t t = *reinterpret_cast<const vec_t*>(q);
+        const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] = f[k];
+    };
+    auto stv = [](float* q, const float (&v)[VEC]) {
+        vec_t t;
+        float* f = reinterpret_cast<float*>(&t);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) f[k] = v[k];
+        *reinterpret_cast<vec_t*>(q) = t;
+    };
+    ldv(p.x_t + i, x);
+    ldv(mo, o);
+    if (p.model_out_type == 2) ldv(mo + second, o2);
+    if (p.cfg) {
+        ldv(mo + static_cast<size_t>(Cm) * p.HW, u);
+        if (p.model_out_type == 2) ldv(mo + static_cast<size_t>(Cm) * p.HW + second, u2);
+    }
     const float c1 = cf[6], c2 = cf[7], sd = cf[8];
     const bool last = (step == 0);
-    const float x0c = pred_x0(p.model_out_type, x, o, o2, cf);
-    // x0eps_coef: the mean's first argument is eps re-derived from the clipped x0 (diffusion.py:335-343, 222-223)
-    const float a_c = p.x0eps ? x * cf[12] - x0c * cf[13] : x;
-    float mean = last ? x0c : c1 * a_c + c2 * x0c;                   // where(cond, mean, pred_x_0)  (diffusion.py:378)
-    float pred = x0c;
-    if (p.cfg) {
-        const float* mu = mo + static_cast<size_t>(Cm) * p.HW;
-        const float u = mu[0];
-        const float u2 = (p.model_out_type == 2) ? mu[second] : 0.f;
-        const float x0u = pred_x0(p.model_out_type, x, u, u2, cf);
-        const float a_u = p.x0eps ? x * cf[12] - x0u * cf[13] : x;
-        const float mean_u = last ? x0u : c1 * a_u + c2 * x0u;
-        mean = mean + p.w * (mean - mean_u);                         // guided, not re-clipped (diffusion.py:384)
-        pred = x0c + p.w * (x0c - x0u);                              // diffusion.py:385
+    const bool noisy = !last && sd > 0.f;
+    float z[VEC];
+    if (noisy) {
+        const long long gi = static_cast<long long>(st->img0) * chw + i;      // element index inside the whole batch
+        if (st->noise) {
+            const float* zp = st->noise + static_cast<long long>(step) * st->noise_step_stride + gi;
+            if (VEC == 1 || (reinterpret_cast<uintptr_t>(zp) & 15u) == 0) {
+                ldv(zp, z);
+            } else {                                                   // caller-owned tensor at an odd offset
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) z[k] = zp[k];
+            }
+        } else {
+            const float4 g = philox_normal4(st->seed, static_cast<uint32_t>(step), static_cast<unsigned long long>(gi) >> 2);
+            const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) z[k] = gv[(VEC == 4) ? k : static_cast<int>(gi & 3)];
+        }
     }
-    if (p.pred_x0) p.pred_x0[i] = pred;
-    if (!last && sd > 0.f) {
-        float z;
-        if (p.noise) z = p.noise[static_cast<long long>(step) * p.noise_step_stride + static_cast<long long>(p.st->img0) * chw + i];
-        else z = philox_normal(p.seed, static_cast<uint32_t>(step), static_cast<unsigned long long>(p.st->img0) * chw + i);
-        mean += sd * z;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        const float x0c = pred_x0(p.model_out_type, x[k], o[k], (p.model_out_type == 2) ? o2[k] : 0.f, cf);
+        // x0eps_coef: the mean's first argument is eps re-derived from the clipped x0 (diffusion.py:335-343, 222-223)
+        const float a_c = p.x0eps ? x[k] * cf[12] - x0c * cf[13] : x[k];
+        float mean = last ? x0c : c1 * a_c + c2 * x0c;               // where(cond, mean, pred_x_0)  (diffusion.py:378)
+        float pred = x0c;
+        if (p.cfg) {
+            const float x0u = pred_x0(p.model_out_type, x[k], u[k], (p.model_out_type == 2) ? u2[k] : 0.f, cf);
+            const float a_u = p.x0eps ? x[k] * cf[12] - x0u * cf[13] : x[k];
+            const float mean_u = last ? x0u : c1 * a_u + c2 * x0u;
+            mean = mean + p.w * (mean - mean_u);                     // guided, not re-clipped (diffusion.py:384)
+            pred = x0c + p.w * (x0c - x0u);                          // diffusion.py:385
+        }
+        if (noisy) mean += sd * z[k];
+        out[k] = mean; pr[k] = pred;
     }
-    p.x_s[i] = mean;
+    if (p.pred_x0) stv(p.pred_x0 + i, pr);
+    stv(p.x_s + i, out);
+}
+
+// ------------------------------------------------------------------------------------------ uint8 tail
+// generate.py:149: (x * 127.5 + 127.5).clamp(0, 255).to(uint8).permute(0, 2, 3, 1) -- one thread per pixel: C coalesced
+// channel-plane reads, C consecutive bytes written
+__global__ void images_to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, long long pixels, int C, int HW) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= pixels) return;
+    const long long b = i / HW;
+    const int pix = static_cast<int>(i - b * HW);
+    const float* xp = x + b * C * HW + pix;
+    uint8_t* op = out + i * C;
+    for (int c = 0; c < C; ++c) {
+        // torch evaluates x * 127.5 + 127.5 as two roundings: no FMA contraction here
+        float v = __fadd_rn(__fmul_rn(xp[static_cast<size_t>(c) * HW], 127.5f), 127.5f);
+        v = fminf(fmaxf(v, 0.f), 255.f);
+        op[c] = static_cast<uint8_t>(v);                                      // .to(uint8) truncates
+    }
 }
 
 }  // namespace
+
+cudaError_t launch_images_to_uint8(const float* x, uint8_t* out, int B, int C, int HW, cudaStream_t stream) {
+    const long long pixels = static_cast<long long>(B) * HW;
+    if (pixels == 0) return cudaSuccess;
+    images_to_uint8_kernel<<<static_cast<unsigned>((pixels + 255) / 256), 256, 0, stream>>>(x, out, pixels, C, HW);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_im2col3x3(const float* x, h16* out, h16* out_lo, int B, int rep, int C, int H, int W, int f16,
                              cudaStream_t stream) {
@@ -292,10 +380,10 @@ cudaError_t launch_attention_f32(const float* qkv, h16* out_hi, h16* out_lo, int
     return cudaGetLastError();
 }
 
-cudaError_t launch_timestep_embedding(const double* t, float* out, int rows, int dim, cudaStream_t stream) {
+cudaError_t launch_timestep_embedding(const double* t, float* out, int rows, int dim, const int* fp32_flag, cudaStream_t stream) {
     const int n = rows * (dim / 2);
     if (n == 0) return cudaSuccess;
-    timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, stream>>>(t, out, rows, dim);
+    timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, stream>>>(t, out, rows, dim, fp32_flag);
     return cudaGetLastError();
 }
 
@@ -334,7 +422,12 @@ cudaError_t launch_sampler_begin_step(SamplerState* st, const float* coef_table,
 cudaError_t launch_sampler_step(const SamplerStepParams& p, cudaStream_t stream) {
     const long long n = static_cast<long long>(p.B) * p.C * p.HW;
     if (n == 0) return cudaSuccess;
-    sampler_step_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(p);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    // 16-byte accesses need whole quads per image plane and aligned bases (an injected-noise tensor at an odd offset
+    // is read with scalar loads inside the kernel)
+    const bool vec4 = (p.HW % 4 == 0) && al16(p.model_out) && al16(p.x_t) && al16(p.x_s) && (p.pred_x0 == nullptr || al16(p.pred_x0));
+    if (vec4) sampler_step_kernel<4><<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, stream>>>(p);
+    else sampler_step_kernel<1><<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -63,7 +63,7 @@ class GaussianDiffusion:
         self.intp_frac, self.w_guide, self.p_uncond, self.x0eps_coef = intp_frac, w_guide, p_uncond, x0eps_coef
 
     # ------------------------------------------------------------------ C structs
-    def sampler_config(self, use_ddim, seed=None):
+    def sampler_config(self, use_ddim, seed=None, t_fp32=False):
         if not use_ddim and self.model_var_type not in _lib.VAR_TYPES:
             raise NotImplementedError(self.model_var_type)          # diffusion.py:161
         if not use_ddim and self.model_var_type == "fixed_medium" and not isinstance(self.intp_frac, float):
@@ -75,11 +75,44 @@ class GaussianDiffusion:
         sc.logsnr_schedule = _lib.SCHEDULES[self.logsnr_fn.schedule]
         sc.use_ddim = int(bool(use_ddim))
         sc.x0eps_coef = int(bool(self.x0eps_coef))                  # diffusion.py:137-140, 180-182, 335-343
+        sc.t_fp32 = int(bool(t_fp32))                               # diffusion.py:421 vs :399
         sc.intp_frac = float(self.intp_frac or 0.)
         sc.logsnr_min, sc.logsnr_max = self.logsnr_fn.logsnr_min, self.logsnr_fn.logsnr_max
         sc.w_guide = float(self.w_guide)
-        sc.seed = int(seed or 0)
+        sc.seed = int(seed or 0) & (2 ** 64 - 1)
         return sc
+
+    @staticmethod
+    def _noise_seed(seed):
+        """Seed of the on-device noise stream of one call.  ``seed=None`` in the reference means "draw from the global
+        generator" (diffusion.py:401-402), i.e. fresh noise on every call; here a fresh 63-bit seed is drawn from
+        torch's global CPU generator, so repeated calls differ and ``torch.manual_seed`` still makes a run repeatable."""
+        if seed is not None:
+            return int(seed)
+        return int(torch.randint(0, 2 ** 63 - 1, (1,), dtype=torch.int64).item())
+
+    @staticmethod
+    def _prepare_label(denoise_fn, label, B, device):
+        """Labels as the C side reads them: int64 (B,) class ids in [0, num_classes] (0 = no class), or fp32 multi-hot
+        (B, num_classes) rows for a multitag UNet (unet.py:290-294).  Shapes and ranges are checked here because the
+        library only sees raw pointers (the reference's F.one_hot raises on an out-of-range id, modules.py:191-196)."""
+        if label is None:
+            return None
+        multitags = bool(getattr(denoise_fn, "multitags", False)) or label.ndim == 2   # (a wrapped UNet hides its flag)
+        num_classes = int(getattr(denoise_fn, "num_classes", 0) or 0)
+        label = label.to(device=device, dtype=torch.float32 if multitags else torch.int64).contiguous()
+        if isinstance(denoise_fn, UNet) and num_classes > 0:
+            if multitags:
+                if tuple(label.shape) != (B, num_classes):
+                    raise ValueError(f"multitag labels must have shape ({B}, {num_classes}), got {tuple(label.shape)}")
+            else:
+                if label.numel() != B:
+                    raise ValueError(f"labels must have one class id per sample ({B}), got shape {tuple(label.shape)}")
+                label = label.reshape(B)
+                lo, hi = int(label.min()), int(label.max())
+                if lo < 0 or hi > num_classes:
+                    raise RuntimeError(f"class ids must lie in [0, {num_classes}] (0 = unconditional), got [{lo}, {hi}]")
+        return label
 
     def step_coefficients(self, use_ddim):
         """[T, 16] fp32 host table (include/vdt_b200.h: vdt_step_coefficients)."""
@@ -100,28 +133,33 @@ class GaussianDiffusion:
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         B = shape[0]
+        gen = None if seed is None else torch.Generator(device).manual_seed(seed)
         if noise is None:
-            gen = None if seed is None else torch.Generator(device).manual_seed(seed)
             x_t = torch.randn(shape, device=device, generator=gen)
         else:
             x_t = noise.to(device)
         x_t = x_t.to(torch.float32).contiguous()
-        multitags = bool(getattr(denoise_fn, "multitags", False))
-        if label is not None:
-            label = label.to(device=device, dtype=torch.float32 if multitags else torch.int64).contiguous()
+        if tuple(x_t.shape) != tuple(shape):
+            raise ValueError(f"noise has shape {tuple(x_t.shape)}, expected {tuple(shape)}")
+        label = self._prepare_label(denoise_fn, label, B, device)
         if step_noise is not None:
             step_noise = step_noise.to(device=device, dtype=torch.float32).contiguous()
-        sc = self.sampler_config(use_ddim, seed)
+            if tuple(step_noise.shape) != (self.sample_timesteps,) + tuple(shape):
+                raise ValueError(f"step_noise must have shape {(self.sample_timesteps,) + tuple(shape)}")
         L = _lib.lib()
         if isinstance(denoise_fn, UNet):
+            # fused path: the per-step normals come from the library's own Philox stream keyed by this call's seed
+            sc = self.sampler_config(use_ddim, self._noise_seed(seed) if (not use_ddim and step_noise is None) else seed)
             plan = denoise_fn.plan_for(shape[2], device)
             out = torch.empty_like(x_t)
             with torch.cuda.device(device):
                 _lib.check(L.vdt_p_sample(plan, C.byref(sc), _lib.ptr(x_t), _lib.ptr(label), _lib.ptr(step_noise),
                                           _lib.ptr(out), B, _lib.current_stream_ptr()))
             return out.cpu()
-        # generic callable: same fused update kernel, one step at a time
-        return self._p_sample_generic(denoise_fn, shape, x_t, label, step_noise, sc, device, seed, use_ddim).cpu()
+        # generic callable: same fused update kernel, one step at a time; the per-step normals continue the generator
+        # that produced x_T, like the reference's single generator (diffusion.py:401-405, 389)
+        sc = self.sampler_config(use_ddim, seed)
+        return self._p_sample_generic(denoise_fn, shape, x_t, label, step_noise, sc, device, gen, use_ddim).cpu()
 
     @torch.no_grad()
     def p_sample_progressive(self, denoise_fn, shape, noise=None, label=None, device="cpu", seed=None, use_ddim=False,
@@ -138,11 +176,11 @@ class GaussianDiffusion:
         B, T = shape[0], self.sample_timesteps
         gen = None if seed is None else torch.Generator(device).manual_seed(seed)
         x = (torch.randn(shape, device=device, generator=gen) if noise is None else noise.to(device)).to(torch.float32).contiguous().clone()
-        if label is not None:
-            label = label.to(device=device, dtype=torch.int64).contiguous()
+        label = self._prepare_label(denoise_fn, label, B, device)
         if step_noise is not None:
             step_noise = step_noise.to(device=device, dtype=torch.float32).contiguous()
-        sc = self.sampler_config(use_ddim, seed)
+        # the reference's progressive loop carries an fp32 step tensor (diffusion.py:421): fp32 s / t and an fp32 sinusoid
+        sc = self.sampler_config(use_ddim, self._noise_seed(seed) if (not use_ddim and step_noise is None) else seed, t_fp32=True)
         plan = denoise_fn.plan_for(shape[2], device)
         Lp = T // pred_freq
         preds = torch.zeros((Lp, B) + tuple(shape[1:]), dtype=torch.float32)
@@ -163,15 +201,13 @@ class GaussianDiffusion:
                 first = stop - 1
         return x.cpu(), preds
 
-    def _p_sample_generic(self, denoise_fn, shape, x_t, label, step_noise, sc, device, seed, use_ddim):
+    def _p_sample_generic(self, denoise_fn, shape, x_t, label, step_noise, sc, device, gen, use_ddim):
         L = _lib.lib()
         B = shape[0]
         coefs = self.step_coefficients(use_ddim)
         use_cfg = (self.w_guide > 0) and (label is not None)        # diffusion.py:368
         T = self.sample_timesteps
         hw = shape[2] * shape[3]
-        if not use_ddim and step_noise is None:
-            gen = None if seed is None else torch.Generator(device).manual_seed(seed)
         with torch.cuda.device(device):
             for ti in reversed(range(T)):
                 t = torch.full((B,), (ti + 1) / T, dtype=torch.float64, device=device)

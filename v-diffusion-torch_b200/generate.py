@@ -57,6 +57,21 @@ def sample_sharded(sample_fn, total, batch_size, seed=1234, gather=True, device=
     return gather_shards(local, total) if gather else local
 
 
+def images_to_uint8(x):
+    """generate.py:149 on the device: fp32 NCHW samples -> uint8 NHWC pixels, (x * 127.5 + 127.5).clamp(0, 255)
+    truncated to uint8 and permuted (0, 2, 3, 1), in one kernel (vdt_images_to_uint8)."""
+    import ctypes as C
+    from . import _lib
+    if x.device.type != "cuda":
+        raise RuntimeError("images_to_uint8 runs on CUDA only; there is no CPU fallback")
+    x = x.to(torch.float32).contiguous()
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, H, W, Cc), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vdt_images_to_uint8(_lib.ptr(x), _lib.ptr(out), B, Cc, H * W, _lib.current_stream_ptr()))
+    return out
+
+
 def load_reference_checkpoint(path, use_ema=False):
     """generate.py:33-44: a reference checkpoint is {"model": sd, "ema": {"shadow": sd-like, ...}, ...}; DDP
     checkpoints carry a "module." prefix; a class-conditional model is recognised by its class_embed.* keys.
@@ -83,6 +98,7 @@ def main():
     ap.add_argument("--total-size", type=int, default=50000)
     ap.add_argument("--save-path", default=None, help="torch.save of the uint8 NHWC images (rank 0)")
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--label-path", default=None, help="multitag models: torch-saved (N, num_classes) attribute table")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -104,20 +120,40 @@ def main():
     model = model.to(device).eval()
     num_classes = model.num_classes
 
+    multitags = bool(model.multitags) and num_classes > 0
+    tag_rows = None
+    if multitags and not args.uncond:
+        # generate.py:119-127 draws rows of the dataset's own attribute table; there is no dataset on this path, so the
+        # table comes from a file: a (N, num_classes) 0/1 tensor saved with torch.save
+        if not args.label_path:
+            raise NotImplementedError("class-conditional multitag sampling needs --label-path (a torch-saved (N, "
+                                      f"{num_classes}) multi-hot attribute table) or --uncond")
+        tag_rows = torch.load(args.label_path, map_location="cpu").float()
+        if tag_rows.ndim != 2 or tag_rows.shape[1] != num_classes:
+            raise ValueError(f"--label-path must hold a (N, {num_classes}) tensor, got {tuple(tag_rows.shape)}")
+
     def sample_fn(n, gen):
         noise = torch.randn((n,) + chw, device=device, generator=gen)
-        if num_classes:
+        if multitags:
+            if args.uncond:
+                label = torch.zeros((n, num_classes), dtype=torch.float32, device=device)            # generate.py:123-124
+            else:
+                pick = torch.randint(len(tag_rows), (n,), device=device, generator=gen).cpu()       # generate.py:126
+                label = tag_rows[pick].to(device)
+        elif num_classes:
             label = torch.zeros(n, dtype=torch.int64, device=device) if args.uncond else \
                 torch.randint(num_classes, (n,), device=device, generator=gen) + 1       # generate.py:132-134
         else:
             label = None
-        return diffusion.p_sample(model, (n,) + chw, noise=noise, label=label, device=device,
+        # every batch draws its own noise seed from this rank's generator: without it the library's on-device stream
+        # would replay the same per-step normals for every batch (ancestral sampling, no injected noise)
+        seed = int(torch.randint(0, 2 ** 62, (1,), device=device, generator=gen).item())
+        return diffusion.p_sample(model, (n,) + chw, noise=noise, label=label, device=device, seed=seed,
                                   use_ddim=args.use_ddim).to(device)
 
     x = sample_sharded(sample_fn, args.total_size, args.batch_size, seed=args.seed, device=device)
     if (not dist.is_initialized() or dist.get_rank() == 0) and args.save_path:
-        img = (x * 127.5 + 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).cpu()   # generate.py:149
-        torch.save(img, args.save_path)
+        torch.save(images_to_uint8(x).cpu(), args.save_path)      # generate.py:149 (the PNG encoding itself is I/O, out of scope)
     if dist.is_initialized():
         dist.barrier()
         dist.destroy_process_group()

@@ -212,6 +212,9 @@ class UNet(nn.Module):
                 y = y.to(device=dev, dtype=torch.int64).contiguous()  # OneHot casts to long (modules.py:191-192)
                 if y.numel() != B:
                     raise ValueError("y must have one entry per batch row")
+                lo, hi = int(y.min()), int(y.max())                   # F.one_hot raises on these too (modules.py:193-196)
+                if lo < 0 or hi > self.num_classes:
+                    raise RuntimeError(f"class ids must lie in [0, {self.num_classes}] (0 = unconditional), got [{lo}, {hi}]")
         else:
             y = None
         out = torch.empty((B, self.out_channels, x.shape[2], x.shape[3]), device=dev, dtype=torch.float32)
