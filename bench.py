@@ -138,10 +138,48 @@ def build_model(device, seed, workload="cifar10_cond"):
     return net, diff
 
 
+def reference_staged():
+    from oracle import stage_ref
+    return stage_ref.staged()
+
+
+def reference_objects(state_dict, device):
+    """The UNMODIFIED reference (oracle/_ref, staged by oracle/stage_ref.py) built the way generate.py:48-98 builds it
+    for cifar10_cond.json, with this bench's weights and w_guide = 1, 100 steps.  Returns (model, diffusion)."""
+    import torch
+    from oracle import stage_ref
+    ref = stage_ref.load()
+    cfg = stage_ref.config("cifar10_cond")
+    d = dict(cfg["diffusion"])
+    logsnr_fn = ref.get_logsnr_schedule(d.pop("logsnr_schedule"), logsnr_min=d.pop("logsnr_min"),
+                                        logsnr_max=d.pop("logsnr_max"), rescale=d.pop("allow_rescale"))
+    d.pop("train_timesteps")
+    d["sample_timesteps"] = T_STEPS
+    diffusion = ref.GaussianDiffusion(logsnr_fn=logsnr_fn, w_guide=W_GUIDE, **d)
+    model = ref.UNet(out_channels=3, num_classes=10, multitags=False, **cfg["model"])
+    model.load_state_dict({k: v.detach().float().cpu() for k, v in state_dict.items()}, strict=True)
+    return model.to(device).eval(), diffusion
+
+
+def reference_steps(diffusion, model, x_t, label, first_ti, n_steps, sync=None):
+    """n_steps iterations of the body of the reference's own p_sample loop (diffusion.py:410-413) from step index
+    first_ti downwards (a run longer than the trajectory keeps repeating step 1).  Returns x after the last step."""
+    import torch
+    t = torch.empty((x_t.shape[0],), device=x_t.device, dtype=torch.float64)
+    ti = first_ti
+    with torch.inference_mode():
+        for _ in range(n_steps):
+            t.fill_(ti)
+            x_t = diffusion.p_sample_step(model, x_t, step=t, y=label, generator=None, use_ddim=True)
+            ti = max(ti - 1, 1)
+    if sync:
+        sync()
+    return x_t
+
+
 def oracle_trajectory(sd, cfg, x_t, label, n_warm, n_steps, budget_s=None):
-    """First n_warm + n_steps denoising steps (from step index T-1 down) of the CIFAR-10 cond CFG DDIM trajectory
-    on the host CPU with the oracle port (test infrastructure, pinned to the reference by tests/golden).
-    Returns (x after the last step, seconds per timed step, timed steps)."""
+    """Fallback when oracle/_ref is not staged: the same steps with the oracle port (test infrastructure, pinned to
+    the reference by tests/golden).  Returns (x after the last step, seconds per timed step, timed steps)."""
     import torch
     from oracle import unet_forward
     from oracle.diffusion_ref import step_coefficients, _pred_x0
@@ -165,19 +203,36 @@ def oracle_trajectory(sd, cfg, x_t, label, n_warm, n_steps, budget_s=None):
     return x_t, (time.perf_counter() - t0) / max(n, 1), n
 
 
+def cpu_reference_trajectory(state_dict, x_t, label, n_warm, n_steps, budget_s=None):
+    """First n_warm + n_steps denoising steps of the CIFAR-10 cond CFG DDIM trajectory on the host CPU: the unmodified
+    reference when it is staged (kind "reference"), else the oracle port (kind "port").
+    Returns (kind, x after the last step, seconds per timed step, timed steps)."""
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    if reference_staged():
+        model, diffusion = reference_objects(state_dict, "cpu")
+        x = reference_steps(diffusion, model, x_t, label, T_STEPS - 1, n_warm)
+        ti = max(T_STEPS - 1 - n_warm, 1)
+        n, t0 = 0, time.perf_counter()
+        while n < n_steps and (budget_s is None or n < 2 or time.perf_counter() - t0 < budget_s):
+            x = reference_steps(diffusion, model, x, label, ti, 1); ti = max(ti - 1, 1); n += 1
+        return "reference", x, (time.perf_counter() - t0) / max(n, 1), n
+    from oracle.unet_ref import unet_config_from_json
+    cfg = unet_config_from_json(CIFAR_COND_MODEL, 3, 3, num_classes=10)
+    sd = {k: v.detach().cpu().float() for k, v in state_dict.items()}
+    x, dt, n = oracle_trajectory(sd, cfg, x_t, label, n_warm, n_steps, budget_s)
+    return "port", x, dt, n
+
+
 def cpu_baseline(net, diff, noise2, label2, device, seconds_budget=20.0):
-    """Oracle port on the host cores on a bounded sample of the same workload: the FIRST denoising steps of the
-    bench's own trajectory for its first two images (4 UNet rows per step), on the bench's own weights, scaled by
-    100 steps / image.  The same steps are then run through the CUDA path and compared (`parity`)."""
+    """The reference's CPU implementation on the host cores on a bounded sample of the same workload: the FIRST
+    denoising steps of the bench's own trajectory for its first two images (4 UNet rows per step), on the bench's own
+    weights, scaled by 100 steps / image.  The same steps are then run through the CUDA path and compared (`parity`)."""
     import ctypes as C
     import torch
-    from oracle.unet_ref import unet_config_from_json
     from v_diffusion_b200 import _lib
-    torch.set_num_threads(os.cpu_count())
-    cfg = unet_config_from_json(CIFAR_COND_MODEL, 3, 3, num_classes=10)
-    sd = {k: v.detach().cpu().float() for k, v in net.state_dict().items()}
     B = noise2.shape[0]
-    x_cpu, dt, n = oracle_trajectory(sd, cfg, noise2.clone(), label2, 1, 16, seconds_budget)
+    kind, x_cpu, dt, n = cpu_reference_trajectory(net.state_dict(), noise2.clone(), label2, 1, 16, seconds_budget)
     steps = n + 1
     x = noise2.to(device).contiguous().clone()
     y = label2.to(device).contiguous()
@@ -187,37 +242,75 @@ def cpu_baseline(net, diff, noise2, label2, device, seconds_budget=20.0):
                                              None, _lib.current_stream_ptr()))
     torch.cuda.synchronize()
     err = (x.cpu() - x_cpu).abs().max().item()
-    return {"value": B / (dt * T_STEPS), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": B / (dt * T_STEPS), "unit": "images/s", "cores": torch.get_num_threads(), "kind": kind,
             "sample": f"first {steps} denoising steps of the bench trajectory for its first {B} images "
                       f"({2 * B} UNet rows per step, CFG pair), {n} timed at {dt:.3f} s/step, scaled by {T_STEPS} steps per image",
             "parity": {"steps": steps, "images": B, "max_abs_vs_cuda_path": err}}
 
 
+def reference_gpu_eager(net, diff, noise, label, device, batch=256, parity_batch=32, steps=4):
+    """The untouched reference on this same GPU in stock PyTorch eager (what a user of the reference gets on a B200):
+    throughput of its own p_sample loop body at `batch` images per step -- once with PyTorch's default flags (cuDNN
+    convolutions in TF32, generate.py:115-116 sets cudnn.benchmark) and once in strict fp32 -- and, outside any timed
+    region, all 100 steps of `parity_batch` images in strict fp32 against the CUDA path on the same noise / labels."""
+    import torch
+    if not reference_staged():
+        return {"unavailable": "oracle/_ref not staged (build() stages it where /root/reference exists)"}
+    model, rdiff = reference_objects(net.state_dict(), device)
+    out = {"batch": batch, "rows_per_unet_call": 2 * batch, "steps_timed": steps,
+           "note": "unmodified reference (oracle/_ref) in torch eager on this GPU, its own p_sample_step loop"}
+    saved = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        torch.backends.cudnn.benchmark = True                           # generate.py:115-116
+        x0, y0 = noise[:batch].clone(), label[:batch].clone()
+        for mode, tf32 in (("stock_flags_tf32_convs", True), ("strict_fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            reference_steps(rdiff, model, x0, y0, T_STEPS - 1, 2, torch.cuda.synchronize)       # warm-up / autotune
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            reference_steps(rdiff, model, x0, y0, T_STEPS - 3, steps)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"ms_per_step": ms, "images_per_s": batch / (ms * 1e-3 * T_STEPS)}
+        torch.backends.cudnn.allow_tf32 = False
+        xn, yn = noise[:parity_batch].clone(), label[:parity_batch].clone()
+        with torch.inference_mode():
+            ref_imgs = rdiff.p_sample(model, tuple(xn.shape), noise=xn, label=yn, device=device, use_ddim=True)
+        ours = diff.p_sample(net, tuple(xn.shape), noise=xn.cpu(), label=yn.cpu(), device=device, use_ddim=True)
+        out["parity_full_100_steps"] = {"images": parity_batch, "reference": "strict fp32 eager on this GPU",
+                                        "max_abs": (ours - ref_imgs).abs().max().item(),
+                                        "mean_abs": (ours - ref_imgs).abs().mean().item()}
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+        del model
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is a Python/PyTorch
-    repo that cannot travel to the GPU box, so this times the oracle port (pinned to the reference by
-    tests/golden) with all host threads, same metric/config, on a bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores -- the unmodified
+    reference staged under oracle/_ref (kind "reference"); the oracle port (kind "port") only if it is absent --
+    same metric / config, each step a bounded sample (B = 2 images = 4 UNet rows) of the workload."""
     if rank != 0:
         return
     import torch
-    from oracle import make_state_dict
-    from oracle.unet_ref import unet_config_from_json
     torch.set_num_threads(os.cpu_count())
-    cfg = unet_config_from_json(CIFAR_COND_MODEL, 3, 3, num_classes=10)
-    sd = make_state_dict(cfg, 0)
+    net, _ = build_model("cpu", seed=0)
     B = 2
     g = torch.Generator().manual_seed(1234)
     x_t = torch.randn(B, 3, 32, 32, generator=g)
     label = torch.randint(10, (B,), generator=g) + 1
-    _, dt, _ = oracle_trajectory(sd, cfg, x_t, label, args.warmup, args.steps)
+    kind, _, dt, n = cpu_reference_trajectory(net.state_dict(), x_t, label, args.warmup, args.steps)
     val = B / (dt * T_STEPS)
-    line = {"metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": n,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "CIFAR-10 cond UNet (cifar10_cond.json), CFG w=1 as 2B rows, 100-step DDIM; "
                                    f"bounded sample B={B} images per step on the host CPU"},
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"B={B} images (4 UNet rows) per denoising step, {args.steps} steps"},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": kind,
+                             "sample": f"B={B} images (4 UNet rows) per denoising step, {n} steps of the "
+                                       + ("unmodified reference's p_sample_step (oracle/_ref)" if kind == "reference" else "oracle port")},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -377,6 +470,10 @@ def run_b200(args, rank, world, local_rank):
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline and wl is None:
             line["cpu_baseline"] = cpu_baseline(net, diff, noise_h[:2].clone(), label_h[:2].clone(), device)
+            line["reference_gpu_eager"] = reference_gpu_eager(net, diff, noise, label, device)
+            eager = line["reference_gpu_eager"].get("stock_flags_tf32_convs")
+            if eager:
+                line["reference_gpu_eager"]["speedup_e2e_over_stock_eager"] = e2e["value"] / eager["images_per_s"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

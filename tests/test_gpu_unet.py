@@ -10,12 +10,14 @@ import numpy as np
 import pytest
 import torch
 
-from tests.cases import UNET_CASES, SAMPLE_CASES, build_inputs, build_sample_inputs
+from tests.cases import (UNET_CASES, SAMPLE_CASES, FULL_CASES, build_inputs, build_sample_inputs, build_full_inputs,
+                         full_state_dict)
 from tests.cases import _cfg as _cfg_case
 
 pytestmark = pytest.mark.gpu
 REL_L2 = 1e-2
 SAMPLE_MAX_ABS = 2e-2
+VALIDATION_MAX_ABS = 1e-3        # north-star: TF32/fp32 validation mode
 
 
 def _model(cfg, seed, operand="fp16"):
@@ -111,13 +113,11 @@ def test_p_sample_vs_reference_golden(golden_dir, name):
                         step_noise=None if case["use_ddim"] else step_noise)
     assert out.device.type == "cpu" and out.shape == ref.shape
     err = (out - ref).abs().max().item()
-    # The bar is the north-star's 2e-2, except where the reference's OWN default GPU numerics (TF32 convolutions,
-    # tests/golden/make_tf32_dev.py) already move the fp32 trajectory by a third of that: a 10-bit-mantissa operand
-    # format cannot track a guidance-amplified (w = 3 -> x7) ancestral trajectory closer than a small multiple of
-    # what the reference's GPU path itself does.  Only ancestral_cfg_v (TF32 deviation 1.03e-2) is affected.
+    # flat north-star bar on every fixture; the reference's own deviation under TF32 convolutions (its default GPU
+    # numerics, tests/golden/make_tf32_dev.py) is printed next to it as calibration only
     tf32 = json.load(open(os.path.join(golden_dir, "ref_tf32_deviation.json")))[name]["max_abs"]
-    bar = max(SAMPLE_MAX_ABS, 3.0 * tf32)
-    print(f"{name}: fused max-abs {err:.3e} (bar {bar:.2e}, reference under TF32 {tf32:.3e})")
+    bar = SAMPLE_MAX_ABS
+    print(f"{name}: fused max-abs {err:.3e} (bar {bar:.1e}; the reference under TF32 convs moves by {tf32:.3e})")
     assert err <= bar
     # (2) generic-callable path with a recorder: per-step model outputs along the trajectory
     rec = []
@@ -158,9 +158,9 @@ def test_p_sample_chunking_and_roundtrip_properties():
 
 
 @pytest.mark.parametrize("name", ["cifar_cond", "small_cond"])
-def test_bf16_operand_mode_calibration(golden_dir, name):
-    """bf16 operands (the north-star's nominal format): same kernels, 8-bit mantissa.  Per-call rel-L2 stays
-    under 1e-2; it is ~4x looser than the fp16 default, which is why fp16 is the default."""
+def test_bf16_operand_mode_forward(golden_dir, name):
+    """bf16 operands (the north-star's nominal format): same kernels, 8-bit mantissa.  A single UNet call stays inside
+    the 1e-2 per-call bar; it is several times looser than the fp16 default."""
     case = UNET_CASES[name]
     ref = torch.from_numpy(np.load(os.path.join(golden_dir, f"unet_{name}.npz"))["out"])
     x, t, y = build_inputs(case)
@@ -170,7 +170,71 @@ def test_bf16_operand_mode_calibration(golden_dir, name):
         out = net(x.cuda(), t.cuda(), None if y is None else y.cuda()).cpu()
         outs[mode] = ((out - ref).norm() / ref.norm()).item()
     print(f"{name}: rel-L2 fp16 {outs['fp16']:.3e} bf16 {outs['bf16']:.3e}")
-    assert outs["bf16"] <= 1.2e-2 and outs["fp16"] <= 0.5 * outs["bf16"]
+    assert outs["bf16"] <= REL_L2 and outs["fp16"] <= 0.5 * outs["bf16"]
+
+
+@pytest.mark.parametrize("name", sorted(SAMPLE_CASES))
+def test_bf16_operand_mode_sampler_status(golden_dir, name):
+    """Honest status of the north-star's "bf16 production mode": with bf16 tensor-core operands the *samples* miss
+    the 2e-2 bar on most fixtures (an 8-bit mantissa on every GEMM operand of a 27-block residual network, amplified
+    by guidance), which is why fp16 -- same width, same tcgen05 rate, 10-bit mantissa, saturating conversions and a
+    range monitor (vdt_plan_saturations) -- is the production format.  The test records the measured numbers and holds
+    bf16 only to 'finite and within 0.25'; the xfail marks the fixtures over the contract bar instead of hiding them."""
+    case = SAMPLE_CASES[name]
+    ucase = UNET_CASES[case["unet"]]
+    ref = torch.from_numpy(np.load(os.path.join(golden_dir, f"sample_{name}.npz"))["out"])
+    net = _model(ucase["cfg"], ucase["seed"], operand="bf16")
+    diff = _diffusion(case)
+    noise, label, step_noise = build_sample_inputs(case, ucase["cfg"])
+    out = diff.p_sample(net, tuple(noise.shape), noise=noise, label=label, device="cuda", use_ddim=case["use_ddim"],
+                        step_noise=None if case["use_ddim"] else step_noise)
+    err = (out - ref).abs().max().item()
+    print(f"{name} [bf16 operands]: max-abs {err:.3e}")
+    assert torch.isfinite(out).all() and err <= 0.25
+    if err > SAMPLE_MAX_ABS:
+        pytest.xfail(f"bf16 operands: {err:.3e} > {SAMPLE_MAX_ABS:.0e} (documented: fp16 is the production format)")
+
+
+def test_fp16_range_monitor_and_bf16_fallback():
+    """fp16 operands saturate at +-65504 instead of overflowing.  A checkpoint whose residual stream leaves that range
+    must be *noticed*: scale the stream far past 65504 (huge in_conv gain on a concat network), check that the plan's
+    saturation counter fires and the output stays finite, that the same network in bf16 operands (fp32 exponent range)
+    counts nothing, and that the in-range network counts nothing either."""
+    import ctypes as C
+    from oracle.unet_ref import make_state_dict
+    from v_diffusion_b200 import UNet, _lib
+    case = UNET_CASES["small_cond"]
+    cfg = case["cfg"]
+    x, t, y = build_inputs(case)
+
+    def run(sd, operand):
+        net = UNet(cfg["in_channels"], cfg["hid_channels"], cfg["out_channels"], cfg["ch_multipliers"],
+                   cfg["num_res_blocks"], cfg["apply_attn"], embedding_dim=cfg["embedding_dim"], head_dim=cfg["head_dim"],
+                   num_heads=cfg["num_heads"], num_classes=cfg["num_classes"], multitags=cfg["multitags"])
+        net.load_state_dict(sd, strict=True)
+        net.operand_dtype = operand
+        net = net.cuda().eval()
+        out = net(x.cuda(), t.cuda(), y.cuda()).cpu()
+        n = C.c_uint64()
+        _lib.check(_lib.lib().vdt_plan_saturations(net.plan_for(case["res"], torch.device("cuda", 0)), C.byref(n), 1))
+        return out, n.value
+
+    sd = make_state_dict(cfg, case["seed"])
+    out, n = run(sd, "fp16")
+    assert n == 0 and torch.isfinite(out).all()
+    big = {k: v.clone() for k, v in sd.items()}
+    big["in_conv.weight"] *= 3.0e5                         # stream (and the raw concat copies of the up path) ~ 1e5..1e6
+    big["in_conv.bias"] *= 3.0e5
+    out16, n16 = run(big, "fp16")
+    outb, nb = run(big, "bf16")
+    print(f"fp16 saturation events {n16}, bf16 {nb}")
+    assert n16 > 0, "the raw stream left the fp16 range but nothing was counted"
+    assert nb == 0
+    assert torch.isfinite(out16).all() and torch.isfinite(outb).all()
+    # bf16 keeps tracking the fp32 oracle on that network; saturated fp16 does not have to
+    from oracle import unet_forward
+    ref = unet_forward(big, cfg, x, t, y)
+    assert ((outb - ref).norm() / ref.norm()).item() <= 3e-2
 
 
 def test_celeba_config_forward_vs_oracle():
@@ -232,7 +296,6 @@ def test_on_device_noise_stream():
     assert torch.equal(a, b) and not torch.equal(a, c) and torch.isfinite(a).all()
 
 
-VALIDATION_MAX_ABS = 1e-3        # north-star: TF32/fp32 validation mode
 
 
 @pytest.mark.parametrize("name", ["cifar_cond", "small_cond", "small_hd64"])
@@ -265,26 +328,28 @@ def test_validation_mode_sampler(golden_dir, name):
     assert err <= VALIDATION_MAX_ABS
 
 
-def test_p_sample_progressive_vs_oracle():
-    """diffusion.py:416-441: x0 previews every pred_freq steps (guided prediction of p_sample_step)."""
-    from oracle import unet_forward, make_state_dict, p_sample
-    case = SAMPLE_CASES["ddim_cfg_v"]
+@pytest.mark.parametrize("name", ["ddim_cfg_v", "ancestral_cfg_v"])
+@pytest.mark.parametrize("operand", ["fp16", "fp16x3"])
+def test_p_sample_progressive_vs_reference_golden(golden_dir, name, operand):
+    """diffusion.py:416-441 against the unmodified reference's own progressive loop, which carries an fp32 step
+    tensor (:421): fp32 s / t quotients and an fp32 sinusoidal embedding.  x0 previews every pred_freq steps."""
+    case = SAMPLE_CASES[name]
     ucase = UNET_CASES[case["unet"]]
-    cfg = ucase["cfg"]
-    sd = make_state_dict(cfg, ucase["seed"])
-    net = _model(cfg, ucase["seed"])
-    diff = _diffusion(case)                                    # T = 8
-    noise, label, _ = build_sample_inputs(case, cfg)
-    x, preds = diff.p_sample_progressive(net, tuple(noise.shape), noise=noise, label=label, device="cuda", use_ddim=True,
-                                         pred_freq=3)
-    rec = []
-    ref = p_sample(lambda a, b, c: unet_forward(sd, cfg, a, b, c), tuple(noise.shape), noise, label, T=case["T"],
-                   model_out_type="v", w_guide=case["w_guide"], use_ddim=True, pred_record=rec)
-    assert (x - ref).abs().max().item() <= SAMPLE_MAX_ABS
-    want = {ti: p for ti, p in rec if (ti + 1) % 3 == 0}       # ti = 5, 2 -> preds[1], preds[0]
-    assert preds.shape[0] == 8 // 3 == 2
-    assert (preds[1] - want[5]).abs().max().item() <= 3 * SAMPLE_MAX_ABS      # guided x0 is amplified by (1 + 2w)
-    assert (preds[0] - want[2]).abs().max().item() <= 3 * SAMPLE_MAX_ABS
+    g = np.load(os.path.join(golden_dir, f"progressive_{name}.npz"))
+    ref, ref_preds, pred_freq = torch.from_numpy(g["out"]), torch.from_numpy(g["preds"]), int(g["pred_freq"])
+    net = _model(ucase["cfg"], ucase["seed"], operand=operand)
+    diff = _diffusion(case)
+    noise, label, step_noise = build_sample_inputs(case, ucase["cfg"])
+    x, preds = diff.p_sample_progressive(net, tuple(noise.shape), noise=noise, label=label, device="cuda",
+                                         use_ddim=case["use_ddim"], pred_freq=pred_freq,
+                                         step_noise=None if case["use_ddim"] else step_noise)
+    assert preds.shape == ref_preds.shape
+    bar = SAMPLE_MAX_ABS if operand == "fp16" else VALIDATION_MAX_ABS
+    ex, ep = (x - ref).abs().max().item(), (preds - ref_preds).abs().max().item()
+    print(f"progressive {name} [{operand}]: final {ex:.3e} previews {ep:.3e} (bar {bar:.0e})")
+    assert ex <= bar
+    # a guided preview is x0_c + w (x0_c - x0_u): the difference of two clipped predictions amplified by w on top
+    assert ep <= bar * (1.0 + case["w_guide"])
 
 
 def test_full_size_chunk_properties():
@@ -360,3 +425,197 @@ def test_c_abi_host_entry_point_matches_python_api():
     assert rc != 0 and b"not finalized" in _lib.lib().vdt_last_error()
     _lib.lib().vdt_plan_destroy(handle)
     del blank
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Full-length trajectories of the real CIFAR-10 networks against the unmodified reference (tests/golden/full_*.npz)
+def _full_model(case, operand):
+    from v_diffusion_b200 import UNet
+    sd, net = full_state_dict(case, UNet)
+    net.load_state_dict(sd, strict=True)
+    net.operand_dtype = operand
+    return net.cuda().eval()
+
+
+def _full_diffusion(case):
+    from v_diffusion_b200 import GaussianDiffusion, get_logsnr_schedule
+    return GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), case["T"], case["model_out_type"], case["var_type"],
+                             "snr_trunc", "mse", intp_frac=case["intp_frac"], w_guide=case["w_guide"])
+
+
+@pytest.mark.parametrize("name", sorted(FULL_CASES))
+@pytest.mark.parametrize("operand", ["fp16", "fp16x3"])
+def test_full_trajectory_vs_reference_golden(golden_dir, name, operand):
+    """BASELINE configs[0] (cifar10_uncond, 10-step DDIM, batch 16, exactly the SURVEY §8d recipe) and configs[1] at
+    batch 8 (cifar10_cond, v-prediction, CFG w = 1, all 100 DDIM steps) on the real 60.8 M-parameter networks.
+    Production mode (fp16 operands): final samples within 2e-2, every per-step model output within 1e-2 rel-L2;
+    validation mode (fp16x3): final samples within 1e-3."""
+    case = FULL_CASES[name]
+    g = np.load(os.path.join(golden_dir, f"full_{name}.npz"))
+    ref, ref_mo = torch.from_numpy(g["out"]), torch.from_numpy(g["model_out"])
+    net = _full_model(case, operand)
+    diff = _full_diffusion(case)
+    noise, label = build_full_inputs(case)
+    out = diff.p_sample(net, tuple(noise.shape), noise=noise, label=label, device="cuda", use_ddim=True)
+    err = (out - ref).abs().max().item()
+    bar = SAMPLE_MAX_ABS if operand == "fp16" else VALIDATION_MAX_ABS
+    print(f"full {name} [{operand}]: final-sample max-abs {err:.3e} (bar {bar:.0e})")
+    assert err <= bar
+    # per-step model outputs along the trajectory (generic-callable path, same kernels), rows the fixture kept
+    keep = case["keep_rows"]
+    rec = []
+
+    def wrapped(x, t, y):
+        o = net(x, t, y)
+        rec.append(o[:keep].cpu())
+        return o
+    out2 = diff.p_sample(wrapped, tuple(noise.shape), noise=noise, label=label, device="cuda", use_ddim=True)
+    assert (out2 - out).abs().max().item() <= 1e-5
+    assert len(rec) == case["T"] == ref_mo.shape[0]
+    rels = [((o - ref_mo[i]).norm() / ref_mo[i].norm()).item() for i, o in enumerate(rec)]
+    print(f"full {name} [{operand}]: per-step rel-L2 worst {max(rels):.3e} median {sorted(rels)[len(rels) // 2]:.3e}")
+    assert max(rels) <= (REL_L2 if operand == "fp16" else 1e-3)
+
+
+def test_seed_none_draws_fresh_noise_and_seed_reproduces():
+    """Ancestral sampling without injected noise: seed=None must not replay one noise trajectory (the reference draws
+    from the global generator, diffusion.py:401-402); an explicit seed -- or torch.manual_seed -- reproduces a run."""
+    case = SAMPLE_CASES["ancestral_x0eps"]
+    ucase = UNET_CASES[case["unet"]]
+    net = _model(ucase["cfg"], ucase["seed"])
+    diff = _diffusion(case)
+    noise, label, _ = build_sample_inputs(case, ucase["cfg"])
+    kw = dict(noise=noise, label=label, device="cuda", use_ddim=False)
+    a = diff.p_sample(net, tuple(noise.shape), **kw)
+    b = diff.p_sample(net, tuple(noise.shape), **kw)
+    assert not torch.equal(a, b)
+    torch.manual_seed(123); c = diff.p_sample(net, tuple(noise.shape), **kw)
+    torch.manual_seed(123); d = diff.p_sample(net, tuple(noise.shape), **kw)
+    assert torch.equal(c, d)
+    e = diff.p_sample(net, tuple(noise.shape), seed=9, **kw)
+    f = diff.p_sample(net, tuple(noise.shape), seed=9, **kw)
+    assert torch.equal(e, f) and not torch.equal(e, a)
+
+
+def test_label_validation():
+    """Out-of-range class ids and wrongly shaped multitag labels raise (F.one_hot raises in the reference,
+    modules.py:191-196; unet.py:291 asserts y.ndim == 2) instead of indexing outside the embedding tables."""
+    case = UNET_CASES["small_cond"]
+    net = _model(case["cfg"], case["seed"])
+    x, t, y = build_inputs(case)
+    with pytest.raises(RuntimeError, match="class ids"):
+        net(x.cuda(), t.cuda(), torch.tensor([0, 11, 3]).cuda())
+    with pytest.raises(RuntimeError, match="class ids"):
+        net(x.cuda(), t.cuda(), torch.tensor([0, -1, 3]).cuda())
+    scase = SAMPLE_CASES["ddim_cfg_v"]
+    diff = _diffusion(scase)
+    noise, label, _ = build_sample_inputs(scase, case["cfg"])
+    with pytest.raises(RuntimeError, match="class ids"):
+        diff.p_sample(net, tuple(noise.shape), noise=noise, label=label + 10, device="cuda", use_ddim=True)
+    with pytest.raises(ValueError, match="one class id per sample"):
+        diff.p_sample(net, tuple(noise.shape), noise=noise, label=label[:2], device="cuda", use_ddim=True)
+    mcase = UNET_CASES["small_multitag"]
+    mnet = _model(mcase["cfg"], mcase["seed"])
+    mdiff = _diffusion(SAMPLE_CASES["ddim_cfg_multitag"])
+    mnoise, mlabel, _ = build_sample_inputs(SAMPLE_CASES["ddim_cfg_multitag"], mcase["cfg"])
+    with pytest.raises(ValueError, match="multitag labels must have shape"):
+        mdiff.p_sample(mnet, tuple(mnoise.shape), noise=mnoise, label=torch.ones(mnoise.shape[0]), device="cuda", use_ddim=True)
+    # p_sample_progressive shares the label preparation: multi-hot float rows reach the C side as fp32
+    a = mdiff.p_sample(mnet, tuple(mnoise.shape), noise=mnoise, label=mlabel, device="cuda", use_ddim=True)
+    b, _ = mdiff.p_sample_progressive(mnet, tuple(mnoise.shape), noise=mnoise, label=mlabel, device="cuda", use_ddim=True, pred_freq=2)
+    assert (a - b).abs().max().item() <= 5e-3              # same trajectory up to the fp32-t rounding of the progressive loop
+
+
+def test_sampler_exec_cache_is_reused_across_noise_tensors_and_seeds():
+    """Per-call values (injected-noise tensor, seed) live in device state: a new noise tensor or seed must not rebuild
+    the workspace or re-capture the CUDA graph (round-1 advice), and the LRU cache keeps the other entries."""
+    import time
+    case = SAMPLE_CASES["ancestral_x0eps"]
+    ucase = UNET_CASES[case["unet"]]
+    net = _model(ucase["cfg"], ucase["seed"])
+    diff = _diffusion(case)
+    noise, label, step_noise = build_sample_inputs(case, ucase["cfg"])
+    ref = diff.p_sample(net, tuple(noise.shape), noise=noise, label=label, device="cuda", use_ddim=False, step_noise=step_noise)
+    diff.p_sample(net, tuple(noise.shape), noise=noise, label=label, device="cuda", use_ddim=False, step_noise=step_noise)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(5):
+        sn = step_noise.clone()                                # a fresh allocation every call
+        out = diff.p_sample(net, tuple(noise.shape), noise=noise, label=label, device="cuda", use_ddim=False, step_noise=sn)
+        assert torch.equal(out, ref)
+        diff.p_sample(net, tuple(noise.shape), noise=noise, label=label, device="cuda", use_ddim=False, seed=100 + k)
+    per_call = (time.perf_counter() - t0) / 10
+    print(f"cached sampler call: {per_call * 1e3:.1f} ms")
+    assert per_call < 0.25          # a rebuild (workspace allocation + eager pass + capture) costs far more
+
+
+def test_images_to_uint8_matches_generate_py():
+    """generate.py:149 on the device: (x * 127.5 + 127.5).clamp(0, 255).to(uint8).permute(0, 2, 3, 1)."""
+    from v_diffusion_b200.generate import images_to_uint8
+    g = torch.Generator().manual_seed(4)
+    for shape in [(5, 3, 32, 32), (3, 1, 28, 28), (2, 3, 64, 64)]:
+        x = (torch.randn(shape, generator=g) * 0.8).cuda()
+        x[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 1.7, -3.0])          # exact ends and out-of-range (guided samples exceed 1)
+        want = (x * 127.5 + 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+        got = images_to_uint8(x)
+        assert got.dtype == torch.uint8 and got.shape == want.shape
+        assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_generate_driver_end_to_end(tmp_path, world):
+    """`python -m v_diffusion_b200.generate` (the sharded batch loop of generate.py:100-150) as a user runs it: a
+    reference-format checkpoint + config JSONs in, uint8 NHWC images out; on 2 GPUs under torchrun with the NCCL image
+    gather.  The gathered images must equal what p_sample gives in-process for every rank's seeded noise / labels."""
+    import subprocess
+    import sys
+    from oracle.unet_ref import make_state_dict
+    from v_diffusion_b200 import GaussianDiffusion, get_logsnr_schedule
+    from v_diffusion_b200.generate import shard_bounds, images_to_uint8
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ucase = UNET_CASES["small_cond"]
+    cfg = ucase["cfg"]
+    sd = make_state_dict(cfg, ucase["seed"])
+    torch.save({"model": {"module." + k: v for k, v in sd.items()}}, tmp_path / "ckpt.pt")     # DDP prefix, generate.py:40-42
+    merged = json.load(open(os.path.join(root, "tests", "golden", "merged_configs.json")))["cifar10_cond"]
+    model_block = dict(in_channels=3, hid_channels=64, ch_multipliers=[1, 2], num_res_blocks=2, apply_attn=[False, True],
+                       drop_rate=0.2, num_heads=1)
+    json.dump({"data": {"name": "cifar10"}, "model": model_block, "diffusion": merged["diffusion"],
+               "conditional": merged["conditional"]}, open(tmp_path / "cfg.json", "w"))
+    json.dump({}, open(tmp_path / "defaults.json", "w"))
+    total, bs, T, seed = 22, 4, 6, 77
+    args = ["--config-path", str(tmp_path / "cfg.json"), "--default-config-path", str(tmp_path / "defaults.json"),
+            "--ckpt-path", str(tmp_path / "ckpt.pt"), "--sample-timesteps", str(T), "--w-guide", "1.0", "--batch-size", str(bs),
+            "--total-size", str(total), "--save-path", str(tmp_path / "out.pt"), "--seed", str(seed)]
+    if world == 1:
+        cmd = [sys.executable, "-m", "v_diffusion_b200.generate"] + args
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+               "127.0.0.1", "--master-port", "29533", "-m", "v_diffusion_b200.generate"] + args
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = torch.load(tmp_path / "out.pt")
+    assert got.dtype == torch.uint8 and tuple(got.shape) == (total, 32, 32, 3)
+    # expected: every rank's slice, batch by batch, with the generator protocol of generate.sample_fn (ancestral sampling:
+    # noise, labels and the per-batch noise seed all come from Generator(seed + rank))
+    net = _model(cfg, ucase["seed"])
+    d = merged["diffusion"]
+    diff = GaussianDiffusion(get_logsnr_schedule(d["logsnr_schedule"], d["logsnr_min"], d["logsnr_max"]), T, d["model_out_type"],
+                             d["model_var_type"], d["reweight_type"], d["loss_type"], intp_frac=d["intp_frac"], w_guide=1.0)
+    want = []
+    for rank in range(world):
+        s0, e0 = shard_bounds(total, rank, world)
+        gen = torch.Generator(device="cuda").manual_seed(seed + rank)
+        for b0 in range(s0, e0, bs):
+            n = min(bs, e0 - b0)
+            noise = torch.randn((n, 3, 32, 32), device="cuda", generator=gen)
+            label = torch.randint(10, (n,), device="cuda", generator=gen) + 1
+            call_seed = int(torch.randint(0, 2 ** 62, (1,), device="cuda", generator=gen).item())
+            want.append(diff.p_sample(net, (n, 3, 32, 32), noise=noise, label=label, device="cuda", seed=call_seed, use_ddim=False))
+    want = images_to_uint8(torch.cat(want).cuda()).cpu()
+    diffpix = (got.int() - want.int()).abs()
+    print(f"generate x{world}: {int((diffpix > 0).sum())} of {diffpix.numel()} uint8 values differ, max {int(diffpix.max())}")
+    assert int(diffpix.max()) == 0
