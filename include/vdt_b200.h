@@ -160,9 +160,9 @@ int vdt_op_groupnorm(const void* src1, int32_t c1, const float* src2, int32_t c2
                      const float* gamma, const float* beta, const float* film, int32_t film_stride, int32_t film_off,
                      int32_t silu, int32_t resample, void* out_act_16, void* out_raw_16, float* out_res,
                      int32_t f16, const void* stats1, const void* stats2, int32_t stat_cols, int32_t in16, void* stream);
-/* attention on qk 16-bit [B*N, 2*hid], v^T 16-bit [B*hid, N] with row pitch round_up(N, 8) -> 16-bit [B*N, hid];
- * any N >= 1 (ragged last key / query tiles are masked) */
-int vdt_op_attention(const void* qk_16, const void* vt_16, void* out_16, int32_t batch, int32_t n, int32_t heads,
+/* attention on qkv 16-bit [B*N, 3*hid] (q | k | v thirds, heads contiguous inside each, the layout proj_in writes)
+ * -> 16-bit [B*N, hid]; any N >= 1 (ragged last key / query tiles are masked) */
+int vdt_op_attention(const void* qkv_16, void* out_16, int32_t batch, int32_t n, int32_t heads,
                      int32_t d, int32_t f16, void* stream);
 /* one sampler update with explicit step index; coef = one row of vdt_step_coefficients (host pointer). */
 int vdt_op_sampler_step(const float* model_out, const float* x_t, const float* noise, float* x_s, int32_t batch,

@@ -238,12 +238,9 @@ def test_attention(L, B, N, heads, d, f16):
     # make the softmax peaky in places so the lazy rescale path (row max jumps by > 2^8) is exercised
     q[:, : N // 2] *= 3.0
     k[:, N // 2:] *= 2.0
-    qk = torch.cat([q.reshape(B * N, hid), k.reshape(B * N, hid)], dim=1).contiguous()
-    Np = (N + 7) // 8 * 8                                                 # row pitch of V^T: 16-byte multiples for TMA
-    vt = torch.full((B * hid, Np), float("nan"), device="cuda", dtype=DT[f16])   # the pad is never read
-    vt[:, :N] = v.permute(0, 2, 3, 1).reshape(B * hid, N)                # V^T [B*hid, N]
+    qkv = torch.cat([q.reshape(B * N, hid), k.reshape(B * N, hid), v.reshape(B * N, hid)], dim=1).contiguous()
     out = torch.zeros(B * N, hid, device="cuda", dtype=DT[f16])
-    _check(L, L.vdt_op_attention(_p(qk), _p(vt), _p(out), B, N, heads, d, f16, None))
+    _check(L, L.vdt_op_attention(_p(qkv), _p(out), B, N, heads, d, f16, None))
     torch.cuda.synchronize()
     qd, kd, vd = (z.double().permute(0, 2, 1, 3) for z in (q, k, v))           # B, h, N, d
     w = torch.softmax(qd @ kd.transpose(-1, -2) / math.sqrt(d), dim=-1)

@@ -107,7 +107,7 @@ def lib():
     L.vdt_step_coefficients.argtypes = [C.POINTER(SamplerConfig), vp]
     L.vdt_op_conv.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp]
     L.vdt_op_groupnorm.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, i32, vp]
-    L.vdt_op_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.vdt_op_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.vdt_op_sampler_step.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, C.c_float, vp]
     L.vdt_stat_slabs_per_image.argtypes = [i32, i32]
     L.vdt_images_to_uint8.argtypes = [vp, vp, i32, i32, i32, vp]

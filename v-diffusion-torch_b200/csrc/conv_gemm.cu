@@ -2,7 +2,7 @@
 //
 // Replaces F.conv2d / F.linear on the reference's hot path (modules.py:79-80, 141-144 as called
 // from unet.py:121,125,134,70-71,203-215,217,232).  NHWC bf16 operands, fp32 accumulation in
-// TMEM, fused epilogue (bias, residual add, SiLU, bf16 / transposed / NCHW stores).
+// TMEM, fused epilogue (bias, residual add, SiLU, 16-bit / NCHW stores).
 //
 // Persistent warp-specialised kernel, one CTA per SM, 192 threads, CTAs paired (cluster of 2) so
 // the tensor cores run in cta_group::2 mode: one 256 x N x 16 MMA spans both SMs, each CTA holding
@@ -286,7 +286,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                 const int col0 = n_tile * p.block_n + c0;
                 if (col0 >= p.Cout) continue;                // warp-uniform
                 float v[32];
-                const bool row_major = (p.out_mode == kOutF32) || (p.out_mode == kOutBF16 && col0 < p.split_col);
+                const bool row_major = p.out_mode != kOutNCHW;
                 if (row_major) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);       // bias is added after the transposition
@@ -315,20 +315,6 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                         else epilogue_rowmajor<F16, false, false, 0>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
                     }
                     __syncwarp();
-                } else if (p.out_mode == kOutBF16) {         // V third of proj_in: transposed per image (coalesced per column)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(p.bias + col0 + j);
-                    if (p.act_silu) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-                    }
-                    if (row_ok) {
-                        const long long img = grow / p.HW;
-                        const int pix = static_cast<int>(grow - img * p.HW);
-                        h16* dst = p.out_t + (img * (p.Cout - p.split_col) + (col0 - p.split_col)) * p.ld_t + pix;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) dst[static_cast<long long>(j) * p.ld_t] = cvt_16(v[j], (F16 ? 1 : 0));
-                    }
                 } else {   // kOutNCHW
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + ((col0 + j < p.Cout) ? __ldg(p.bias + col0 + j) : 0.f);

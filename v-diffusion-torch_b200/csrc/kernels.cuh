@@ -23,8 +23,7 @@ constexpr int kConvMaxSegs = 6;   // 3x3 body + 1x1 skip, each x3 in the split-p
 
 enum ConvOutMode : int {
     kOutF32 = 0,        // fp32 [M, ld]            (+bias, +residual, optional SiLU)
-    kOutBF16 = 1,       // 16-bit [M, ld] for columns < split_col; columns >= split_col are written
-                        // transposed per image: out_t[(img * (Cout - split_col) + col - split_col) * ld_t + pix]
+    kOutBF16 = 1,       // 16-bit [M, ld]
     kOutNCHW = 2,       // fp32 [img, Cout, HW]    (network output, Cout may be tiny)
 };
 
@@ -42,20 +41,18 @@ struct alignas(64) ConvParams {
     int M, Cout;                       // valid rows / columns
     int out_mode;
     int ld;                            // row stride (elements) of out_f32 / out_bf16 / residual
-    int split_col, HW;
+    int HW;
     int act_silu;
     int f16;                           // operand / 16-bit output format: 1 fp16, 0 bf16
     const float* bias;                 // [Cout]
     const float* residual;             // fp32 [M, ld] or null
     float* out_f32;
     h16* out_bf16;
-    h16* out_t;
     // optional GroupNorm partial statistics of the row-major output (after bias/residual): for every slab of
     // 32 consecutive rows and every stat_cols (4 or 2) consecutive columns, (sum, sum of squares):
     // stats[slab * Cout/stat_cols + col/stat_cols], slab = m_tile * 4 + (row in tile) / 32
     float2* stats;
     int stat_cols;
-    int ld_t;                          // row pitch (elements) of out_t: HW rounded up to 8 (TMA needs 16-byte pitches)
     // optional device counter of fp16 range events: incremented (once per warp and 32x32 chunk) when a value written in
     // the fp16 operand format had |x| > 65504 and was clamped by the saturating conversion
     unsigned long long* sat_count;
@@ -114,15 +111,14 @@ cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream);
 // Self-attention softmax(q^T k / sqrt(d)) v per image and head, flash-style on tcgen05 (attention.cu)
 // ------------------------------------------------------------------------------------------------
 struct alignas(64) AttnParams {
-    CUtensorMap qk_map;                // 2-D (2*hid, B*N) bf16, box (64, 128): q at col h*d, k at hid + h*d
-    CUtensorMap k_map;                 // same tensor, box (64, 64)
-    CUtensorMap vt_map;                // 2-D (N, B*hid) 16-bit with row pitch round_up(N, 8), box (64, d): V^T per image/head
+    CUtensorMap q_map;                 // 2-D (3*hid, B*N) 16-bit, box (64, 128): q | k | v thirds, heads contiguous in each
+    CUtensorMap kv_map;                // same tensor, box (64, 64): K tiles at column hid + h*d, V tiles at 2*hid + h*d
     int B, N, heads, d, hid;
     int f16;
     float scale_log2e;                 // log2(e) / sqrt(d)
     h16* out;                         // 16-bit [B*N, hid]
 };
-cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
+cudaError_t launch_attention(const AttnParams& p, int num_sms, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // Small kernels (pointwise.cu)

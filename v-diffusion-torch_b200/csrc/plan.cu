@@ -665,8 +665,8 @@ struct ConvSpec {
     int n = 0, h = 0, w = 0;
     const h16* wpacked = nullptr; int cout = 0; int wrows = 0;   // weight rows actually allocated
     const float* bias = nullptr; const float* residual = nullptr;
-    int out_mode = kOutF32; float* out_f32 = nullptr; h16* out_bf16 = nullptr; h16* out_t = nullptr;
-    int ld = 0, split_col = 0, act_silu = 0, f16 = 1;
+    int out_mode = kOutF32; float* out_f32 = nullptr; h16* out_bf16 = nullptr;
+    int ld = 0, act_silu = 0, f16 = 1;
     float2* stats = nullptr;
     int stat_cols = 4;
     unsigned long long* sat_count = nullptr;
@@ -724,10 +724,9 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     cp->num_n_tiles = (s.cout + cp->block_n - 1) / cp->block_n;
     CKI(make_map_2d(&cp->b_map, s.wpacked, s.wrows, ktot, ktot, cp->block_n / 2));   // each CTA of a pair fetches half
     cp->M = (int)M; cp->Cout = s.cout; cp->out_mode = s.out_mode; cp->ld = s.ld;
-    cp->split_col = s.split_col ? s.split_col : (1 << 30); cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16;
-    cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->out_t = s.out_t; cp->stat_cols = s.stat_cols;
+    cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16;
+    cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->stat_cols = s.stat_cols;
     cp->stats = (slabs > 0 && (s.a3 || flat_ok || geo_pointwise)) ? s.stats : nullptr;   // statistics slabs never span two images
-    cp->ld_t = (s.h * s.w + 7) & ~7;
     cp->sat_count = s.sat_count;
     if (s.out_mode != kOutNCHW && s.cout % 32 != 0) return fail("output channels must be a multiple of 32 (got %d)", s.cout);
     return 0;
@@ -868,7 +867,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             int hd, nh;
             attn_dims(c, b.cin, &hd, &nh);
             const int hidd = hd * nh, N = HW;
-            h16 *a, *a_lo = nullptr, *qk = nullptr, *vt = nullptr, *o, *o_lo = nullptr;
+            h16 *a, *a_lo = nullptr, *qkv = nullptr, *o, *o_lo = nullptr;
             CKI(ex->acquire((size_t)R * HW * b.cin * 2, (void**)&a));
             if (sp) CKI(ex->acquire((size_t)R * HW * b.cin * 2, (void**)&a_lo));
             GroupNormParams g{};
@@ -880,28 +879,26 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             add_gn(g);
             CKI(ex->acquire((size_t)R * N * hidd * 2, (void**)&o));
             if (!sp) {
-                CKI(ex->acquire((size_t)R * N * 2 * hidd * 2, (void**)&qk));
-                CKI(ex->acquire((size_t)R * ((N + 7) & ~7) * hidd * 2, (void**)&vt));
-                {   // one GEMM for q | k | v: q,k row-major [R*N, 2*hid]; the v third is written transposed, V^T [R*hid, N]
+                CKI(ex->acquire((size_t)R * N * 3 * hidd * 2, (void**)&qkv));
+                {   // one GEMM for q | k | v, all row-major [R*N, 3*hid]: the attention kernel reads V as an MN-major operand
                     ConvSpec s;
                     s.f16 = p->f16; s.stat_cols = p->stat_cols; s.sat_count = p->sat_count;
                     s.a1 = a; s.c1 = b.cin; s.ld1 = b.cin; s.n = R; s.h = res; s.w = res; s.wpacked = b.w1; s.cout = 3 * hidd;
-                    s.wrows = 3 * hidd; s.bias = p->W(n + ".proj_in.bias"); s.out_mode = kOutBF16; s.out_bf16 = qk; s.out_t = vt;
-                    s.ld = 2 * hidd; s.split_col = 2 * hidd;
+                    s.wrows = 3 * hidd; s.bias = p->W(n + ".proj_in.bias"); s.out_mode = kOutBF16; s.out_bf16 = qkv;
+                    s.ld = 3 * hidd;
                     CKI(add_conv(s));
                 }
                 ex->release(a);
                 std::unique_ptr<AttnParams> ap(new AttnParams());
                 memset(ap.get(), 0, sizeof(AttnParams));
-                CKI(make_map_2d(&ap->qk_map, qk, (long long)R * N, 2 * hidd, 2 * hidd, 128));
-                CKI(make_map_2d(&ap->k_map, qk, (long long)R * N, 2 * hidd, 2 * hidd, 64));
-                CKI(make_map_2d(&ap->vt_map, vt, (long long)R * hidd, N, (N + 7) & ~7, hd));   // columns >= N are zero-filled by TMA
+                CKI(make_map_2d(&ap->q_map, qkv, (long long)R * N, 3 * hidd, 3 * hidd, 128));
+                CKI(make_map_2d(&ap->kv_map, qkv, (long long)R * N, 3 * hidd, 3 * hidd, 64));
                 ap->B = R; ap->N = N; ap->heads = nh; ap->d = hd; ap->hid = hidd; ap->f16 = p->f16;
                 ap->scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)hd));
                 ap->out = o;
                 ex->attns.push_back(std::move(ap));
                 ex->steps.push_back({S_ATTN, (int)ex->attns.size() - 1});
-                ex->release(qk); ex->release(vt);
+                ex->release(qkv);
             } else {
                 // split-precision validation mode: q | k | v in fp32, attention on CUDA cores in fp32
                 float* qkv32;
@@ -996,7 +993,7 @@ static int run_steps(vdt_plan* p, Exec* ex, cudaStream_t st, std::vector<cudaEve
         switch (s.kind) {
             case S_CONV: e = launch_conv_gemm(*ex->convs[s.idx], p->num_sms, st); break;
             case S_GN: e = launch_groupnorm(ex->gns[s.idx], st); break;
-            case S_ATTN: e = launch_attention(*ex->attns[s.idx], st); break;
+            case S_ATTN: e = launch_attention(*ex->attns[s.idx], p->num_sms, st); break;
             case S_IM2COL: { auto& a = ex->im2cols[s.idx]; e = launch_im2col3x3(a.x, a.out, a.out_lo, a.B, a.rep, a.C, a.H, a.W, a.f16, st); break; }
             case S_TEMB: { auto& a = ex->tembs[s.idx]; e = launch_timestep_embedding(a.t, a.out, a.rows, a.dim, a.fp32_flag, st); break; }
             case S_LINEAR: { auto& a = ex->linears[s.idx]; e = launch_linear_f32(a.x, a.W, a.b, a.out, a.rows, a.K, a.N, a.silu, st); break; }
@@ -1465,18 +1462,20 @@ extern "C" int vdt_op_groupnorm(const void* src1, int32_t c1, const float* src2,
     return 0;
 }
 
-extern "C" int vdt_op_attention(const void* qk, const void* vt, void* out, int32_t batch, int32_t n, int32_t heads, int32_t d,
+extern "C" int vdt_op_attention(const void* qkv, void* out, int32_t batch, int32_t n, int32_t heads, int32_t d,
                                 int32_t f16, void* stream) {
     const int hid = heads * d;
     std::unique_ptr<AttnParams> ap(new AttnParams());
     memset(ap.get(), 0, sizeof(AttnParams));
-    CKI(make_map_2d(&ap->qk_map, qk, (long long)batch * n, 2 * hid, 2 * hid, 128));
-    CKI(make_map_2d(&ap->k_map, qk, (long long)batch * n, 2 * hid, 2 * hid, 64));
-    CKI(make_map_2d(&ap->vt_map, vt, (long long)batch * hid, n, (n + 7) & ~7, d));
+    CKI(make_map_2d(&ap->q_map, qkv, (long long)batch * n, 3 * hid, 3 * hid, 128));
+    CKI(make_map_2d(&ap->kv_map, qkv, (long long)batch * n, 3 * hid, 3 * hid, 64));
     ap->B = batch; ap->N = n; ap->heads = heads; ap->d = d; ap->hid = hid; ap->f16 = f16;
     ap->scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)d));
     ap->out = (h16*)out;
-    cudaError_t e = launch_attention(*ap, reinterpret_cast<cudaStream_t>(stream));
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = launch_attention(*ap, nsm, reinterpret_cast<cudaStream_t>(stream));
     ++g_launches;
     if (e != cudaSuccess) return fail("attention launch failed: %s", cudaGetErrorString(e));
     return 0;

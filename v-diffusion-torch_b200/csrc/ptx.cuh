@@ -192,12 +192,26 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
+// Same for an MN-major operand (the MMA's N -- or M -- index is the contiguous one in memory, e.g. V [key][d] as the
+// B operand of P V): tiles of 64 MN-elements (one 128-byte swizzle row) x 8 K-rows = 1024 bytes; SBO = distance
+// between consecutive groups of 8 K-rows (1024 B when the rows of one 64-wide chunk are stored back to back),
+// LBO = distance between consecutive 64-element MN chunks.  Advancing K by 16 rows = +2048 bytes.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
 // Instruction descriptor, kind::f16: D fp32, A/B both fp16 (format 0) or both bf16 (format 1), both
 // K-major, M x N.
 __host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, int fp16) {
     return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(m >> 4) << 24);
 }
+constexpr uint32_t kIdescBMajorMN = 1u << 16;   // B operand is MN-major (bit 15 would be the A operand)
 __device__ __forceinline__ void umma_16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
