@@ -64,10 +64,9 @@ def gn_case(H, c, st, src, in16, film):
 
 
 def attn_case(N, d):
-    qk = torch.randn(R * N, 2 * d, device=dev, generator=g).half()
-    vt = torch.randn(R * d, N, device=dev, generator=g).half()
+    qkv = torch.randn(R * N, 3 * d, device=dev, generator=g).half()
     o = torch.empty(R * N, d, device=dev, dtype=torch.float16)
-    ms = timed(lambda: L.vdt_op_attention(p(qk), p(vt), p(o), R, N, 1, d, 1, None), 5)
+    ms = timed(lambda: L.vdt_op_attention(p(qkv), p(o), R, N, 1, d, 1, None), 5)
     fl = 4.0 * R * N * N * d
     print(f"attention N={N} d={d}: {ms:.3f} ms {fl / ms / 1e9 if ms else 0:.0f} TFLOP/s")
 

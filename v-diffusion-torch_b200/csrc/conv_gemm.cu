@@ -55,21 +55,49 @@ __device__ __forceinline__ TileCoord tile_origin(const ConvParams& p, int m_tile
     return t;
 }
 
+// work item w -> (M tile of this CTA, N tile, output parity class of the sub-pixel upsampling conv); the parity runs
+// fastest so that the four items sharing an A region are in flight together
+struct WorkItem { int m_tile, n_tile, par; };
+__device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int w, int rank) {
+    WorkItem it;
+    it.par = 0;
+    if (p.ups) { it.par = w & 3; w >>= 2; }
+    it.m_tile = (w / p.num_n_tiles) * 2 + rank;
+    it.n_tile = w % p.num_n_tiles;
+    return it;
+}
+
 // Row-major epilogue of one 32-row x 32-column chunk after the smem transposition: lane = (row % 4 group rsub,
 // 4 columns cq), all 32 rows valid.  Compile-time variants keep the instruction count low (the epilogue warps
 // are issue-bound otherwise); ragged tiles and SiLU epilogues take epilogue_rowmajor_generic.
-template <bool F16, bool F32OUT, bool RESID, int STATS>   // STATS: 0 none, 4 / 2 = columns per statistics entry
-__device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const float4* tile, int lane, long long wrow0, int col0, int slab) {
+// MAP: 0 rows are stored where they were computed; 1 sub-pixel upsampling conv (ConvParams::ups): row = low-res pixel,
+// stored at its high-resolution position of parity `par`; 2 upsampled identity skip (ConvParams::resid_up): the residual
+// of output pixel (y, x) is low-res pixel (y >> 1, x >> 1).  Both need power-of-two square maps (map_shift).
+template <bool F16, bool F32OUT, bool RESID, int STATS, int MAP>   // STATS: 0 none, 4 / 2 = columns per statistics entry
+__device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const float4* tile, int lane, long long wrow0, int col0, int slab,
+                                                  const float4 b4, int par) {
     const int cq = lane & 7, rsub = lane >> 3;
     const size_t off0 = static_cast<size_t>(wrow0 + rsub) * p.ld + col0 + cq * 4;
     const size_t step = static_cast<size_t>(4) * p.ld;
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq * 4));
+    // row remaps: a 32-row slab never crosses an image (HW is a power of two >= 32 here)
+    const int sh = (MAP != 0) ? p.map_shift : 0, wmask = (1 << sh) - 1;
+    const long long img = (MAP != 0) ? (wrow0 >> (2 * sh)) : 0;
+    const int pix0 = (MAP != 0) ? static_cast<int>(wrow0 & ((1ll << (2 * sh)) - 1)) + rsub : 0;   // pixel of this lane's first row
+    const size_t colo = static_cast<size_t>(col0 + cq * 4);
+    // MAP 1: high-res row = img * 4HW + (2y + py) * 2W + 2x + px = base + 4 * pix - 2 * x
+    const long long ups_base = (MAP == 1) ? (img << (2 * sh + 2)) + (static_cast<long long>(par >> 1) << (sh + 1)) + (par & 1) : 0;
     float4 res[8];
     if (RESID) {                                             // all eight loads in flight before anything is stored
-        const float* rp = p.residual + off0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            res[i] = ldg_nc_v4_issue(rp + i * step);
+        for (int i = 0; i < 8; ++i) {
+            if (MAP == 2) {
+                const int pix = pix0 + 4 * i;
+                const long long src = (img << (2 * sh - 2)) + ((pix >> (sh + 1)) << (sh - 1)) + ((pix & wmask) >> 1);
+                res[i] = ldg_nc_v4_issue(p.residual + static_cast<size_t>(src) * p.ld + colo);
+            } else {
+                res[i] = ldg_nc_v4_issue(p.residual + off0 + i * step);
+            }
+        }
         compiler_fence();
     }
     float ssum = 0.f, ssq = 0.f, ssum1 = 0.f, ssq1 = 0.f;
@@ -81,10 +109,15 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
         o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
         if (RESID) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
         {
+            size_t off = off0 + i * step;
+            if (MAP == 1) {
+                const int pix = pix0 + 4 * i;
+                off = static_cast<size_t>(ups_base + 4ll * pix - 2 * (pix & wmask)) * p.ld + colo;
+            }
             if (F32OUT)
-                *reinterpret_cast<float4*>(p.out_f32 + off0 + i * step) = o;
+                *reinterpret_cast<float4*>(p.out_f32 + off) = o;
             else {
-                *reinterpret_cast<uint2*>(p.out_bf16 + off0 + i * step) = make_uint2(pack_16(o.x, o.y, (F16 ? 1 : 0)), pack_16(o.z, o.w, (F16 ? 1 : 0)));
+                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_16(o.x, o.y, (F16 ? 1 : 0)), pack_16(o.z, o.w, (F16 ? 1 : 0)));
                 if (F16) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
             }
             if (STATS == 4) {
@@ -107,6 +140,10 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
             ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, 16); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, 16);
         }
         if (rsub == 0) {
+            if (MAP == 1) {                                  // the parity classes of an image own consecutive slab groups
+                const int simg = slab / p.stat_slabs_img;
+                slab = (simg * 4 + par) * p.stat_slabs_img + (slab - simg * p.stat_slabs_img);
+            }
             float2* st = p.stats + static_cast<size_t>(slab) * (p.Cout / (STATS ? STATS : 1));
             if (STATS == 4) {
                 st[(col0 >> 2) + cq] = make_float2(ssum, ssq);
@@ -120,10 +157,9 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
 
 // Same with every option and bound checked at run time (ragged tiles, SiLU epilogues).
 __device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, const float4* tile, int lane, int q, int m_tile,
-                                                       long long wrow0, int col0) {
+                                                       long long wrow0, int col0, const float4 b4, int par) {
     const int cq = lane & 7, rsub = lane >> 3;
     const bool tile_ok = m_tile < p.num_m_tiles;
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cq * 4));
     float ssum = 0.f, ssq = 0.f, ssum1 = 0.f, ssq1 = 0.f;   // (x, y) and (z, w) halves; merged for 4-column entries
     for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + rsub;
@@ -131,10 +167,24 @@ __device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, cons
         const bool ok = tile_ok && (q * 32 + rr < p.rows_per_tile) && (g < p.M);
         if (!ok) continue;
         float4 o = tile[rr * 8 + (cq ^ (rr & 7))];
-        const size_t off = static_cast<size_t>(g) * p.ld + col0 + cq * 4;
+        long long orow = g;                                  // output row
+        if (p.ups) {                                         // low-res pixel (img, y, x) -> high-res pixel (2y + py, 2x + px)
+            const long long img = g / p.HW;
+            const int pix = static_cast<int>(g - img * p.HW);
+            const int y = pix / p.ups_w, x = pix - y * p.ups_w;
+            orow = img * 4 * p.HW + static_cast<long long>(2 * y + (par >> 1)) * (2 * p.ups_w) + 2 * x + (par & 1);
+        }
+        const size_t off = static_cast<size_t>(orow) * p.ld + col0 + cq * 4;
         o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
         if (p.residual) {
-            const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+            size_t roff = off;
+            if (p.resid_up) {                                // identity skip of an upsampling block: nearest source pixel
+                const long long img = g / p.HW;
+                const int pix = static_cast<int>(g - img * p.HW);
+                const int y = pix / p.out_w, x = pix - y * p.out_w;
+                roff = static_cast<size_t>(img * (p.HW >> 2) + static_cast<long long>(y >> 1) * (p.out_w >> 1) + (x >> 1)) * p.ld + col0 + cq * 4;
+            }
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + roff));
             o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
         }
         if (p.act_silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
@@ -154,8 +204,16 @@ __device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, cons
         ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, 8); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, 8);
         ssum1 += __shfl_xor_sync(0xffffffffu, ssum1, 16); ssq1 += __shfl_xor_sync(0xffffffffu, ssq1, 16);
         if (rsub == 0 && tile_ok) {                          // a quarter without valid rows still writes its zeros
-            float2* st = p.stats + static_cast<size_t>(m_tile * 4 + q) * (p.Cout / p.stat_cols);
-            if (p.stat_cols == 4) {
+            int slab = m_tile * 4 + q;
+            bool real = true;
+            if (p.ups) {                                     // the parity classes of an image own consecutive slab groups
+                const int img = slab / p.stat_slabs_img;
+                real = img < p.M / p.HW;                     // the zero-filled images of a ragged last tile own no slabs here
+                slab = (img * 4 + par) * p.stat_slabs_img + (slab - img * p.stat_slabs_img);
+            }
+            float2* st = p.stats + static_cast<size_t>(slab) * (p.Cout / p.stat_cols);
+            if (!real) {
+            } else if (p.stat_cols == 4) {
                 st[(col0 >> 2) + cq] = make_float2(ssum + ssum1, ssq + ssq1);
             } else {
                 st[(col0 >> 1) + cq * 2] = make_float2(ssum, ssq);
@@ -200,7 +258,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
 
     // work item w = (pair of M tiles, N tile); this CTA takes M tile 2*mp + rank (a phantom tile past the
     // end is all zero-filled loads and masked stores)
-    const int total_items = ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles;
+    const int total_items = ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles * (p.ups ? 4 : 1);
     int kblocks_total = 0;
     for (int s = 0; s < p.num_segs; ++s) kblocks_total += p.seg_taps[s] * p.seg_kblocks[s];
 
@@ -212,14 +270,16 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
             // both CTAs' boxes complete on the leader's barrier
             const uint32_t tx_bytes = 2u * static_cast<uint32_t>(p.rows_per_tile * kBK * 2 + half_n * kBK * 2);
             for (int w = pair; w < total_items; w += num_pairs_resident) {
-                const int m_tile = (w / p.num_n_tiles) * 2 + rank, n_tile = w % p.num_n_tiles;
-                const TileCoord o = tile_origin(p, m_tile);
-                int kcol = 0;
+                const WorkItem it = decode_item(p, w, rank);
+                const int n_tile = it.n_tile, py = it.par >> 1, px = it.par & 1;
+                const TileCoord o = tile_origin(p, it.m_tile);
+                int kcol = it.par * kblocks_total * kBK;   // sub-pixel conv: every parity class has its own weight columns
                 for (int s = 0; s < p.num_segs; ++s) {
                     const int taps = p.seg_taps[s];
                     for (int tap = 0; tap < taps; ++tap) {
-                        const int dy = (taps == 9) ? tap / 3 - 1 : 0;
-                        const int dx = (taps == 9) ? tap % 3 - 1 : 0;
+                        // 9: 3x3, pad 1; 4: the 2x2 neighbourhood of a parity class of the sub-pixel upsampling conv; 1: pointwise
+                        const int dy = (taps == 9) ? tap / 3 - 1 : (taps == 4) ? (tap >> 1) - 1 + py : 0;
+                        const int dx = (taps == 9) ? tap % 3 - 1 : (taps == 4) ? (tap & 1) - 1 + px : 0;
                         for (int kb = 0; kb < p.seg_kblocks[s]; ++kb) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* a_dst = smem + stage * kStageBytes;
@@ -267,27 +327,43 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         const int row = q * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = pair; w < total_items; w += num_pairs_resident) {
-            const int m_tile = (w / p.num_n_tiles) * 2 + rank, n_tile = w % p.num_n_tiles;
+            const WorkItem it = decode_item(p, w, rank);
+            const int m_tile = it.m_tile, n_tile = it.n_tile;
             const long long grow = static_cast<long long>(m_tile) * p.rows_per_tile + row;
             const bool row_ok = (row < p.rows_per_tile) && (grow < p.M) && (m_tile < p.num_m_tiles);
-            if (p.residual && row_ok) {
+            if (p.residual && row_ok && !p.resid_up) {
                 // the main loop of this tile is still running: pull this warp's residual lines (one 128-byte line
                 // per row and 32-column chunk) into L2 so the epilogue's loads below do not pay DRAM latency
                 const float* rp = p.residual + static_cast<size_t>(grow) * p.ld + n_tile * p.block_n;
                 for (int c0 = chunk_par * 32; c0 < p.block_n; c0 += 64) prefetch_l2(rp + c0);
             }
+            // this warp's bias vectors for its (up to four) chunks of the tile, fetched while the main loop still runs:
+            // inside the chunk loop the load's L2 latency would be exposed once per chunk, which is what bounds the
+            // epilogue-heavy GEMMs (K = 64 / 256: in_conv, proj_in, proj_out)
+            float4 bias_c[4];
+            {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int colk = n_tile * p.block_n + chunk_par * 32 + 64 * k;
+                    bias_c[k] = (chunk_par * 32 + 64 * k < p.block_n && colk < p.Cout)
+                                    ? __ldg(reinterpret_cast<const float4*>(p.bias + colk + (lane & 7) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kMaxBN);
-            for (int c0 = chunk_par * 32; c0 < p.block_n; c0 += 64) {
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+                const int c0 = chunk_par * 32 + 64 * kc;
+                if (c0 >= p.block_n) break;
+                const float4 b4 = bias_c[kc];
                 uint32_t r[32];
                 tmem_ld32(t_row + static_cast<uint32_t>(c0), r);
                 tmem_ld_wait();
                 const int col0 = n_tile * p.block_n + c0;
                 if (col0 >= p.Cout) continue;                // warp-uniform
                 float v[32];
-                const bool row_major = p.out_mode != kOutNCHW;
-                if (row_major) {
+                {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);       // bias is added after the transposition
                     // thread-per-row registers -> swizzled smem tile -> lane = (row % 4 group, 4 columns): every
@@ -300,32 +376,35 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                     const long long wrow0 = static_cast<long long>(m_tile) * p.rows_per_tile + q * 32;
                     const bool f32o = p.out_mode == kOutF32, resid = p.residual != nullptr, st = p.stats != nullptr;
                     const bool all_valid = (m_tile < p.num_m_tiles) && (q * 32 + 32 <= p.rows_per_tile) && (wrow0 + 32 <= p.M);
-                    if (!all_valid || p.act_silu) {          // ragged tile / rare variants: run-time checked generic path
-                        epilogue_rowmajor_generic(p, tile, lane, q, m_tile, wrow0, col0);
+                    const bool mapped = p.ups || p.resid_up;
+                    const int slab = m_tile * 4 + q, par = it.par;
+                    if (!all_valid || p.act_silu || (mapped && p.map_shift < 3)) {   // ragged tile / rare variants: run-time checked generic path
+                        epilogue_rowmajor_generic(p, tile, lane, q, m_tile, wrow0, col0, b4, par);
+                    } else if (p.ups) {                      // sub-pixel upsampling conv1: scattered rows, no residual
+                        if (f32o) {                          // (fp32 out: split-precision mode / two-pass GroupNorm fallback)
+                            if (st && p.stat_cols == 4) epilogue_rowmajor<F16, true, false, 4, 1>(p, tile, lane, wrow0, col0, slab, b4, par);
+                            else if (st) epilogue_rowmajor<F16, true, false, 2, 1>(p, tile, lane, wrow0, col0, slab, b4, par);
+                            else epilogue_rowmajor<F16, true, false, 0, 1>(p, tile, lane, wrow0, col0, slab, b4, par);
+                        } else if (st && p.stat_cols == 4) epilogue_rowmajor<F16, false, false, 4, 1>(p, tile, lane, wrow0, col0, slab, b4, par);
+                        else if (st) epilogue_rowmajor<F16, false, false, 2, 1>(p, tile, lane, wrow0, col0, slab, b4, par);
+                        else epilogue_rowmajor<F16, false, false, 0, 1>(p, tile, lane, wrow0, col0, slab, b4, par);
+                    } else if (p.resid_up) {                 // conv2 of an upsampling block: residual gathered from the low-res stream
+                        if (st && p.stat_cols == 4) epilogue_rowmajor<F16, true, true, 4, 2>(p, tile, lane, wrow0, col0, slab, b4, par);
+                        else if (st) epilogue_rowmajor<F16, true, true, 2, 2>(p, tile, lane, wrow0, col0, slab, b4, par);
+                        else epilogue_rowmajor<F16, true, true, 0, 2>(p, tile, lane, wrow0, col0, slab, b4, par);
                     } else if (f32o) {
-                        if (resid && st && p.stat_cols == 4) epilogue_rowmajor<F16, true, true, 4>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
-                        else if (resid && st) epilogue_rowmajor<F16, true, true, 2>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
-                        else if (resid) epilogue_rowmajor<F16, true, true, 0>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
-                        else if (st && p.stat_cols == 4) epilogue_rowmajor<F16, true, false, 4>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
-                        else if (st) epilogue_rowmajor<F16, true, false, 2>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
-                        else epilogue_rowmajor<F16, true, false, 0>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
+                        if (resid && st && p.stat_cols == 4) epilogue_rowmajor<F16, true, true, 4, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
+                        else if (resid && st) epilogue_rowmajor<F16, true, true, 2, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
+                        else if (resid) epilogue_rowmajor<F16, true, true, 0, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
+                        else if (st && p.stat_cols == 4) epilogue_rowmajor<F16, true, false, 4, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
+                        else if (st) epilogue_rowmajor<F16, true, false, 2, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
+                        else epilogue_rowmajor<F16, true, false, 0, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
                     } else {
-                        if (st && p.stat_cols == 4) epilogue_rowmajor<F16, false, false, 4>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
-                        else if (st) epilogue_rowmajor<F16, false, false, 2>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
-                        else epilogue_rowmajor<F16, false, false, 0>(p, tile, lane, wrow0, col0, m_tile * 4 + q);
+                        if (st && p.stat_cols == 4) epilogue_rowmajor<F16, false, false, 4, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
+                        else if (st) epilogue_rowmajor<F16, false, false, 2, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
+                        else epilogue_rowmajor<F16, false, false, 0, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
                     }
                     __syncwarp();
-                } else {   // kOutNCHW
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + ((col0 + j < p.Cout) ? __ldg(p.bias + col0 + j) : 0.f);
-                    if (row_ok) {
-                        const long long img = grow / p.HW;
-                        const int pix = static_cast<int>(grow - img * p.HW);
-                        float* dst = p.out_f32 + (img * p.Cout + col0) * p.HW + pix;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < p.Cout) dst[static_cast<long long>(j) * p.HW] = v[j];
-                    }
                 }
             }
             tc_fence_before();
@@ -359,7 +438,7 @@ cudaError_t launch_conv_gemm(const ConvParams& p, int num_sms, cudaStream_t stre
         if (e != cudaSuccess) return e;
         attr_set[dev].store(true, std::memory_order_release);
     }
-    const int items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    const int items = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles * (p.ups ? 4 : 1);
     if (items <= 0) return cudaSuccess;
     const int pairs = items < num_sms / 2 ? items : num_sms / 2;
     if (p.f16) conv_gemm_kernel<true><<<2 * pairs, kThreads, kSmemBytes, stream>>>(p);

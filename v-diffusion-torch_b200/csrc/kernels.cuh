@@ -24,7 +24,6 @@ constexpr int kConvMaxSegs = 6;   // 3x3 body + 1x1 skip, each x3 in the split-p
 enum ConvOutMode : int {
     kOutF32 = 0,        // fp32 [M, ld]            (+bias, +residual, optional SiLU)
     kOutBF16 = 1,       // 16-bit [M, ld]
-    kOutNCHW = 2,       // fp32 [img, Cout, HW]    (network output, Cout may be tiny)
 };
 
 struct alignas(64) ConvParams {
@@ -53,6 +52,20 @@ struct alignas(64) ConvParams {
     // stats[slab * Cout/stat_cols + col/stat_cols], slab = m_tile * 4 + (row in tile) / 32
     float2* stats;
     int stat_cols;
+    // Sub-pixel form of "3x3 conv on a 2x nearest-upsampled input" (unet.py:127-128, 141 of an upsampling
+    // ResidualBlock): ups = 1 -> the A operand is the LOW-resolution tensor [n, h, w, c]; each work item also carries a
+    // parity class (py, px) of output pixels (2y + py, 2x + px), for which only a 2x2 neighbourhood of low-resolution
+    // pixels contributes, with the 3x3 weights that fall on the same source pixel pre-summed: 4 parities x 4 taps instead
+    // of 9 taps on 4x the pixels (16/36 of the MACs, the upsampled tensor never exists).  Packed weight columns:
+    // [parity][segment][tap = ty * 2 + tx][cin]; tap (ty, tx) of parity (py, px) reads low-res pixel (y + ty - 1 + py,
+    // x + tx - 1 + px).  Output rows are scattered to their high-resolution positions; M, HW, the tiling and the
+    // statistics slabs count LOW-resolution pixels (slab of parity p: ((img * 4 + p) * stat_slabs_img + slab in image)).
+    int ups, ups_w, stat_slabs_img;
+    // resid_up = 1: `residual` is the low-resolution fp32 tensor [M/4, ld] of an upsampling block's identity skip
+    // (unet.py:138): output pixel (y, x) of an out_w-wide image adds pixel (y >> 1, x >> 1)
+    int resid_up, out_w;
+    int map_shift;                     // log2 of ups_w (ups) / out_w (resid_up) when the map is square with power-of-two
+                                       // sides (the fast epilogues then remap rows with shifts), else -1 (generic epilogue)
     // optional device counter of fp16 range events: incremented (once per warp and 32x32 chunk) when a value written in
     // the fp16 operand format had |x| > 65504 and was clamped by the saturating conversion
     unsigned long long* sat_count;
@@ -154,6 +167,11 @@ cudaError_t launch_class_embed_silu(const float* e, const int64_t* y, const floa
 // sqrt(max(nnz(y[r]), 1))) + b) with W the stock nn.Linear weight [E, num_classes] (y == nullptr: SiLU only)
 cudaError_t launch_class_embed_multitag_silu(const float* e, const float* y, const float* w_cls, const float* b_cls,
                                              int num_classes, float* out, int rows, int E, cudaStream_t stream);
+
+// out[img, co, y, x] = bias[co] + sum over the 9 taps of y[pixel shifted by the tap, tap * Cout + co] (zero padding):
+// the gather half of the network's last 3x3 conv, whose GEMM half is a pointwise GEMM with N = 9 * Cout (pointwise.cu)
+cudaError_t launch_tapsum3x3(const float* y, const float* bias, float* out, int B, int H, int W, int Cout, int ld,
+                             cudaStream_t stream);
 
 // generate.py:149: fp32 NCHW images in [-1, 1] -> uint8 NHWC, (x * 127.5 + 127.5).clamp(0, 255) truncated
 cudaError_t launch_images_to_uint8(const float* x, uint8_t* out, int B, int C, int HW, cudaStream_t stream);

@@ -140,6 +140,31 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ src, h16* __restric
     const h16 hi = to_h16(w, f16);
     dst[(long long)o * ktot + koff + tap * I + i] = part == 0 ? hi : to_h16(w - h16_to_float(hi, f16), f16);
 }
+// Sub-pixel form of conv3x3(nearest_upsample_2x(x)) (kernels.cuh: ConvParams::ups): for output parity (py, px) the
+// 3x3 taps that read the same low-resolution pixel are summed (fp32) into a 2x2 kernel; row r of the 3x3 kernel lands on
+// low-res row offset floor((py + r - 1) / 2), i.e. py = 0: {r0} -> ty 0, {r1, r2} -> ty 1; py = 1: {r0, r1} -> ty 0,
+// {r2} -> ty 1 (same for columns).  dst columns: par * par_stride + koff + (ty * 2 + tx) * I + i.
+__global__ void pack_conv_ups_kernel(const float* __restrict__ src, h16* __restrict__ dst, int O, int I, int ktot, int par_stride,
+                                     int koff, int f16, int part) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n = (long long)O * I * 16;
+    if (idx >= n) return;
+    const int i = (int)(idx % I);
+    const int t = (int)((idx / I) % 4);
+    const int par = (int)((idx / ((long long)I * 4)) % 4);
+    const int o = (int)(idx / ((long long)I * 16));
+    const int py = par >> 1, px = par & 1, ty = t >> 1, tx = t & 1;
+    float w = 0.f;
+    for (int r = 0; r < 3; ++r) {
+        if (((py + r + 1) >> 1) - 1 + (1 - py) != ty) continue;   // floor((py + r - 1) / 2) relative to the first source row
+        for (int c = 0; c < 3; ++c) {
+            if (((px + c + 1) >> 1) - 1 + (1 - px) != tx) continue;
+            w += src[((long long)o * I + i) * 9 + r * 3 + c];
+        }
+    }
+    const h16 hi = to_h16(w, f16);
+    dst[(long long)o * ktot + (long long)par * par_stride + koff + t * I + i] = part == 0 ? hi : to_h16(w - h16_to_float(hi, f16), f16);
+}
 // in_conv: [O][C][3][3] -> [O][64], column tap*C + c (matches im2col3x3), zero padded
 __global__ void pack_inconv_w_kernel(const float* __restrict__ src, h16* __restrict__ dst, int O, int C, int f16, int ktot,
                                      int koff, int part) {
@@ -150,6 +175,18 @@ __global__ void pack_inconv_w_kernel(const float* __restrict__ src, h16* __restr
     if (col < 9 * C) { const int tap = col / C, c = col % C; v = src[((long long)o * C + c) * 9 + tap]; }
     const h16 hi = to_h16(v, f16);
     dst[(long long)o * ktot + koff + col] = part == 0 ? hi : to_h16(v - h16_to_float(hi, f16), f16);
+}
+// out_conv: [O][C][3][3] -> tap-major rows [tap * O + o][C] (zero rows up to the padded row count): the B operand of the
+// pointwise GEMM whose nine column groups the tap-sum kernel gathers (pointwise.cu: tapsum3x3_kernel)
+__global__ void pack_outconv_t_kernel(const float* __restrict__ src, h16* __restrict__ dst, int O, int C, int f16, int ktot,
+                                      int koff, int part) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 9 * O * C) return;
+    const int c = idx % C, row = idx / C;
+    const int tap = row / O, o = row % O;
+    const float v = src[((long long)o * C + c) * 9 + tap];
+    const h16 hi = to_h16(v, f16);
+    dst[(long long)row * ktot + koff + c] = part == 0 ? hi : to_h16(v - h16_to_float(hi, f16), f16);
 }
 __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,7 +243,8 @@ struct Block {
     float* bias2 = nullptr;   // conv2.bias (+ skip.bias)
 };
 
-enum StepKind { S_CONV, S_GN, S_ATTN, S_IM2COL, S_TEMB, S_LINEAR, S_CLSEMB, S_BEGIN, S_SAMPLE, S_ATTN_F32 };
+enum StepKind { S_CONV, S_GN, S_ATTN, S_IM2COL, S_TEMB, S_LINEAR, S_CLSEMB, S_BEGIN, S_SAMPLE, S_ATTN_F32, S_TAPSUM };
+struct TapsumArgs { const float* y; const float* bias; float* out; int B, H, W, Cout, ld; };
 struct LinearArgs { const float *x, *W, *b; float* out; int rows, K, N, silu; };
 struct Im2colArgs { const float* x; h16* out; h16* out_lo; int B, rep, C, H, W, f16; };
 struct AttnF32Args { const float* qkv; h16 *hi, *lo; int B, N, heads, d, f16; };
@@ -234,6 +272,7 @@ struct Exec {
     std::vector<TembArgs> tembs;
     std::vector<ClsArgs> clss;
     std::vector<BeginArgs> begins;
+    std::vector<TapsumArgs> tapsums;
     std::vector<SamplerStepParams> samples;
     // fixed I/O staging
     float* xin = nullptr;        // forward: fp32 NCHW [rows, Cin, HW] | sampler: x_t [rows/rep, C, HW]
@@ -292,7 +331,9 @@ struct vdt_plan {
     bool finalized = false;
     // packed globals
     h16* w_in = nullptr;                 // in_conv [hid][64]
-    h16* w_out = nullptr;                // out_conv.2 [Cout][9*c0]
+    h16* w_out = nullptr;                // out_conv.2 tap-major [out_rows][c0]: row tap * Cout + co (pack_outconv_t_kernel)
+    int out_rows = 0;                     // 9 * out_channels rounded up to 32
+    float* zero_bias = nullptr;           // [out_rows] zeros (the real bias is added by the tap-sum kernel)
     float* w_fc_all = nullptr;            // [film_total][E]
     float* b_fc_all = nullptr;            // [film_total]
     std::vector<void*> owned;
@@ -526,6 +567,17 @@ static int pack_conv(const float* src, h16* dst, int O, int I, int taps, int kto
     return 0;
 }
 
+// sub-pixel upsampling conv: columns [parity][segment W_hi | W_hi | W_lo][tap][cin]
+static int pack_conv_ups(const float* src, h16* dst, int O, int I, int f16, int split) {
+    const long long n = (long long)O * I * 16;
+    const int km = split ? 3 : 1, K = 4 * I;
+    for (int part = 0; part < km; ++part) {
+        pack_conv_ups_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src, dst, O, I, 4 * km * K, km * K, part * K, f16, part == 2 ? 1 : 0);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
 extern "C" int vdt_plan_finalize(vdt_plan* p) {
     if (!p) return fail("null plan");
     for (auto& w : p->weights)
@@ -549,8 +601,13 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
     for (auto& b : p->blocks) {
         const std::string& n = b.name;
         if (b.kind == 0) {
-            CKI(dev_alloc(p, &b.w1, (size_t)b.cout * 9 * b.cin * km));
-            CKI(pack_conv(p->W(n + ".conv1.weight"), b.w1, b.cout, b.cin, 9, 9 * b.cin * km, 0, p->f16, sp));
+            if (b.resample == kResUp) {                  // nearest-upsample folded into conv1 (sub-pixel form, 16 taps in all)
+                CKI(dev_alloc(p, &b.w1, (size_t)b.cout * 16 * b.cin * km));
+                CKI(pack_conv_ups(p->W(n + ".conv1.weight"), b.w1, b.cout, b.cin, p->f16, sp));
+            } else {
+                CKI(dev_alloc(p, &b.w1, (size_t)b.cout * 9 * b.cin * km));
+                CKI(pack_conv(p->W(n + ".conv1.weight"), b.w1, b.cout, b.cin, 9, 9 * b.cin * km, 0, p->f16, sp));
+            }
             const bool skipconv = b.cin != b.cout;
             const int k2 = (9 * b.cout + (skipconv ? b.cin : 0)) * km;
             CKI(dev_alloc(p, &b.w2, (size_t)b.cout * k2));
@@ -574,9 +631,15 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
         }
     }
     const int c0 = hid * c.ch_multipliers[0];
-    // out_conv weight rows are padded to 16 output channels (zero rows) so the TMA box never leaves the tensor
-    CKI(dev_alloc(p, &p->w_out, (size_t)16 * 9 * c0 * km));
-    CKI(pack_conv(p->W("out_conv.2.weight"), p->w_out, c.out_channels, c0, 9, 9 * c0 * km, 0, p->f16, sp));
+    // out_conv as a pointwise GEMM over tap-major weight rows (9 * Cout, padded with zero rows to a multiple of 32)
+    p->out_rows = (9 * c.out_channels + 31) / 32 * 32;
+    CKI(dev_alloc(p, &p->w_out, (size_t)p->out_rows * c0 * km));
+    CKI(dev_alloc(p, &p->zero_bias, (size_t)p->out_rows));
+    for (int part = 0; part < km; ++part) {            // split mode: K segments W_hi | W_hi | W_lo
+        pack_outconv_t_kernel<<<(9 * c.out_channels * c0 + 255) / 256, 256>>>(p->W("out_conv.2.weight"), p->w_out, c.out_channels, c0, p->f16,
+                                                                              c0 * km, c0 * part, part == 2 ? 1 : 0);
+        CK(cudaGetLastError());
+    }
     CK(cudaDeviceSynchronize());
     p->finalized = true;
     return 0;
@@ -628,7 +691,6 @@ extern "C" int vdt_plan_flops(const vdt_plan* p, double* conv, double* attn, dou
 
 // ================================================================================================ conv setup
 static int pick_block_n(int cout) {
-    if (cout <= 16) return 16;
     if (cout <= 256) return cout;
     for (int bn = 256; bn >= 32; bn -= 32)
         if (cout % bn == 0) return bn;
@@ -670,6 +732,8 @@ struct ConvSpec {
     float2* stats = nullptr;
     int stat_cols = 4;
     unsigned long long* sat_count = nullptr;
+    int ups = 0;          // sub-pixel 2x-upsampling conv: a3 is the LOW-res tensor [n, h, w, c3], the output is [n, 2h, 2w, cout]
+    int resid_up = 0;     // residual is the low-res tensor [n, h/2, w/2, ld] of an upsampling block's identity skip
 };
 
 static int setup_conv(const ConvSpec& s, ConvParams* cp) {
@@ -690,8 +754,9 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
         CKI(conv_geom(s.n, s.h, s.w, &g));
         for (int k = 0; k < n3; ++k) {
             CKI(make_map_nhwc(&cp->a_map[seg], a3s[k], s.n, s.h, s.w, s.c3, g.box_h, g.box_n));
-            cp->seg_taps[seg] = 9; cp->seg_kblocks[seg] = s.c3 / 64; ktot += 9 * s.c3; ++seg;
+            cp->seg_taps[seg] = s.ups ? 4 : 9; cp->seg_kblocks[seg] = s.c3 / 64; ktot += (s.ups ? 4 : 9) * s.c3; ++seg;
         }
+        if (s.ups) ktot *= 4;                            // one set of weight columns per output parity class
         cp->pointwise = 0; cp->tiles_per_image = g.tiles_per_image; cp->box_h = g.box_h; cp->box_n = g.box_n;
         cp->rows_per_tile = g.rows_per_tile; cp->num_m_tiles = g.num_m_tiles;
         for (int k = 0; k < n1; ++k) {
@@ -727,8 +792,15 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     cp->HW = s.h * s.w; cp->act_silu = s.act_silu; cp->f16 = s.f16;
     cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->stat_cols = s.stat_cols;
     cp->stats = (slabs > 0 && (s.a3 || flat_ok || geo_pointwise)) ? s.stats : nullptr;   // statistics slabs never span two images
+    cp->ups = s.ups; cp->ups_w = s.w; cp->stat_slabs_img = slabs; cp->resid_up = s.resid_up; cp->out_w = s.w;
+    cp->map_shift = -1;                                  // fast row remaps need square power-of-two maps of >= 64 (ups) / 256 pixels
+    if ((s.ups || s.resid_up) && s.h == s.w && (s.w & (s.w - 1)) == 0)
+        for (int k = 3; k < 16; ++k) if ((1 << k) == s.w) cp->map_shift = k;
+    if (s.ups && (s.a1 || !s.a3)) return fail("internal: the sub-pixel upsampling conv takes a single 3x3 operand");
+    if (s.ups && s.stats && 4 * slabs != stat_slabs_per_image(2 * s.h, 2 * s.w)) cp->stats = nullptr;   // callers check fusability first
+    if (s.resid_up && ((s.h | s.w) & 1)) return fail("internal: upsampled residual needs even output sizes");
     cp->sat_count = s.sat_count;
-    if (s.out_mode != kOutNCHW && s.cout % 32 != 0) return fail("output channels must be a multiple of 32 (got %d)", s.cout);
+    if (s.cout % 32 != 0) return fail("output channels must be a multiple of 32 (got %d)", s.cout);
     return 0;
 }
 
@@ -795,23 +867,30 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             const bool skipconv = b.cin != b.cout;
             const int ro = b.resample == kResDown ? res / 2 : b.resample == kResUp ? res * 2 : res;
             const size_t HWo = (size_t)ro * ro;
+            // an upsampling block never materialises the upsampled tensors: norm1 runs at the input resolution, conv1 is
+            // the sub-pixel form of conv3x3(upsample(.)) and conv2's identity-skip residual reads the low-res stream
+            const bool up = b.resample == kResUp;
+            if (up && skipconv) return fail("internal: an upsampling block with a skip conv is not part of the reference (%s)", n.c_str());
+            const int ra = up ? res : ro;                       // resolution of conv1's A operand
+            const size_t HWa = (size_t)ra * ra;
             h16 *a1, *xraw = nullptr, *a1_lo = nullptr, *xraw_lo = nullptr; float* xres = nullptr;
-            CKI(ex->acquire((size_t)R * HWo * cin * 2, (void**)&a1));
-            if (sp) CKI(ex->acquire((size_t)R * HWo * cin * 2, (void**)&a1_lo));
+            CKI(ex->acquire((size_t)R * HWa * cin * 2, (void**)&a1));
+            if (sp) CKI(ex->acquire((size_t)R * HWa * cin * 2, (void**)&a1_lo));
             if (skipconv) CKI(ex->acquire((size_t)R * HW * cin * 2, (void**)&xraw));
             if (skipconv && sp) CKI(ex->acquire((size_t)R * HW * cin * 2, (void**)&xraw_lo));
-            if (b.resample != kResNone) CKI(ex->acquire((size_t)R * HWo * cin * 4, (void**)&xres));
+            if (b.resample == kResDown) CKI(ex->acquire((size_t)R * HWo * cin * 4, (void**)&xres));
             GroupNormParams g{};
             g.f16 = p->f16; g.stat_cols = p->stat_cols; g.sat_count = p->sat_count;
             g.src1 = h; g.C1 = hch; g.src2 = src2; g.C2 = c2; g.B = R; g.H = res; g.W = res;
             if (fusable(hch, c2, res)) { g.stats1 = hst; g.stats2 = st2; g.meanrstd = meanrstd; g.stat_slabs = stat_slabs_per_image(res, res); }
             g.gamma = p->W(n + ".norm1.weight"); g.beta = p->W(n + ".norm1.bias");
-            g.silu = 1; g.resample = b.resample; g.out_act = a1; g.out_raw = xraw; g.out_res = xres;
+            g.silu = 1; g.resample = up ? kResNone : b.resample; g.out_act = a1; g.out_raw = xraw; g.out_res = xres;
             g.out_act_lo = a1_lo; g.out_raw_lo = xraw_lo;
             add_gn(g);
             // conv1: its output only feeds norm2, so it is kept in the 16-bit operand format when norm2 can use
             // the epilogue statistics (otherwise fp32 for the two-pass fallback)
-            const bool fuse2 = fusable(b.cout, 0, ro);
+            const bool fuse2 = fusable(b.cout, 0, ro) &&
+                               (!up || 4 * stat_slabs_per_image(res, res) == stat_slabs_per_image(ro, ro));
             // (split-precision mode keeps every stream tensor fp32)
             const bool h1_16 = fuse2 && !sp;
             void* h1; float2* h1st = nullptr;
@@ -820,7 +899,8 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             {
                 ConvSpec s;
                 s.f16 = p->f16; s.stat_cols = p->stat_cols; s.sat_count = p->sat_count;
-                s.a3 = a1; s.a3_lo = a1_lo; s.c3 = cin; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w1; s.cout = b.cout; s.wrows = b.cout;
+                s.a3 = a1; s.a3_lo = a1_lo; s.c3 = cin; s.n = R; s.h = ra; s.w = ra; s.wpacked = b.w1; s.cout = b.cout; s.wrows = b.cout;
+                s.ups = up ? 1 : 0;
                 s.bias = p->W(n + ".conv1.bias"); s.ld = b.cout; s.stats = h1st;
                 if (h1_16) { s.out_mode = kOutBF16; s.out_bf16 = (h16*)h1; } else { s.out_mode = kOutF32; s.out_f32 = (float*)h1; }
                 CKI(add_conv(s));
@@ -851,7 +931,8 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
                 s.a3 = a2; s.a3_lo = a2_lo; s.c3 = b.cout; s.n = R; s.h = ro; s.w = ro; s.wpacked = b.w2; s.cout = b.cout; s.wrows = b.cout;
                 if (skipconv) { s.a1 = xraw; s.a1_lo = xraw_lo; s.c1 = cin; s.ld1 = cin; }
                 s.bias = b.bias2;
-                s.residual = skipconv ? nullptr : (b.resample != kResNone ? xres : h);
+                s.residual = skipconv ? nullptr : (b.resample == kResDown ? xres : h);
+                s.resid_up = (up && !skipconv) ? 1 : 0;
                 s.out_mode = kOutF32; s.out_f32 = hout; s.ld = b.cout; s.stats = houtst;
                 CKI(add_conv(s));
             }
@@ -949,11 +1030,19 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
         g.gamma = p->W("out_conv.0.weight"); g.beta = p->W("out_conv.0.bias");
         g.silu = 1; g.resample = kResNone; g.out_act = a; g.out_act_lo = a_lo;
         add_gn(g);
+        // 3x3 conv with a handful of output channels: pointwise GEMM Y[pixel, tap * Cout + co] (the activation is read
+        // once instead of once per tap) + the tap-sum gather into the NCHW network output (pointwise.cu)
+        float* ytap;
+        CKI(ex->acquire((size_t)R * HW * p->out_rows * 4, (void**)&ytap));
         ConvSpec s;
         s.f16 = p->f16; s.stat_cols = p->stat_cols; s.sat_count = p->sat_count;
-        s.a3 = a; s.a3_lo = a_lo; s.c3 = hch; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_out; s.cout = c.out_channels; s.wrows = 16;
-        s.bias = p->W("out_conv.2.bias"); s.out_mode = kOutNCHW; s.out_f32 = ex->yout; s.ld = 0;
+        s.a1 = a; s.a1_lo = a_lo; s.c1 = hch; s.ld1 = hch; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_out;
+        s.cout = p->out_rows; s.wrows = p->out_rows; s.bias = p->zero_bias; s.out_mode = kOutF32; s.out_f32 = ytap; s.ld = p->out_rows;
         CKI(add_conv(s));
+        ex->tapsums.push_back({ytap, p->W("out_conv.2.bias"), ex->yout, R, res, res, c.out_channels, p->out_rows});
+        ex->steps.push_back({S_TAPSUM, (int)ex->tapsums.size() - 1});
+        ex->release(ytap);
+        if (a_lo) ex->release(a_lo);
         ex->release(a);
         if (!h_on_stack) { ex->release(h); ex->release(hst); }
     }
@@ -1005,6 +1094,7 @@ static int run_steps(vdt_plan* p, Exec* ex, cudaStream_t st, std::vector<cudaEve
             }
             case S_BEGIN: { auto& a = ex->begins[s.idx]; e = launch_sampler_begin_step(a.st, a.table, a.t_rows, a.nrows, a.T, st); break; }
             case S_SAMPLE: e = launch_sampler_step(ex->samples[s.idx], st); break;
+            case S_TAPSUM: { auto& a = ex->tapsums[s.idx]; e = launch_tapsum3x3(a.y, a.bias, a.out, a.B, a.H, a.W, a.Cout, a.ld, st); break; }
             case S_ATTN_F32: { auto& a = ex->attn32s[s.idx]; e = launch_attention_f32(a.qkv, a.hi, a.lo, a.B, a.N, a.heads, a.d, a.f16, st); break; }
         }
         if (e != cudaSuccess) return fail("kernel launch failed (step kind %d): %s", (int)s.kind, cudaGetErrorString(e));

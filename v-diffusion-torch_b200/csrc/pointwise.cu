@@ -329,6 +329,40 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerStepPara
     stv(p.x_s + i, out);
 }
 
+// ------------------------------------------------------------------------------------------ out_conv tap sum
+// The network's last 3x3 conv has only Cout = out_channels (3 / 6 / 1) output channels: as an implicit GEMM its A operand
+// would be fetched nine times (once per tap) for an N tile of 16 columns.  It is computed instead as ONE pointwise GEMM
+// Y[p, tap * Cout + co] = sum_c act[p, c] * W[co, c, tap] (A read once) followed by this gather:
+//   out[img, co, y, x] = bias[co] + sum_tap Y[pixel (y + dy, x + dx), tap * Cout + co]   (taps outside the image drop out)
+// One thread per output pixel; consecutive threads own consecutive pixels, so the NCHW stores are coalesced and the nine
+// gathered rows of a warp are 32 consecutive 128-byte (ld = 32) rows each.
+__global__ void __launch_bounds__(256) tapsum3x3_kernel(const float* __restrict__ y, const float* __restrict__ bias,
+                                                        float* __restrict__ out, long long pixels, int H, int W, int Cout, int ld) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= pixels) return;
+    const int HW = H * W;
+    const long long img = i / HW;
+    const int pix = static_cast<int>(i - img * HW);
+    const int yy = pix / W, xx = pix - yy * W;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = (c < Cout) ? __ldg(bias + c) : 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int y2 = yy + dy, x2 = xx + dx;
+        if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
+        const float* src = y + (img * HW + y2 * W + x2) * ld + tap * Cout;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+            if (c < Cout) acc[c] += __ldg(src + c);
+    }
+    float* dst = out + img * Cout * HW + pix;
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+        if (c < Cout) dst[static_cast<size_t>(c) * HW] = acc[c];
+}
+
 // ------------------------------------------------------------------------------------------ uint8 tail
 // generate.py:149: (x * 127.5 + 127.5).clamp(0, 255).to(uint8).permute(0, 2, 3, 1) -- one thread per pixel: C coalesced
 // channel-plane reads, C consecutive bytes written
@@ -348,6 +382,15 @@ __global__ void images_to_uint8_kernel(const float* __restrict__ x, uint8_t* __r
 }
 
 }  // namespace
+
+cudaError_t launch_tapsum3x3(const float* y, const float* bias, float* out, int B, int H, int W, int Cout, int ld,
+                             cudaStream_t stream) {
+    const long long pixels = static_cast<long long>(B) * H * W;
+    if (pixels == 0) return cudaSuccess;
+    if (Cout > 16) return cudaErrorInvalidValue;
+    tapsum3x3_kernel<<<static_cast<unsigned>((pixels + 255) / 256), 256, 0, stream>>>(y, bias, out, pixels, H, W, Cout, ld);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_images_to_uint8(const float* x, uint8_t* out, int B, int C, int HW, cudaStream_t stream) {
     const long long pixels = static_cast<long long>(B) * HW;
