@@ -74,7 +74,7 @@ __device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int w, int 
 // stored at its high-resolution position of parity `par`; 2 upsampled identity skip (ConvParams::resid_up): the residual
 // of output pixel (y, x) is low-res pixel (y >> 1, x >> 1).  Both need power-of-two square maps (map_shift).
 template <bool F16, bool F32OUT, bool RESID, int STATS, int MAP>   // STATS: 0 none, 4 / 2 = columns per statistics entry
-__device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const float4* tile, int lane, long long wrow0, int col0, int slab,
+__device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, uint32_t tile, int lane, long long wrow0, int col0, int slab,
                                                   const float4 b4, int par) {
     const int cq = lane & 7, rsub = lane >> 3;
     const size_t off0 = static_cast<size_t>(wrow0 + rsub) * p.ld + col0 + cq * 4;
@@ -105,7 +105,7 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + rsub;
-        float4 o = tile[rr * 8 + (cq ^ (rr & 7))];
+        float4 o = lds_v4(tile + static_cast<uint32_t>(rr * 8 + (cq ^ (rr & 7))) * 16u);
         o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
         if (RESID) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
         {
@@ -156,7 +156,7 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, const flo
 }
 
 // Same with every option and bound checked at run time (ragged tiles, SiLU epilogues).
-__device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, const float4* tile, int lane, int q, int m_tile,
+__device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, uint32_t tile, int lane, int q, int m_tile,
                                                        long long wrow0, int col0, const float4 b4, int par) {
     const int cq = lane & 7, rsub = lane >> 3;
     const bool tile_ok = m_tile < p.num_m_tiles;
@@ -166,7 +166,7 @@ __device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, cons
         const long long g = wrow0 + rr;
         const bool ok = tile_ok && (q * 32 + rr < p.rows_per_tile) && (g < p.M);
         if (!ok) continue;
-        float4 o = tile[rr * 8 + (cq ^ (rr & 7))];
+        float4 o = lds_v4(tile + static_cast<uint32_t>(rr * 8 + (cq ^ (rr & 7))) * 16u);
         long long orow = g;                                  // output row
         if (p.ups) {                                         // low-res pixel (img, y, x) -> high-res pixel (2y + py, 2x + px)
             const long long img = g / p.HW;
@@ -325,6 +325,20 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
         const int chunk_par = (warp - 2) >> 2;               // this warp takes the 32-column chunks of this parity
         const int row = q * 32 + lane;
+        const uint32_t epi_base = smem_u32(epi_smem);
+        // which compile-time epilogue serves this launch (the same for every tile): -1 = generic (SiLU epilogues, row
+        // remaps on maps that are not power-of-two squares, 16-bit output with a residual)
+        int variant = -1;
+        {
+            const bool f32o = p.out_mode == kOutF32, resid = p.residual != nullptr;
+            const int sti = (p.stats == nullptr) ? 2 : (p.stat_cols == 4 ? 0 : 1);
+            const bool mapped = p.ups || p.resid_up;
+            if (p.act_silu || (mapped && p.map_shift < 3) || (!f32o && resid)) variant = -1;
+            else if (p.ups) variant = (f32o ? 9 : 12) + sti;
+            else if (p.resid_up) variant = f32o ? 15 + sti : -1;
+            else if (f32o) variant = (resid ? 0 : 3) + sti;
+            else variant = 6 + sti;
+        }
         int acc = 0; uint32_t acc_phase = 0;
         for (int w = pair; w < total_items; w += num_pairs_resident) {
             const WorkItem it = decode_item(p, w, rank);
@@ -352,6 +366,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kMaxBN);
+            const int nkc = (p.block_n - chunk_par * 32 + 63) / 64;    // 32-column chunks of the tile this warp owns (0 .. 4)
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) {
                 const int c0 = chunk_par * 32 + 64 * kc;
@@ -360,56 +375,49 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                 uint32_t r[32];
                 tmem_ld32(t_row + static_cast<uint32_t>(c0), r);
                 tmem_ld_wait();
+                if (kc == nkc - 1) {
+                    // this warp's last read of the accumulator: hand it back to the MMA thread now, before the stores of
+                    // the chunk (relaxed arrive: a release fence here would stall the warp until its global stores drained)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster_relaxed(&acc_empty[acc], 0);   // the leader waits for both CTAs' drains
+                }
                 const int col0 = n_tile * p.block_n + c0;
                 if (col0 >= p.Cout) continue;                // warp-uniform
-                float v[32];
                 {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);       // bias is added after the transposition
                     // thread-per-row registers -> swizzled smem tile -> lane = (row % 4 group, 4 columns): every
                     // global access below is 4 rows x 128 (fp32) / 64 (16-bit) contiguous bytes per warp instruction
-                    float4* tile = reinterpret_cast<float4*>(epi_smem + (warp - 2) * (32 * 128));
+                    const uint32_t tile = epi_base + static_cast<uint32_t>(warp - 2) * (32u * 128u);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        tile[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j)                // (the bias is added after the transposition)
+                        sts_v4(tile + static_cast<uint32_t>(lane * 8 + (j ^ (lane & 7))) * 16u,
+                               make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                           __uint_as_float(r[4 * j + 3])));
                     __syncwarp();
                     const long long wrow0 = static_cast<long long>(m_tile) * p.rows_per_tile + q * 32;
-                    const bool f32o = p.out_mode == kOutF32, resid = p.residual != nullptr, st = p.stats != nullptr;
                     const bool all_valid = (m_tile < p.num_m_tiles) && (q * 32 + 32 <= p.rows_per_tile) && (wrow0 + 32 <= p.M);
-                    const bool mapped = p.ups || p.resid_up;
                     const int slab = m_tile * 4 + q, par = it.par;
-                    if (!all_valid || p.act_silu || (mapped && p.map_shift < 3)) {   // ragged tile / rare variants: run-time checked generic path
-                        epilogue_rowmajor_generic(p, tile, lane, q, m_tile, wrow0, col0, b4, par);
-                    } else if (p.ups) {                      // sub-pixel upsampling conv1: scattered rows, no residual
-                        if (f32o) {                          // (fp32 out: split-precision mode / two-pass GroupNorm fallback)
-                            if (st && p.stat_cols == 4) epilogue_rowmajor<F16, true, false, 4, 1>(p, tile, lane, wrow0, col0, slab, b4, par);
-                            else if (st) epilogue_rowmajor<F16, true, false, 2, 1>(p, tile, lane, wrow0, col0, slab, b4, par);
-                            else epilogue_rowmajor<F16, true, false, 0, 1>(p, tile, lane, wrow0, col0, slab, b4, par);
-                        } else if (st && p.stat_cols == 4) epilogue_rowmajor<F16, false, false, 4, 1>(p, tile, lane, wrow0, col0, slab, b4, par);
-                        else if (st) epilogue_rowmajor<F16, false, false, 2, 1>(p, tile, lane, wrow0, col0, slab, b4, par);
-                        else epilogue_rowmajor<F16, false, false, 0, 1>(p, tile, lane, wrow0, col0, slab, b4, par);
-                    } else if (p.resid_up) {                 // conv2 of an upsampling block: residual gathered from the low-res stream
-                        if (st && p.stat_cols == 4) epilogue_rowmajor<F16, true, true, 4, 2>(p, tile, lane, wrow0, col0, slab, b4, par);
-                        else if (st) epilogue_rowmajor<F16, true, true, 2, 2>(p, tile, lane, wrow0, col0, slab, b4, par);
-                        else epilogue_rowmajor<F16, true, true, 0, 2>(p, tile, lane, wrow0, col0, slab, b4, par);
-                    } else if (f32o) {
-                        if (resid && st && p.stat_cols == 4) epilogue_rowmajor<F16, true, true, 4, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
-                        else if (resid && st) epilogue_rowmajor<F16, true, true, 2, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
-                        else if (resid) epilogue_rowmajor<F16, true, true, 0, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
-                        else if (st && p.stat_cols == 4) epilogue_rowmajor<F16, true, false, 4, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
-                        else if (st) epilogue_rowmajor<F16, true, false, 2, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
-                        else epilogue_rowmajor<F16, true, false, 0, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
-                    } else {
-                        if (st && p.stat_cols == 4) epilogue_rowmajor<F16, false, false, 4, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
-                        else if (st) epilogue_rowmajor<F16, false, false, 2, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
-                        else epilogue_rowmajor<F16, false, false, 0, 0>(p, tile, lane, wrow0, col0, slab, b4, par);
+#define VDT_EPI(F32, RES, ST, MAP) epilogue_rowmajor<F16, F32, RES, ST, MAP>(p, tile, lane, wrow0, col0, slab, b4, par); break
+                    switch (all_valid ? variant : -1) {      // ragged tiles take the run-time checked generic path
+                        case 0: VDT_EPI(true, true, 4, 0);   case 1: VDT_EPI(true, true, 2, 0);   case 2: VDT_EPI(true, true, 0, 0);
+                        case 3: VDT_EPI(true, false, 4, 0);  case 4: VDT_EPI(true, false, 2, 0);  case 5: VDT_EPI(true, false, 0, 0);
+                        case 6: VDT_EPI(false, false, 4, 0); case 7: VDT_EPI(false, false, 2, 0); case 8: VDT_EPI(false, false, 0, 0);
+                        // sub-pixel upsampling conv1: rows scattered to their high-resolution positions, no residual
+                        case 9: VDT_EPI(true, false, 4, 1);   case 10: VDT_EPI(true, false, 2, 1);  case 11: VDT_EPI(true, false, 0, 1);
+                        case 12: VDT_EPI(false, false, 4, 1); case 13: VDT_EPI(false, false, 2, 1); case 14: VDT_EPI(false, false, 0, 1);
+                        // conv2 of an upsampling block: residual gathered from the low-resolution stream
+                        case 15: VDT_EPI(true, true, 4, 2);   case 16: VDT_EPI(true, true, 2, 2);   case 17: VDT_EPI(true, true, 0, 2);
+                        default: epilogue_rowmajor_generic(p, tile, lane, q, m_tile, wrow0, col0, b4, par); break;
                     }
+#undef VDT_EPI
                     __syncwarp();
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&acc_empty[acc], 0);   // the leader's MMA thread waits for both CTAs' drains
+            if (nkc <= 0) {                                  // a warp without a chunk in this tile still has to arrive
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(&acc_empty[acc], 0);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }

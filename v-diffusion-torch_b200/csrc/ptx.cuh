@@ -120,6 +120,28 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
         : "memory");
 }
 
+// Same without release semantics: no memory barrier is generated.  For hand-offs whose payload is not generic-proxy
+// memory (e.g. "this warp's tcgen05.ld of the accumulator have completed": ordered by tcgen05.wait::ld and
+// tcgen05.fence::before_thread_sync), where a release fence would only make the warp wait for its own global stores.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+// 16-byte shared-memory accesses by 32-bit shared address (a pointer that went through integer arithmetic loses its
+// address space and would be accessed with generic LD / ST, which take the slow path for shared memory)
+__device__ __forceinline__ void sts_v4(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // ---- clusters ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
