@@ -92,7 +92,8 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, uint32_t 
         for (int i = 0; i < 8; ++i) {
             if (MAP == 2) {
                 const int pix = pix0 + 4 * i;
-                const long long src = (img << (2 * sh - 2)) + ((pix >> (sh + 1)) << (sh - 1)) + ((pix & wmask) >> 1);
+                const int shl = (MAP == 2) ? sh - 1 : 0;           // log2 of the low-resolution width
+                const long long src = (img << (2 * shl)) + ((pix >> (sh + 1)) << shl) + ((pix & wmask) >> 1);
                 res[i] = ldg_nc_v4_issue(p.residual + static_cast<size_t>(src) * p.ld + colo);
             } else {
                 res[i] = ldg_nc_v4_issue(p.residual + off0 + i * step);

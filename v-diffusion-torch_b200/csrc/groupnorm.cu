@@ -6,14 +6,17 @@
 // and the channel concat feeding it (unet.py:315) by reading two sources.
 //
 // Statistics: normally the producing conv epilogue has already written per-(32-row slab, 4-channel)
-// partial (sum, sum of squares) next to the tensor (ConvParams::stats); this kernel combines the
-// partials of its image in a fixed order (deterministic, fp64) and is then a single streaming pass:
-// read fp32 (or 16-bit) once, write the 16-bit operand once.  Images are split over several CTAs.
+// partial (sum, sum of squares) next to the tensor (ConvParams::stats); a tiny finalize launch combines the
+// partials of every image in a fixed order (deterministic, fp64) and the apply kernel is then a single
+// streaming pass: read fp32 (or 16-bit) once, write the 16-bit operand once.  Images are split over several CTAs.
 // Fallback (groups that are not a multiple of 4 channels, or a concat seam inside a group): one CTA
 // per sample makes its own statistics pass first (thread t owns VEC consecutive channels of one
 // group and every PPH-th pixel; private fp32 partials combined once through shared memory).
 // Optionally also writes the raw concat in 16 bits (operand of the 1x1 skip conv) and the resampled
 // raw input in fp32 (identity-skip residual of a resampling block).
+#include <atomic>
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -114,13 +117,13 @@ __device__ __forceinline__ void store_f32(float* p, const float (&v)[VEC]) {
     }
 }
 
-// Combines the conv epilogue's partial statistics of one image into (mean, rstd) per group: 8 threads per
-// group, fixed summation order, fp64.  Works for any even channels-per-group and for groups that straddle the
-// seam of a channel concat.
-__global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const GroupNormParams p) {
-    const int b = blockIdx.x, tid = threadIdx.x;
+// Combines the conv epilogue's partial statistics of one image into (mean, rstd) of group g: the eight threads
+// part8 = 0..7 of an aligned 8-lane group each walk every eighth entry in a fixed order (fp64), then combine with a
+// fixed shuffle tree -- deterministic, independent of how the image is split over CTAs.  Works for any channels-per-
+// group that is a multiple of stat_cols and for groups that straddle the seam of a channel concat.  All 8 lanes return
+// the result.
+__device__ __forceinline__ float2 group_mean_rstd(const GroupNormParams& p, int b, int g, int part8) {
     const int C = p.C1 + p.C2, HW = p.H * p.W, cpg = C / kGroups;
-    const int g = tid >> 3, part8 = tid & 7;
     // entries of stat_cols channels; a group may straddle the concat seam, so each entry picks its source
     const int sc = p.stat_cols, sub = cpg / sc, slabs = p.stat_slabs;
     const int e1 = p.C1 / sc, e2 = p.C2 / sc;              // entries per slab in source 1 / 2
@@ -154,13 +157,20 @@ __global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const GroupNorm
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) { ds += __shfl_xor_sync(0xffffffffu, ds, o); dss += __shfl_xor_sync(0xffffffffu, dss, o); }
-    if (part8 == 0) {
-        const double n = static_cast<double>(cpg) * HW;
-        const double mean = ds / n;
-        double var = dss / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        p.meanrstd[b * kGroups + g] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(kEps))));
-    }
+    const double n = static_cast<double>(cpg) * HW;
+    const double mean = ds / n;
+    double var = dss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    return make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(kEps))));
+}
+
+// One 256-thread CTA per image: (mean, rstd) of the 32 groups from the conv epilogue's partials.  A separate, tiny launch:
+// folding this into every CTA of the apply kernel was measured slower (+6 ms per step: the dependent prologue delays each
+// CTA's first loads) than the 73 launch latencies it saves.
+__global__ void __launch_bounds__(256) groupnorm_finalize_kernel(const GroupNormParams p) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float2 mr = group_mean_rstd(p, b, tid >> 3, tid & 7);
+    if ((tid & 7) == 0) p.meanrstd[b * kGroups + (tid >> 3)] = mr;
 }
 
 template <int VEC, bool FUSED, bool IN16, bool F16>
@@ -391,7 +401,39 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
 
 }  // namespace
 
+// The SM's L1 / shared-memory split is configured per kernel, and two kernels only share an SM when they agree on it.  The
+// conv and attention kernels need (almost) all of it as shared memory; asking for the same carve-out here (VDT_GN_CARVEOUT=1)
+// lets GroupNorm CTAs of one lane run next to a resident conv CTA of the other lane (plan.cu: vdt_plan::lanes).  Measured on
+// one box (profiles/r2h_lanes_carveout_ab.txt): the kernel itself loses 12 % without its L1 (83.4 -> 93.5 ms per step),
+// which the overlap (+1.6 %) does not pay back, so the default keeps the driver's split.
+template <typename K>
+static cudaError_t prefer_smem_carveout(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+static cudaError_t configure_groupnorm_kernels() {
+    static std::atomic<bool> done[kMaxDevices];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    const char* on = getenv("VDT_GN_CARVEOUT");              // default: leave the driver's split
+    if (!(on && on[0] == '1')) { done[dev].store(true, std::memory_order_release); return cudaSuccess; }
+#define VDT_GN_CFG(V, FU, I16, F) if (e == cudaSuccess) e = prefer_smem_carveout(groupnorm_kernel<V, FU, I16, F>)
+    VDT_GN_CFG(4, true, true, true);   VDT_GN_CFG(4, true, true, false);  VDT_GN_CFG(4, true, false, true);  VDT_GN_CFG(4, true, false, false);
+    VDT_GN_CFG(2, true, true, true);   VDT_GN_CFG(2, true, true, false);  VDT_GN_CFG(2, true, false, true);  VDT_GN_CFG(2, true, false, false);
+    VDT_GN_CFG(4, false, false, true); VDT_GN_CFG(4, false, false, false); VDT_GN_CFG(2, false, false, true); VDT_GN_CFG(2, false, false, false);
+#undef VDT_GN_CFG
+    if (e == cudaSuccess) e = prefer_smem_carveout(groupnorm_finalize_kernel);
+    if (e == cudaSuccess) done[dev].store(true, std::memory_order_release);
+    return e;
+}
+
 cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream) {
+    {
+        const cudaError_t ce = configure_groupnorm_kernels();
+        if (ce != cudaSuccess) return ce;
+    }
     const int C = p.C1 + p.C2;
     if (C % kGroups != 0 || p.B <= 0) return cudaErrorInvalidValue;
     const int cpg = C / kGroups;
@@ -404,7 +446,15 @@ cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream) {
     if (fused && (p.stat_slabs != stat_slabs_per_image(p.H, p.W) || p.stat_slabs <= 0 || (p.stat_cols != 2 && p.stat_cols != 4) || cpg % p.stat_cols != 0 ||
                   p.C1 % p.stat_cols != 0 || (p.C2 > 0 && p.stats2 == nullptr))) return cudaErrorInvalidValue;
     if (p.in16 && (p.C2 != 0 || !fused)) return cudaErrorInvalidValue;
-    int PPH = 1024 / CV;
+    // threads per CTA: 256 by default (16 K registers, ~1 KB of shared memory), so that a GroupNorm CTA fits on an SM next
+    // to a resident conv / attention CTA of the other lane (plan.cu: vdt_plan::lanes); VDT_GN_THREADS overrides
+    static int max_threads = 0;
+    if (max_threads == 0) {
+        const char* e = getenv("VDT_GN_THREADS");
+        max_threads = e ? atoi(e) : 256;
+        if (max_threads < 32 || max_threads > 1024) max_threads = 256;
+    }
+    int PPH = (max_threads > CV ? max_threads : CV) / CV;
     const int work = (p.resample == kResDown) ? HW / 4 : HW;
     if (PPH > work) PPH = work;
     if (PPH > 8) PPH = 8;                             // >= 8 pixels of work per thread at 32x32 / 256 ch

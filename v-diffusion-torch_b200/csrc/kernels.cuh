@@ -97,7 +97,8 @@ struct GroupNormParams {
     const float* src2; int C2;         // fp32 [B, HW, C2] or null: channels C1..C1+C2 (virtual concat)
     int in16;                          // src1 holds 16-bit values in the launch's operand format (C2 must be 0)
     // partial statistics written by the producing conv epilogue (ConvParams::stats); when stats1 is set the
-    // kernel is a single streaming pass, otherwise it makes a statistics pass of its own
+    // kernel is a single streaming pass (after a tiny finalize launch that combines the partials of every image into the
+    // 32 (mean, rstd) pairs in a fixed order), otherwise it makes a statistics pass of its own
     const float2* stats1; const float2* stats2;
     int stat_cols;                     // columns per statistics entry (4, or 2 when groups are not a multiple of 4 channels)
     int stat_slabs;                    // statistics slabs per image = stat_slabs_per_image(H, W)

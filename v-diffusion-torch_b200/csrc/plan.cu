@@ -348,13 +348,23 @@ struct vdt_plan {
     // cannot be captured); ordering against the caller's stream is kept with two events
     cudaStream_t work = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    // The chunks of a sampling batch are independent samples: they alternate between two lanes (streams, each with its
+    // own workspace and step graph), so that one chunk's HBM-bound kernels (GroupNorm, small-N attention, 1x1 GEMMs)
+    // can run on the SMs' spare warps while the other chunk's tensor-bound conv kernel holds the tensor cores.
+    int lanes = 2;
+    cudaStream_t work2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     ~vdt_plan() {
         if (work) cudaStreamSynchronize(work);
+        if (work2) cudaStreamSynchronize(work2);
         execs.clear();
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         if (work) cudaStreamDestroy(work);
+        if (work2) cudaStreamDestroy(work2);
         for (auto& w : weights) if (w.dev) cudaFree(w.dev);
         for (void* p : owned) cudaFree(p);
     }
@@ -464,6 +474,8 @@ extern "C" int vdt_plan_create(const vdt_unet_config* cfg, vdt_plan** out) {
     p->split = c.operand_dtype == 2;
     const char* ng = getenv("VDT_NO_GRAPH");
     p->use_graph = !(ng && ng[0] == '1');
+    const char* ln = getenv("VDT_LANES");
+    if (ln && ln[0] == '1') p->lanes = 1;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
         int n = 0;
@@ -583,6 +595,7 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
     for (auto& w : p->weights)
         if (!w.loaded) return fail("missing key in state_dict: %s", w.name.c_str());
     if (p->work) CK(cudaStreamSynchronize(p->work));        // re-finalize after re-loading a key: nothing may still run
+    if (p->work2) CK(cudaStreamSynchronize(p->work2));
     p->execs.clear();
     for (void* q : p->owned) cudaFree(q);
     p->owned.clear();
@@ -1186,6 +1199,7 @@ static int exec_cache_make_room(vdt_plan* p) {
         for (auto it = p->execs.begin(); it != p->execs.end(); ++it)
             if (it->second->last_use < victim->second->last_use) victim = it;
         if (p->work) CK(cudaStreamSynchronize(p->work));
+        if (p->work2) CK(cudaStreamSynchronize(p->work2));
         p->execs.erase(victim);
     }
     return 0;
@@ -1343,14 +1357,14 @@ extern "C" int vdt_step_coefficients(const vdt_sampler_config* scp, float* out) 
 }
 
 // ================================================================================================ sampler
-static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs, bool has_label, Exec** out) {
+static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs, bool has_label, int lane, Exec** out) {
     const bool cfg = sc.w_guide > 0.0 && has_label;            // diffusion.py:368
     const int rep = cfg ? 2 : 1;
     // the key holds what shapes the workspace, the coefficient table and the kernel parameters baked into the graph;
     // per-call values (seed, injected-noise tensor, fp32-t mode of p_sample_progressive) live in the device-side
     // SamplerState and are rewritten before every call
     char key[192];
-    snprintf(key, sizeof(key), "smp:%d:%d:%d:%d:%d:%d:%d:%d:%d:%.17g:%.17g:%.17g:%.17g", imgs, (int)has_label,
+    snprintf(key, sizeof(key), "smp%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%.17g:%.17g:%.17g:%.17g", lane, imgs, (int)has_label,
              sc.sample_timesteps, sc.model_out_type, sc.model_var_type, sc.logsnr_schedule, sc.use_ddim, sc.x0eps_coef, sc.t_fp32,
              sc.intp_frac, sc.logsnr_min, sc.logsnr_max, sc.w_guide);
     CKI(exec_cache_lookup(p, key, out));
@@ -1421,10 +1435,24 @@ extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, fl
     const int64_t* row_label = (c.num_classes > 0 && !mt) ? static_cast<const int64_t*>(label) : nullptr;   // an unconditional UNet ignores y (unet.py:289)
     const int rep = cfg ? 2 : 1;
     const int chunk = std::max(1, c.max_rows / rep);
-    for (int i0 = 0; i0 < batch; i0 += chunk) {
+    const int nchunks = (batch + chunk - 1) / chunk;
+    // two lanes when there is more than one chunk (per-launch profiling needs a single ordered stream)
+    const int lanes = (p->lanes > 1 && nchunks > 1 && !g_profile.load()) ? 2 : 1;
+    if (lanes == 2) {
+        if (!p->work2) {
+            CK(cudaStreamCreateWithFlags(&p->work2, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+        }
+        CK(cudaEventRecord(p->ev_fork, p->work));
+        CK(cudaStreamWaitEvent(p->work2, p->ev_fork, 0));
+    }
+    for (int i0 = 0, ci = 0; i0 < batch; i0 += chunk, ++ci) {
         const int imgs = std::min(chunk, batch - i0);
+        const int lane = ci % lanes;
+        st = lane ? p->work2 : p->work;
         Exec* ex;
-        CKI(get_sampler_exec(p, sc, imgs, label != nullptr, &ex));
+        CKI(get_sampler_exec(p, sc, imgs, label != nullptr, lane, &ex));
         CK(cudaMemcpyAsync(ex->xin, x + (size_t)i0 * CHW, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
         if (mt) {
             const int n = ex->rows * c.num_classes;
@@ -1443,6 +1471,10 @@ extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, fl
         CK(cudaMemcpyAsync(x + (size_t)i0 * CHW, ex->xin, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
         if (pred_x0 && num_steps > 0)
             CK(cudaMemcpyAsync(pred_x0 + (size_t)i0 * CHW, ex->pred, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (lanes == 2) {
+        CK(cudaEventRecord(p->ev_join, p->work2));
+        CK(cudaStreamWaitEvent(p->work, p->ev_join, 0));
     }
     return leave_work(p, user);
 }
