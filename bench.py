@@ -403,17 +403,21 @@ def run_b200(args, rank, world, local_rank):
     conv_tflops = fc.value * rows / (fam_ms[0] * 1e-3) / 1e12 if fam_ms[0] > 0 else 0.0
     peaks = read_peaks()
     prof_total = sum(fam_ms)
-    # DRAM bytes per conv launch from the committed `ncu` capture of this same step (profiles/), scaled by rows
-    traffic = None
+    # DRAM bytes per conv launch: cannot be measured outside a profiler, so it comes from the committed ncu capture of
+    # this same step (scripts/gpu_profile_round.sh + summarize_profiles.py write it with the commit it was taken on)
+    traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_conv_dram_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_conv_dram_traffic.json")) as f:
             tr = json.load(f)
-        traffic = tr["avg_dram_bytes_per_conv_launch_scaled_to_rows"] * min(rows, args.max_rows) / tr["rows"] if wl is None else None
+        if wl is None:
+            traffic = tr["avg_dram_bytes_per_conv_launch_scaled_to_rows"] * min(rows, args.max_rows) / tr["rows"]
+            traffic_src = f"profiles/r2_conv_dram_traffic.json (ncu capture at commit {tr.get('git_head')}, {tr.get('summarised_utc')})"
     except Exception:
         traffic = None
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all conv/1x1 launches of a step)",
                 "achieved": conv_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": conv_tflops / peaks["tflops"],
                 "peak_source": peaks["source"] + " sustained bf16 cuBLAS", "traffic": traffic,
+                "traffic_source": traffic_src,
                 "traffic_note": "avg dram__bytes_read+write per conv launch (ncu, one chunk of chunk_rows UNet rows); "
                                 "launches_per_step counts every chunk's launches",
                 "algorithmic_flop_per_launch_avg": fc.value * rows / max(1, fam_n[0]),

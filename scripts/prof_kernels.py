@@ -71,6 +71,24 @@ def attn_case(N, d):
     print(f"attention N={N} d={d}: {ms:.3f} ms {fl / ms / 1e9 if ms else 0:.0f} TFLOP/s")
 
 
+def sampler_case(B=4096, C=3, H=32):
+    """the fused per-step sampler update at BASELINE configs[1] size: v (2B rows), x_t in, x_s out"""
+    from v_diffusion_b200 import GaussianDiffusion, get_logsnr_schedule
+    diff = GaussianDiffusion(get_logsnr_schedule("cosine"), 100, "v", "fixed_medium", "snr_trunc", "mse", intp_frac=0.3, w_guide=1.0)
+    coefs = diff.step_coefficients(use_ddim=True)
+    mo = torch.randn(2 * B, C, H, H, device=dev, generator=g)
+    x = torch.randn(B, C, H, H, device=dev, generator=g)
+    out = torch.empty_like(x)
+    row = coefs[50].contiguous()
+    ms = timed(lambda: L.vdt_op_sampler_step(p(mo), p(x), None, p(out), B, C, H * H, 1, 3, 50, p(row), 1.0, None), 5)
+    byts = 4.0 * B * C * H * H * 4
+    print(f"sampler_step B={B} CFG: {ms:.4f} ms {byts / ms / 1e6 if ms else 0:.0f} GB/s (the hook allocates / frees its state and syncs)")
+
+
+if "--sampler" in sys.argv:
+    sampler_case()
+    torch.cuda.synchronize()
+    sys.exit(0)
 if "--small" in sys.argv:
     conv_case(32, 64, 256, 1, False, True)                 # in_conv-like: K = 64, fp32 out + stats
     conv_case(16, 256, 512, 1, False, False, out16=True)   # q|k projection: K = 256, 16-bit out
