@@ -90,6 +90,12 @@ int vdt_plan_finalize(vdt_plan* plan);
 int vdt_unet_forward(vdt_plan* plan, const float* x, const double* t, const void* y, float* out, int32_t batch,
                      void* stream);
 
+/* UNet.forward in .train() mode: the same network with nn.Dropout(drop_rate, inplace=True) active between act2 and conv2 of
+ * every ResidualBlock (unet.py:135, 146).  The masks come from this library's Philox4x32-10 stream keyed by (seed, block,
+ * element); drop_rate = 0 is bit-identical to vdt_unet_forward.  Forward only: the UNet backward is not part of this slice. */
+int vdt_unet_forward_train(vdt_plan* plan, const float* x, const double* t, const void* y, float* out, int32_t batch,
+                           float drop_rate, uint64_t seed, void* stream);
+
 /* GaussianDiffusion.p_sample(denoise_fn=UNet, shape, noise, label, use_ddim) — diffusion.py:394-414,
  * with p_sample_step (360-392) and p_mean_var (317-356) fused into one kernel per step and the step
  * captured as a CUDA graph.  noise fp32 [B, C, R, R] (x_T); label NULL, int64 [B], or fp32 multi-hot [B, num_classes] (multitags); step_noise NULL or
@@ -108,6 +114,20 @@ int vdt_p_sample_range(vdt_plan* plan, const vdt_sampler_config* sc, float* x, c
 /* Same with HOST buffers (pinned or pageable); copies in/out inside the call and synchronises. */
 int vdt_p_sample_host(vdt_plan* plan, const vdt_sampler_config* sc, const float* noise, const void* label,
                       const float* step_noise, float* out, int32_t batch);
+
+/* ---- training step, first slice: GaussianDiffusion.train_loss around the model call (diffusion.py:492-545) ------- */
+enum { VDT_REWEIGHT_CONSTANT = 0, VDT_REWEIGHT_SNR = 1, VDT_REWEIGHT_SNR_TRUNC = 2, VDT_REWEIGHT_SNR_1PLUS = 3 };
+/* Per-sample scalars from continuous times t in [0, 1] (HOST fp64 [B], Trainer.loss train_utils.py:137-147): out HOST
+ * [B][16] floats, the vdt_step_coefficients slots 0-5, 11-13 (alpha, sigma, rsqrt(sigmoid l), exp(-l/2), sigmoid l,
+ * sigmoid -l, l, rsqrt(sigmoid -l), exp(l/2)); only the schedule fields of sc are read. */
+int vdt_train_coefficients(const vdt_sampler_config* sc, const double* t_host, int32_t batch, float* out);
+/* q_sample (diffusion.py:242-245): x_t = x_0 * alpha_t + eps * sigma_t; device fp32 [B, C*H*W]; coef_dev = the table above on the device. */
+int vdt_q_sample(const float* x0, const float* noise, const float* coef_dev, float* x_t, int32_t batch, int32_t chw, void* stream);
+/* from_model_out_to_pred + the re-weighted MSE (diffusion.py:466-490, 518-541): loss fp32 [B]; grad_out (optional, shaped
+ * like model_out) receives d loss.mean() / d model_out, the tensor autograd would hand to the UNet's backward pass. */
+int vdt_train_loss(const float* model_out, const float* x0, const float* noise, const float* x_t, const float* coef_dev,
+                   float* loss, float* grad_out, int32_t batch, int32_t c, int32_t hw, int32_t model_out_type,
+                   int32_t reweight_type, void* stream);
 
 /* The tail of generate.py's batch loop (generate.py:149): fp32 NCHW samples -> uint8 NHWC pixels,
  * (x * 127.5 + 127.5).clamp(0, 255).to(uint8).permute(0, 2, 3, 1).  x fp32 [B, C, HW], out uint8 [B, HW, C]; device pointers. */
@@ -160,6 +180,11 @@ int vdt_op_groupnorm(const void* src1, int32_t c1, const float* src2, int32_t c2
                      const float* gamma, const float* beta, const float* film, int32_t film_stride, int32_t film_off,
                      int32_t silu, int32_t resample, void* out_act_16, void* out_raw_16, float* out_res,
                      int32_t f16, const void* stats1, const void* stats2, int32_t stat_cols, int32_t in16, void* stream);
+/* GroupNorm + SiLU with training dropout on a plain fp32 NHWC tensor (two-pass statistics): the op norm2 -> act2 -> dropout
+ * of a ResidualBlock in .train() mode, exposed for the mask-statistics test. */
+int vdt_op_groupnorm_dropout(const void* src1, int32_t c1, int32_t batch, int32_t h, int32_t w, const float* gamma,
+                             const float* beta, int32_t silu, void* out_act_16, int32_t f16, float drop_p, uint64_t seed,
+                             int32_t layer, void* stream);
 /* attention on qkv 16-bit [B*N, 3*hid] (q | k | v thirds, heads contiguous inside each, the layout proj_in writes)
  * -> 16-bit [B*N, hid]; any N >= 1 (ragged last key / query tiles are masked) */
 int vdt_op_attention(const void* qkv_16, void* out_16, int32_t batch, int32_t n, int32_t heads,

@@ -156,3 +156,30 @@ def full_state_dict(case, unet_cls):
         torch.set_rng_state(state)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     return dezero_(sd, case["dezero_seed"]), net
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GaussianDiffusion.train_loss (diffusion.py:492-545; BASELINE configs[4]): x_0 ~ U[-1, 1], t ~ U[0, 1) fp64, eps ~ N(0, 1),
+# labels 1..10.  The fixtures hold what the reference computes around the model call: x_t, the per-sample loss and the
+# autograd gradient of loss.mean() with respect to the model output.
+TRAIN_CASES = {
+    # the config[4] objective: v-prediction, truncated-SNR reweighting (max of the x0 and eps errors)
+    "v_snr_trunc": dict(unet="small_cond", seed=41, B=4, res=16, model_out_type="v", reweight_type="snr_trunc"),
+    "eps_snr_trunc": dict(unet="small_cond", seed=42, B=3, res=16, model_out_type="eps", reweight_type="snr_trunc"),
+    "x0_snr_trunc": dict(unet="small_cond", seed=43, B=3, res=16, model_out_type="x0", reweight_type="snr_trunc"),
+    "both_snr_trunc": dict(unet="small_hd64", seed=44, B=2, res=32, model_out_type="both", reweight_type="snr_trunc"),
+    # single-target reweightings compare the target with the RAW model output (diffusion.py:541), reproduced as is
+    "x0_constant": dict(unet="small_cond", seed=45, B=3, res=16, model_out_type="x0", reweight_type="constant"),
+    "eps_snr": dict(unet="small_cond", seed=46, B=3, res=16, model_out_type="eps", reweight_type="snr"),
+    "v_snr_1plus": dict(unet="small_cond", seed=47, B=3, res=16, model_out_type="v", reweight_type="snr_1plus"),
+}
+
+
+def build_train_inputs(case, cfg):
+    g = torch.Generator().manual_seed(case["seed"] + 3000)
+    shape = (case["B"], cfg["in_channels"], case["res"], case["res"])
+    x0 = torch.rand(shape, generator=g) * 2 - 1
+    t = torch.rand(case["B"], generator=g, dtype=torch.float64)
+    noise = torch.randn(shape, generator=g)
+    y = (torch.randint(10, (case["B"],), generator=g) + 1) if cfg["num_classes"] else None
+    return x0, t, noise, y

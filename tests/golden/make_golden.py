@@ -32,8 +32,8 @@ from v_diffusion.diffusion import logsnr_to_posterior, logsnr_to_posterior_ddim 
 from v_diffusion.functions import get_timestep_embedding  # noqa: E402
 
 from oracle.unet_ref import make_state_dict, state_dict_shapes  # noqa: E402
-from tests.cases import (UNET_CASES, SAMPLE_CASES, FULL_CASES, build_inputs, build_sample_inputs,  # noqa: E402
-                         build_full_inputs, full_state_dict)
+from tests.cases import (UNET_CASES, SAMPLE_CASES, FULL_CASES, TRAIN_CASES, build_inputs, build_sample_inputs,  # noqa: E402
+                         build_full_inputs, full_state_dict, build_train_inputs)
 
 torch.set_num_threads(os.cpu_count())
 
@@ -141,6 +141,32 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"full_{name}.npz"), out=x.numpy(), model_out=mo.numpy())
         print("full", name, tuple(x.shape), tuple(mo.shape), float(x.abs().mean()), float(x.abs().max()),
               f"{time.time() - t0:.1f}s")
+
+    # ---- train_loss (diffusion.py:492-545): x_t, per-sample loss, d loss.mean() / d model_out by the reference's autograd
+    for name, case in TRAIN_CASES.items():
+        cfg = UNET_CASES[case["unet"]]["cfg"]
+        net = ref_unet(cfg, UNET_CASES[case["unet"]]["seed"])
+        x0, t, noise, y = build_train_inputs(case, cfg)
+        diff = GaussianDiffusion(
+            logsnr_fn=get_logsnr_schedule("cosine", -20., 20., rescale=False), sample_timesteps=1000,
+            model_out_type=case["model_out_type"], model_var_type="fixed_large", reweight_type=case["reweight_type"],
+            loss_type="mse", p_uncond=0.1)
+        seen = {}
+
+        def fn(x_t, tt, yy):
+            with torch.no_grad():
+                o = net(x_t, tt, None if yy is None else yy.clone())
+            o = o.detach().requires_grad_(True)
+            seen["x_t"], seen["out"] = x_t.detach().clone(), o
+            return o
+        torch.manual_seed(case["seed"])                 # the p_uncond mask is drawn from the global CPU generator (:527-529)
+        yy = None if y is None else y.clone()
+        loss = diff.train_loss(fn, x_0=x0, t=t, y=yy, noise=noise)
+        loss.mean().backward()
+        np.savez_compressed(os.path.join(HERE, f"train_{name}.npz"), x_t=seen["x_t"].numpy(), model_out=seen["out"].detach().numpy(),
+                            loss=loss.detach().numpy(), grad_out=seen["out"].grad.numpy(),
+                            y_after=(yy.numpy() if yy is not None else np.zeros(0)))
+        print("train", name, loss.detach().numpy())
 
     # ---- coefficient known answers (T = 100, cosine +-20) straight from the reference functions
     T = 100

@@ -280,3 +280,38 @@ def test_sampler_step(L, mot, cfg, last):
     if not last:
         mean = mean + row[8].cuda() * z
     assert (out - mean).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("f16", [1, 0])
+def test_groupnorm_dropout_mask_statistics(L, f16):
+    """norm2 -> act2 -> dropout of a ResidualBlock in .train() mode (unet.py:135, 146): every surviving element equals the
+    un-dropped activation / (1 - p), the dropped fraction is p within sampling error, masks repeat for a (seed, layer) pair
+    and differ across seeds and layers."""
+    B, H, Cc, p = 4, 16, 256, 0.2
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, H, H, Cc, device="cuda", generator=g) * 1.7 + 0.3
+    gamma = torch.rand(Cc, device="cuda", generator=g) + 0.5
+    beta = torch.randn(Cc, device="cuda", generator=g) * 0.1
+
+    def run(seed, layer):
+        out = torch.zeros(B, H, H, Cc, device="cuda", dtype=DT[f16])
+        _check(L, L.vdt_op_groupnorm_dropout(_p(x), Cc, B, H, H, _p(gamma), _p(beta), 1, _p(out), f16, C.c_float(p), seed, layer, None))
+        torch.cuda.synchronize()
+        return out.float()
+    ref = F.silu(F.group_norm(x.permute(0, 3, 1, 2), 32, gamma, beta, 1e-6)).permute(0, 2, 3, 1)
+    a = run(11, 3)
+    kept = a != 0
+    frac = 1.0 - kept.float().mean().item()
+    n = a.numel()
+    assert abs(frac - p) < 5 * math.sqrt(p * (1 - p) / n) + 1e-3, frac      # (+ the few activations that are exactly 0)
+    err = ((a - ref / (1 - p)).abs() * kept).max().item()
+    assert err <= 3e-2 * EPS[f16] * 4
+    assert torch.equal(a, run(11, 3))
+    b, c = run(12, 3), run(11, 4)
+    for other in (b, c):
+        agree = ((other != 0) == kept).float().mean().item()
+        assert abs(agree - (p * p + (1 - p) ** 2)) < 0.01, agree             # independent masks agree with probability p^2 + (1-p)^2
+    # every channel and every pixel sees its share of drops (no structure along either axis)
+    per_c = 1.0 - kept.float().mean(dim=(0, 1, 2))
+    per_px = 1.0 - kept.float().mean(dim=3)
+    assert (per_c - p).abs().max().item() < 0.08 and (per_px - p).abs().max().item() < 0.15

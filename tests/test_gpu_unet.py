@@ -10,8 +10,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.cases import (UNET_CASES, SAMPLE_CASES, FULL_CASES, build_inputs, build_sample_inputs, build_full_inputs,
-                         full_state_dict)
+from tests.cases import (UNET_CASES, SAMPLE_CASES, FULL_CASES, TRAIN_CASES, build_inputs, build_sample_inputs,
+                         build_full_inputs, full_state_dict, build_train_inputs)
 from tests.cases import _cfg as _cfg_case
 
 pytestmark = pytest.mark.gpu
@@ -619,3 +619,72 @@ def test_generate_driver_end_to_end(tmp_path, world):
     diffpix = (got.int() - want.int()).abs()
     print(f"generate x{world}: {int((diffpix > 0).sum())} of {diffpix.numel()} uint8 values differ, max {int(diffpix.max())}")
     assert int(diffpix.max()) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Training step, first slice: GaussianDiffusion.train_loss around the model call
+@pytest.mark.parametrize("name", sorted(TRAIN_CASES))
+def test_train_loss_vs_reference_golden(golden_dir, name):
+    """q_sample + from_model_out_to_pred + re-weighted MSE (diffusion.py:492-545) against the unmodified reference:
+    (1) with the reference's own model output injected, x_t, the per-sample loss and d loss.mean() / d model_out (the
+    reference's autograd) must agree to fp32 rounding; (2) with this package's UNet as denoise_fn the loss agrees within
+    the operand format's accuracy.  The p_uncond label dropout acts on the caller's y after the model call only."""
+    from v_diffusion_b200 import GaussianDiffusion, get_logsnr_schedule
+    case = TRAIN_CASES[name]
+    ucase = UNET_CASES[case["unet"]]
+    cfg = ucase["cfg"]
+    g = np.load(os.path.join(golden_dir, f"train_{name}.npz"))
+    x0, t, noise, y = build_train_inputs(case, cfg)
+    diff = GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), 1000, case["model_out_type"], "fixed_large",
+                             case["reweight_type"], "mse", p_uncond=0.1)
+    ref_out = torch.from_numpy(g["model_out"]).cuda()
+    seen = {}
+
+    def injected(x_t, tt, yy):
+        seen["x_t"] = x_t.clone()
+        return ref_out
+    torch.manual_seed(case["seed"])                        # the label-dropout mask comes from the global CPU generator
+    yy = None if y is None else y.clone().cuda()
+    loss, grad = diff.train_loss(injected, x0.cuda(), t, yy, noise=noise.cuda(), return_grad=True)
+    assert (seen["x_t"].cpu() - torch.from_numpy(g["x_t"])).abs().max().item() <= 1e-6
+    np.testing.assert_allclose(loss.cpu().numpy(), g["loss"], rtol=2e-6)
+    ref_grad = torch.from_numpy(g["grad_out"])
+    assert (grad.cpu() - ref_grad).abs().max().item() <= 2e-6 * max(1.0, ref_grad.abs().max().item())
+    if y is not None:
+        assert np.array_equal(yy.cpu().numpy(), g["y_after"])   # same mask, same in-place side effect, loss unaffected
+    # (2) the CUDA UNet as the model (eval mode: the fixture's reference ran in eval mode too)
+    for operand, tol in (("fp16", 1e-2), ("fp16x3", 1e-4)):
+        net = _model(cfg, ucase["seed"], operand=operand)
+        l2 = diff.train_loss(net, x0.cuda(), t.cuda(), None if y is None else y.clone().cuda(), noise=noise.cuda())
+        rel = ((l2.cpu() - torch.from_numpy(g["loss"])).abs() / torch.from_numpy(g["loss"])).max().item()
+        print(f"train_loss {name} [{operand}]: worst relative loss error {rel:.3e}")
+        assert rel <= tol
+
+
+def test_train_mode_forward_dropout():
+    """UNet.forward in .train() mode (nn.Dropout(drop_rate, inplace=True) between act2 and conv2, unet.py:135, 146): with
+    drop_rate = 0 it is bit-identical to .eval(); with drop_rate > 0 the masks follow the per-call seed drawn from torch's
+    global generator (reproducible under manual_seed, fresh otherwise) and the output stays a perturbation of the eval one."""
+    from oracle.unet_ref import make_state_dict
+    from v_diffusion_b200 import UNet
+    case = UNET_CASES["small_cond"]
+    cfg = case["cfg"]
+    x, t, y = build_inputs(case)
+
+    def build(drop):
+        net = UNet(cfg["in_channels"], cfg["hid_channels"], cfg["out_channels"], cfg["ch_multipliers"], cfg["num_res_blocks"],
+                   cfg["apply_attn"], embedding_dim=cfg["embedding_dim"], drop_rate=drop, head_dim=cfg["head_dim"],
+                   num_heads=cfg["num_heads"], num_classes=cfg["num_classes"])
+        net.load_state_dict(make_state_dict(cfg, case["seed"]), strict=True)
+        return net.cuda()
+    ev = build(0.2).eval()(x.cuda(), t.cuda(), y.cuda())
+    assert torch.equal(build(0.0).train()(x.cuda(), t.cuda(), y.cuda()), ev)
+    net = build(0.2).train()
+    torch.manual_seed(3); a = net(x.cuda(), t.cuda(), y.cuda())
+    torch.manual_seed(3); b = net(x.cuda(), t.cuda(), y.cuda())
+    c = net(x.cuda(), t.cuda(), y.cuda())
+    assert torch.equal(a, b) and not torch.equal(a, c) and torch.isfinite(a).all()
+    rel = ((a - ev).norm() / ev.norm()).item()
+    print(f"train-mode forward, drop 0.2: rel-L2 distance to the eval output {rel:.3f}")
+    assert 0.02 < rel < 1.5
+    assert torch.equal(net.eval()(x.cuda(), t.cuda(), y.cuda()), ev)          # .eval() switches it off again

@@ -21,6 +21,7 @@ VAR_TYPES = {"fixed_small": 0, "fixed_large": 1, "fixed_medium": 2}
 SCHEDULES = {"cosine": 0, "linear": 1, "sigmoid": 2, "legacy": 3}
 COEF_STRIDE = 16
 OPERAND_DTYPES = {"fp16": 0, "bf16": 1, "fp16x3": 2}
+REWEIGHT_TYPES = {"constant": 0, "snr": 1, "snr_trunc": 2, "snr_1plus": 3}
 
 
 class UNetConfig(C.Structure):
@@ -110,6 +111,11 @@ def lib():
     L.vdt_op_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.vdt_op_sampler_step.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, C.c_float, vp]
     L.vdt_stat_slabs_per_image.argtypes = [i32, i32]
+    L.vdt_unet_forward_train.argtypes = [vp, vp, vp, vp, vp, i32, C.c_float, C.c_uint64, vp]
+    L.vdt_op_groupnorm_dropout.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, C.c_float, C.c_uint64, i32, vp]
+    L.vdt_train_coefficients.argtypes = [C.POINTER(SamplerConfig), vp, i32, vp]
+    L.vdt_q_sample.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+    L.vdt_train_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.vdt_images_to_uint8.argtypes = [vp, vp, i32, i32, i32, vp]
     L.vdt_plan_saturations.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
     _lib = L
@@ -121,7 +127,8 @@ EXPORTS = ["vdt_last_error", "vdt_version", "vdt_kernel_launches", "vdt_plan_cre
            "vdt_plan_finalize", "vdt_unet_forward", "vdt_p_sample", "vdt_p_sample_range", "vdt_p_sample_host",
            "vdt_step_coefficients", "vdt_plan_flops", "vdt_profile_enable", "vdt_profile_read",
            "vdt_op_conv", "vdt_op_groupnorm", "vdt_op_attention", "vdt_op_sampler_step", "vdt_stat_slabs_per_image",
-           "vdt_plan_saturations", "vdt_images_to_uint8"]
+           "vdt_plan_saturations", "vdt_images_to_uint8",
+           "vdt_train_coefficients", "vdt_q_sample", "vdt_train_loss", "vdt_unet_forward_train", "vdt_op_groupnorm_dropout"]
 
 
 def check(rc):

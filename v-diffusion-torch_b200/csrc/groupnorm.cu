@@ -276,6 +276,20 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
         }
     };
 
+    // training dropout (only ever on an un-resampled norm2 output): one Philox call per (pixel, 4-channel vector)
+    const bool drop = p.drop_p > 0.f;
+    const uint32_t drop_thr = drop ? static_cast<uint32_t>(fminf(p.drop_p, 0.99999994f) * 4294967296.0f) : 0u;
+    const float drop_scale = drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    const unsigned long long dseed = drop ? *p.drop_seed : 0ull;
+    auto dropout = [&](float (&y)[VEC], int pix) {
+        const unsigned long long e = (static_cast<unsigned long long>(b) * HW + pix) * C + c;      // first element of the vector
+        const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(e >> 2), static_cast<uint32_t>(e >> 34), static_cast<uint32_t>(p.drop_layer), 0x44524f50u),
+                                   make_uint2(static_cast<uint32_t>(dseed), static_cast<uint32_t>(dseed >> 32)));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) y[i] = (w[(VEC == 4) ? i : ((c >> 1) & 1) * 2 + i] < drop_thr) ? 0.f : y[i] * drop_scale;
+    };
+
     if (p.resample == kResDown) {
         const int Wo = p.W / 2, HWo = HW / 4;
         h16* oa = p.out_act + static_cast<size_t>(b) * HWo * C + c;
@@ -345,6 +359,7 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
                         for (int i = 0; i < VEC; ++i) amax = fmaxf(amax, fabsf(x[i]));
                     }
                     norm_act(x, y);
+                    if (drop) dropout(y, pix + u * PPH);
                     store_16n<VEC>(oa + static_cast<size_t>(pix + u * PPH) * C, y, (F16 ? 1 : 0));
                 }
             }
@@ -355,13 +370,13 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             load_px(pix + PPH, x1);
             load_px(pix + 2 * PPH, x2);
             load_px(pix + 3 * PPH, x3);
-            norm_act(x0, y); store_16n<VEC>(oa + static_cast<size_t>(pix) * C, y, (F16 ? 1 : 0));
+            norm_act(x0, y); if (drop) dropout(y, pix); store_16n<VEC>(oa + static_cast<size_t>(pix) * C, y, (F16 ? 1 : 0));
             if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix) * C, y, (F16 ? 1 : 0));
-            norm_act(x1, y); store_16n<VEC>(oa + static_cast<size_t>(pix + PPH) * C, y, (F16 ? 1 : 0));
+            norm_act(x1, y); if (drop) dropout(y, pix + PPH); store_16n<VEC>(oa + static_cast<size_t>(pix + PPH) * C, y, (F16 ? 1 : 0));
             if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + PPH) * C, y, (F16 ? 1 : 0));
-            norm_act(x2, y); store_16n<VEC>(oa + static_cast<size_t>(pix + 2 * PPH) * C, y, (F16 ? 1 : 0));
+            norm_act(x2, y); if (drop) dropout(y, pix + 2 * PPH); store_16n<VEC>(oa + static_cast<size_t>(pix + 2 * PPH) * C, y, (F16 ? 1 : 0));
             if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + 2 * PPH) * C, y, (F16 ? 1 : 0));
-            norm_act(x3, y); store_16n<VEC>(oa + static_cast<size_t>(pix + 3 * PPH) * C, y, (F16 ? 1 : 0));
+            norm_act(x3, y); if (drop) dropout(y, pix + 3 * PPH); store_16n<VEC>(oa + static_cast<size_t>(pix + 3 * PPH) * C, y, (F16 ? 1 : 0));
             if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix + 3 * PPH) * C, y, (F16 ? 1 : 0));
             if (ow) {
                 if (F16) {
@@ -382,6 +397,7 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
             float x0[VEC], y0[VEC];
             load_px(pix, x0);
             norm_act(x0, y0);
+            if (drop) dropout(y0, pix);
             store_16n<VEC>(oa + static_cast<size_t>(pix) * C, y0, (F16 ? 1 : 0));
             if (oa_lo) store_lo<VEC>(oa_lo + static_cast<size_t>(pix) * C, y0, (F16 ? 1 : 0));
             if (ow) {
@@ -446,6 +462,7 @@ cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream) {
     if (fused && (p.stat_slabs != stat_slabs_per_image(p.H, p.W) || p.stat_slabs <= 0 || (p.stat_cols != 2 && p.stat_cols != 4) || cpg % p.stat_cols != 0 ||
                   p.C1 % p.stat_cols != 0 || (p.C2 > 0 && p.stats2 == nullptr))) return cudaErrorInvalidValue;
     if (p.in16 && (p.C2 != 0 || !fused)) return cudaErrorInvalidValue;
+    if (p.drop_p > 0.f && (p.resample != kResNone || p.drop_seed == nullptr || p.drop_p >= 1.f)) return cudaErrorInvalidValue;
     // threads per CTA: 256 by default (16 K registers, ~1 KB of shared memory), so that a GroupNorm CTA fits on an SM next
     // to a resident conv / attention CTA of the other lane (plan.cu: vdt_plan::lanes); VDT_GN_THREADS overrides
     static int max_threads = 0;

@@ -116,6 +116,12 @@ struct GroupNormParams {
     h16* out_act_lo;                  // split-precision mode: second halves, lo = round16(x - float(round16(x)))
     h16* out_raw_lo;
     float* out_res;                    // optional fp32 [B, H'W', C]: resampled raw input (identity-skip residual)
+    // training-mode dropout on the output activation (nn.Dropout(p, inplace=True) between act2 and conv2, unet.py:135,
+    // 146): element (sample, pixel, channel) is zeroed when its Philox4x32-10 word, keyed by (*drop_seed, drop_layer),
+    // falls below drop_p * 2^32, and scaled by 1 / (1 - drop_p) otherwise.  drop_p = 0: no dropout (sampling path).
+    float drop_p;
+    const unsigned long long* drop_seed;   // device word: rewritten before every training forward, read by the captured graph
+    int drop_layer;
     unsigned long long* sat_count;     // optional device counter of fp16 range events (see ConvParams::sat_count): raw
                                        // stream values clamped by out_raw's conversion, saturated 16-bit inputs read
 };
@@ -210,5 +216,15 @@ struct SamplerStepParams {
     int x0eps;                         // posterior mean = c1 * eps + c2 * x0, eps re-derived from the clipped x0
 };
 cudaError_t launch_sampler_step(const SamplerStepParams& p, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// Training-step kernels (train.cu): GaussianDiffusion.train_loss around the model call (diffusion.py:492-545)
+// ------------------------------------------------------------------------------------------------
+// coef: device [B][kCoefStride] rows of vdt_train_coefficients.  x_t = x_0 * alpha_t + eps * sigma_t per sample.
+cudaError_t launch_q_sample(const float* x0, const float* eps, const float* coef, float* x_t, int B, int chw, cudaStream_t stream);
+// per-sample re-weighted MSE (type: 0 x0, 1 eps, 2 both, 3 v; reweight: 0 constant, 1 snr, 2 snr_trunc, 3 snr_1plus) and,
+// when grad_out is given, d loss.mean() / d model_out
+cudaError_t launch_train_loss(const float* model_out, const float* x0, const float* noise, const float* x_t, const float* coef,
+                              float* loss, float* grad_out, int B, int C, int HW, int type, int reweight, cudaStream_t stream);
 
 }  // namespace vdt

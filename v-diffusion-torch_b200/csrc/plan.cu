@@ -215,6 +215,9 @@ __global__ void sampler_init_state_kernel(SamplerState* st, int next_step, int i
         st->noise = noise; st->noise_step_stride = noise_stride; st->seed = seed; st->pad = 0;
     }
 }
+__global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *p = v;
+}
 __global__ void iota_i64_kernel(int64_t* p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;
@@ -282,6 +285,8 @@ struct Exec {
     float* y_multi = nullptr;    // multitag labels: fp32 multi-hot [emb_rows, num_classes]
     int* film_row = nullptr;     // [rows] (sampler)
     SamplerState* state = nullptr;
+    unsigned long long* drop_seed = nullptr;   // training forward: seed of this call's dropout masks (device word read by the graph)
+    float drop_p = 0.f;
     float* pred = nullptr;       // sampler: (guided) x0 prediction of the last executed step [rows/rep, C, HW]
     float* coef_table = nullptr; // [T][kCoefStride] (sampler)
     // sampler signature this exec was built for
@@ -931,6 +936,9 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             g2.gamma = p->W(n + ".norm2.weight"); g2.beta = p->W(n + ".norm2.bias");
             g2.film = film; g2.film_row = film_row; g2.film_stride = p->film_total; g2.film_off = b.film_off;
             g2.silu = 1; g2.resample = kResNone; g2.out_act = a2;
+            if (ex->drop_p > 0.f) {                      // training mode: nn.Dropout between act2 and conv2 (unet.py:135, 146)
+                g2.drop_p = ex->drop_p; g2.drop_seed = ex->drop_seed; g2.drop_layer = (int)ex->gns.size();
+            }
             add_gn(g2);
             ex->release(h1);
             if (h1st) ex->release(h1st);
@@ -1205,9 +1213,9 @@ static int exec_cache_make_room(vdt_plan* p) {
     return 0;
 }
 
-static int get_forward_exec(vdt_plan* p, int rows, bool has_y, Exec** out) {
-    char key[64];
-    snprintf(key, sizeof(key), "fwd:%d:%d", rows, (int)has_y);
+static int get_forward_exec(vdt_plan* p, int rows, bool has_y, float drop_p, Exec** out) {
+    char key[96];
+    snprintf(key, sizeof(key), "fwd:%d:%d:%.9g", rows, (int)has_y, (double)drop_p);
     CKI(exec_cache_lookup(p, key, out));
     if (*out) return 0;
     CKI(exec_cache_make_room(p));
@@ -1216,6 +1224,8 @@ static int get_forward_exec(vdt_plan* p, int rows, bool has_y, Exec** out) {
     const vdt_unet_config& c = p->cfg;
     const size_t HW = (size_t)c.resolution * c.resolution;
     ex->rows = rows; ex->emb_rows = rows; ex->sampler = false; ex->has_y = has_y; ex->rep = 1;
+    ex->drop_p = drop_p;
+    if (drop_p > 0.f) CKI(ex->acquire(sizeof(unsigned long long), (void**)&ex->drop_seed));
     CKI(ex->acquire(rows * HW * c.in_channels * 4, (void**)&ex->xin));
     CKI(ex->acquire(rows * HW * c.out_channels * 4, (void**)&ex->yout));
     CKI(ex->acquire(rows * sizeof(double), (void**)&ex->t_rows));
@@ -1230,10 +1240,11 @@ static int get_forward_exec(vdt_plan* p, int rows, bool has_y, Exec** out) {
     return 0;
 }
 
-extern "C" int vdt_unet_forward(vdt_plan* p, const float* x, const double* t, const void* y, float* out, int32_t batch,
-                                void* stream) {
+static int unet_forward_impl(vdt_plan* p, const float* x, const double* t, const void* y, float* out, int32_t batch,
+                             float drop_p, unsigned long long seed, void* stream) {
     if (!p || !x || !t || !out) return fail("null argument");
     if (!p->finalized) return fail("plan not finalized (load every state_dict key, then vdt_plan_finalize)");
+    if (!(drop_p >= 0.f && drop_p < 1.f)) return fail("drop_rate must lie in [0, 1) (got %g)", (double)drop_p);
     cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
     CKI(enter_work(p, user));
     cudaStream_t st = p->work;
@@ -1242,7 +1253,7 @@ extern "C" int vdt_unet_forward(vdt_plan* p, const float* x, const double* t, co
     for (int b0 = 0; b0 < batch; b0 += c.max_rows) {
         const int rows = std::min(c.max_rows, batch - b0);
         Exec* ex;
-        CKI(get_forward_exec(p, rows, y != nullptr, &ex));
+        CKI(get_forward_exec(p, rows, y != nullptr, drop_p, &ex));
         CK(cudaMemcpyAsync(ex->xin, x + (size_t)b0 * c.in_channels * HW, rows * HW * c.in_channels * 4, cudaMemcpyDeviceToDevice, st));
         CK(cudaMemcpyAsync(ex->t_rows, t + b0, rows * sizeof(double), cudaMemcpyDeviceToDevice, st));
         if (y && c.multitags)
@@ -1250,10 +1261,24 @@ extern "C" int vdt_unet_forward(vdt_plan* p, const float* x, const double* t, co
                                (size_t)rows * c.num_classes * 4, cudaMemcpyDeviceToDevice, st));
         else if (y)
             CK(cudaMemcpyAsync(ex->y_rows, static_cast<const int64_t*>(y) + b0, rows * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        if (ex->drop_seed) {                             // every chunk of the batch draws its own masks
+            set_u64_kernel<<<1, 1, 0, st>>>(ex->drop_seed, seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(b0 + 1));
+            CK(cudaGetLastError());
+        }
         CKI(run_exec(p, ex, st));
         CK(cudaMemcpyAsync(out + (size_t)b0 * c.out_channels * HW, ex->yout, rows * HW * c.out_channels * 4, cudaMemcpyDeviceToDevice, st));
     }
     return leave_work(p, user);
+}
+
+extern "C" int vdt_unet_forward(vdt_plan* p, const float* x, const double* t, const void* y, float* out, int32_t batch,
+                                void* stream) {
+    return unet_forward_impl(p, x, t, y, out, batch, 0.f, 0ull, stream);
+}
+
+extern "C" int vdt_unet_forward_train(vdt_plan* p, const float* x, const double* t, const void* y, float* out, int32_t batch,
+                                      float drop_rate, uint64_t seed, void* stream) {
+    return unet_forward_impl(p, x, t, y, out, batch, drop_rate, (unsigned long long)seed, stream);
 }
 
 // ================================================================================================ schedule (host, fp64)
@@ -1353,6 +1378,55 @@ extern "C" int vdt_step_coefficients(const vdt_sampler_config* scp, float* out) 
         o[14] = sc.x0eps_coef ? 1.0f : 0.0f;         // lets vdt_op_sampler_step pick the (eps, x0) form from the row alone
         o[15] = 0.0f;
     }
+    return 0;
+}
+
+// ================================================================================================ training step
+// Per-sample scalars of GaussianDiffusion.train_loss from the continuous times t (host, fp64): the log-SNR is evaluated in
+// fp64 and rounded to fp32 by broadcast_to (diffusion.py:23-26, 293-295); every derived scalar is then fp32 math on that
+// fp32 log-SNR, like the reference's TorchScript converters (diffusion.py:206-245).  Row layout = vdt_step_coefficients'
+// slots that make sense here: 0 alpha, 1 sigma, 2 rsqrt(sigmoid l), 3 exp(-l/2), 4 sigmoid l, 5 sigmoid -l, 11 l,
+// 12 rsqrt(sigmoid -l), 13 exp(l/2).
+extern "C" int vdt_train_coefficients(const vdt_sampler_config* scp, const double* t_host, int32_t batch, float* out) {
+    if (!scp || !t_host || !out) return fail("null argument");
+    for (int i = 0; i < batch; ++i) {
+        double l_d;
+        CKI(logsnr_d(*scp, t_host[i], &l_d));
+        const float l = (float)l_d;
+        float* o = out + (size_t)i * kCoefStride;
+        for (int k = 0; k < kCoefStride; ++k) o[k] = 0.f;
+        const float sp = 1.0f / (1.0f + std::exp(-l)), sn = 1.0f / (1.0f + std::exp(l));
+        o[0] = std::sqrt(sp); o[1] = std::sqrt(sn);
+        o[2] = 1.0f / std::sqrt(sp); o[3] = std::exp(-0.5f * l);
+        o[4] = sp; o[5] = sn; o[11] = l;
+        o[12] = 1.0f / std::sqrt(sn); o[13] = std::exp(0.5f * l);
+    }
+    return 0;
+}
+
+extern "C" int vdt_q_sample(const float* x0, const float* noise, const float* coef_dev, float* x_t, int32_t batch, int32_t chw,
+                            void* stream) {
+    if (!x0 || !noise || !coef_dev || !x_t) return fail("null argument");
+    if (chw % 4) return fail("C*H*W must be a multiple of 4 (got %d)", chw);
+    cudaError_t e = launch_q_sample(x0, noise, coef_dev, x_t, batch, chw, reinterpret_cast<cudaStream_t>(stream));
+    ++g_launches;
+    if (e != cudaSuccess) return fail("q_sample launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int vdt_train_loss(const float* model_out, const float* x0, const float* noise, const float* x_t, const float* coef_dev,
+                              float* loss, float* grad_out, int32_t batch, int32_t c, int32_t hw, int32_t model_out_type,
+                              int32_t reweight_type, void* stream) {
+    if (!model_out || !x0 || !noise || !x_t || !coef_dev || !loss) return fail("null argument");
+    if (model_out_type < 0 || model_out_type > 3) return fail("unknown model_out_type %d", model_out_type);
+    if (reweight_type < 0 || reweight_type > 3) return fail("unknown reweight_type %d", reweight_type);
+    if (reweight_type != 2 && model_out_type == VDT_OUT_BOTH)
+        return fail("a single-target reweighting compares the target with the raw model output (diffusion.py:541): "
+                    "shapes differ for model_out_type \"both\"");
+    cudaError_t e = launch_train_loss(model_out, x0, noise, x_t, coef_dev, loss, grad_out, batch, c, hw, model_out_type, reweight_type,
+                                      reinterpret_cast<cudaStream_t>(stream));
+    ++g_launches;
+    if (e != cudaSuccess) return fail("train_loss launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -1564,11 +1638,13 @@ extern "C" int vdt_op_conv(const void* x, int32_t batch, int32_t h, int32_t w, i
     return rc;
 }
 
-extern "C" int vdt_op_groupnorm(const void* src1, int32_t c1, const float* src2, int32_t c2, int32_t batch, int32_t h,
-                                int32_t w, const float* gamma, const float* beta, const float* film, int32_t film_stride,
-                                int32_t film_off, int32_t silu, int32_t resample, void* out_act, void* out_raw, float* out_res,
-                                int32_t f16, const void* stats1, const void* stats2, int32_t stat_cols, int32_t in16, void* stream) {
+static int op_groupnorm_impl(const void* src1, int32_t c1, const float* src2, int32_t c2, int32_t batch, int32_t h,
+                             int32_t w, const float* gamma, const float* beta, const float* film, int32_t film_stride,
+                             int32_t film_off, int32_t silu, int32_t resample, void* out_act, void* out_raw, float* out_res,
+                             int32_t f16, const void* stats1, const void* stats2, int32_t stat_cols, int32_t in16, float drop_p,
+                             const unsigned long long* drop_seed_dev, int32_t drop_layer, void* stream) {
     GroupNormParams g{};
+    g.drop_p = drop_p; g.drop_seed = drop_seed_dev; g.drop_layer = drop_layer;
     g.f16 = f16; g.stats1 = (const float2*)stats1; g.stats2 = (const float2*)stats2; g.in16 = in16; g.stat_cols = stat_cols == 2 ? 2 : 4;
     g.stat_slabs = stat_slabs_per_image(h, w);
     if (stats1 && g.stat_slabs <= 0) return fail("no conv-epilogue statistics layout for %dx%d feature maps", h, w);
@@ -1582,6 +1658,29 @@ extern "C" int vdt_op_groupnorm(const void* src1, int32_t c1, const float* src2,
     if (scratch) { cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)); cudaFree(scratch); }
     if (e != cudaSuccess) return fail("groupnorm launch failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+extern "C" int vdt_op_groupnorm(const void* src1, int32_t c1, const float* src2, int32_t c2, int32_t batch, int32_t h,
+                                int32_t w, const float* gamma, const float* beta, const float* film, int32_t film_stride,
+                                int32_t film_off, int32_t silu, int32_t resample, void* out_act, void* out_raw, float* out_res,
+                                int32_t f16, const void* stats1, const void* stats2, int32_t stat_cols, int32_t in16, void* stream) {
+    return op_groupnorm_impl(src1, c1, src2, c2, batch, h, w, gamma, beta, film, film_stride, film_off, silu, resample, out_act,
+                             out_raw, out_res, f16, stats1, stats2, stat_cols, in16, 0.f, nullptr, 0, stream);
+}
+
+extern "C" int vdt_op_groupnorm_dropout(const void* src1, int32_t c1, int32_t batch, int32_t h, int32_t w, const float* gamma,
+                                        const float* beta, int32_t silu, void* out_act, int32_t f16, float drop_p, uint64_t seed,
+                                        int32_t layer, void* stream) {
+    if (!(drop_p > 0.f && drop_p < 1.f)) return fail("drop_p must lie in (0, 1)");
+    unsigned long long* ds = nullptr;
+    CK(cudaMalloc(&ds, sizeof(unsigned long long)));
+    const unsigned long long sv = seed;
+    CK(cudaMemcpy(ds, &sv, sizeof(sv), cudaMemcpyHostToDevice));
+    const int rc = op_groupnorm_impl(src1, c1, nullptr, 0, batch, h, w, gamma, beta, nullptr, 0, 0, silu, 0, out_act, nullptr, nullptr,
+                                     f16, nullptr, nullptr, 4, 0, drop_p, ds, layer, stream);
+    cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+    cudaFree(ds);
+    return rc;
 }
 
 extern "C" int vdt_op_attention(const void* qkv, void* out, int32_t batch, int32_t n, int32_t heads, int32_t d,

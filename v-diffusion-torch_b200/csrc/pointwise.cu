@@ -208,16 +208,6 @@ __global__ void sampler_begin_step_kernel(SamplerState* st, const float* __restr
 // Philox4x32-10 counter RNG + Box-Muller for on-device ancestral noise (used only when no noise
 // tensor is injected; the stream is this library's own, not torch's).  One counter value yields the four
 // normals of elements 4q .. 4q+3.
-__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
-    }
-    return ctr;
-}
 __device__ __forceinline__ float4 philox_normal4(unsigned long long seed, uint32_t step, unsigned long long quad) {
     const uint4 r = philox4x32(make_uint4(static_cast<uint32_t>(quad), static_cast<uint32_t>(quad >> 32), step, 0u),
                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));

@@ -284,6 +284,19 @@ __device__ __forceinline__ float4 ldg_nc_v4_issue(const float* p) {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 
+// ---- counter RNG ---------------------------------------------------------------------------------
+// Philox4x32-10: four 32-bit words per (counter, key); used for on-device ancestral noise and for training dropout.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
 // ---- small math --------------------------------------------------------------------------------
 __device__ __forceinline__ float ex2_approx(float x) {   // 2^x, one MUFU op (max rel. error 2^-22), flushes denormals
     float y;

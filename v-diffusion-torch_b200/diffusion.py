@@ -201,6 +201,57 @@ class GaussianDiffusion:
                 first = stop - 1
         return x.cpu(), preds
 
+    # ------------------------------------------------------------------ train_loss (diffusion.py:492-545)
+    @torch.no_grad()
+    def train_loss(self, denoise_fn, x_0, t, y, noise=None, return_grad=False):
+        """Forward half of the training step around the model call (first slice of SURVEY §8 f2): q_sample, the model
+        call, from_model_out_to_pred and the re-weighted MSE, as two fused kernels.  Returns the per-sample loss (B,) on
+        x_0's device; with ``return_grad`` also d loss.mean() / d model_out -- the tensor the reference's autograd hands
+        to the UNet's backward pass (the UNet backward itself is not part of this slice).
+
+        Reproduced as is: the label-dropout mask of ``p_uncond`` is applied to ``y`` in place AFTER the model call
+        (diffusion.py:527-529 vs :508), so it changes the caller's tensor but never the loss; single-target reweightings
+        compare the target with the raw model output (:541)."""
+        if self.loss_type != "mse":
+            raise NotImplementedError("loss_type 'kl' (likelihood evaluation, diffusion.py:446-464) is out of scope")
+        if self.model_var_type == "learned":
+            raise AssertionError("mse loss needs a fixed variance type")          # diffusion.py:519
+        if self.reweight_type not in _lib.REWEIGHT_TYPES:
+            raise AssertionError(self.reweight_type)                              # diffusion.py:520
+        if x_0.device.type != "cuda":
+            raise RuntimeError("v_diffusion_b200 trains on CUDA (sm_100a) only; there is no CPU fallback")
+        dev = x_0.device
+        B = x_0.shape[0]
+        x_0 = x_0.to(torch.float32).contiguous()
+        noise = torch.randn_like(x_0) if noise is None else noise.to(device=dev, dtype=torch.float32).contiguous()
+        L = _lib.lib()
+        sc = self.sampler_config(use_ddim=True)
+        t_host = t.detach().to(device="cpu", dtype=torch.float64).reshape(-1).contiguous()
+        if t_host.numel() != B:
+            raise ValueError("t must have one entry per sample")
+        coef_h = torch.empty((B, _lib.COEF_STRIDE), dtype=torch.float32)
+        _lib.check(L.vdt_train_coefficients(C.byref(sc), _lib.ptr(t_host), B, _lib.ptr(coef_h)))
+        coef = coef_h.to(dev)
+        x_t = torch.empty_like(x_0)
+        chw = x_0[0].numel()
+        with torch.cuda.device(dev):
+            _lib.check(L.vdt_q_sample(_lib.ptr(x_0), _lib.ptr(noise), _lib.ptr(coef), _lib.ptr(x_t), B, chw, _lib.current_stream_ptr()))
+        model_out = denoise_fn(x_t, t, y).to(torch.float32).contiguous()
+        if self.p_uncond and y is not None:                                        # diffusion.py:527-529: after the model call
+            keep = torch.rand((y.shape[0],)) > self.p_uncond
+            y *= keep.to(device=y.device, dtype=y.dtype).reshape((-1,) + (1,) * (y.ndim - 1))
+        Cc, hw = x_0.shape[1], x_0.shape[2] * x_0.shape[3]
+        want = (2 if self.model_out_type == "both" else 1) * Cc
+        if model_out.shape != (B, want) + tuple(x_0.shape[2:]):
+            raise ValueError(f"model output has shape {tuple(model_out.shape)}, expected {(B, want) + tuple(x_0.shape[2:])}")
+        loss = torch.empty((B,), dtype=torch.float32, device=dev)
+        grad = torch.empty_like(model_out) if return_grad else None
+        with torch.cuda.device(dev):
+            _lib.check(L.vdt_train_loss(_lib.ptr(model_out), _lib.ptr(x_0), _lib.ptr(noise), _lib.ptr(x_t), _lib.ptr(coef),
+                                        _lib.ptr(loss), _lib.ptr(grad), B, Cc, hw, _lib.OUT_TYPES[self.model_out_type],
+                                        _lib.REWEIGHT_TYPES[self.reweight_type], _lib.current_stream_ptr()))
+        return (loss, grad) if return_grad else loss
+
     def _p_sample_generic(self, denoise_fn, shape, x_t, label, step_noise, sc, device, gen, use_ddim):
         L = _lib.lib()
         B = shape[0]

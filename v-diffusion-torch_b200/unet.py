@@ -83,7 +83,7 @@ class UNet(nn.Module):
             apply_attn = [apply_attn] * levels
         self.apply_attn = list(apply_attn)
         self.num_res_blocks = num_res_blocks
-        self.drop_rate = drop_rate                              # eval-only path: dropout is the identity
+        self.drop_rate = drop_rate                              # active in .train() (forward only); identity in .eval()
         if head_dim is None and num_heads is None:
             num_heads = 1
         self.head_dim, self.num_heads = head_dim, num_heads
@@ -191,8 +191,9 @@ class UNet(nn.Module):
     # ------------------------------------------------------------------ forward (unet.py:286-322)
     @torch.no_grad()
     def forward(self, x, t, y=None):
-        if self.training:
-            raise RuntimeError("this UNet implements the sampling path only: call .eval() first")
+        # .train(): forward with dropout active (unet.py:135, 146); the masks come from the library's Philox stream, seeded
+        # per call from torch's global CPU generator (nn.Dropout draws from the global generator too).  Forward only.
+        train = bool(self.training and self.drop_rate > 0.)
         if x.ndim != 4 or x.shape[1] != self.in_channels or x.shape[2] != x.shape[3]:
             raise ValueError(f"expected x of shape (B, {self.in_channels}, R, R), got {tuple(x.shape)}")
         dev = x.device
@@ -219,6 +220,11 @@ class UNet(nn.Module):
             y = None
         out = torch.empty((B, self.out_channels, x.shape[2], x.shape[3]), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().vdt_unet_forward(plan, _lib.ptr(x), _lib.ptr(t), _lib.ptr(y), _lib.ptr(out), B,
-                                                   _lib.current_stream_ptr()))
+            if train:
+                seed = int(torch.randint(0, 2 ** 63 - 1, (1,), dtype=torch.int64).item())
+                _lib.check(_lib.lib().vdt_unet_forward_train(plan, _lib.ptr(x), _lib.ptr(t), _lib.ptr(y), _lib.ptr(out), B,
+                                                             float(self.drop_rate), seed, _lib.current_stream_ptr()))
+            else:
+                _lib.check(_lib.lib().vdt_unet_forward(plan, _lib.ptr(x), _lib.ptr(t), _lib.ptr(y), _lib.ptr(out), B,
+                                                       _lib.current_stream_ptr()))
         return out
