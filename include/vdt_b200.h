@@ -168,6 +168,16 @@ int vdt_profile_read(double* ms4, uint64_t* launches4);
 int vdt_op_conv(const void* x_16_nhwc, int32_t batch, int32_t h, int32_t w, int32_t cin, const float* w_oihw,
                 int32_t cout, int32_t ksize, const float* bias, const float* residual, float* out_nhwc, int32_t f16,
                 void* out16, void* stats_out, int32_t stat_cols, void* stream);
+/* Backward of a conv layer (F.conv2d under autograd, modules.py:141-144), first slice of the training step.
+ * dgrad: dX fp32 NHWC [B, H, W, cin] = conv(dY, W rotated 180 degrees with its channel axes swapped) on the forward kernel;
+ *        dy 16-bit NHWC [B, H, W, cout], w fp32 OIHW [cout, cin, k, k].
+ * wgrad: dW fp32 OIHW [cout, cin, k, k] = sum over pixels of dY[p][co] * X[p + tap][ci] (tcgen05, both operands MN-major,
+ *        K split over CTAs with a fixed-order reduction); optional dbias fp32 [cout] = sum over pixels of dY.  x, dy 16-bit
+ *        NHWC.  Needs cout % 128 == 0, cin % 64 == 0 and feature maps that tile into 128-pixel boxes. */
+int vdt_op_conv_dgrad(const void* dy_16_nhwc, int32_t batch, int32_t h, int32_t w, int32_t cin, const float* w_oihw, int32_t cout,
+                      int32_t ksize, float* dx_nhwc, int32_t f16, void* stream);
+int vdt_op_conv_wgrad(const void* x_16_nhwc, const void* dy_16_nhwc, int32_t batch, int32_t h, int32_t w, int32_t cin, int32_t cout,
+                      int32_t ksize, float* dw_oihw, float* dbias, int32_t f16, void* stream);
 /* Rows of the statistics table vdt_op_conv writes per image: stats_out is [batch * slabs (+ 4 rows of slack: the last
  * M tile always writes its four quarters)][cout / stat_cols] (sum, sumsq)
  * float2, one slab per 32-row quarter of an M tile of the conv kernel's image-aligned tiling; 0 = this feature-map size

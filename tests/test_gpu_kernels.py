@@ -315,3 +315,45 @@ def test_groupnorm_dropout_mask_statistics(L, f16):
     per_c = 1.0 - kept.float().mean(dim=(0, 1, 2))
     per_px = 1.0 - kept.float().mean(dim=3)
     assert (per_c - p).abs().max().item() < 0.08 and (per_px - p).abs().max().item() < 0.15
+
+
+BWD_CASES = [
+    # B, H, cin, cout, k
+    (4, 32, 256, 256, 3),       # the dominant shape of the CIFAR network
+    (3, 16, 512, 256, 3),       # concat block conv1: two input-channel blocks, odd batch
+    (5, 8, 256, 256, 3),        # two images per 128-pixel tile, zero-filled tail
+    (2, 32, 512, 256, 1),       # 1x1 skip conv
+    (2, 16, 128, 128, 3),
+    (2, 64, 192, 384, 3),       # CelebA-style widths (192-wide input-channel block)
+]
+
+
+@pytest.mark.parametrize("f16", [1, 0])
+@pytest.mark.parametrize("B,H,cin,cout,k", BWD_CASES)
+def test_conv_backward_vs_autograd(L, B, H, cin, cout, k, f16):
+    """dgrad and wgrad (+ bias grad) of a conv layer against torch autograd in fp64 on the same 16-bit-rounded operands."""
+    g = torch.Generator(device="cuda").manual_seed(H + cin + k)
+    x = torch.randn(B, H, H, cin, device="cuda", generator=g).to(DT[f16])
+    dy = torch.randn(B, H, H, cout, device="cuda", generator=g).to(DT[f16])
+    w = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k))
+    dx = torch.zeros(B, H, H, cin, device="cuda")
+    dw = torch.zeros(cout, cin, k, k, device="cuda")
+    db = torch.zeros(cout, device="cuda")
+    _check(L, L.vdt_op_conv_dgrad(_p(dy), B, H, H, cin, _p(w), cout, k, _p(dx), f16, None))
+    _check(L, L.vdt_op_conv_wgrad(_p(x), _p(dy), B, H, H, cin, cout, k, _p(dw), _p(db), f16, None))
+    torch.cuda.synchronize()
+    xd = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    wd = w.to(DT[f16]).double().requires_grad_(True)           # dgrad multiplies by the 16-bit-rounded weight
+    bd = torch.zeros(cout, device="cuda", dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(xd, wd, bd, padding=k // 2)
+    y.backward(dy.double().permute(0, 3, 1, 2))
+    ref_dx = xd.grad.permute(0, 2, 3, 1)
+    print(f"conv backward {cin}->{cout} k{k} @{H}: dgrad rel {_rel(dx, ref_dx):.2e} wgrad rel {_rel(dw, wd.grad):.2e} dbias rel {_rel(db, bd.grad):.2e}")
+    assert _rel(dx, ref_dx) <= 2e-3 * EPS[f16] + 1e-5        # fp32 accumulation of exact 16-bit products
+    assert _rel(dw, wd.grad) <= 1e-4
+    assert _rel(db, bd.grad) <= 1e-5
+    # deterministic: fixed-order split reduction
+    dw2 = torch.zeros_like(dw)
+    _check(L, L.vdt_op_conv_wgrad(_p(x), _p(dy), B, H, H, cin, cout, k, _p(dw2), None, f16, None))
+    torch.cuda.synchronize()
+    assert torch.equal(dw, dw2)

@@ -227,4 +227,22 @@ cudaError_t launch_q_sample(const float* x0, const float* eps, const float* coef
 cudaError_t launch_train_loss(const float* model_out, const float* x0, const float* noise, const float* x_t, const float* coef,
                               float* loss, float* grad_out, int B, int C, int HW, int type, int reweight, cudaStream_t stream);
 
+// weight gradient of a 3x3 / 1x1 conv (wgrad.cu): dW[co][ci][tap] = sum_p dY[p][co] * X[p + shift(tap)][ci]
+struct alignas(64) WgradParams {
+    CUtensorMap dy_map;                // 4-D (Cout, W, H, N) 16-bit, box (64, W, box_h, box_n), SWIZZLE_128B
+    CUtensorMap x_map;                 // 4-D (Cin, W, H, N) 16-bit, same box
+    int taps;                          // 9 or 1
+    int Cout, Cin;
+    int co_blocks;                     // Cout / 128
+    int ci_block, ci_blocks;           // input channels per accumulator (<= 256, multiple of 64), Cin / ci_block
+    int tap_groups;                    // ceil(taps / 2): two taps' accumulators fill TMEM
+    int splits;                        // K splits (pixel-tile ranges)
+    int num_tiles, tiles_per_image, box_h, box_n, rows_per_tile;   // the forward conv's 128-pixel tiling (rows_per_tile == 128)
+    int f16;
+    float* partial;                    // fp32 [splits][taps][Cout][Cin]
+};
+int wgrad_splits(const WgradParams& p, int num_sms);
+// runs the GEMM, the fixed-order split reduction into dw (fp32 OIHW) and, when dbias is given, db[co] = sum_p dY[p][co]
+cudaError_t launch_wgrad(const WgradParams& p, float* dw, float* dbias, const h16* dy, long long rows, cudaStream_t stream);
+
 }  // namespace vdt

@@ -165,6 +165,17 @@ __global__ void pack_conv_ups_kernel(const float* __restrict__ src, h16* __restr
     const h16 hi = to_h16(w, f16);
     dst[(long long)o * ktot + (long long)par * par_stride + koff + t * I + i] = part == 0 ? hi : to_h16(w - h16_to_float(hi, f16), f16);
 }
+// data gradient of a conv as a conv: dX = conv(dY, W') with W'[ci][co][tap'] = W[co][ci][taps - 1 - tap'] (transposed
+// channels, 180-degree rotated filter); packed like a forward weight whose "output" channels are the conv's inputs
+__global__ void pack_conv_dgrad_kernel(const float* __restrict__ src, h16* __restrict__ dst, int O, int I, int taps, int f16) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long n = (long long)O * I * taps;
+    if (idx >= n) return;
+    const int o = (int)(idx % O);
+    const int tap = (int)((idx / O) % taps);
+    const int i = (int)(idx / ((long long)O * taps));
+    dst[(long long)i * taps * O + (long long)tap * O + o] = to_h16(src[((long long)o * I + i) * taps + (taps - 1 - tap)], f16);
+}
 // in_conv: [O][C][3][3] -> [O][64], column tap*C + c (matches im2col3x3), zero padded
 __global__ void pack_inconv_w_kernel(const float* __restrict__ src, h16* __restrict__ dst, int O, int C, int f16, int ktot,
                                      int koff, int part) {
@@ -1657,6 +1668,81 @@ static int op_groupnorm_impl(const void* src1, int32_t c1, const float* src2, in
     ++g_launches;
     if (scratch) { cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)); cudaFree(scratch); }
     if (e != cudaSuccess) return fail("groupnorm launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---- backward of a conv layer, first slice of the training step ---------------------------------------
+extern "C" int vdt_op_conv_dgrad(const void* dy, int32_t batch, int32_t h, int32_t w, int32_t cin, const float* w_oihw, int32_t cout,
+                                 int32_t ksize, float* dx, int32_t f16, void* stream) {
+    if (ksize != 1 && ksize != 3) return fail("ksize must be 1 or 3");
+    if (cout % 64 || cin % 32) return fail("dgrad needs cout %% 64 == 0 and cin %% 32 == 0 (got %d -> %d)", cin, cout);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int taps = ksize * ksize;
+    h16* wp = nullptr;
+    CK(cudaMalloc(&wp, (size_t)cin * taps * cout * 2));
+    const long long n = (long long)cout * cin * taps;
+    pack_conv_dgrad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w_oihw, wp, cout, cin, taps, f16);
+    int rc = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail("dgrad weight pack failed: %s", cudaGetErrorString(e));
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (rc == 0) {
+        ConvSpec s;                                    // the conv kernel with the roles of the channel counts swapped
+        s.f16 = f16;
+        if (ksize == 3) { s.a3 = (const h16*)dy; s.c3 = cout; } else { s.a1 = (const h16*)dy; s.c1 = cout; s.ld1 = cout; }
+        s.n = batch; s.h = h; s.w = w; s.wpacked = wp; s.cout = cin; s.wrows = cin;
+        float* zero = nullptr;
+        CK(cudaMalloc(&zero, (size_t)cin * 4));
+        CK(cudaMemsetAsync(zero, 0, (size_t)cin * 4, st));
+        s.bias = zero; s.out_mode = kOutF32; s.out_f32 = dx; s.ld = cin;
+        std::unique_ptr<ConvParams> cp(new ConvParams());
+        rc = setup_conv(s, cp.get());
+        if (rc == 0) {
+            e = launch_conv_gemm(*cp, nsm, st);
+            ++g_launches;
+            if (e != cudaSuccess) rc = fail("dgrad launch failed: %s", cudaGetErrorString(e));
+        }
+        e = cudaStreamSynchronize(st);
+        cudaFree(zero);
+        if (rc == 0 && e != cudaSuccess) rc = fail("dgrad kernel failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(wp);
+    return rc;
+}
+
+extern "C" int vdt_op_conv_wgrad(const void* x, const void* dy, int32_t batch, int32_t h, int32_t w, int32_t cin, int32_t cout,
+                                 int32_t ksize, float* dw_oihw, float* dbias, int32_t f16, void* stream) {
+    if (ksize != 1 && ksize != 3) return fail("ksize must be 1 or 3");
+    if (cout % 128 || cin % 64) return fail("wgrad needs cout %% 128 == 0 and cin %% 64 == 0 (got %d -> %d)", cin, cout);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    ConvGeom g;
+    CKI(conv_geom(batch, h, w, &g));
+    if (g.rows_per_tile != 128) return fail("wgrad needs feature maps that tile into 128-pixel boxes (got %dx%d)", h, w);
+    std::unique_ptr<WgradParams> wp(new WgradParams());
+    memset(wp.get(), 0, sizeof(WgradParams));
+    CKI(make_map_nhwc(&wp->dy_map, dy, batch, h, w, cout, g.box_h, g.box_n));
+    CKI(make_map_nhwc(&wp->x_map, x, batch, h, w, cin, g.box_h, g.box_n));
+    wp->taps = ksize * ksize; wp->Cout = cout; wp->Cin = cin; wp->co_blocks = cout / 128;
+    wp->ci_block = cin <= 256 ? cin : (cin % 256 == 0 ? 256 : (cin % 192 == 0 ? 192 : (cin % 128 == 0 ? 128 : 64)));
+    wp->ci_blocks = cin / wp->ci_block;
+    wp->tap_groups = (wp->taps + 1) / 2;
+    wp->num_tiles = g.num_m_tiles; wp->tiles_per_image = g.tiles_per_image; wp->box_h = g.box_h; wp->box_n = g.box_n;
+    wp->rows_per_tile = g.rows_per_tile; wp->f16 = f16;
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    wp->splits = wgrad_splits(*wp, nsm);
+    float* partial = nullptr;
+    CK(cudaMalloc(&partial, (size_t)wp->splits * wp->taps * cout * cin * 4));
+    wp->partial = partial;
+    cudaError_t e = launch_wgrad(*wp, dw_oihw, dbias, (const h16*)dy, (long long)batch * h * w, st);
+    g_launches += 2 + (dbias ? 1 : 0);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(partial);
+    if (e != cudaSuccess) return fail("wgrad launch failed: %s", cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return fail("wgrad kernel failed: %s", cudaGetErrorString(e2));
     return 0;
 }
 
