@@ -85,6 +85,25 @@ def sampler_case(B=4096, C=3, H=32):
     print(f"sampler_step B={B} CFG: {ms:.4f} ms {byts / ms / 1e6 if ms else 0:.0f} GB/s (the hook allocates / frees its state and syncs)")
 
 
+def backward_case(B=128, H=32, cin=256, cout=256, k=3):
+    """conv backward at the BASELINE configs[4] batch (128 per GPU): dgrad on the forward kernel, wgrad kernel"""
+    x = torch.randn(B, H, H, cin, device=dev, generator=g).half()
+    dy = torch.randn(B, H, H, cout, device=dev, generator=g).half()
+    w = torch.randn(cout, cin, k, k, device=dev, generator=g) / math.sqrt(cin * k * k)
+    dx = torch.empty(B, H, H, cin, device=dev)
+    dw = torch.empty(cout, cin, k, k, device=dev)
+    for _ in range(1 if once else 3):
+        L.vdt_op_conv_dgrad(p(dy), B, H, H, cin, p(w), cout, k, p(dx), 1, None)
+        L.vdt_op_conv_wgrad(p(x), p(dy), B, H, H, cin, cout, k, p(dw), None, 1, None)
+    torch.cuda.synchronize()
+    print(f"conv backward {cin}->{cout} k{k} @{H} B={B}: {2.0 * B * H * H * cout * cin * k * k / 1e12:.3f} TFLOP each for dgrad and wgrad")
+
+
+if "--backward" in sys.argv:
+    backward_case()
+    backward_case(128, 16, 256, 256, 3)
+    backward_case(128, 32, 512, 256, 3)
+    sys.exit(0)
 if "--sampler" in sys.argv:
     sampler_case()
     torch.cuda.synchronize()
