@@ -11,7 +11,8 @@ UNet, numpy/python fp64 for the schedule and the posterior coefficients) of
 * ``v_diffusion/models/unet.py``  UNet.forward           (unet.py:286-322)
 * ``v_diffusion/functions.py``    get_timestep_embedding (functions.py:11-29)
 * ``v_diffusion/diffusion.py``    get_logsnr_schedule, logsnr_to_posterior[_ddim],
-  p_mean_var, p_sample_step, p_sample                    (diffusion.py:42-414)
+  p_mean_var, p_sample_step, p_sample[_progressive]      (diffusion.py:42-441)
+  q_sample, from_model_out_to_pred, train_loss (mse)     (diffusion.py:242-245, 466-545)
 
 Parity pin: ``tests/golden/make_golden.py`` imports the *unmodified reference*
 from ``/root/reference`` in the build container, runs it on seeded inputs and
@@ -21,5 +22,5 @@ the oracle is pinned to the reference itself (not "parity unpinned").
 """
 from .unet_ref import unet_forward, make_state_dict, unet_config_from_json, dezero_  # noqa: F401
 from .diffusion_ref import (  # noqa: F401
-    logsnr_schedule, step_coefficients, p_sample, timestep_embedding,
+    logsnr_schedule, step_coefficients, p_sample, timestep_embedding, train_loss,
 )

@@ -203,3 +203,40 @@ def p_sample(denoise_fn: Callable, shape, noise: torch.Tensor, label: Optional[t
             mean = mean + torch.tensor(co["std"][ti]) * step_noise[ti]
         x_t = mean
     return x_t
+
+
+# ----------------------------------------------------------------------------- training loss
+def train_loss(denoise_fn: Callable, x_0: torch.Tensor, t: torch.Tensor, y, noise: torch.Tensor, *, model_out_type: str,
+               reweight_type: str = "snr_trunc", schedule: str = "cosine", logsnr_min: float = -20., logsnr_max: float = 20.):
+    """GaussianDiffusion.train_loss for loss_type "mse" (diffusion.py:492-545) and the converters it uses
+    (from_model_out_to_pred 466-490, q_sample 242-245, pred_*_from_* 206-239).  Returns (per-sample loss, x_t).
+    The p_uncond label mask acts on ``y`` after the model call (diffusion.py:527-529) and is not restated: it cannot
+    change the loss."""
+    lt = torch.from_numpy(logsnr_schedule(t.double().numpy(), schedule, logsnr_min, logsnr_max).astype(np.float32))
+    lt = lt.reshape(-1, 1, 1, 1)                                      # broadcast_to: cast to x's dtype (diffusion.py:23-26)
+    x_t = x_0 * torch.sigmoid(lt).sqrt() + noise * torch.sigmoid(-lt).sqrt()
+    out = denoise_fn(x_t, t, y)
+    if model_out_type == "v":
+        x0p = x_t * torch.sigmoid(lt).sqrt() - out * torch.sigmoid(-lt).sqrt()
+        epsp = x_t * torch.sigmoid(-lt).sqrt() + out * torch.sigmoid(lt).sqrt()
+        vp = out
+    else:
+        if model_out_type == "x0":
+            x0p = out
+            epsp = x_t * torch.sigmoid(-lt).rsqrt() - x0p * (lt * 0.5).exp()
+        elif model_out_type == "eps":
+            epsp = out
+            x0p = x_t * torch.sigmoid(lt).rsqrt() - epsp * (-lt * 0.5).exp()
+        elif model_out_type == "both":
+            x0p = _pred_x0(x_t, out, lt, "both")
+            epsp = x_t * torch.sigmoid(-lt).rsqrt() - x0p * (lt * 0.5).exp()
+        else:
+            raise NotImplementedError(model_out_type)
+        vp = -x0p * torch.sigmoid(-lt).sqrt() + epsp * torch.sigmoid(lt).sqrt()
+    fm = lambda z: z.flatten(1).mean(dim=1)
+    if reweight_type == "snr_trunc":
+        return torch.maximum(fm((x_0 - x0p) ** 2), fm((noise - epsp) ** 2)), x_t
+    # single-target reweightings compare with the RAW model output (diffusion.py:541), reproduced as is
+    target = {"constant": x_0, "snr": noise,
+              "snr_1plus": -x_0 * torch.sigmoid(-lt).sqrt() + noise * torch.sigmoid(lt).sqrt()}[reweight_type]
+    return fm((target - out) ** 2), x_t

@@ -9,8 +9,8 @@ import torch
 
 from oracle import unet_forward, make_state_dict, step_coefficients, p_sample, timestep_embedding
 from oracle.unet_ref import unet_config_from_json
-from tests.cases import (UNET_CASES, SAMPLE_CASES, FULL_CASES, CIFAR_COND, CIFAR_UNCOND, CELEBA, build_inputs,
-                         build_sample_inputs, build_full_inputs, full_state_dict)
+from tests.cases import (UNET_CASES, SAMPLE_CASES, FULL_CASES, TRAIN_CASES, CIFAR_COND, CIFAR_UNCOND, CELEBA, build_inputs,
+                         build_sample_inputs, build_full_inputs, full_state_dict, build_train_inputs)
 
 
 def _load(golden_dir, name):
@@ -125,6 +125,29 @@ def test_full_trajectory_configs1_matches_reference(golden_dir):
     assert len(rec) == 100
     for i, (ti, o) in enumerate(rec):
         assert ((o - mo[i]).norm() / mo[i].norm()).item() <= 2e-4, ti
+
+
+@pytest.mark.parametrize("name", sorted(TRAIN_CASES))
+def test_train_loss_matches_reference(golden_dir, name):
+    """GaussianDiffusion.train_loss (diffusion.py:492-545) restated in the oracle, against the reference's own x_t,
+    model output and per-sample loss (the fixture's model output is also what the oracle's UNet computes)."""
+    from oracle import train_loss
+    case = TRAIN_CASES[name]
+    ucase = UNET_CASES[case["unet"]]
+    cfg = ucase["cfg"]
+    g = _load(golden_dir, f"train_{name}.npz")
+    sd = make_state_dict(cfg, ucase["seed"])
+    x0, t, noise, y = build_train_inputs(case, cfg)
+    seen = {}
+
+    def fn(x_t, tt, yy):
+        seen["out"] = unet_forward(sd, cfg, x_t, tt, yy)
+        return seen["out"]
+    loss, x_t = train_loss(fn, x0, t, y, noise, model_out_type=case["model_out_type"], reweight_type=case["reweight_type"])
+    assert (x_t - torch.from_numpy(g["x_t"])).abs().max().item() <= 1e-6
+    mo = torch.from_numpy(g["model_out"])
+    assert ((seen["out"] - mo).norm() / mo.norm()).item() <= 1e-4
+    np.testing.assert_allclose(loss.numpy(), g["loss"], rtol=2e-4)
 
 
 def test_step_coefficients_known_answers(golden_dir):
