@@ -357,3 +357,17 @@ def test_conv_backward_vs_autograd(L, B, H, cin, cout, k, f16):
     _check(L, L.vdt_op_conv_wgrad(_p(x), _p(dy), B, H, H, cin, cout, k, _p(dw2), None, f16, None))
     torch.cuda.synchronize()
     assert torch.equal(dw, dw2)
+
+
+def test_attention_cta_pair_variant_matches():
+    """The opt-in cta_group::2 attention variant (VDT_ATTN_PAIR=1; measured slower, kept selectable) computes the same thing:
+    run the attention parity cases that qualify (even number of query tiles, d % 128 == 0) in a child process with it on."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VDT_ATTN_PAIR="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), "-q", "-m", "gpu", "-k",
+                        "test_attention and (1024 or 256 or 4096) and not pair"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-500:]
+    assert "passed" in r.stdout

@@ -297,7 +297,9 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA)
-        if (lane == 0 && rank == 0) {
+        // The whole warp walks the loop (warp-uniform control flow and operands); one elected lane issues each
+        // instruction, so the descriptors stay in uniform registers (ptx.cuh: elect_one).
+        if (rank == 0) {
             const uint32_t idesc = umma_idesc_16(2 * kBM, p.block_n, (F16 ? 1 : 0));
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -311,13 +313,17 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                     const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
                     const uint64_t adesc = umma_desc_sw128(a_addr);
                     const uint64_t bdesc = umma_desc_sw128(a_addr + kABytes);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k)
-                        umma_16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit_2cta(&empty_bar[stage], static_cast<uint16_t>(3));        // frees the slot in both CTAs
+                        for (int k = 0; k < kBK / 16; ++k)
+                            umma_16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        umma_commit_2cta(&empty_bar[stage], static_cast<uint16_t>(3));        // frees the slot in both CTAs
+                    }
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_2cta(&acc_full[acc], static_cast<uint16_t>(3));       // both halves complete -> both epilogues
+                if (elect_one()) umma_commit_2cta(&acc_full[acc], static_cast<uint16_t>(3));       // both halves complete -> both epilogues
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

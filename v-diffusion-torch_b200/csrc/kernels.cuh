@@ -133,6 +133,7 @@ cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream);
 struct alignas(64) AttnParams {
     CUtensorMap q_map;                 // 2-D (3*hid, B*N) 16-bit, box (64, 128): q | k | v thirds, heads contiguous in each
     CUtensorMap kv_map;                // same tensor, box (64, 64): K tiles at column hid + h*d, V tiles at 2*hid + h*d
+    CUtensorMap k2_map;                // same tensor, box (64, 32): a CTA's half of a K tile in the CTA-pair variant
     int B, N, heads, d, hid;
     int f16;
     float scale_log2e;                 // log2(e) / sqrt(d)

@@ -1006,6 +1006,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
                 memset(ap.get(), 0, sizeof(AttnParams));
                 CKI(make_map_2d(&ap->q_map, qkv, (long long)R * N, 3 * hidd, 3 * hidd, 128));
                 CKI(make_map_2d(&ap->kv_map, qkv, (long long)R * N, 3 * hidd, 3 * hidd, 64));
+                CKI(make_map_2d(&ap->k2_map, qkv, (long long)R * N, 3 * hidd, 3 * hidd, 32));
                 ap->B = R; ap->N = N; ap->heads = nh; ap->d = hd; ap->hid = hidd; ap->f16 = p->f16;
                 ap->scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)hd));
                 ap->out = o;
@@ -1776,6 +1777,7 @@ extern "C" int vdt_op_attention(const void* qkv, void* out, int32_t batch, int32
     memset(ap.get(), 0, sizeof(AttnParams));
     CKI(make_map_2d(&ap->q_map, qkv, (long long)batch * n, 3 * hid, 3 * hid, 128));
     CKI(make_map_2d(&ap->kv_map, qkv, (long long)batch * n, 3 * hid, 3 * hid, 64));
+    CKI(make_map_2d(&ap->k2_map, qkv, (long long)batch * n, 3 * hid, 3 * hid, 32));
     ap->B = batch; ap->N = n; ap->heads = heads; ap->d = d; ap->hid = hid; ap->f16 = f16;
     ap->scale_log2e = (float)(1.4426950408889634 / std::sqrt((double)d));
     ap->out = (h16*)out;

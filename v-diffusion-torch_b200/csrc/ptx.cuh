@@ -142,6 +142,21 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
     return v;
 }
 
+// One lane of a converged warp.  tcgen05.mma / tcgen05.commit are issued by one thread, but from warp-uniform code:
+// when the whole warp walks the issue loop and only the instruction itself sits under `if (elect_one())`, the
+// descriptors stay in uniform registers and each MMA costs a handful of instructions.  Under `if (lane == 0)` the
+// compiler must assume divergence and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~20
+// instructions per MMA), which bounds kernels whose MMAs are short (attention's 128x64x16: 32 cycles each).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred px;\n\t"
+        "elect.sync _|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- clusters ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

@@ -85,8 +85,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // D[co 128][ci bn] += A^T B with A = dY tile, B = X tile, both MN-major (bits 15 / 16 of the descriptor)
+        {
+            // D[co 128][ci bn] += A^T B with A = dY tile, B = X tile, both MN-major (bits 15 / 16 of the descriptor).  The whole
+            // warp walks the loop; one elected lane issues each instruction (ptx.cuh: elect_one)
             const uint32_t idesc = umma_idesc_16(128, bn, (F16 ? 1 : 0)) | kIdescBMajorMN | (1u << 15);
             int ia = 0, ib = 0;
             for (int t = t_begin; t < t_end; ++t, ++ia) {
@@ -97,16 +98,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
                     const int sb = ib & 1;
                     mbar_wait(&b_full[sb], (ib >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(a_smem + sa * kABytes), b_addr = smem_u32(b_smem + sb * kBBytesMax);
+                    const uint64_t adesc = umma_desc_sw128_mn(smem_u32(a_smem + sa * kABytes), kChunk);
+                    const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(b_smem + sb * kBBytesMax), kChunk);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < kPix / 16; ++kk)       // 16 pixels per MMA: +2048 bytes in both operands
-                        umma_16(tmem_base + static_cast<uint32_t>(k * 256), umma_desc_sw128_mn(a_addr + kk * 2048, kChunk),
-                                umma_desc_sw128_mn(b_addr + kk * 2048, kChunk), idesc, (t > t_begin || kk > 0) ? 1u : 0u);
-                    umma_commit(&b_empty[sb]);
+                        for (int kk = 0; kk < kPix / 16; ++kk)   // 16 pixels per MMA: +2048 bytes (= 128 descriptor units) in both operands
+                            umma_16(tmem_base + static_cast<uint32_t>(k * 256), adesc + static_cast<uint64_t>(kk * 128),
+                                    bdesc + static_cast<uint64_t>(kk * 128), idesc, (t > t_begin || kk > 0) ? 1u : 0u);
+                        umma_commit(&b_empty[sb]);
+                    }
+                    __syncwarp();
                 }
-                umma_commit(&a_empty[sa]);
+                if (elect_one()) umma_commit(&a_empty[sa]);
+                __syncwarp();
             }
-            umma_commit(acc_full);
+            if (elect_one()) umma_commit(acc_full);
+            __syncwarp();
         }
     } else {
         // ---- epilogue: warp q reads TMEM lanes 32q .. 32q+31 (= output channels), 32 input channels at a time
