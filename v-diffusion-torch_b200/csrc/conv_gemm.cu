@@ -265,7 +265,8 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // (the whole warp walks the loop, one elected lane issues: coordinates and descriptors stay warp-uniform)
+        {
             int stage = 0; uint32_t phase = 0;
             const int half_n = p.block_n >> 1;
             // both CTAs' boxes complete on the leader's barrier
@@ -285,9 +286,12 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* a_dst = smem + stage * kStageBytes;
                             uint8_t* b_dst = a_dst + kABytes;
-                            if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
-                            tma_load_4d_2cta(a_dst, &p.a_map[s], &full_bar[stage], kb * kBK, o.c1 + dx, o.c2 + dy, o.c3);
-                            tma_load_2d_2cta(b_dst, &p.b_map, &full_bar[stage], kcol, n_tile * p.block_n + rank * half_n);
+                            if (elect_one()) {
+                                if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
+                                tma_load_4d_2cta(a_dst, &p.a_map[s], &full_bar[stage], kb * kBK, o.c1 + dx, o.c2 + dy, o.c3);
+                                tma_load_2d_2cta(b_dst, &p.b_map, &full_bar[stage], kcol, n_tile * p.block_n + rank * half_n);
+                            }
+                            __syncwarp();
                             kcol += kBK;
                             if (++stage == kStages) { stage = 0; phase ^= 1; }
                         }
