@@ -129,7 +129,8 @@ __device__ __forceinline__ void attention_body(const AttnParams& p) {
     // (the S / P buffers are double-buffered: slot g & 1, parity (g >> 1) & 1)
     if (warp == 0) {
         // ------------------------------------------------------------------ Q + K producer
-        if (lane == 0) {
+        // (warp-uniform loop, one elected lane issues the copies)
+        {
             int g = 0, it_n = 0;
             for (int w = cta; w < total_items; w += ncta, ++it_n) {
                 const Item it = decode_item(w, qsteps, p.heads, ipc);
@@ -137,29 +138,35 @@ __device__ __forceinline__ void attention_body(const AttnParams& p) {
                 const long long row0 = static_cast<long long>(it.b0) * N + static_cast<long long>(qt) * kQRows;
                 const long long krow0 = static_cast<long long>(it.b0) * N;
                 mbar_wait(sm.q_empty, (it_n & 1) ^ 1);      // the previous item's last S = Q K^T has retired
-                if (rank == 0) mbar_expect_tx(sm.q_full, static_cast<uint32_t>(NC * dch * 16384));
-                for (int c = 0; c < dch; ++c) {
-                    if (TWO) tma_load_2d_2cta(sm.q + c * 16384, &p.q_map, sm.q_full, it.h * d + c * 64, static_cast<int>(row0));
-                    else tma_load_2d(sm.q + c * 16384, &p.q_map, sm.q_full, it.h * d + c * 64, static_cast<int>(row0));
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(sm.q_full, static_cast<uint32_t>(NC * dch * 16384));
+                    for (int c = 0; c < dch; ++c) {
+                        if (TWO) tma_load_2d_2cta(sm.q + c * 16384, &p.q_map, sm.q_full, it.h * d + c * 64, static_cast<int>(row0));
+                        else tma_load_2d(sm.q + c * 16384, &p.q_map, sm.q_full, it.h * d + c * 64, static_cast<int>(row0));
+                    }
                 }
+                __syncwarp();
                 for (int j = 0; j < nt; ++j, ++g) {
                     const int s = g % S;
                     mbar_wait(&sm.k_empty[s], ((g / S) & 1) ^ 1);
-                    if (rank == 0) mbar_expect_tx(&sm.k_full[s], static_cast<uint32_t>(dch * 8192));
-                    for (int c = 0; c < dch; ++c) {
-                        if (TWO)                            // this CTA's 32 of the tile's 64 keys (its N half of S)
-                            tma_load_2d_2cta(sm.k(s) + c * 4096, &p.k2_map, &sm.k_full[s], p.hid + it.h * d + c * 64,
-                                             static_cast<int>(krow0) + j * kKeys + rank * 32);
-                        else
-                            tma_load_2d(sm.k(s) + c * 8192, &p.kv_map, &sm.k_full[s], p.hid + it.h * d + c * 64,
-                                        static_cast<int>(krow0) + j * kKeys);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(&sm.k_full[s], static_cast<uint32_t>(dch * 8192));
+                        for (int c = 0; c < dch; ++c) {
+                            if (TWO)                        // this CTA's 32 of the tile's 64 keys (its N half of S)
+                                tma_load_2d_2cta(sm.k(s) + c * 4096, &p.k2_map, &sm.k_full[s], p.hid + it.h * d + c * 64,
+                                                 static_cast<int>(krow0) + j * kKeys + rank * 32);
+                            else
+                                tma_load_2d(sm.k(s) + c * 8192, &p.kv_map, &sm.k_full[s], p.hid + it.h * d + c * 64,
+                                            static_cast<int>(krow0) + j * kKeys);
+                        }
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 10) {
         // ------------------------------------------------------------------ V producer
-        if (lane == 0) {
+        {
             int g = 0;
             const int vch = TWO ? dch / 2 : dch;            // 64-feature chunks this CTA holds: its N half of O += P V
             for (int w = cta; w < total_items; w += ncta) {
@@ -168,12 +175,15 @@ __device__ __forceinline__ void attention_body(const AttnParams& p) {
                 for (int j = 0; j < nt; ++j, ++g) {
                     const int s = g % S;
                     mbar_wait(&sm.v_empty[s], ((g / S) & 1) ^ 1);
-                    if (rank == 0) mbar_expect_tx(&sm.v_full[s], static_cast<uint32_t>(dch * 8192));
-                    for (int c = 0; c < vch; ++c) {        // chunk c: 64 keys x 64 features, one 128-byte row per key
-                        const int col = 2 * p.hid + it.h * d + (rank * vch + c) * 64;
-                        if (TWO) tma_load_2d_2cta(sm.v(s) + c * 8192, &p.kv_map, &sm.v_full[s], col, static_cast<int>(krow0) + j * kKeys);
-                        else tma_load_2d(sm.v(s) + c * 8192, &p.kv_map, &sm.v_full[s], col, static_cast<int>(krow0) + j * kKeys);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(&sm.v_full[s], static_cast<uint32_t>(dch * 8192));
+                        for (int c = 0; c < vch; ++c) {    // chunk c: 64 keys x 64 features, one 128-byte row per key
+                            const int col = 2 * p.hid + it.h * d + (rank * vch + c) * 64;
+                            if (TWO) tma_load_2d_2cta(sm.v(s) + c * 8192, &p.kv_map, &sm.v_full[s], col, static_cast<int>(krow0) + j * kKeys);
+                            else tma_load_2d(sm.v(s) + c * 8192, &p.kv_map, &sm.v_full[s], col, static_cast<int>(krow0) + j * kKeys);
+                        }
                     }
+                    __syncwarp();
                 }
             }
         }

@@ -367,20 +367,28 @@ struct vdt_plan {
     // The chunks of a sampling batch are independent samples: they alternate between two lanes (streams, each with its
     // own workspace and step graph), so that one chunk's HBM-bound kernels (GroupNorm, small-N attention, 1x1 GEMMs)
     // can run on the SMs' spare warps while the other chunk's tensor-bound conv kernel holds the tensor cores.
-    int lanes = 2;
-    cudaStream_t work2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int lanes = 2;                        // VDT_LANES = 1 .. kMaxLanes overrides
+    static constexpr int kMaxLanes = 4;
+    cudaStream_t lane_stream[kMaxLanes] = {};   // [0] unused: lane 0 is `work`
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
+    int sync_lanes() {
+        for (int l = 1; l < kMaxLanes; ++l)
+            if (lane_stream[l] && cudaStreamSynchronize(lane_stream[l]) != cudaSuccess) return 1;
+        return 0;
+    }
 
     ~vdt_plan() {
         if (work) cudaStreamSynchronize(work);
-        if (work2) cudaStreamSynchronize(work2);
+        sync_lanes();
         execs.clear();
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
         if (ev_fork) cudaEventDestroy(ev_fork);
-        if (ev_join) cudaEventDestroy(ev_join);
+        for (int l = 1; l < kMaxLanes; ++l) {
+            if (ev_join[l]) cudaEventDestroy(ev_join[l]);
+            if (lane_stream[l]) cudaStreamDestroy(lane_stream[l]);
+        }
         if (work) cudaStreamDestroy(work);
-        if (work2) cudaStreamDestroy(work2);
         for (auto& w : weights) if (w.dev) cudaFree(w.dev);
         for (void* p : owned) cudaFree(p);
     }
@@ -491,7 +499,7 @@ extern "C" int vdt_plan_create(const vdt_unet_config* cfg, vdt_plan** out) {
     const char* ng = getenv("VDT_NO_GRAPH");
     p->use_graph = !(ng && ng[0] == '1');
     const char* ln = getenv("VDT_LANES");
-    if (ln && ln[0] == '1') p->lanes = 1;
+    if (ln && ln[0] >= '1' && ln[0] <= '0' + vdt_plan::kMaxLanes && ln[1] == 0) p->lanes = ln[0] - '0';
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
         int n = 0;
@@ -611,7 +619,7 @@ extern "C" int vdt_plan_finalize(vdt_plan* p) {
     for (auto& w : p->weights)
         if (!w.loaded) return fail("missing key in state_dict: %s", w.name.c_str());
     if (p->work) CK(cudaStreamSynchronize(p->work));        // re-finalize after re-loading a key: nothing may still run
-    if (p->work2) CK(cudaStreamSynchronize(p->work2));
+    if (p->sync_lanes()) return fail("a lane stream failed to synchronise: %s", cudaGetErrorString(cudaGetLastError()));
     p->execs.clear();
     for (void* q : p->owned) cudaFree(q);
     p->owned.clear();
@@ -1205,7 +1213,7 @@ static int run_exec(vdt_plan* p, Exec* ex, cudaStream_t st) {
 
 // The plan keeps a handful of execs (workspace + captured graph per batch size / sampler signature).  A miss on a full
 // cache evicts the least recently used entry only; queued work may still use its buffers, hence the stream sync.
-constexpr size_t kMaxExecs = 4;
+constexpr size_t kMaxExecs = vdt_plan::kMaxLanes + 2;   // one sampler exec per lane + a ragged tail + a plain forward
 static int exec_cache_lookup(vdt_plan* p, const std::string& key, Exec** out) {
     auto it = p->execs.find(key);
     if (it == p->execs.end()) { *out = nullptr; return 0; }
@@ -1219,7 +1227,7 @@ static int exec_cache_make_room(vdt_plan* p) {
         for (auto it = p->execs.begin(); it != p->execs.end(); ++it)
             if (it->second->last_use < victim->second->last_use) victim = it;
         if (p->work) CK(cudaStreamSynchronize(p->work));
-        if (p->work2) CK(cudaStreamSynchronize(p->work2));
+        if (p->sync_lanes()) return fail("a lane stream failed to synchronise: %s", cudaGetErrorString(cudaGetLastError()));
         p->execs.erase(victim);
     }
     return 0;
@@ -1522,21 +1530,23 @@ extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, fl
     const int rep = cfg ? 2 : 1;
     const int chunk = std::max(1, c.max_rows / rep);
     const int nchunks = (batch + chunk - 1) / chunk;
-    // two lanes when there is more than one chunk (per-launch profiling needs a single ordered stream)
-    const int lanes = (p->lanes > 1 && nchunks > 1 && !g_profile.load()) ? 2 : 1;
-    if (lanes == 2) {
-        if (!p->work2) {
-            CK(cudaStreamCreateWithFlags(&p->work2, cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-        }
+    // several lanes when there is more than one chunk (per-launch profiling needs a single ordered stream)
+    const int lanes = g_profile.load() ? 1 : std::max(1, std::min(p->lanes, nchunks));
+    if (lanes > 1) {
+        if (!p->ev_fork) CK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
         CK(cudaEventRecord(p->ev_fork, p->work));
-        CK(cudaStreamWaitEvent(p->work2, p->ev_fork, 0));
+        for (int l = 1; l < lanes; ++l) {
+            if (!p->lane_stream[l]) {
+                CK(cudaStreamCreateWithFlags(&p->lane_stream[l], cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&p->ev_join[l], cudaEventDisableTiming));
+            }
+            CK(cudaStreamWaitEvent(p->lane_stream[l], p->ev_fork, 0));
+        }
     }
     for (int i0 = 0, ci = 0; i0 < batch; i0 += chunk, ++ci) {
         const int imgs = std::min(chunk, batch - i0);
         const int lane = ci % lanes;
-        st = lane ? p->work2 : p->work;
+        st = lane ? p->lane_stream[lane] : p->work;
         Exec* ex;
         CKI(get_sampler_exec(p, sc, imgs, label != nullptr, lane, &ex));
         CK(cudaMemcpyAsync(ex->xin, x + (size_t)i0 * CHW, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
@@ -1558,9 +1568,9 @@ extern "C" int vdt_p_sample_range(vdt_plan* p, const vdt_sampler_config* scp, fl
         if (pred_x0 && num_steps > 0)
             CK(cudaMemcpyAsync(pred_x0 + (size_t)i0 * CHW, ex->pred, imgs * CHW * 4, cudaMemcpyDeviceToDevice, st));
     }
-    if (lanes == 2) {
-        CK(cudaEventRecord(p->ev_join, p->work2));
-        CK(cudaStreamWaitEvent(p->work, p->ev_join, 0));
+    for (int l = 1; l < lanes; ++l) {
+        CK(cudaEventRecord(p->ev_join[l], p->lane_stream[l]));
+        CK(cudaStreamWaitEvent(p->work, p->ev_join[l], 0));
     }
     return leave_work(p, user);
 }

@@ -64,23 +64,29 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // warp-uniform loop; one elected lane issues the copies
             int ia = 0, ib = 0;
             for (int t = t_begin; t < t_end; ++t, ++ia) {
                 const int y0 = (t % p.tiles_per_image) * p.box_h, n0 = (t / p.tiles_per_image) * p.box_n;
                 const int sa = ia & 1;
                 mbar_wait(&a_empty[sa], ((ia >> 1) & 1) ^ 1);
-                mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(2 * p.rows_per_tile * 128));
-                for (int c = 0; c < 2; ++c)
-                    tma_load_4d(a_smem + sa * kABytes + c * kChunk, &p.dy_map, &a_full[sa], co_blk * 128 + c * 64, 0, y0, n0);
+                if (elect_one()) {
+                    mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(2 * p.rows_per_tile * 128));
+                    for (int c = 0; c < 2; ++c)
+                        tma_load_4d(a_smem + sa * kABytes + c * kChunk, &p.dy_map, &a_full[sa], co_blk * 128 + c * 64, 0, y0, n0);
+                }
+                __syncwarp();
                 for (int k = 0; k < ntaps; ++k, ++ib) {
                     const int tap = tap0 + k;
                     const int dy = (p.taps == 9) ? tap / 3 - 1 : 0, dx = (p.taps == 9) ? tap % 3 - 1 : 0;
                     const int sb = ib & 1;
                     mbar_wait(&b_empty[sb], ((ib >> 1) & 1) ^ 1);
-                    mbar_expect_tx(&b_full[sb], static_cast<uint32_t>(bchunks * p.rows_per_tile * 128));
-                    for (int c = 0; c < bchunks; ++c)
-                        tma_load_4d(b_smem + sb * kBBytesMax + c * kChunk, &p.x_map, &b_full[sb], ci_blk * bn + c * 64, dx, y0 + dy, n0);
+                    if (elect_one()) {
+                        mbar_expect_tx(&b_full[sb], static_cast<uint32_t>(bchunks * p.rows_per_tile * 128));
+                        for (int c = 0; c < bchunks; ++c)
+                            tma_load_4d(b_smem + sb * kBBytesMax + c * kChunk, &p.x_map, &b_full[sb], ci_blk * bn + c * 64, dx, y0 + dy, n0);
+                    }
+                    __syncwarp();
                 }
             }
         }
