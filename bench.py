@@ -382,7 +382,13 @@ def run_b200(args, rank, world, local_rank):
         barrier()
     launches = L.vdt_kernel_launches() - n0
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
+    per_rank = None
     if world > 1:
+        # every rank's own device time and median SM clock, so that the spread behind the max is visible
+        mine = torch.tensor([ms.item() / K, float(clocks.summary().get("sm_mhz") or 0.0)], device=device, dtype=torch.float64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(t[0].item(), 3) for t in allr], "sm_mhz": [t[1].item() for t in allr]}
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = ms.item()
     ms_step = ms_total / K
@@ -472,6 +478,8 @@ def run_b200(args, rank, world, local_rank):
                            "operands": net.operand_dtype + " tensor-core operands (same tcgen05 kind::f16 rate as bf16)",
                            "accumulate": "fp32", "residual_stream": "fp32"},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if world == 1 and not args.no_cpu_baseline and wl is None:
             line["cpu_baseline"] = cpu_baseline(net, diff, noise_h[:2].clone(), label_h[:2].clone(), device)
             line["reference_gpu_eager"] = reference_gpu_eager(net, diff, noise, label, device)

@@ -562,8 +562,8 @@ def test_images_to_uint8_matches_generate_py():
         assert torch.equal(got, want)
 
 
-@pytest.mark.parametrize("world", [1, 2])
-def test_generate_driver_end_to_end(tmp_path, world):
+@pytest.mark.parametrize("world,schedule", [(1, "static"), (2, "static"), (1, "dynamic"), (2, "dynamic")])
+def test_generate_driver_end_to_end(tmp_path, world, schedule):
     """`python -m v_diffusion_b200.generate` (the sharded batch loop of generate.py:100-150) as a user runs it: a
     reference-format checkpoint + config JSONs in, uint8 NHWC images out; on 2 GPUs under torchrun with the NCCL image
     gather.  The gathered images must equal what p_sample gives in-process for every rank's seeded noise / labels."""
@@ -588,7 +588,7 @@ def test_generate_driver_end_to_end(tmp_path, world):
     total, bs, T, seed = 22, 4, 6, 77
     args = ["--config-path", str(tmp_path / "cfg.json"), "--default-config-path", str(tmp_path / "defaults.json"),
             "--ckpt-path", str(tmp_path / "ckpt.pt"), "--sample-timesteps", str(T), "--w-guide", "1.0", "--batch-size", str(bs),
-            "--total-size", str(total), "--save-path", str(tmp_path / "out.pt"), "--seed", str(seed)]
+            "--total-size", str(total), "--save-path", str(tmp_path / "out.pt"), "--seed", str(seed), "--schedule", schedule]
     if world == 1:
         cmd = [sys.executable, "-m", "v_diffusion_b200.generate"] + args
     else:
@@ -606,9 +606,12 @@ def test_generate_driver_end_to_end(tmp_path, world):
     diff = GaussianDiffusion(get_logsnr_schedule(d["logsnr_schedule"], d["logsnr_min"], d["logsnr_max"]), T, d["model_out_type"],
                              d["model_var_type"], d["reweight_type"], d["loss_type"], intp_frac=d["intp_frac"], w_guide=1.0)
     want = []
-    for rank in range(world):
-        s0, e0 = shard_bounds(total, rank, world)
-        gen = torch.Generator(device="cuda").manual_seed(seed + rank)
+    # static: rank r owns a contiguous slice and one generator (seed + r); dynamic: global batch k has its own
+    # generator (seed + k) whichever rank claims it from the queue
+    slices = [(shard_bounds(total, r, world), seed + r) for r in range(world)] if schedule == "static" else \
+        [((b0, min(b0 + bs, total)), seed + b0 // bs) for b0 in range(0, total, bs)]
+    for (s0, e0), gseed in slices:
+        gen = torch.Generator(device="cuda").manual_seed(gseed)
         for b0 in range(s0, e0, bs):
             n = min(bs, e0 - b0)
             noise = torch.randn((n, 3, 32, 32), device="cuda", generator=gen)
@@ -617,7 +620,7 @@ def test_generate_driver_end_to_end(tmp_path, world):
             want.append(diff.p_sample(net, (n, 3, 32, 32), noise=noise, label=label, device="cuda", seed=call_seed, use_ddim=False))
     want = images_to_uint8(torch.cat(want).cuda()).cpu()
     diffpix = (got.int() - want.int()).abs()
-    print(f"generate x{world}: {int((diffpix > 0).sum())} of {diffpix.numel()} uint8 values differ, max {int(diffpix.max())}")
+    print(f"generate x{world} {schedule}: {int((diffpix > 0).sum())} of {diffpix.numel()} uint8 values differ, max {int(diffpix.max())}")
     assert int(diffpix.max()) == 0
 
 

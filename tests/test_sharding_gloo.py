@@ -60,3 +60,45 @@ def test_sample_sharded_world2(tmp_path):
     g0 = torch.rand(4, generator=torch.Generator().manual_seed(100))      # per-rank seeds: seed + rank
     g1 = torch.rand(4, generator=torch.Generator().manual_seed(101))
     assert torch.allclose(f0[:4, 2, 0, 0], g0) and torch.allclose(f0[6:10, 2, 0, 0], g1)
+
+
+def _queue_worker(rank, world, port, total, batch, out_dir):
+    import time
+    from v_diffusion_b200.generate import sample_balanced
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ran = []
+
+    def sample_fn(n, gen):
+        time.sleep(0.05 if rank == 0 else 0.2)           # rank 1 is the slow GPU
+        ran.append(n)
+        x = torch.zeros(n, 2, 2, 2)
+        x[:, 0] = torch.rand(n, generator=gen).view(n, 1, 1)
+        x[:, 1] = rank
+        return x
+    full = sample_balanced(sample_fn, total, batch, seed=100)
+    again = sample_balanced(sample_fn, total, batch, seed=100)            # a second queue on the same store
+    torch.save((full, again, ran), os.path.join(out_dir, f"q{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sample_balanced_world2_matches_single_process(tmp_path):
+    """The dynamic batch queue: every batch runs exactly once, the faster rank runs more of them, and the images do
+    not depend on who ran what (batch k is seeded seed + k) -- equal to a single-process run."""
+    from v_diffusion_b200.generate import sample_balanced
+    total, batch, world = 38, 4, 2
+    mp.spawn(_queue_worker, args=(world, _free_port(), total, batch, str(tmp_path)), nprocs=world, join=True)
+    (f0, a0, r0), (f1, a1, r1) = (torch.load(tmp_path / f"q{r}.pt") for r in range(world))
+    assert torch.equal(f0, f1) and f0.shape == (38, 2, 2, 2)
+    assert torch.equal(f0[:, 0], a0[:, 0])                                 # the second call drew the same numbers
+    assert sum(r0) + sum(r1) == 2 * total and len(r0) > len(r1)            # nothing twice, the fast rank did more
+
+    def sample_fn(n, gen):
+        x = torch.zeros(n, 2, 2, 2)
+        x[:, 0] = torch.rand(n, generator=gen).view(n, 1, 1)
+        return x
+    single = sample_balanced(sample_fn, total, batch, seed=100)
+    assert torch.equal(single[:, 0], f0[:, 0])
+    want = torch.cat([torch.rand(min(4, total - 4 * k), generator=torch.Generator().manual_seed(100 + k)) for k in range(10)])
+    assert torch.equal(single[:, 0, 0, 0], want)

@@ -8,8 +8,11 @@ final gather of the images (as in Trainer.sample_fn, train_utils.py:181-183).
         --ckpt-path ckpt.pt --use-ddim --sample-timesteps 100 --w-guide 1.0 --total-size 32768 --save-path out.pt
 """
 import argparse
+import json
 import math
 import os
+import sys
+import time
 
 import torch
 import torch.distributed as dist
@@ -57,6 +60,57 @@ def sample_sharded(sample_fn, total, batch_size, seed=1234, gather=True, device=
     return gather_shards(local, total) if gather else local
 
 
+_queue_calls = 0
+
+
+def sample_balanced(sample_fn, total, batch_size, seed=1234, gather=True, device=None):
+    """Dynamic variant of `sample_sharded` for boxes whose GPUs do not run at the same speed (under the 1 kW power cap
+    the per-GPU step times of an 8-GPU box spread by 4.5 - 8.7 %, profiles/r2j_bench_8gpu_*_per_rank.json; it only pays
+    when that spread exceeds one batch, profiles/r2j_generate_static_vs_dynamic_8gpu.txt): the global batches
+    ``0 .. ceil(total / batch_size) - 1`` sit in one queue and every rank claims the next index with an atomic add on
+    the process group's store, so a faster GPU simply runs more batches.  Batch k always uses generator seed
+    ``seed + k``, which makes the result independent of which rank ran it and of the world size.
+    Returns the (total, C, H, W) tensor on every rank (one all_reduce over a zero-initialised buffer: every row is
+    written by exactly one rank), or with ``gather=False`` the list of (first_row, tensor) this rank produced."""
+    global _queue_calls
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    nb = (total + batch_size - 1) // batch_size
+    if multi:
+        store = dist.distributed_c10d._get_default_store()
+        key = f"vdt_b200_batch_queue_{_queue_calls}"
+        _queue_calls += 1
+        claim = lambda: store.add(key, 1) - 1
+    else:
+        counter = iter(range(nb + 1))
+        claim = lambda: next(counter)
+    mine = []
+    while True:
+        k = claim()
+        if k >= nb:
+            break
+        b0 = k * batch_size
+        gen = torch.Generator(device=device if device is not None else "cpu").manual_seed(seed + k)
+        mine.append((b0, sample_fn(min(batch_size, total - b0), gen)))
+    if not gather:
+        return mine
+    if multi:
+        # every rank learns the sample shape from whoever ran batch 0 (a slow rank may have claimed nothing)
+        shape = [tuple(mine[0][1].shape[1:]) + (str(mine[0][1].dtype),)] if mine and mine[0][0] == 0 else [None]
+        owner = [None] * dist.get_world_size()
+        dist.all_gather_object(owner, shape[0])
+        shape = next(o for o in owner if o is not None)
+        dtype = getattr(torch, shape[-1].split(".")[-1])
+        dev = device if device is not None else (mine[0][1].device if mine else "cpu")
+        full = torch.zeros((total,) + tuple(shape[:-1]), dtype=dtype, device=dev)
+    else:
+        full = torch.zeros((total,) + tuple(mine[0][1].shape[1:]), dtype=mine[0][1].dtype, device=mine[0][1].device)
+    for b0, x in mine:
+        full[b0: b0 + x.shape[0]] = x
+    if multi:
+        dist.all_reduce(full)
+    return full
+
+
 def images_to_uint8(x):
     """generate.py:149 on the device: fp32 NCHW samples -> uint8 NHWC pixels, (x * 127.5 + 127.5).clamp(0, 255)
     truncated to uint8 and permuted (0, 2, 3, 1), in one kernel (vdt_images_to_uint8)."""
@@ -98,6 +152,10 @@ def main():
     ap.add_argument("--total-size", type=int, default=50000)
     ap.add_argument("--save-path", default=None, help="torch.save of the uint8 NHWC images (rank 0)")
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--schedule", choices=["static", "dynamic"], default="static",
+                    help="static: rank r owns a contiguous slice (seeds seed + rank); dynamic: a shared batch queue, "
+                         "batch k seeded seed + k (same images at any world size; faster GPUs run more batches)")
+    ap.add_argument("--warmup-batches", type=int, default=0, help="untimed batches before the reported wall-clock")
     ap.add_argument("--label-path", default=None, help="multitag models: torch-saved (N, num_classes) attribute table")
     args = ap.parse_args()
 
@@ -151,7 +209,30 @@ def main():
         return diffusion.p_sample(model, (n,) + chw, noise=noise, label=label, device=device, seed=seed,
                                   use_ddim=args.use_ddim).to(device)
 
-    x = sample_sharded(sample_fn, args.total_size, args.batch_size, seed=args.seed, device=device)
+    run = sample_balanced if args.schedule == "dynamic" else sample_sharded
+    calls = [0]
+
+    def counted(n, gen):
+        calls[0] += 1
+        return sample_fn(n, gen)
+    if args.warmup_batches:                                   # graph capture and workspace allocation outside the clock
+        for _ in range(args.warmup_batches):
+            sample_fn(args.batch_size, torch.Generator(device=device).manual_seed(0))
+    torch.cuda.synchronize()
+    if dist.is_initialized():
+        dist.barrier()
+    t0 = time.perf_counter()
+    x = run(counted, args.total_size, args.batch_size, seed=args.seed, device=device)
+    torch.cuda.synchronize()
+    seconds = time.perf_counter() - t0
+    per_rank = [calls[0]]
+    if dist.is_initialized():
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, calls[0])
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        print(json.dumps({"schedule": args.schedule, "images": args.total_size, "seconds": seconds,
+                          "images_per_s": args.total_size / seconds, "n_gpus": world, "batches_per_rank": per_rank}),
+              file=sys.stderr, flush=True)
     if (not dist.is_initialized() or dist.get_rank() == 0) and args.save_path:
         torch.save(images_to_uint8(x).cpu(), args.save_path)      # generate.py:149 (the PNG encoding itself is I/O, out of scope)
     if dist.is_initialized():
