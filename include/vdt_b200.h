@@ -195,6 +195,15 @@ int vdt_op_groupnorm(const void* src1, int32_t c1, const float* src2, int32_t c2
 int vdt_op_groupnorm_dropout(const void* src1, int32_t c1, int32_t batch, int32_t h, int32_t w, const float* gamma,
                              const float* beta, int32_t silu, void* out_act_16, int32_t f16, float drop_p, uint64_t seed,
                              int32_t layer, void* stream);
+/* Backward of norm -> FiLM -> SiLU -> dropout (the activation chain of a ResidualBlock, unet.py:131-135, 143-146): x and
+ * grad_out fp32 [batch, h*w, c] (c in 128 / 256 / 512 / 1024), grad_out = gradient at the activation; film = null or
+ * [batch][2c] (shift | scale per sample); (drop_p, seed, layer) name the forward's dropout stream (drop_p = 0: none).
+ * Writes grad_x [batch, h*w, c], grad_gamma / grad_beta [c] and, when given, grad_film [batch][2c] (d shift | d scale).
+ * Replaces autograd through F.group_norm / F.silu / F.dropout (torch/nn/functional.py) on this chain. */
+int vdt_op_groupnorm_backward(const float* x, const float* grad_out, int32_t c, int32_t batch, int32_t h, int32_t w,
+                              const float* gamma, const float* beta, const float* film, int32_t silu, float drop_p,
+                              uint64_t seed, int32_t layer, float* grad_x, float* grad_gamma, float* grad_beta,
+                              float* grad_film, void* stream);
 /* attention on qkv 16-bit [B*N, 3*hid] (q | k | v thirds, heads contiguous inside each, the layout proj_in writes)
  * -> 16-bit [B*N, hid]; any N >= 1 (ragged last key / query tiles are masked) */
 int vdt_op_attention(const void* qkv_16, void* out_16, int32_t batch, int32_t n, int32_t heads,

@@ -22,3 +22,7 @@ ls -la gpurun_out/${tag}_*.ncu-rep
 timeout 300 python scripts/prof_kernels.py > gpurun_out/${tag}_kernel_timings.txt 2>&1
 timeout 120 python scripts/prof_kernels.py --sampler >> gpurun_out/${tag}_kernel_timings.txt 2>&1
 tail -n 20 gpurun_out/${tag}_kernel_timings.txt
+# 4. the training slice's backward kernels at the configs[4] batch (128): time + DRAM bytes per launch
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
+    --log-file gpurun_out/${tag}_backward_launches.csv python scripts/prof_kernels.py --backward --once > gpurun_out/${tag}_ncu_backward.log 2>&1
+echo "== backward launch list: $(wc -l < gpurun_out/${tag}_backward_launches.csv) lines"

@@ -99,7 +99,23 @@ def backward_case(B=128, H=32, cin=256, cout=256, k=3):
     print(f"conv backward {cin}->{cout} k{k} @{H} B={B}: {2.0 * B * H * H * cout * cin * k * k / 1e12:.3f} TFLOP each for dgrad and wgrad")
 
 
+def gn_backward_case(B=128, H=32, Cc=256):
+    """GroupNorm -> FiLM -> SiLU -> dropout backward (gn_backward.cu) at the configs[4] batch"""
+    import ctypes as C
+    x = torch.randn(B, H, H, Cc, device=dev, generator=g)
+    go = torch.randn(B, H, H, Cc, device=dev, generator=g)
+    gamma, beta = torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev)
+    film = torch.randn(B, 2 * Cc, device=dev, generator=g) * 0.1
+    gx, gg, gb, gf = torch.empty_like(x), torch.empty(Cc, device=dev), torch.empty(Cc, device=dev), torch.empty_like(film)
+    for _ in range(1 if once else 3):
+        L.vdt_op_groupnorm_backward(p(x), p(go), Cc, B, H, H, p(gamma), p(beta), p(film), 1, C.c_float(0.2), 7, 3, p(gx), p(gg), p(gb), p(gf), None)
+    torch.cuda.synchronize()
+    # (the op allocates its scratch per call: kernel times come from the ncu launch list, scripts/gpu_profile_round.sh step 4)
+    print(f"groupnorm backward C{Cc} @{H} B={B}: two streaming passes, {x.numel() * 4 * 5 / 1e6:.0f} MB algorithmic (x and dA read twice, dx written)")
+
+
 if "--backward" in sys.argv:
+    gn_backward_case()
     backward_case()
     backward_case(128, 16, 256, 256, 3)
     backward_case(128, 32, 512, 256, 3)

@@ -317,6 +317,68 @@ def test_groupnorm_dropout_mask_statistics(L, f16):
     assert (per_c - p).abs().max().item() < 0.08 and (per_px - p).abs().max().item() < 0.15
 
 
+GN_BWD_CASES = [
+    # B, H, W, C, film, silu, drop_p
+    (4, 32, 32, 256, True, 1, 0.0),      # norm2 of the CIFAR network: FiLM + SiLU
+    (3, 16, 16, 512, False, 1, 0.0),     # norm1 of a concat block
+    (5, 8, 8, 256, True, 1, 0.2),        # training mode: dropout mask regenerated from the forward's stream
+    (2, 28, 28, 128, True, 0, 0.0),      # no activation (out_conv-style norm), odd pixel count per slab
+    (2, 7, 9, 1024, False, 1, 0.3),
+]
+
+
+@pytest.mark.parametrize("case", GN_BWD_CASES)
+def test_groupnorm_backward_vs_autograd(L, case):
+    """Backward of GroupNorm(32, 1e-6) -> FiLM -> SiLU -> dropout (unet.py:131-135, 143-146) against fp64 autograd through
+    F.group_norm / F.silu with the forward kernel's own dropout mask: grad_x, grad_gamma, grad_beta and the FiLM
+    (shift, scale) gradients."""
+    B, H, W, Cc, film_on, silu, p = case
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = torch.randn(B, H, W, Cc, device="cuda", generator=g) * 1.3 + 0.4
+    gamma = torch.rand(Cc, device="cuda", generator=g) + 0.5
+    beta = torch.randn(Cc, device="cuda", generator=g) * 0.2
+    film = (torch.randn(B, 2 * Cc, device="cuda", generator=g) * 0.3) if film_on else None
+    go = torch.randn(B, H, W, Cc, device="cuda", generator=g)
+    seed, layer = 1234567, 9
+    mask = None
+    if p > 0:
+        # the forward's mask: the dropout op has no FiLM input, but the mask only depends on (seed, layer, element index)
+        out = torch.zeros(B, H, W, Cc, device="cuda", dtype=torch.float16)
+        _check(L, L.vdt_op_groupnorm_dropout(_p(x), Cc, B, H, W, _p(gamma), _p(beta), 0, _p(out), 1, C.c_float(p), seed, layer, None))
+        torch.cuda.synchronize()
+        mask = (out != 0).double() / (1 - p)
+    xd = x.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    fd = film.double().requires_grad_(True) if film_on else None
+    y = F.group_norm(xd.permute(0, 3, 1, 2), 32, gd, bd, 1e-6).permute(0, 2, 3, 1)
+    if film_on:
+        y = y * (1 + fd[:, Cc:].view(B, 1, 1, Cc)) + fd[:, :Cc].view(B, 1, 1, Cc)        # unet.py:145: shift first, scale second
+    if silu:
+        y = F.silu(y)
+    if mask is not None:
+        y = y * mask
+    (y * go.double()).sum().backward()
+    gx = torch.empty_like(x)
+    gg, gb = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+    gf = torch.empty(B, 2 * Cc, device="cuda") if film_on else None
+    _check(L, L.vdt_op_groupnorm_backward(_p(x), _p(go), Cc, B, H, W, _p(gamma), _p(beta), _p(film) if film_on else None, silu,
+                                          C.c_float(p), seed, layer, _p(gx), _p(gg), _p(gb), _p(gf) if film_on else None, None))
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return ((a.double() - b).norm() / b.norm()).item()
+    errs = {"x": rel(gx, xd.grad), "gamma": rel(gg, gd.grad), "beta": rel(gb, bd.grad)}
+    if film_on:
+        errs["film"] = rel(gf, fd.grad)
+    print(f"groupnorm backward {case}: " + ", ".join(f"d{k} {v:.2e}" for k, v in errs.items()))
+    assert max(errs.values()) < 2e-5, errs
+    gx2 = torch.empty_like(x)
+    _check(L, L.vdt_op_groupnorm_backward(_p(x), _p(go), Cc, B, H, W, _p(gamma), _p(beta), _p(film) if film_on else None, silu,
+                                          C.c_float(p), seed, layer, _p(gx2), _p(gg), _p(gb), _p(gf) if film_on else None, None))
+    torch.cuda.synchronize()
+    assert torch.equal(gx, gx2)                                  # fixed-order reductions: bit-reproducible
+
+
 BWD_CASES = [
     # B, H, cin, cout, k
     (4, 32, 256, 256, 3),       # the dominant shape of the CIFAR network

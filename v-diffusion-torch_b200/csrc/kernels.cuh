@@ -127,6 +127,22 @@ struct GroupNormParams {
 };
 cudaError_t launch_groupnorm(const GroupNormParams& p, cudaStream_t stream);
 
+// Backward of GroupNorm -> FiLM -> SiLU -> dropout (gn_backward.cu) for an fp32 [B, HW, C] input with C in
+// {128, 256, 512, 1024}; grad_out is the gradient at the activation (the forward's 16-bit rounding is straight-through).
+struct GroupNormBwdParams {
+    const float* x; const float* grad_out;
+    const float* gamma; const float* beta;
+    const float* film;                 // null or [B][2C]: shift(C) | scale(C) of every sample
+    int B, HW, C, silu;
+    float drop_p; unsigned long long drop_seed; int drop_layer;   // the forward's dropout stream (GroupNormParams)
+    void* scratch;                     // groupnorm_backward_scratch_bytes(B, HW, C)
+    float* grad_x;                     // [B, HW, C]
+    float* grad_gamma; float* grad_beta;   // [C]
+    float* grad_film;                  // null or [B][2C]: d shift | d scale
+};
+size_t groupnorm_backward_scratch_bytes(int B, int HW, int C, int* slabs_out = nullptr);
+cudaError_t launch_groupnorm_backward(const GroupNormBwdParams& p, cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------------
 // Self-attention softmax(q^T k / sqrt(d)) v per image and head, flash-style on tcgen05 (attention.cu)
 // ------------------------------------------------------------------------------------------------

@@ -1780,6 +1780,30 @@ extern "C" int vdt_op_groupnorm_dropout(const void* src1, int32_t c1, int32_t ba
     return rc;
 }
 
+extern "C" int vdt_op_groupnorm_backward(const float* x, const float* grad_out, int32_t c, int32_t batch, int32_t h, int32_t w,
+                                         const float* gamma, const float* beta, const float* film, int32_t silu, float drop_p,
+                                         uint64_t seed, int32_t layer, float* grad_x, float* grad_gamma, float* grad_beta,
+                                         float* grad_film, void* stream) {
+    if (!x || !grad_out || !gamma || !beta || !grad_x || !grad_gamma || !grad_beta) return fail("null argument");
+    if (batch < 1 || h < 1 || w < 1) return fail("empty input");
+    if (c % 128 != 0 || c > 1024 || 256 % (c / 4) != 0)
+        return fail("groupnorm backward takes 128, 256, 512 or 1024 channels (got %d)", c);
+    if (!(drop_p >= 0.f && drop_p < 1.f)) return fail("drop_p must lie in [0, 1)");
+    GroupNormBwdParams q{};
+    q.x = x; q.grad_out = grad_out; q.gamma = gamma; q.beta = beta; q.film = film;
+    q.B = batch; q.HW = h * w; q.C = c; q.silu = silu;
+    q.drop_p = drop_p; q.drop_seed = seed; q.drop_layer = layer;
+    q.grad_x = grad_x; q.grad_gamma = grad_gamma; q.grad_beta = grad_beta; q.grad_film = grad_film;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CK(cudaMalloc(&q.scratch, groupnorm_backward_scratch_bytes(batch, h * w, c)));
+    cudaError_t e = launch_groupnorm_backward(q, st);
+    g_launches += 5;
+    cudaStreamSynchronize(st);
+    cudaFree(q.scratch);
+    if (e != cudaSuccess) return fail("groupnorm backward: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int vdt_op_attention(const void* qkv, void* out, int32_t batch, int32_t n, int32_t heads, int32_t d,
                                 int32_t f16, void* stream) {
     const int hid = heads * d;
