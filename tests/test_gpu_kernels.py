@@ -421,6 +421,80 @@ def test_conv_backward_vs_autograd(L, B, H, cin, cout, k, f16):
     assert torch.equal(dw, dw2)
 
 
+@pytest.mark.parametrize("f16", [1, 0])
+@pytest.mark.parametrize("B,H,Cc", [(4, 16, 256), (2, 32, 256)])
+def test_residual_block_backward_composed_from_kernels(L, B, H, Cc, f16):
+    """A 256 -> 256 ResidualBlock (unet.py:106-148, eval-mode dropout) forward and backward, composed from this library's
+    kernels only -- GroupNorm fwd / bwd, conv fwd / dgrad / wgrad -- against fp64 autograd of the same block: the output,
+    d x, every parameter gradient and the FiLM (t_emb projection) gradient.  16-bit operands round activations, weights and
+    the gradients fed to dgrad / wgrad; everything else is fp32."""
+    g = torch.Generator(device="cuda").manual_seed(31 + H)
+    x = torch.randn(B, H, H, Cc, device="cuda", generator=g) * 1.2
+    film = torch.randn(B, 2 * Cc, device="cuda", generator=g) * 0.3
+    go = torch.randn(B, H, H, Cc, device="cuda", generator=g)
+    P = {}
+    for i in (1, 2):
+        P[f"g{i}"] = torch.rand(Cc, device="cuda", generator=g) + 0.5
+        P[f"be{i}"] = torch.randn(Cc, device="cuda", generator=g) * 0.2
+        P[f"w{i}"] = torch.randn(Cc, Cc, 3, 3, device="cuda", generator=g) / math.sqrt(Cc * 9)
+        P[f"b{i}"] = torch.randn(Cc, device="cuda", generator=g) * 0.1
+    dt = DT[f16]
+
+    def gn(src, gamma, beta, ftab):
+        out = torch.empty(B, H, H, Cc, device="cuda", dtype=dt)
+        _check(L, L.vdt_op_groupnorm(_p(src), Cc, None, 0, B, H, H, _p(gamma), _p(beta), _p(ftab), 2 * Cc, 0, 1, 0, _p(out), None, None,
+                                     f16, None, None, 4, 0, None))
+        return out
+
+    def conv(a, w, b, resid):
+        out = torch.empty(B, H, H, Cc, device="cuda")
+        _check(L, L.vdt_op_conv(_p(a), B, H, H, Cc, _p(w), Cc, 3, _p(b), _p(resid), _p(out), f16, None, None, 4, None))
+        return out
+
+    def conv_bwd(a, dy, w):
+        dy16 = dy.to(dt)
+        dx, dw, db = torch.empty(B, H, H, Cc, device="cuda"), torch.empty_like(w), torch.empty(Cc, device="cuda")
+        _check(L, L.vdt_op_conv_dgrad(_p(dy16), B, H, H, Cc, _p(w), Cc, 3, _p(dx), f16, None))
+        _check(L, L.vdt_op_conv_wgrad(_p(a), _p(dy16), B, H, H, Cc, Cc, 3, _p(dw), _p(db), f16, None))
+        return dx, dw, db
+
+    def gn_bwd(src, dy, gamma, beta, ftab):
+        dx, dg, db = torch.empty_like(src), torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+        df = torch.empty_like(ftab) if ftab is not None else None
+        _check(L, L.vdt_op_groupnorm_backward(_p(src), _p(dy), Cc, B, H, H, _p(gamma), _p(beta), _p(ftab), 1, C.c_float(0.0), 0, 0,
+                                              _p(dx), _p(dg), _p(db), _p(df), None))
+        return dx, dg, db, df
+    # forward
+    a1 = gn(x, P["g1"], P["be1"], None)
+    h1 = conv(a1, P["w1"], P["b1"], None)
+    a2 = gn(h1, P["g2"], P["be2"], film)
+    out = conv(a2, P["w2"], P["b2"], x)
+    # backward
+    got = {}
+    da2, got["w2"], got["b2"] = conv_bwd(a2, go, P["w2"])
+    dh1, got["g2"], got["be2"], got["film"] = gn_bwd(h1, da2, P["g2"], P["be2"], film)
+    da1, got["w1"], got["b1"] = conv_bwd(a1, dh1, P["w1"])
+    dxg, got["g1"], got["be1"], _ = gn_bwd(x, da1, P["g1"], P["be1"], None)
+    got["x"] = dxg + go                                           # identity skip
+    torch.cuda.synchronize()
+    # fp64 autograd of the same block
+    R = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    xd, fd = x.double().requires_grad_(True), film.double().requires_grad_(True)
+    nchw = lambda t: t.permute(0, 3, 1, 2)
+    y = F.silu(F.group_norm(nchw(xd), 32, R["g1"], R["be1"], 1e-6))
+    y = F.conv2d(y, R["w1"], R["b1"], padding=1)
+    y = F.group_norm(y, 32, R["g2"], R["be2"], 1e-6)
+    y = F.silu(y * (1 + fd[:, Cc:].view(B, Cc, 1, 1)) + fd[:, :Cc].view(B, Cc, 1, 1))
+    y = F.conv2d(y, R["w2"], R["b2"], padding=1) + nchw(xd)
+    y.backward(nchw(go.double()))
+    want = {k: v.grad for k, v in R.items()}
+    want["x"], want["film"] = xd.grad, fd.grad
+    errs = {"out": _rel(out, y.detach().permute(0, 2, 3, 1))}
+    errs.update({"d" + k: _rel(got[k], want[k]) for k in sorted(got)})
+    print(f"ResidualBlock fwd+bwd {Cc}ch @{H} B={B} {'fp16' if f16 else 'bf16'}: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    assert max(errs.values()) <= 8e-3 * EPS[f16], errs          # measured: 5.6e-4 (fp16), 4.3e-3 (bf16)
+
+
 def test_attention_cta_pair_variant_matches():
     """The opt-in cta_group::2 attention variant (VDT_ATTN_PAIR=1; measured slower, kept selectable) computes the same thing:
     run the attention parity cases that qualify (even number of query tiles, d % 128 == 0) in a child process with it on."""
