@@ -105,6 +105,25 @@ def main(tag):
     if os.path.exists(tp):
         open(os.path.join(PR, f"{tag}_kernel_timings.txt"), "w").write(
             f"# commit {stamp['git_head']}; scripts/prof_kernels.py: CUDA-event timings of single launches (not under a profiler)\n" + open(tp).read())
+    bp = os.path.join(GO, f"{tag}_backward_launches.csv")
+    if os.path.exists(bp):
+        fields, per = split_launch_csv(bp)
+        num = lambda r: float(r["Metric Value"].replace(",", ""))
+        mb = lambda r: num(r) * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(r["Metric Unit"], 1e-6)
+        t = [(r["Kernel Name"], num(r)) for r in per["gpu__time_duration.sum"]]
+        rd = [mb(r) for r in per["dram__bytes_read.sum"]]
+        wr = [mb(r) for r in per["dram__bytes_write.sum"]]
+        unit = per["gpu__time_duration.sum"][0]["Metric Unit"]
+        scale = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "nsecond": 1e-3, "ms": 1e3, "msecond": 1e3}.get(unit, 1.0)
+        with open(os.path.join(PR, f"{tag}_backward_launches.txt"), "w") as f:
+            f.write(f"# commit {stamp['git_head']}; ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none\n"
+                    "# python scripts/prof_kernels.py --backward --once: GroupNorm backward C256 @32 B=128 (five launches), then conv backward\n"
+                    "# (dgrad on conv_gemm_kernel incl. its weight-pack kernels, wgrad + split reduction + bias grad) for 256->256 k3 @32, @16 and 512->256 k3 @32, B=128\n"
+                    "# kernel, duration us, DRAM MB read + written\n")
+            for (name, dur), r, w in zip(t, rd, wr):
+                if name.startswith("void at::") or name.startswith("at::"):      # torch's own input-generation kernels
+                    continue
+                f.write(f"{name[:70]:70s} {dur * scale:10.1f} {r + w:10.1f}\n")
     # SASS opcode histogram of the shipped library: proves tcgen05 / TMEM / TMA (B200_PROFILING.md)
     sass = sh(f"cuobjdump -sass {ROOT}/v-diffusion-torch_b200/lib/libvdt_b200.so")
     ops = collections.Counter()
