@@ -34,7 +34,8 @@ def sh(cmd):
 
 
 def head():
-    return sh(f"git -C {ROOT} rev-parse --short HEAD").strip()
+    """the last commit that changed what was measured (kernel sources, host runtime, bench) -- later commits are docs / evidence"""
+    return sh(f"git -C {ROOT} log -1 --format=%h -- v-diffusion-torch_b200 bench.py scripts/prof_kernels.py").strip()
 
 
 def split_launch_csv(path):
@@ -105,6 +106,26 @@ def main(tag):
     if os.path.exists(tp):
         open(os.path.join(PR, f"{tag}_kernel_timings.txt"), "w").write(
             f"# commit {stamp['git_head']}; scripts/prof_kernels.py: CUDA-event timings of single launches (not under a profiler)\n" + open(tp).read())
+    rp = os.path.join(GO, f"{tag}_kernels.ncu-rep")
+    if os.path.exists(rp):
+        # per-instruction warp-stall samples of the attention kernel (source page of the same capture)
+        page = sh(f"ncu -i {rp} --page source --csv --kernel-name regex:attention_kernel")
+        lines = page.splitlines()
+        hdr = next((i for i, l in enumerate(lines) if l.startswith('"Address"')), None)
+        if hdr is not None:
+            rows = list(csv.DictReader(lines[hdr:]))
+            reasons = [k for k in rows[0] if k.startswith("stall_") and "Not Issued" not in k]
+            tot = sum(int(r["# Samples"] or 0) for r in rows)
+            dur = sh(f"ncu -i {rp} --page raw --csv --metrics gpu__time_duration.sum,sm__pipe_tensor_subunit_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum "
+                     f"--kernel-name regex:attention_kernel").strip().splitlines()[-1]
+            with open(os.path.join(PR, f"{tag}_attention_stalls.txt"), "w") as f:
+                f.write(f"# commit {stamp['git_head']}; ncu --set full --import-source on, persistent attention_kernel<fp16>, N=1024 d=256, 1024 images\n"
+                        f"# raw metrics row (gpu__time_duration ms, ...): {dur[-120:]}\n"
+                        f"# warp-stall samples by SASS instruction (total {tot}); columns: samples, share, times executed, instruction, top stall reasons\n")
+                for r in sorted(rows, key=lambda r: -int(r["# Samples"] or 0))[:40]:
+                    n = int(r["# Samples"] or 0)
+                    top = sorted(((k[6:], int(r[k] or 0)) for k in reasons), key=lambda kv: -kv[1])[:3]
+                    f.write(f"{n:7d} {100.0 * n / max(1, tot):5.1f}% {r['Instructions Executed']:>9s}  {r['Source'].strip()[:80]:80s} {top}\n")
     bp = os.path.join(GO, f"{tag}_backward_launches.csv")
     if os.path.exists(bp):
         fields, per = split_launch_csv(bp)
