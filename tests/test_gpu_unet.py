@@ -157,6 +157,54 @@ def test_p_sample_chunking_and_roundtrip_properties():
     assert (c - b[perm]).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("name", ["ddim_cfg_v", "ancestral_cfg_v", "ddim_cfg_multitag"])
+def test_cfg_shared_prefix_is_bit_identical(name, monkeypatch):
+    """Under CFG the cond / uncond rows of a sample share in_conv, norm1 and conv1 of block 0 (computed once per sample:
+    they do not depend on the label).  Same arithmetic in the same order: the samples must be bit-identical to the
+    row-by-row path (VDT_NO_CFG_SHARE=1), for one chunk and for several ragged chunks."""
+    case = SAMPLE_CASES[name]
+    ucase = UNET_CASES[case["unet"]]
+    diff = _diffusion(case)
+    noise, label, step_noise = build_sample_inputs(case, ucase["cfg"])
+    outs = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("VDT_NO_CFG_SHARE", "1")
+        for max_rows in (64, 6):
+            net = _model(ucase["cfg"], ucase["seed"])            # a fresh plan: the switch is read when an exec is built
+            net.max_rows = max_rows
+            outs.append(diff.p_sample(net, tuple(noise.shape), noise=noise, label=label, device="cuda", use_ddim=case["use_ddim"],
+                                      step_noise=step_noise))
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+    assert torch.isfinite(outs[0]).all()
+
+
+def test_p_sample_edge_batches():
+    """Edge batches of the sampler: empty (nothing launched, empty tensor back), a single image and an odd batch under CFG
+    (2B rows, ragged last tile) reproduce the same images as inside a larger batch; a noise tensor of the wrong shape and
+    an unknown output type raise like the reference (ValueError / NotImplementedError, diffusion.py:253-257)."""
+    from v_diffusion_b200 import GaussianDiffusion, get_logsnr_schedule
+    case = SAMPLE_CASES["ddim_cfg_v"]
+    ucase = UNET_CASES[case["unet"]]
+    net = _model(ucase["cfg"], ucase["seed"])
+    diff = _diffusion(case)
+    g = torch.Generator().manual_seed(9)
+    noise = torch.randn(5, 3, 16, 16, generator=g)
+    label = torch.randint(0, 11, (5,), generator=g)
+    full = diff.p_sample(net, (5, 3, 16, 16), noise=noise, label=label, device="cuda", use_ddim=True)
+    empty = diff.p_sample(net, (0, 3, 16, 16), noise=noise[:0], label=label[:0], device="cuda", use_ddim=True)
+    assert tuple(empty.shape) == (0, 3, 16, 16) and empty.device.type == "cpu"
+    one = diff.p_sample(net, (1, 3, 16, 16), noise=noise[2:3], label=label[2:3], device="cuda", use_ddim=True)
+    three = diff.p_sample(net, (3, 3, 16, 16), noise=noise[1:4], label=label[1:4], device="cuda", use_ddim=True)
+    assert (one - full[2:3]).abs().max().item() <= 1e-5 and (three - full[1:4]).abs().max().item() <= 1e-5
+    with pytest.raises(ValueError):
+        diff.p_sample(net, (5, 3, 16, 16), noise=noise[:4], label=label, device="cuda", use_ddim=True)
+    with pytest.raises(NotImplementedError):
+        GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), 10, "velocity", "fixed_large", "constant", "mse")
+    with pytest.raises(RuntimeError):                        # no CPU fallback
+        diff.p_sample(net, (1, 3, 16, 16), noise=noise[:1], label=label[:1], device="cpu", use_ddim=True)
+
+
 @pytest.mark.parametrize("name", ["cifar_cond", "small_cond"])
 def test_bf16_operand_mode_forward(golden_dir, name):
     """bf16 operands (the north-star's nominal format): same kernels, 8-bit mantissa.  A single UNet call stays inside

@@ -72,7 +72,8 @@ __device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int w, int 
 // are issue-bound otherwise); ragged tiles and SiLU epilogues take epilogue_rowmajor_generic.
 // MAP: 0 rows are stored where they were computed; 1 sub-pixel upsampling conv (ConvParams::ups): row = low-res pixel,
 // stored at its high-resolution position of parity `par`; 2 upsampled identity skip (ConvParams::resid_up): the residual
-// of output pixel (y, x) is low-res pixel (y >> 1, x >> 1).  Both need power-of-two square maps (map_shift).
+// of output pixel (y, x) is low-res pixel (y >> 1, x >> 1); 3 shared residual (ConvParams::resid_rep == 2): image i adds
+// residual image i >> 1.  All three need power-of-two square maps (map_shift).
 template <bool F16, bool F32OUT, bool RESID, int STATS, int MAP>   // STATS: 0 none, 4 / 2 = columns per statistics entry
 __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, uint32_t tile, int lane, long long wrow0, int col0, int slab,
                                                   const float4 b4, int par) {
@@ -94,6 +95,9 @@ __device__ __forceinline__ void epilogue_rowmajor(const ConvParams& p, uint32_t 
                 const int pix = pix0 + 4 * i;
                 const int shl = (MAP == 2) ? sh - 1 : 0;           // log2 of the low-resolution width
                 const long long src = (img << (2 * shl)) + ((pix >> (sh + 1)) << shl) + ((pix & wmask) >> 1);
+                res[i] = ldg_nc_v4_issue(p.residual + static_cast<size_t>(src) * p.ld + colo);
+            } else if (MAP == 3) {
+                const long long src = ((img >> 1) << (2 * sh)) + (pix0 + 4 * i);
                 res[i] = ldg_nc_v4_issue(p.residual + static_cast<size_t>(src) * p.ld + colo);
             } else {
                 res[i] = ldg_nc_v4_issue(p.residual + off0 + i * step);
@@ -184,6 +188,9 @@ __device__ __noinline__ void epilogue_rowmajor_generic(const ConvParams& p, uint
                 const int pix = static_cast<int>(g - img * p.HW);
                 const int y = pix / p.out_w, x = pix - y * p.out_w;
                 roff = static_cast<size_t>(img * (p.HW >> 2) + static_cast<long long>(y >> 1) * (p.out_w >> 1) + (x >> 1)) * p.ld + col0 + cq * 4;
+            } else if (p.resid_rep > 1) {                    // rows of resid_rep consecutive images share one residual image
+                const long long img = g / p.HW;
+                roff = static_cast<size_t>((img / p.resid_rep) * p.HW + (g - img * p.HW)) * p.ld + col0 + cq * 4;
             }
             const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.residual + roff));
             o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
@@ -343,10 +350,11 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         {
             const bool f32o = p.out_mode == kOutF32, resid = p.residual != nullptr;
             const int sti = (p.stats == nullptr) ? 2 : (p.stat_cols == 4 ? 0 : 1);
-            const bool mapped = p.ups || p.resid_up;
+            const bool mapped = p.ups || p.resid_up || p.resid_rep > 1;
             if (p.act_silu || (mapped && p.map_shift < 3) || (!f32o && resid)) variant = -1;
             else if (p.ups) variant = (f32o ? 9 : 12) + sti;
             else if (p.resid_up) variant = f32o ? 15 + sti : -1;
+            else if (p.resid_rep > 1) variant = (f32o && resid && p.resid_rep == 2) ? 18 + sti : -1;
             else if (f32o) variant = (resid ? 0 : 3) + sti;
             else variant = 6 + sti;
         }
@@ -418,6 +426,8 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                         case 12: VDT_EPI(false, false, 4, 1); case 13: VDT_EPI(false, false, 2, 1); case 14: VDT_EPI(false, false, 0, 1);
                         // conv2 of an upsampling block: residual gathered from the low-resolution stream
                         case 15: VDT_EPI(true, true, 4, 2);   case 16: VDT_EPI(true, true, 2, 2);   case 17: VDT_EPI(true, true, 0, 2);
+                        // conv2 of block 0 under CFG: the cond / uncond rows of a sample share the residual (in_conv's output)
+                        case 18: VDT_EPI(true, true, 4, 3);   case 19: VDT_EPI(true, true, 2, 3);   case 20: VDT_EPI(true, true, 0, 3);
                         default: epilogue_rowmajor_generic(p, tile, lane, q, m_tile, wrow0, col0, b4, par); break;
                     }
 #undef VDT_EPI

@@ -127,8 +127,9 @@ __device__ __forceinline__ float2 group_mean_rstd(const GroupNormParams& p, int 
     // entries of stat_cols channels; a group may straddle the concat seam, so each entry picks its source
     const int sc = p.stat_cols, sub = cpg / sc, slabs = p.stat_slabs;
     const int e1 = p.C1 / sc, e2 = p.C2 / sc;              // entries per slab in source 1 / 2
-    const float2* s1 = p.stats1 + static_cast<size_t>(b) * slabs * e1;
-    const float2* s2 = p.stats2 ? p.stats2 + static_cast<size_t>(b) * slabs * e2 : nullptr;
+    const int b1 = p.rep1 > 1 ? b / p.rep1 : b, b2 = p.rep2 > 1 ? b / p.rep2 : b;     // shared sources (GroupNormParams::rep1)
+    const float2* s1 = p.stats1 + static_cast<size_t>(b1) * slabs * e1;
+    const float2* s2 = p.stats2 ? p.stats2 + static_cast<size_t>(b2) * slabs * e2 : nullptr;
     double ds = 0.0, dss = 0.0;
     const int ent0 = g * sub;                                // first entry of this group over the concatenated channels
     if (ent0 + sub <= e1 || ent0 >= e1) {
@@ -187,9 +188,10 @@ __global__ void __launch_bounds__(1024, 1) groupnorm_kernel(const GroupNormParam
     const int pp = active ? tid / CV : 0;
     const int c = cv * VEC;                          // first channel owned by this thread
     const bool from1 = c < p.C1;
-    const float* src = from1 ? static_cast<const float*>(p.src1) + static_cast<size_t>(b) * HW * p.C1 + c
-                             : p.src2 + static_cast<size_t>(b) * HW * p.C2 + (c - p.C1);
-    const h16* src16 = static_cast<const h16*>(p.src1) + static_cast<size_t>(b) * HW * p.C1 + c;   // IN16 only
+    const int b1 = p.rep1 > 1 ? b / p.rep1 : b, b2 = p.rep2 > 1 ? b / p.rep2 : b;     // rows that share a source image
+    const float* src = from1 ? static_cast<const float*>(p.src1) + static_cast<size_t>(b1) * HW * p.C1 + c
+                             : p.src2 + static_cast<size_t>(b2) * HW * p.C2 + (c - p.C1);
+    const h16* src16 = static_cast<const h16*>(p.src1) + static_cast<size_t>(b1) * HW * p.C1 + c;   // IN16 only
     const int sC = from1 ? p.C1 : p.C2;
     float amax = 0.f;                                // fp16 range events seen by this thread (see GroupNormParams::sat_count)
     auto load_px = [&](int pix, float (&v)[VEC]) {

@@ -45,6 +45,8 @@ struct alignas(64) ConvParams {
     int f16;                           // operand / 16-bit output format: 1 fp16, 0 bf16
     const float* bias;                 // [Cout]
     const float* residual;             // fp32 [M, ld] or null
+    int resid_rep;                     // > 1: output image i adds residual image i / resid_rep ([M / resid_rep, ld]; CFG row pairs
+                                       // share the residual computed before the first FiLM); power-of-two HW takes the fast epilogue
     float* out_f32;
     h16* out_bf16;
     // optional GroupNorm partial statistics of the row-major output (after bias/residual): for every slab of
@@ -96,6 +98,9 @@ struct GroupNormParams {
     const void* src1; int C1;          // fp32 (or 16-bit when in16) [B, HW, C1]
     const float* src2; int C2;         // fp32 [B, HW, C2] or null: channels C1..C1+C2 (virtual concat)
     int in16;                          // src1 holds 16-bit values in the launch's operand format (C2 must be 0)
+    // rep1 / rep2 > 1: output sample b reads image b / rep of that source (and its statistics): under CFG the cond /
+    // uncond rows of a sample share every tensor computed before the first FiLM (in_conv, norm1 + conv1 of block 0)
+    int rep1, rep2;
     // partial statistics written by the producing conv epilogue (ConvParams::stats); when stats1 is set the
     // kernel is a single streaming pass (after a tiny finalize launch that combines the partials of every image into the
     // 32 (mean, rstd) pairs in a fixed order), otherwise it makes a statistics pass of its own

@@ -771,6 +771,7 @@ struct ConvSpec {
     unsigned long long* sat_count = nullptr;
     int ups = 0;          // sub-pixel 2x-upsampling conv: a3 is the LOW-res tensor [n, h, w, c3], the output is [n, 2h, 2w, cout]
     int resid_up = 0;     // residual is the low-res tensor [n, h/2, w/2, ld] of an upsampling block's identity skip
+    int resid_rep = 0;    // > 1: residual holds n / resid_rep images, shared by consecutive output images (CFG row pairs)
 };
 
 static int setup_conv(const ConvSpec& s, ConvParams* cp) {
@@ -830,8 +831,10 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     cp->bias = s.bias; cp->residual = s.residual; cp->out_f32 = s.out_f32; cp->out_bf16 = s.out_bf16; cp->stat_cols = s.stat_cols;
     cp->stats = (slabs > 0 && (s.a3 || flat_ok || geo_pointwise)) ? s.stats : nullptr;   // statistics slabs never span two images
     cp->ups = s.ups; cp->ups_w = s.w; cp->stat_slabs_img = slabs; cp->resid_up = s.resid_up; cp->out_w = s.w;
+    cp->resid_rep = s.residual ? s.resid_rep : 0;
+    if (s.resid_rep > 1 && (s.resid_up || s.ups || s.n % s.resid_rep != 0)) return fail("internal: shared residual on a resampling conv");
     cp->map_shift = -1;                                  // fast row remaps need square power-of-two maps of >= 64 (ups) / 256 pixels
-    if ((s.ups || s.resid_up) && s.h == s.w && (s.w & (s.w - 1)) == 0)
+    if ((s.ups || s.resid_up || s.resid_rep > 1) && s.h == s.w && (s.w & (s.w - 1)) == 0)
         for (int k = 3; k < 16; ++k) if ((1 << k) == s.w) cp->map_shift = k;
     if (s.ups && (s.a1 || !s.a3)) return fail("internal: the sub-pixel upsampling conv takes a single 3x3 operand");
     if (s.ups && s.stats && 4 * slabs != stat_slabs_per_image(2 * s.h, 2 * s.w)) cp->stats = nullptr;   // callers check fusability first
@@ -864,41 +867,57 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
         return ((size_t)imgs * stat_slabs_per_image(r, r) + 4) * (size_t)(ch / scols) * sizeof(float2);
     };
     const bool sp = p->split != 0;
+    auto fusable = [scols](int c1, int c2, int r) {   // can a GroupNorm over concat(c1, c2) at r x r use epilogue statistics?
+        const int cpg = (c1 + c2) / 32;
+        // groups may straddle the concat seam (finalize handles it); no statistics slab may mix two images
+        return cpg % scols == 0 && c1 % scols == 0 && stat_slabs_per_image(r, r) > 0;
+    };
+    // Under CFG the cond / uncond rows of a sample (rows 2i, 2i + 1) see the same x_t and t and differ only in the class
+    // embedding, which first enters at the FiLM of block 0's norm2: in_conv, norm1 and conv1 of block 0 are computed once
+    // per SAMPLE, norm2 / conv2's identity skip / the last up block's concat read the shared tensors (GroupNormParams::rep1,
+    // ConvParams::resid_rep).  Same arithmetic in the same order: results are bit-identical to the row-by-row path.
+    bool share0 = ex->rep == 2 && !sp && !p->blocks.empty() && getenv("VDT_NO_CFG_SHARE") == nullptr;
+    if (share0) {
+        const auto& b0 = p->blocks[0];
+        share0 = b0.kind == 0 && !b0.concat && b0.cin == b0.cout && b0.cin == hid && b0.resample == kResNone &&
+                 fusable(hid, 0, res) && fusable(b0.cout, 0, res);
+    }
+    const int R0 = share0 ? R / ex->rep : R;                // rows of the tensors computed before the first FiLM
     h16* patches; h16* patches_lo = nullptr; float* h; float2* hst;
     const size_t hw0 = (size_t)res * res;
-    CKI(ex->acquire((size_t)R * hw0 * 64 * 2, (void**)&patches));
-    if (sp) CKI(ex->acquire((size_t)R * hw0 * 64 * 2, (void**)&patches_lo));
-    ex->im2cols.push_back({ex->xin, patches, patches_lo, R / ex->rep, ex->rep, c.in_channels, res, res, p->f16});
+    CKI(ex->acquire((size_t)R0 * hw0 * 64 * 2, (void**)&patches));
+    if (sp) CKI(ex->acquire((size_t)R0 * hw0 * 64 * 2, (void**)&patches_lo));
+    ex->im2cols.push_back({ex->xin, patches, patches_lo, R / ex->rep, share0 ? 1 : ex->rep, c.in_channels, res, res, p->f16});
     ex->steps.push_back({S_IM2COL, (int)ex->im2cols.size() - 1});
-    CKI(ex->acquire((size_t)R * hw0 * hid * 4, (void**)&h));
-    CKI(ex->acquire(stats_bytes(R, res, hid), (void**)&hst));
+    CKI(ex->acquire((size_t)R0 * hw0 * hid * 4, (void**)&h));
+    CKI(ex->acquire(stats_bytes(R0, res, hid), (void**)&hst));
     {
         ConvSpec s;
         s.f16 = p->f16; s.stat_cols = p->stat_cols; s.sat_count = p->sat_count;
-        s.a1 = patches; s.a1_lo = patches_lo; s.c1 = 64; s.ld1 = 64; s.n = R; s.h = res; s.w = res; s.wpacked = p->w_in; s.cout = hid; s.wrows = hid;
+        s.a1 = patches; s.a1_lo = patches_lo; s.c1 = 64; s.ld1 = 64; s.n = R0; s.h = res; s.w = res; s.wpacked = p->w_in; s.cout = hid; s.wrows = hid;
         s.bias = p->W("in_conv.bias"); s.out_mode = kOutF32; s.out_f32 = h; s.ld = hid; s.stats = hst;
         CKI(add_conv(s));
     }
     ex->release(patches);
     float2* meanrstd;                                 // (mean, rstd) scratch shared by all GroupNorms (stream-ordered)
     CKI(ex->acquire((size_t)R * 32 * sizeof(float2), (void**)&meanrstd));
-    struct Skip { float* ptr; float2* stats; int ch; };
+    struct Skip { float* ptr; float2* stats; int ch; int rep; };   // rep 2: R / 2 images shared by the rows of a CFG pair
     std::vector<Skip> stack;
-    stack.push_back({h, hst, hid});
+    stack.push_back({h, hst, hid, share0 ? ex->rep : 1});
     bool h_on_stack = true;      // h aliases the top stack entry -> must not be released when replaced
     int hch = hid;
-    auto fusable = [scols](int c1, int c2, int r) {   // can a GroupNorm over concat(c1, c2) at r x r use epilogue statistics?
-        const int cpg = (c1 + c2) / 32;
-        // groups may straddle the concat seam (finalize handles it); no statistics slab may mix two images
-        return cpg % scols == 0 && c1 % scols == 0 && stat_slabs_per_image(r, r) > 0;
-    };
+    int h_rep = share0 ? ex->rep : 1;                       // > 1 only between in_conv and block 0's norm2
 
     for (auto& b : p->blocks) {
         const std::string& n = b.name;
         const int HW = res * res;
         if (b.kind == 0) {
-            const float* src2 = nullptr; int c2 = 0; float* src2_buf = nullptr; float2* st2 = nullptr;
-            if (b.concat) { Skip sk = stack.back(); stack.pop_back(); src2 = sk.ptr; c2 = sk.ch; src2_buf = sk.ptr; st2 = sk.stats; }
+            const float* src2 = nullptr; int c2 = 0; float* src2_buf = nullptr; float2* st2 = nullptr; int rep2 = 1;
+            if (b.concat) { Skip sk = stack.back(); stack.pop_back(); src2 = sk.ptr; c2 = sk.ch; src2_buf = sk.ptr; st2 = sk.stats; rep2 = sk.rep; }
+            // rows of norm1 / conv1: the shared count while h is still label-independent (block 0 under CFG, see share0)
+            const int Rn = R / h_rep;
+            if (h_rep > 1 && (b.concat || b.cin != b.cout || b.resample != kResNone))
+                return fail("internal: shared rows reach a block that cannot take them (%s)", n.c_str());
             const int cin = hch + c2;
             if (cin != b.cin) return fail("internal: channel bookkeeping mismatch at %s (%d vs %d)", n.c_str(), cin, b.cin);
             const bool skipconv = b.cin != b.cout;
@@ -911,14 +930,15 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             const int ra = up ? res : ro;                       // resolution of conv1's A operand
             const size_t HWa = (size_t)ra * ra;
             h16 *a1, *xraw = nullptr, *a1_lo = nullptr, *xraw_lo = nullptr; float* xres = nullptr;
-            CKI(ex->acquire((size_t)R * HWa * cin * 2, (void**)&a1));
-            if (sp) CKI(ex->acquire((size_t)R * HWa * cin * 2, (void**)&a1_lo));
+            CKI(ex->acquire((size_t)Rn * HWa * cin * 2, (void**)&a1));
+            if (sp) CKI(ex->acquire((size_t)Rn * HWa * cin * 2, (void**)&a1_lo));
             if (skipconv) CKI(ex->acquire((size_t)R * HW * cin * 2, (void**)&xraw));
             if (skipconv && sp) CKI(ex->acquire((size_t)R * HW * cin * 2, (void**)&xraw_lo));
             if (b.resample == kResDown) CKI(ex->acquire((size_t)R * HWo * cin * 4, (void**)&xres));
             GroupNormParams g{};
             g.f16 = p->f16; g.stat_cols = p->stat_cols; g.sat_count = p->sat_count;
-            g.src1 = h; g.C1 = hch; g.src2 = src2; g.C2 = c2; g.B = R; g.H = res; g.W = res;
+            g.src1 = h; g.C1 = hch; g.src2 = src2; g.C2 = c2; g.B = Rn; g.H = res; g.W = res;
+            g.rep2 = rep2 > 1 ? rep2 : 0;                   // the in_conv output popped by the last up block may be shared
             if (fusable(hch, c2, res)) { g.stats1 = hst; g.stats2 = st2; g.meanrstd = meanrstd; g.stat_slabs = stat_slabs_per_image(res, res); }
             g.gamma = p->W(n + ".norm1.weight"); g.beta = p->W(n + ".norm1.bias");
             g.silu = 1; g.resample = up ? kResNone : b.resample; g.out_act = a1; g.out_raw = xraw; g.out_res = xres;
@@ -931,12 +951,13 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             // (split-precision mode keeps every stream tensor fp32)
             const bool h1_16 = fuse2 && !sp;
             void* h1; float2* h1st = nullptr;
-            CKI(ex->acquire((size_t)R * HWo * b.cout * (h1_16 ? 2 : 4), &h1));
-            if (fuse2) CKI(ex->acquire(stats_bytes(R, ro, b.cout), (void**)&h1st));
+            if (h_rep > 1 && !h1_16) return fail("internal: shared rows need the single-pass norm2 (%s)", n.c_str());
+            CKI(ex->acquire((size_t)Rn * HWo * b.cout * (h1_16 ? 2 : 4), &h1));
+            if (fuse2) CKI(ex->acquire(stats_bytes(Rn, ro, b.cout), (void**)&h1st));
             {
                 ConvSpec s;
                 s.f16 = p->f16; s.stat_cols = p->stat_cols; s.sat_count = p->sat_count;
-                s.a3 = a1; s.a3_lo = a1_lo; s.c3 = cin; s.n = R; s.h = ra; s.w = ra; s.wpacked = b.w1; s.cout = b.cout; s.wrows = b.cout;
+                s.a3 = a1; s.a3_lo = a1_lo; s.c3 = cin; s.n = Rn; s.h = ra; s.w = ra; s.wpacked = b.w1; s.cout = b.cout; s.wrows = b.cout;
                 s.ups = up ? 1 : 0;
                 s.bias = p->W(n + ".conv1.bias"); s.ld = b.cout; s.stats = h1st;
                 if (h1_16) { s.out_mode = kOutBF16; s.out_bf16 = (h16*)h1; } else { s.out_mode = kOutF32; s.out_f32 = (float*)h1; }
@@ -950,7 +971,9 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             if (sp) CKI(ex->acquire((size_t)R * HWo * b.cout * 2, (void**)&a2_lo));
             GroupNormParams g2{};
             g2.f16 = p->f16; g2.stat_cols = p->stat_cols; g2.sat_count = p->sat_count;
-            g2.src1 = h1; g2.C1 = b.cout; g2.B = R; g2.H = ro; g2.W = ro; g2.in16 = h1_16 ? 1 : 0; g2.stats1 = h1st; g2.meanrstd = meanrstd; g2.stat_slabs = stat_slabs_per_image(ro, ro);
+            g2.src1 = h1; g2.C1 = b.cout; g2.B = R; g2.H = ro; g2.W = ro; g2.in16 = h1_16 ? 1 : 0;
+            g2.stats1 = h1st; g2.meanrstd = meanrstd; g2.stat_slabs = stat_slabs_per_image(ro, ro);
+            g2.rep1 = h_rep > 1 ? h_rep : 0;                // every row of a CFG pair normalises the shared conv1 output with its own FiLM
             g2.out_act_lo = a2_lo;
             g2.gamma = p->W(n + ".norm2.weight"); g2.beta = p->W(n + ".norm2.bias");
             g2.film = film; g2.film_row = film_row; g2.film_stride = p->film_total; g2.film_off = b.film_off;
@@ -973,6 +996,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
                 s.bias = b.bias2;
                 s.residual = skipconv ? nullptr : (b.resample == kResDown ? xres : h);
                 s.resid_up = (up && !skipconv) ? 1 : 0;
+                s.resid_rep = (h_rep > 1 && s.residual == h) ? h_rep : 0;
                 s.out_mode = kOutF32; s.out_f32 = hout; s.ld = b.cout; s.stats = houtst;
                 CKI(add_conv(s));
             }
@@ -983,7 +1007,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             if (xres) ex->release(xres);
             if (src2_buf) { ex->release(src2_buf); ex->release(st2); }
             if (!h_on_stack) { ex->release(h); ex->release(hst); }
-            h = hout; hst = houtst; hch = b.cout; h_on_stack = false; res = ro;
+            h = hout; hst = houtst; hch = b.cout; h_on_stack = false; res = ro; h_rep = 1;
         } else {
             int hd, nh;
             attn_dims(c, b.cin, &hd, &nh);
@@ -1055,7 +1079,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
             if (!h_on_stack) { ex->release(h); ex->release(hst); }
             h = hout; hst = houtst; h_on_stack = false;
         }
-        if (b.push) { stack.push_back({h, hst, hch}); h_on_stack = true; }
+        if (b.push) { stack.push_back({h, hst, hch, 1}); h_on_stack = true; }
     }
     if (!stack.empty()) return fail("internal: skip stack not empty (%d)", (int)stack.size());
     // ---- out_conv

@@ -141,6 +141,8 @@ class GaussianDiffusion:
         x_t = x_t.to(torch.float32).contiguous()
         if tuple(x_t.shape) != tuple(shape):
             raise ValueError(f"noise has shape {tuple(x_t.shape)}, expected {tuple(shape)}")
+        if B == 0:                                           # an empty batch has nothing to launch
+            return x_t.cpu()
         label = self._prepare_label(denoise_fn, label, B, device)
         if step_noise is not None:
             step_noise = step_noise.to(device=device, dtype=torch.float32).contiguous()
