@@ -176,18 +176,19 @@ __global__ void __launch_bounds__(kThreads) gn_bwd_finalize_kernel(const BwdArgs
     }
 }
 
-// d gamma / d beta: fixed-order sum over the samples
-__global__ void gn_bwd_param_kernel(const BwdArgs p) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// d gamma / d beta: one warp per channel, lanes stride over the samples, fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(256) gn_bwd_param_kernel(const BwdArgs p) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= p.C) return;
     double dg = 0.0, db = 0.0;
-    for (int b = 0; b < p.B; ++b) {
+    for (int b = lane; b < p.B; b += 32) {
         const float2 t = p.ab[static_cast<size_t>(b) * p.C + c];
         const double fs = p.film ? 1.0 + p.film[static_cast<size_t>(b) * 2 * p.C + p.C + c] : 1.0;
         db += fs * t.x; dg += fs * t.y;
     }
-    p.grad_gamma[c] = static_cast<float>(dg);
-    p.grad_beta[c] = static_cast<float>(db);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { dg += __shfl_xor_sync(0xffffffffu, dg, o); db += __shfl_xor_sync(0xffffffffu, db, o); }
+    if (lane == 0) { p.grad_gamma[c] = static_cast<float>(dg); p.grad_beta[c] = static_cast<float>(db); }
 }
 
 // pass 2: dx
@@ -242,7 +243,7 @@ cudaError_t launch_groupnorm_backward(const GroupNormBwdParams& q, cudaStream_t 
     gn_stats_kernel<<<q.B, kThreads, kThreads * sizeof(float2), stream>>>(q.x, mr, q.HW, q.C);
     gn_bwd_reduce_kernel<<<dim3(slabs, q.B), kThreads, kThreads * 4 * sizeof(float2), stream>>>(p);
     gn_bwd_finalize_kernel<<<q.B, kThreads, q.C * sizeof(double2), stream>>>(p);
-    gn_bwd_param_kernel<<<(q.C + 127) / 128, 128, 0, stream>>>(p);
+    gn_bwd_param_kernel<<<(q.C + 7) / 8, 256, 0, stream>>>(p);
     gn_bwd_apply_kernel<<<dim3(slabs, q.B), kThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
