@@ -406,6 +406,8 @@ def run_b200(args, rank, world, local_rank):
     L.vdt_plan_flops(plan, C.byref(fc), C.byref(fa), C.byref(fl))
     rows = (2 if use_cfg else 1) * B
     flop_per_row = fc.value + fa.value + fl.value
+    fexec = C.c_double()
+    L.vdt_plan_conv_flops_executed(plan, 1 if use_cfg else 0, C.byref(fexec))
     conv_tflops = fc.value * rows / (fam_ms[0] * 1e-3) / 1e12 if fam_ms[0] > 0 else 0.0
     peaks = read_peaks()
     prof_total = sum(fam_ms)
@@ -427,6 +429,9 @@ def run_b200(args, rank, world, local_rank):
                 "traffic_note": "avg dram__bytes_read+write per conv launch (ncu, one chunk of chunk_rows UNet rows); "
                                 "launches_per_step counts every chunk's launches",
                 "algorithmic_flop_per_launch_avg": fc.value * rows / max(1, fam_n[0]),
+                "executed_over_algorithmic_conv_flops": fexec.value / fc.value,
+                "executed_note": "achieved / frac count the reference graph's FLOPs; the kernels execute fewer (sub-pixel "
+                                 "upsampling convs, the CFG pair's shared label-independent prefix) -- multiply by this ratio for the tensor-pipe rate",
                 "avg_launch_ms": fam_ms[0] / max(1, fam_n[0]), "launches_per_step": int(fam_n[0]),
                 "step_share": {"conv": fam_ms[0] / prof_total, "groupnorm": fam_ms[1] / prof_total,
                                "attention": fam_ms[2] / prof_total, "other": fam_ms[3] / prof_total},

@@ -153,6 +153,9 @@ uint64_t vdt_kernel_launches(void);
 /* Algorithmic FLOPs (1 MAC = 2 FLOP) of one UNet.forward batch row, split like SURVEY §6:
  * convolutions (incl. 1x1), attention matmuls, embedding linears. */
 int vdt_plan_flops(const vdt_plan* plan, double* conv, double* attn, double* linear);
+/* FLOPs per UNet row the conv kernels execute (padded in_conv / out_conv GEMMs, sub-pixel upsampling convs; with
+ * cfg_rows != 0 the label-independent prefix -- in_conv and conv1 of block 0 -- counted once per CFG row pair). */
+int vdt_plan_conv_flops_executed(const vdt_plan* plan, int32_t cfg_rows, double* out);
 
 /* Per-kernel-family device timing.  While enabled, steps run eagerly (no graph) with a CUDA-event pair
  * around every launch on the launching stream; vdt_profile_read returns accumulated milliseconds and launch

@@ -113,6 +113,7 @@ def lib():
     L.vdt_stat_slabs_per_image.argtypes = [i32, i32]
     L.vdt_unet_forward_train.argtypes = [vp, vp, vp, vp, vp, i32, C.c_float, C.c_uint64, vp]
     L.vdt_op_groupnorm_dropout.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, C.c_float, C.c_uint64, i32, vp]
+    L.vdt_plan_conv_flops_executed.argtypes = [vp, i32, vp]
     L.vdt_op_groupnorm_backward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, C.c_float, C.c_uint64, i32, vp, vp, vp, vp, vp]
     L.vdt_op_conv_dgrad.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, vp]
     L.vdt_op_conv_wgrad.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]
@@ -132,7 +133,8 @@ EXPORTS = ["vdt_last_error", "vdt_version", "vdt_kernel_launches", "vdt_plan_cre
            "vdt_op_conv", "vdt_op_groupnorm", "vdt_op_attention", "vdt_op_sampler_step", "vdt_stat_slabs_per_image",
            "vdt_plan_saturations", "vdt_images_to_uint8",
            "vdt_train_coefficients", "vdt_q_sample", "vdt_train_loss", "vdt_unet_forward_train", "vdt_op_groupnorm_dropout",
-           "vdt_op_conv_dgrad", "vdt_op_conv_wgrad", "vdt_op_groupnorm_backward"]
+           "vdt_op_conv_dgrad", "vdt_op_conv_wgrad", "vdt_op_groupnorm_backward",
+           "vdt_plan_conv_flops_executed"]
 
 
 def check(rc):

@@ -726,6 +726,46 @@ extern "C" int vdt_plan_flops(const vdt_plan* p, double* conv, double* attn, dou
     return 0;
 }
 
+// Can in_conv / norm1 / conv1 of block 0 be shared by the rows of a CFG pair (build_unet_steps: share0)?
+static bool cfg_prefix_shareable(const vdt_plan* p) {
+    if (p->split || p->blocks.empty() || getenv("VDT_NO_CFG_SHARE") != nullptr) return false;
+    const auto& b0 = p->blocks[0];
+    const int res = p->cfg.resolution, sc = p->stat_cols;
+    const bool stats_ok = stat_slabs_per_image(res, res) > 0 && (p->hid / 32) % sc == 0 && p->hid % sc == 0;
+    return b0.kind == 0 && !b0.concat && b0.cin == b0.cout && b0.cin == p->hid && b0.resample == kResNone && stats_ok;
+}
+
+// FLOPs the conv kernels actually execute per UNet row (vdt_plan_flops counts the reference's graph): in_conv runs K = 64
+// for its 9 * Cin <= 64 patch columns, out_conv 32 output columns for its 9 * Cout, the conv1 of an upsampling block 16 of
+// its 36 tap-GEMMs (sub-pixel form), and with cfg_rows != 0 the label-independent prefix runs once per CFG row pair.
+extern "C" int vdt_plan_conv_flops_executed(const vdt_plan* p, int32_t cfg_rows, double* out) {
+    if (!p || !out) return fail("null argument");
+    const vdt_unet_config& c = p->cfg;
+    const double hid = p->hid, res = c.resolution;
+    const double share = (cfg_rows && cfg_prefix_shareable(p)) ? 0.5 : 1.0;
+    double fc = share * 2.0 * res * res * hid * 64.0;
+    bool first = true;
+    for (const auto& b : p->blocks) {
+        const double r = b.res_in, hw = r * r;
+        if (b.kind == 0) {
+            const double ro = b.resample == kResDown ? r / 2 : b.resample == kResUp ? r * 2 : r;
+            const double taps1 = b.resample == kResUp ? 4.0 : 9.0;
+            fc += (first ? share : 1.0) * 2.0 * ro * ro * b.cout * taps1 * b.cin + 2.0 * ro * ro * b.cout * 9.0 * b.cout;
+            if (b.cin != b.cout) fc += 2.0 * ro * ro * b.cout * b.cin;
+        } else {
+            int hd, nh;
+            attn_dims(c, b.cin, &hd, &nh);
+            const double hidd = (double)hd * nh;
+            fc += 2.0 * hw * b.cin * 3 * hidd + 2.0 * hw * hidd * b.cin;
+        }
+        first = false;
+    }
+    const int ncols = ((9 * c.out_channels + 31) / 32) * 32;
+    fc += 2.0 * res * res * ncols * hid * c.ch_multipliers[0];
+    *out = fc;
+    return 0;
+}
+
 // ================================================================================================ conv setup
 static int pick_block_n(int cout) {
     if (cout <= 256) return cout;
@@ -876,12 +916,7 @@ static int build_unet_steps(vdt_plan* p, Exec* ex, const float* film, const int*
     // embedding, which first enters at the FiLM of block 0's norm2: in_conv, norm1 and conv1 of block 0 are computed once
     // per SAMPLE, norm2 / conv2's identity skip / the last up block's concat read the shared tensors (GroupNormParams::rep1,
     // ConvParams::resid_rep).  Same arithmetic in the same order: results are bit-identical to the row-by-row path.
-    bool share0 = ex->rep == 2 && !sp && !p->blocks.empty() && getenv("VDT_NO_CFG_SHARE") == nullptr;
-    if (share0) {
-        const auto& b0 = p->blocks[0];
-        share0 = b0.kind == 0 && !b0.concat && b0.cin == b0.cout && b0.cin == hid && b0.resample == kResNone &&
-                 fusable(hid, 0, res) && fusable(b0.cout, 0, res);
-    }
+    const bool share0 = ex->rep == 2 && cfg_prefix_shareable(p);
     const int R0 = share0 ? R / ex->rep : R;                // rows of the tensors computed before the first FiLM
     h16* patches; h16* patches_lo = nullptr; float* h; float2* hst;
     const size_t hw0 = (size_t)res * res;
