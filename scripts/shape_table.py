@@ -13,11 +13,15 @@ s=rows[idx[int(sys.argv[2]) if len(sys.argv)>2 else -1]:]
 labels=[]
 L=3; nrb=3; attn=[0,1,1]; hid=256
 res=32
-def add_res(name,cin,cout,rs,level):
+# CFG: in_conv, norm1 and conv1 of block 0 run once per sample = on half of the rows (plan.cu: cfg_prefix_shareable)
+SHARED=' [shared by the CFG pair: R/2 rows]'
+def add_res(name,cin,cout,rs,level,shared=False):
     global res
     ro = res//2 if rs=='down' else res*2 if rs=='up' else res
-    labels.append(('GN', f'norm1 C{cin}@{res}'+(' '+rs if rs else '')+(' +raw' if cin!=cout else ''), cin*res*res))
-    labels.append(('CONV', f'conv1 3x3 {cin}->{cout}@{ro}'+(' subpixel' if rs=='up' else ''), 2*ro*ro*cout*9*cin))
+    f = 0.5 if shared else 1
+    sfx = SHARED if shared else ''
+    labels.append(('GN', f'norm1 C{cin}@{res}'+(' '+rs if rs else '')+(' +raw' if cin!=cout else '')+sfx, cin*res*res*f))
+    labels.append(('CONV', f'conv1 3x3 {cin}->{cout}@{ro}'+(' subpixel' if rs=='up' else '')+sfx, 2*ro*ro*cout*9*cin*f))
     labels.append(('GN', f'norm2 C{cout}@{ro} in16', cout*ro*ro))
     labels.append(('CONV', f'conv2 3x3 {cout}->{cout}@{ro}'+(f'+skip1x1 {cin}' if cin!=cout else ''), 2*ro*ro*cout*(9*cout+(cin if cin!=cout else 0))))
     res=ro
@@ -27,9 +31,11 @@ def add_attn(c):
     labels.append(('CONV', f'proj_in 1x1 {c}->{3*c}@{res}', 2*res*res*c*3*c))
     labels.append(('ATTN', f'attn N={res*res}', 4*(res*res)**2*c))
     labels.append(('CONV', f'proj_out 1x1 {c}->{c}@{res}', 2*res*res*c*c))
-labels.append(('CONV','in_conv',2*32*32*256*27))
+import os
+share = os.environ.get('VDT_NO_CFG_SHARE') is None
+labels.append(('CONV','in_conv'+(SHARED if share else ''),2*32*32*256*27*(0.5 if share else 1)))
 for i in range(L):
-    for j in range(nrb): add_res('d',256,256,None,i)
+    for j in range(nrb): add_res('d',256,256,None,i,shared=(share and i==0 and j==0))
     if i!=L-1: add_res('d',256,256,'down',i)
 add_res('m',256,256,None,0) if False else None
 # middle: Res, Attn, Res (no level attn flag use)
@@ -69,7 +75,7 @@ for (kind,name),(n,t,work) in agg.items():
         in16='in16' in name
         b=work*R*((2 if in16 else 4)+2)
         extra=''
-        print(f'{kind:5s} {name:40s} n={n:3d} avg_us={t/n:8.1f} total_ms={t/1e3:7.3f}  min-bytes {b/1e6:8.1f} MB -> {b/(t/n*1e-6)/1e12:5.2f} TB/s')
+        print(f'{kind:5s} {name:40.40s} n={n:3d} avg_us={t/n:8.1f} total_ms={t/1e3:7.3f}  min-bytes {b/1e6:8.1f} MB -> {b/(t/n*1e-6)/1e12:5.2f} TB/s')
     else:
         print(f'{kind:5s} {name:40s} n={n:3d} avg_us={t/n:8.1f} total_ms={t/1e3:7.3f}  {work*R/(t/n*1e-6)/1e12:7.1f} TFLOP/s')
 print(dict(tot))

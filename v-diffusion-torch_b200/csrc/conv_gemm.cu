@@ -62,7 +62,10 @@ __device__ __forceinline__ WorkItem decode_item(const ConvParams& p, int w, int 
     WorkItem it;
     it.par = 0;
     if (p.ups) { it.par = w & 3; w >>= 2; }
-    it.m_tile = (w / p.num_n_tiles) * 2 + rank;
+    const int mp = w / p.num_n_tiles;
+    // pair_tiles = T > 0: the two CTAs of a pair take tile mp % T of two consecutive images (which share their residual
+    // image, ConvParams::resid_rep), so both read the same residual tile at the same time
+    it.m_tile = p.pair_tiles > 0 ? (2 * (mp / p.pair_tiles) + rank) * p.pair_tiles + mp % p.pair_tiles : mp * 2 + rank;
     it.n_tile = w % p.num_n_tiles;
     return it;
 }
@@ -367,7 +370,12 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
             if (p.residual && row_ok && !p.resid_up) {
                 // the main loop of this tile is still running: pull this warp's residual lines (one 128-byte line
                 // per row and 32-column chunk) into L2 so the epilogue's loads below do not pay DRAM latency
-                const float* rp = p.residual + static_cast<size_t>(grow) * p.ld + n_tile * p.block_n;
+                long long rrow = grow;
+                if (p.resid_rep > 1) {                       // shared residual: image i reads image i / resid_rep
+                    const long long img = grow / p.HW;
+                    rrow = (img / p.resid_rep) * p.HW + (grow - img * p.HW);
+                }
+                const float* rp = p.residual + static_cast<size_t>(rrow) * p.ld + n_tile * p.block_n;
                 for (int c0 = chunk_par * 32; c0 < p.block_n; c0 += 64) prefetch_l2(rp + c0);
             }
             // this warp's bias vectors for its (up to four) chunks of the tile, fetched while the main loop still runs:

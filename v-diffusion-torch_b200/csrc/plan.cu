@@ -872,6 +872,12 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     cp->stats = (slabs > 0 && (s.a3 || flat_ok || geo_pointwise)) ? s.stats : nullptr;   // statistics slabs never span two images
     cp->ups = s.ups; cp->ups_w = s.w; cp->stat_slabs_img = slabs; cp->resid_up = s.resid_up; cp->out_w = s.w;
     cp->resid_rep = s.residual ? s.resid_rep : 0;
+    {
+        const char* pt = getenv("VDT_PAIR_TILES");
+        if (cp->resid_rep == 2 && !cp->pointwise && cp->box_n == 1 && cp->tiles_per_image >= 1 &&
+            cp->num_m_tiles == s.n * cp->tiles_per_image && s.n % 2 == 0 && !(pt && pt[0] == '0'))
+            cp->pair_tiles = cp->tiles_per_image;
+    }
     if (s.resid_rep > 1 && (s.resid_up || s.ups || s.n % s.resid_rep != 0)) return fail("internal: shared residual on a resampling conv");
     cp->map_shift = -1;                                  // fast row remaps need square power-of-two maps of >= 64 (ups) / 256 pixels
     if ((s.ups || s.resid_up || s.resid_rep > 1) && s.h == s.w && (s.w & (s.w - 1)) == 0)
