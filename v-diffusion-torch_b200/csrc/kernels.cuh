@@ -45,6 +45,7 @@ struct alignas(64) ConvParams {
     int f16;                           // operand / 16-bit output format: 1 fp16, 0 bf16
     const float* bias;                 // [Cout]
     const float* residual;             // fp32 [M, ld] or null
+    int prefetch_next;                 // 1: the TMA warp prefetches the next work item's A rows into L2 (VDT_CONV_PREFETCH=1; measured slower, off by default)
     int pair_tiles;                    // tiles per image when a CTA pair works on the same tile of two consecutive images, else 0
     int resid_rep;                     // > 1: output image i adds residual image i / resid_rep ([M / resid_rep, ld]; CFG row pairs
                                        // share the residual computed before the first FiLM); power-of-two HW takes the fast epilogue

@@ -873,6 +873,10 @@ static int setup_conv(const ConvSpec& s, ConvParams* cp) {
     cp->ups = s.ups; cp->ups_w = s.w; cp->stat_slabs_img = slabs; cp->resid_up = s.resid_up; cp->out_w = s.w;
     cp->resid_rep = s.residual ? s.resid_rep : 0;
     {
+        const char* pf = getenv("VDT_CONV_PREFETCH");         // measured slower (-3 % images/s): opt-in only
+        cp->prefetch_next = (pf && pf[0] == '1') ? 1 : 0;
+    }
+    {
         const char* pt = getenv("VDT_PAIR_TILES");
         if (cp->resid_rep == 2 && !cp->pointwise && cp->box_n == 1 && cp->tiles_per_image >= 1 &&
             cp->num_m_tiles == s.n * cp->tiles_per_image && s.n % 2 == 0 && !(pt && pt[0] == '0'))
