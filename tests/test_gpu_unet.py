@@ -641,7 +641,7 @@ def test_generate_driver_end_to_end(tmp_path, world, schedule):
         cmd = [sys.executable, "-m", "v_diffusion_b200.generate"] + args
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-               "127.0.0.1", "--master-port", "29533", "-m", "v_diffusion_b200.generate"] + args
+               "127.0.0.1", "--master-port", "29533" if schedule == "static" else "29534", "-m", "v_diffusion_b200.generate"] + args
     env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
     r = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
