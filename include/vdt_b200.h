@@ -164,6 +164,19 @@ enum { VDT_PROF_CONV = 0, VDT_PROF_GROUPNORM = 1, VDT_PROF_ATTENTION = 2, VDT_PR
 int vdt_profile_enable(int on);
 int vdt_profile_read(double* ms4, uint64_t* launches4);
 
+/* ---- optimizer step of the reference trainer (train_utils.py:159-166) -------------------------------------------
+ * nn.utils.clip_grad_norm_(params, max_norm) -> torch.optim.AdamW.step() (train.py:158) -> EMA.update() (utils.py:144-149),
+ * without a host sync: vdt_grad_sq_accumulate adds one gradient tensor's sum of squares to a device double (zero it once
+ * per step; fixed summation order), vdt_adamw_ema_step then updates one parameter tensor in place: g *= min(1, max_norm /
+ * (sqrt(total) + 1e-6)) (skipped when grad_sq_total is null or max_norm <= 0), p *= 1 - lr * wd, Adam moments, bias-corrected
+ * update with `step` = the 1-based step count, and shadow += (1 - ema_decay) * (p - shadow) when ema_shadow is given
+ * (ema_decay = min(decay, (1 + num_updates) / (10 + num_updates)) is the caller's, utils.py:146). */
+int64_t vdt_grad_sq_scratch_bytes(int64_t n);
+int vdt_grad_sq_accumulate(const float* grad, int64_t n, void* scratch, int64_t scratch_bytes, double* sq_accum, void* stream);
+int vdt_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema_shadow, int64_t n,
+                       double lr, double beta1, double beta2, double eps, double weight_decay, int32_t step,
+                       const double* grad_sq_total, double max_norm, double ema_decay, void* stream);
+
 /* ---- kernel-level entry points (used by the parity tests; device pointers) ------------------------- */
 /* f16: 1 = fp16 operands, 0 = bf16.  conv2d(k x k, pad k/2) on 16-bit NHWC input with fp32 OIHW weights -> fp32 NHWC
  * (+bias, +residual), or 16-bit NHWC when out16 is given.  stats_out (optional): GroupNorm partial statistics,

@@ -739,3 +739,40 @@ def test_train_mode_forward_dropout():
     print(f"train-mode forward, drop 0.2: rel-L2 distance to the eval output {rel:.3f}")
     assert 0.02 < rel < 1.5
     assert torch.equal(net.eval()(x.cuda(), t.cuda(), y.cuda()), ev)          # .eval() switches it off again
+
+
+def test_optimizer_step_vs_torch_adamw_and_reference_ema():
+    """clip_grad_norm_ -> AdamW.step -> EMA.update of the reference trainer (train_utils.py:159-166, train.py:158,
+    utils.py:144-149; hyper-parameters of cifar10_cond.json) as two fused kernels per tensor: parameters, both Adam moments
+    and the EMA shadow follow torch's own optimizer over several steps, with the clip active on some steps and not on others."""
+    from v_diffusion_b200.optim import AdamWEMA
+    g = torch.Generator(device="cuda").manual_seed(3)
+    shapes = {"conv.weight": (256, 64, 3, 3), "conv.bias": (256,), "fc.weight": (70, 33), "odd": (7,)}
+    mine = {k: torch.randn(s, device="cuda", generator=g) * 0.1 for k, s in shapes.items()}
+    ref = {k: torch.nn.Parameter(v.clone()) for k, v in mine.items()}
+    lr, betas, wd, max_norm, decay = 2e-4, (0.9, 0.999), 0.001, 1.0, 0.9999
+    opt_ref = torch.optim.AdamW(list(ref.values()), lr=lr, betas=betas, weight_decay=wd)
+    shadow_ref = {k: v.detach().clone() for k, v in ref.items()}
+    opt = AdamWEMA(mine, lr=lr, betas=betas, weight_decay=wd, grad_norm=max_norm, ema_decay=decay)
+    worst = 0.0
+    for step, scale in enumerate([3.0, 1e-4, 0.5, 2.0], start=1):       # total norms above and below max_norm
+        grads = {k: torch.randn(s, device="cuda", generator=g) * scale for k, s in shapes.items()}
+        for k, p in ref.items():
+            p.grad = grads[k].clone()
+        total = torch.nn.utils.clip_grad_norm_(list(ref.values()), max_norm=max_norm)
+        opt_ref.step()
+        d = min(decay, (1 + step) / (10 + step))
+        for k, p in ref.items():
+            shadow_ref[k] += (1 - d) * (p.data - shadow_ref[k])
+        sq = opt.step(grads)
+        torch.cuda.synchronize()
+        assert abs(sq.item() ** 0.5 - total.item()) <= 1e-5 * total.item()
+        for k in shapes:
+            stt = opt_ref.state[ref[k]]
+            for a, b in ((mine[k], ref[k].data), (opt.exp_avg[k], stt["exp_avg"]), (opt.exp_avg_sq[k], stt["exp_avg_sq"]),
+                         (opt.shadow[k], shadow_ref[k])):
+                worst = max(worst, ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item())
+    print(f"optimizer step: worst rel-L2 over params / moments / EMA shadow after 4 steps {worst:.2e}")
+    assert worst <= 2e-6
+    again = opt.step(grads).item()
+    assert again == opt.step(grads).item()                              # fixed-order norm reduction

@@ -251,6 +251,14 @@ cudaError_t launch_q_sample(const float* x0, const float* eps, const float* coef
 cudaError_t launch_train_loss(const float* model_out, const float* x0, const float* noise, const float* x_t, const float* coef,
                               float* loss, float* grad_out, int B, int C, int HW, int type, int reweight, cudaStream_t stream);
 
+// optimizer step of the reference trainer (train_utils.py:159-166): sum of squared gradients of one tensor added to *accum
+// (deterministic), then clip + AdamW + EMA for one parameter tensor; scratch = grad_sq_scratch_bytes(n)
+size_t grad_sq_scratch_bytes(long long n);
+cudaError_t launch_grad_sq(const float* g, long long n, void* scratch, double* accum, cudaStream_t stream);
+cudaError_t launch_adamw_ema(float* p, const float* g, float* m, float* v, float* shadow, long long n, double lr, double beta1,
+                             double beta2, double eps, double wd, int step, const double* grad_sq_total, float max_norm,
+                             double ema_decay, cudaStream_t stream);
+
 // weight gradient of a 3x3 / 1x1 conv (wgrad.cu): dW[co][ci][tap] = sum_p dY[p][co] * X[p + shift(tap)][ci]
 struct alignas(64) WgradParams {
     CUtensorMap dy_map;                // 4-D (Cout, W, H, N) 16-bit, box (64, W, box_h, box_n), SWIZZLE_128B

@@ -1519,6 +1519,28 @@ extern "C" int vdt_train_loss(const float* model_out, const float* x0, const flo
     return 0;
 }
 
+extern "C" int vdt_grad_sq_accumulate(const float* grad, int64_t n, void* scratch, int64_t scratch_bytes, double* sq_accum, void* stream) {
+    if (!grad || !sq_accum || !scratch) return fail("null argument");
+    if (n < 0 || (size_t)scratch_bytes < grad_sq_scratch_bytes(n)) return fail("scratch too small: %lld bytes needed", (long long)grad_sq_scratch_bytes(n));
+    cudaError_t e = launch_grad_sq(grad, n, scratch, sq_accum, reinterpret_cast<cudaStream_t>(stream));
+    ++g_launches;
+    if (e != cudaSuccess) return fail("grad_sq launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+extern "C" int64_t vdt_grad_sq_scratch_bytes(int64_t n) { return (int64_t)grad_sq_scratch_bytes(n); }
+
+extern "C" int vdt_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema_shadow, int64_t n,
+                                  double lr, double beta1, double beta2, double eps, double weight_decay, int32_t step,
+                                  const double* grad_sq_total, double max_norm, double ema_decay, void* stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq) return fail("null argument");
+    if (step < 1) return fail("step counts from 1 (torch.optim state['step'] after its increment)");
+    cudaError_t e = launch_adamw_ema(param, grad, exp_avg, exp_avg_sq, ema_shadow, n, lr, beta1, beta2, eps, weight_decay, step,
+                                     grad_sq_total, (float)max_norm, ema_decay, reinterpret_cast<cudaStream_t>(stream));
+    ++g_launches;
+    if (e != cudaSuccess) return fail("adamw_ema launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // ================================================================================================ sampler
 static int get_sampler_exec(vdt_plan* p, const vdt_sampler_config& sc, int imgs, bool has_label, int lane, Exec** out) {
     const bool cfg = sc.w_guide > 0.0 && has_label;            // diffusion.py:368

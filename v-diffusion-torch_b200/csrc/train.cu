@@ -7,6 +7,8 @@
 // Every per-sample scalar comes from a [B][16] coefficient table computed on the host in the reference's rounding chain
 // (vdt_train_coefficients: log-SNR in fp64 -> fp32, sigmoid / sqrt / exp in fp32).  Products and sums are rounded
 // separately (no FMA contraction), as the reference's chain of element-wise tensor ops rounds them.
+#include <cmath>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -138,6 +140,103 @@ cudaError_t launch_train_loss(const float* model_out, const float* x0, const flo
                               float* loss, float* grad_out, int B, int C, int HW, int type, int reweight, cudaStream_t stream) {
     if (B == 0) return cudaSuccess;
     train_loss_kernel<<<B, 256, 0, stream>>>(model_out, x0, noise, x_t, coef, loss, grad_out, B, C, HW, type, reweight);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Optimizer step of the reference trainer (train_utils.py:159-166): clip_grad_norm_ -> AdamW.step -> EMA.update
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kSqBlock = 256;
+constexpr int kSqItemsPerBlock = kSqBlock * 16;             // fixed tiling: the result does not depend on the grid
+
+// sum of g^2 over one tensor: fp32 products, per-thread fp32 partials over a fixed stride, block tree in fp64, one
+// partial per block; the last block to finish (ticket) adds the partials in index order -> deterministic
+__global__ void __launch_bounds__(kSqBlock) grad_sq_kernel(const float* __restrict__ g, long long n, double* __restrict__ partial,
+                                                           unsigned int* __restrict__ ticket, double* __restrict__ accum) {
+    __shared__ double red[kSqBlock];
+    __shared__ bool last;
+    const long long base = static_cast<long long>(blockIdx.x) * kSqItemsPerBlock;
+    float s = 0.f;
+    for (int k = 0; k < 16; ++k) {
+        const long long i = base + k * kSqBlock + threadIdx.x;
+        if (i < n) { const float v = g[i]; s = fmaf(v, v, s); }
+    }
+    red[threadIdx.x] = static_cast<double>(s);
+    __syncthreads();
+    for (int o = kSqBlock / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = red[0];
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) t += partial[b];
+        *accum += t;                                           // tensors are accumulated one launch after the other (stream order)
+        *ticket = 0u;
+    }
+}
+
+// One parameter tensor: gradient clipping coefficient from the total squared norm (device scalar, no host sync),
+// decoupled weight decay, Adam moments, bias-corrected update (torch/optim/adamw.py, single-tensor form) and the EMA
+// shadow update shadow += (1 - decay) * (param - shadow) (utils.py:144-149).
+__global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, float* __restrict__ shadow, long long n,
+                                                        float decay_mul, float w1, float beta2, float w2, float eps, float step_size,
+                                                        float inv_bc2_sqrt, const double* __restrict__ grad_sq_total, float max_norm,
+                                                        float ema_w) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    float coef = 1.f;
+    if (grad_sq_total != nullptr && max_norm > 0.f) {          // clip_grad_norm_: max_norm / (total_norm + 1e-6), clamped to 1
+        const float total = static_cast<float>(sqrt(*grad_sq_total));
+        coef = fminf(__fdiv_rn(max_norm, __fadd_rn(total, 1e-6f)), 1.f);
+    }
+    const float gi = __fmul_rn(g[i], coef);
+    float pi = __fmul_rn(p[i], decay_mul);                                                           // param.mul_(1 - lr * wd)
+    const float mi = __fadd_rn(m[i], __fmul_rn(w1, __fsub_rn(gi, m[i])));                            // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = __fadd_rn(__fmul_rn(v[i], beta2), __fmul_rn(__fmul_rn(w2, gi), gi));            // mul_(beta2).addcmul_(g, g, 1 - beta2)
+    const float denom = __fadd_rn(__fmul_rn(__fsqrt_rn(vi), inv_bc2_sqrt), eps);                      // (sqrt / scalar) is sqrt * (1 / scalar) in ATen
+    pi = __fsub_rn(pi, __fmul_rn(step_size, __fdiv_rn(mi, denom)));
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (shadow != nullptr) shadow[i] = __fadd_rn(shadow[i], __fmul_rn(ema_w, __fsub_rn(pi, shadow[i])));
+}
+
+}  // namespace
+
+size_t grad_sq_scratch_bytes(long long n) {
+    const long long blocks = (n + kSqItemsPerBlock - 1) / kSqItemsPerBlock;
+    return static_cast<size_t>(blocks) * sizeof(double) + 16;
+}
+cudaError_t launch_grad_sq(const float* g, long long n, void* scratch, double* accum, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const long long blocks = (n + kSqItemsPerBlock - 1) / kSqItemsPerBlock;
+    double* partial = static_cast<double*>(scratch);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + blocks);
+    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    grad_sq_kernel<<<static_cast<unsigned int>(blocks), kSqBlock, 0, stream>>>(g, n, partial, ticket, accum);
+    return cudaGetLastError();
+}
+cudaError_t launch_adamw_ema(float* p, const float* g, float* m, float* v, float* shadow, long long n, double lr, double beta1,
+                             double beta2, double eps, double wd, int step, const double* grad_sq_total, float max_norm,
+                             double ema_decay, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    // scalar prologue of torch.optim's single-tensor AdamW: python floats (doubles), each cast to fp32 where it meets a tensor
+    const double bc1 = 1.0 - std::pow(beta1, step), bc2 = 1.0 - std::pow(beta2, step);
+    const float step_size = static_cast<float>(lr / bc1);
+    const float inv_bc2_sqrt = 1.0f / static_cast<float>(std::sqrt(bc2));
+    adamw_ema_kernel<<<static_cast<unsigned int>((n + 255) / 256), 256, 0, stream>>>(
+        p, g, m, v, shadow, n, static_cast<float>(1.0 - lr * wd), static_cast<float>(1.0 - beta1), static_cast<float>(beta2),
+        static_cast<float>(1.0 - beta2), static_cast<float>(eps), step_size, inv_bc2_sqrt, grad_sq_total, max_norm,
+        static_cast<float>(1.0 - ema_decay));
     return cudaGetLastError();
 }
 
