@@ -84,9 +84,9 @@ __device__ __forceinline__ void attention_body(const AttnParams& p) {
     sm.v0 = base; base += 2 * dch * 8192;
     sm.p0 = base; base += 2 * 16384;
     uint64_t* bars = reinterpret_cast<uint64_t*>(base);
-    sm.q_full = bars; sm.q_empty = bars + 1; sm.k_full = bars + 2; sm.v_full = bars + 6; sm.k_empty = bars + 10;
-    sm.v_empty = bars + 14; sm.s_full = bars + 18; sm.p_full = bars + 20; sm.o_empty = bars + 22;
-    sm.tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+    sm.q_full = bars; sm.q_empty = bars + 1; sm.k_full = bars + 2; sm.v_full = sm.k_full + kMaxStages; sm.k_empty = sm.v_full + kMaxStages;
+    sm.v_empty = sm.k_empty + kMaxStages; sm.s_full = sm.v_empty + kMaxStages; sm.p_full = sm.s_full + 2; sm.o_empty = sm.p_full + 2;
+    sm.tmem_slot = reinterpret_cast<uint32_t*>(sm.o_empty + 1);
     const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
     constexpr int NC = TWO ? 2 : 1;                          // CTAs that arrive on the leader-side barriers
     float* xch = reinterpret_cast<float*>(base + 256);      // [2][2][128]: double-buffered row-max exchange; reused for l
