@@ -224,6 +224,11 @@ int vdt_op_groupnorm_backward(const float* x, const float* grad_out, int32_t c, 
  * -> 16-bit [B*N, hid]; any N >= 1 (ragged last key / query tiles are masked) */
 int vdt_op_attention(const void* qkv_16, void* out_16, int32_t batch, int32_t n, int32_t heads,
                      int32_t d, int32_t f16, void* stream);
+/* Backward of the attention core (autograd through the einsum / softmax / einsum of unet.py:55-64), reference-grade: fp32 on
+ * CUDA cores, two passes (per query row: softmax statistics, D = dO . O, dQ; per key row: dK, dV), nothing N x N stored.
+ * qkv fp32 [B*N, 3*hid] (q | k | v thirds, heads contiguous), grad_out fp32 [B*N, hid] -> grad_qkv fp32 [B*N, 3*hid]. */
+int vdt_op_attention_backward(const float* qkv, const float* grad_out, float* grad_qkv, int32_t batch, int32_t n, int32_t heads,
+                              int32_t d, void* stream);
 /* one sampler update with explicit step index; coef = one row of vdt_step_coefficients (host pointer). */
 int vdt_op_sampler_step(const float* model_out, const float* x_t, const float* noise, float* x_s, int32_t batch,
                         int32_t c, int32_t hw, int32_t cfg, int32_t model_out_type, int32_t step, const float* coef_host,

@@ -495,6 +495,93 @@ def test_residual_block_backward_composed_from_kernels(L, B, H, Cc, f16):
     assert max(errs.values()) <= 8e-3 * EPS[f16], errs          # measured: 5.6e-4 (fp16), 4.3e-3 (bf16)
 
 
+@pytest.mark.parametrize("B,N,heads,d", [(2, 64, 1, 256), (3, 256, 4, 64), (1, 100, 2, 128), (1, 1024, 1, 256), (2, 49, 3, 192)])
+def test_attn_core_backward_vs_autograd(L, B, N, heads, d):
+    """dQ, dK, dV of softmax(q k^T / sqrt(d)) v (unet.py:55-64) from the fp32 two-pass backward against fp64 autograd."""
+    g = torch.Generator(device="cuda").manual_seed(N + heads + d)
+    hid = heads * d
+    qkv = torch.randn(B * N, 3 * hid, device="cuda", generator=g)
+    qkv[:, :hid] *= 1.5                                           # some peaky rows
+    go = torch.randn(B * N, hid, device="cuda", generator=g)
+    dqkv = torch.zeros_like(qkv)
+    _check(L, L.vdt_op_attention_backward(_p(qkv), _p(go), _p(dqkv), B, N, heads, d, None))
+    torch.cuda.synchronize()
+    x = qkv.double().requires_grad_(True)
+    q, k, v = (x[:, i * hid:(i + 1) * hid].reshape(B, N, heads, d).permute(0, 2, 1, 3) for i in range(3))
+    w = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1)
+    out = (w @ v).permute(0, 2, 1, 3).reshape(B * N, hid)
+    out.backward(go.double())
+    errs = [_rel(dqkv[:, i * hid:(i + 1) * hid], x.grad[:, i * hid:(i + 1) * hid]) for i in range(3)]
+    print(f"attention backward B={B} N={N} heads={heads} d={d}: dq {errs[0]:.1e} dk {errs[1]:.1e} dv {errs[2]:.1e}")
+    assert max(errs) <= 2e-5
+    again = torch.zeros_like(qkv)
+    _check(L, L.vdt_op_attention_backward(_p(qkv), _p(go), _p(again), B, N, heads, d, None))
+    torch.cuda.synchronize()
+    assert torch.equal(dqkv, again)
+
+
+@pytest.mark.parametrize("f16", [1, 0])
+def test_attn_block_backward_composed_from_kernels(L, f16):
+    """An AttentionBlock (unet.py:33-81: GroupNorm -> 1x1 proj_in -> softmax(q k^T / sqrt(d)) v -> 1x1 proj_out -> + x) forward
+    and backward composed from this library's kernels only, against fp64 autograd: output, d x and every parameter gradient.
+    Forward on the tensor-core kernels (16-bit q | k | v and output); the core's backward is the fp32 reference-grade kernel."""
+    B, H, Cc, heads = 3, 16, 256, 1
+    N, d, hid = H * H, 256, 256
+    dt = DT[f16]
+    g = torch.Generator(device="cuda").manual_seed(41)
+    x = torch.randn(B, H, H, Cc, device="cuda", generator=g) * 1.1
+    go = torch.randn(B, H, H, Cc, device="cuda", generator=g)
+    P = {"g": torch.rand(Cc, device="cuda", generator=g) + 0.5, "be": torch.randn(Cc, device="cuda", generator=g) * 0.2,
+         "w_in": torch.randn(3 * hid, Cc, 1, 1, device="cuda", generator=g) / math.sqrt(Cc), "b_in": torch.randn(3 * hid, device="cuda", generator=g) * 0.1,
+         "w_out": torch.randn(Cc, hid, 1, 1, device="cuda", generator=g) / math.sqrt(hid), "b_out": torch.randn(Cc, device="cuda", generator=g) * 0.1}
+    # forward
+    a = torch.empty(B, H, H, Cc, device="cuda", dtype=dt)
+    _check(L, L.vdt_op_groupnorm(_p(x), Cc, None, 0, B, H, H, _p(P["g"]), _p(P["be"]), None, 0, 0, 0, 0, _p(a), None, None, f16, None, None,
+                                 4, 0, None))
+    qkv32 = torch.empty(B, H, H, 3 * hid, device="cuda")
+    qkv16 = torch.empty(B, H, H, 3 * hid, device="cuda", dtype=dt)
+    _check(L, L.vdt_op_conv(_p(a), B, H, H, Cc, _p(P["w_in"]), 3 * hid, 1, _p(P["b_in"]), None, _p(qkv32), f16, _p(qkv16), None, 4, None))
+    o16 = torch.empty(B * N, hid, device="cuda", dtype=dt)
+    _check(L, L.vdt_op_attention(_p(qkv16), _p(o16), B, N, heads, d, f16, None))
+    out = torch.empty(B, H, H, Cc, device="cuda")
+    _check(L, L.vdt_op_conv(_p(o16), B, H, H, hid, _p(P["w_out"]), Cc, 1, _p(P["b_out"]), _p(x), _p(out), f16, None, None, 4, None))
+    # backward
+    got = {}
+    go16 = go.to(dt)
+    do = torch.empty(B, H, H, hid, device="cuda")
+    got["w_out"], got["b_out"] = torch.empty_like(P["w_out"]), torch.empty(Cc, device="cuda")
+    _check(L, L.vdt_op_conv_dgrad(_p(go16), B, H, H, hid, _p(P["w_out"]), Cc, 1, _p(do), f16, None))
+    _check(L, L.vdt_op_conv_wgrad(_p(o16), _p(go16), B, H, H, hid, Cc, 1, _p(got["w_out"]), _p(got["b_out"]), f16, None))
+    dqkv = torch.empty(B * N, 3 * hid, device="cuda")
+    qkvf = qkv16.float().reshape(B * N, 3 * hid).contiguous()
+    _check(L, L.vdt_op_attention_backward(_p(qkvf), _p(do), _p(dqkv), B, N, heads, d, None))
+    dqkv16 = dqkv.to(dt)
+    da = torch.empty(B, H, H, Cc, device="cuda")
+    got["w_in"], got["b_in"] = torch.empty_like(P["w_in"]), torch.empty(3 * hid, device="cuda")
+    _check(L, L.vdt_op_conv_dgrad(_p(dqkv16), B, H, H, Cc, _p(P["w_in"]), 3 * hid, 1, _p(da), f16, None))
+    _check(L, L.vdt_op_conv_wgrad(_p(a), _p(dqkv16), B, H, H, Cc, 3 * hid, 1, _p(got["w_in"]), _p(got["b_in"]), f16, None))
+    dx, got["g"], got["be"] = torch.empty_like(x), torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+    _check(L, L.vdt_op_groupnorm_backward(_p(x), _p(da), Cc, B, H, H, _p(P["g"]), _p(P["be"]), None, 0, C.c_float(0.0), 0, 0,
+                                          _p(dx), _p(got["g"]), _p(got["be"]), None, None))
+    got["x"] = dx + go
+    torch.cuda.synchronize()
+    # fp64 autograd of the same block
+    R = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    xd = x.double().requires_grad_(True)
+    y = F.group_norm(xd.permute(0, 3, 1, 2), 32, R["g"], R["be"], 1e-6)
+    qkv = F.conv2d(y, R["w_in"], R["b_in"]).permute(0, 2, 3, 1).reshape(B, N, 3 * hid)
+    q, k, v = (qkv[..., i * hid:(i + 1) * hid].reshape(B, N, heads, d).permute(0, 2, 1, 3) for i in range(3))
+    o = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1) @ v).permute(0, 2, 1, 3).reshape(B, H, H, hid)
+    yo = F.conv2d(o.permute(0, 3, 1, 2), R["w_out"], R["b_out"]) + xd.permute(0, 3, 1, 2)
+    yo.backward(go.double().permute(0, 3, 1, 2))
+    want = {k: v.grad for k, v in R.items()}
+    want["x"] = xd.grad
+    errs = {"out": _rel(out, yo.detach().permute(0, 2, 3, 1))}
+    errs.update({"d" + k: _rel(got[k], want[k]) for k in sorted(got)})
+    print(f"AttentionBlock fwd+bwd {Cc}ch N={N} B={B} {'fp16' if f16 else 'bf16'}: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    assert max(errs.values()) <= 8e-3 * EPS[f16], errs          # measured: 7.7e-4 (fp16), 5.8e-3 (bf16)
+
+
 def test_attention_cta_pair_variant_matches():
     """The opt-in cta_group::2 attention variant (VDT_ATTN_PAIR=1; measured slower, kept selectable) computes the same thing:
     run the attention parity cases that qualify (even number of query tiles, d % 128 == 0) in a child process with it on."""

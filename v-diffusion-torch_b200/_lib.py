@@ -114,6 +114,7 @@ def lib():
     L.vdt_unet_forward_train.argtypes = [vp, vp, vp, vp, vp, i32, C.c_float, C.c_uint64, vp]
     L.vdt_op_groupnorm_dropout.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, C.c_float, C.c_uint64, i32, vp]
     L.vdt_plan_conv_flops_executed.argtypes = [vp, i32, vp]
+    L.vdt_op_attention_backward.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     L.vdt_grad_sq_scratch_bytes.argtypes = [C.c_int64]
     L.vdt_grad_sq_scratch_bytes.restype = C.c_int64
     L.vdt_grad_sq_accumulate.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp]
@@ -139,7 +140,8 @@ EXPORTS = ["vdt_last_error", "vdt_version", "vdt_kernel_launches", "vdt_plan_cre
            "vdt_plan_saturations", "vdt_images_to_uint8",
            "vdt_train_coefficients", "vdt_q_sample", "vdt_train_loss", "vdt_unet_forward_train", "vdt_op_groupnorm_dropout",
            "vdt_op_conv_dgrad", "vdt_op_conv_wgrad", "vdt_op_groupnorm_backward",
-           "vdt_plan_conv_flops_executed", "vdt_grad_sq_scratch_bytes", "vdt_grad_sq_accumulate", "vdt_adamw_ema_step"]
+           "vdt_plan_conv_flops_executed", "vdt_grad_sq_scratch_bytes", "vdt_grad_sq_accumulate", "vdt_adamw_ema_step",
+           "vdt_op_attention_backward"]
 
 
 def check(rc):

@@ -163,6 +163,10 @@ struct alignas(64) AttnParams {
     h16* out;                         // 16-bit [B*N, hid]
 };
 cudaError_t launch_attention(const AttnParams& p, int num_sms, cudaStream_t stream);
+// backward of the attention core in fp32 on CUDA cores (attention_bwd.cu; reference-grade, not the tensor-core kernel):
+// qkv fp32 [B*N, 3*hid], dout fp32 [B*N, hid] -> dqkv fp32 [B*N, 3*hid]; stat_scratch = B*N*heads float2
+cudaError_t launch_attention_backward_f32(const float* qkv, const float* dout, float* dqkv, void* stat_scratch, int B, int N, int heads,
+                                          int d, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // Small kernels (pointwise.cu)

@@ -1895,6 +1895,22 @@ extern "C" int vdt_op_groupnorm_backward(const float* x, const float* grad_out, 
     return 0;
 }
 
+extern "C" int vdt_op_attention_backward(const float* qkv, const float* grad_out, float* grad_qkv, int32_t batch, int32_t n, int32_t heads,
+                                         int32_t d, void* stream) {
+    if (!qkv || !grad_out || !grad_qkv) return fail("null argument");
+    if (batch < 1 || n < 1 || heads < 1) return fail("empty input");
+    if (d != 64 && d != 128 && d != 192 && d != 256) return fail("attention backward takes head dims 64, 128, 192 or 256 (got %d)", d);
+    void* stat = nullptr;
+    CK(cudaMalloc(&stat, (size_t)batch * n * heads * sizeof(float2)));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = launch_attention_backward_f32(qkv, grad_out, grad_qkv, stat, batch, n, heads, d, st);
+    g_launches += 2;
+    cudaStreamSynchronize(st);
+    cudaFree(stat);
+    if (e != cudaSuccess) return fail("attention backward: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int vdt_op_attention(const void* qkv, void* out, int32_t batch, int32_t n, int32_t heads, int32_t d,
                                 int32_t f16, void* stream) {
     const int hid = heads * d;
