@@ -220,6 +220,19 @@ int vdt_op_groupnorm_backward(const float* x, const float* grad_out, int32_t c, 
                               const float* gamma, const float* beta, const float* film, int32_t silu, float drop_p,
                               uint64_t seed, int32_t layer, float* grad_x, float* grad_gamma, float* grad_beta,
                               float* grad_film, void* stream);
+/* The same GroupNorm kernel with the FiLM table and the training dropout stream both given: norm2 -> FiLM -> act2 -> dropout
+ * of a ResidualBlock in .train() mode (unet.py:143-146) on a plain fp32 NHWC tensor; drop_p = 0: no dropout.  The mask is the
+ * one vdt_op_groupnorm_backward regenerates from (seed, layer). */
+int vdt_op_groupnorm_train(const void* src1, int32_t c1, int32_t batch, int32_t h, int32_t w, const float* gamma,
+                           const float* beta, const float* film, int32_t film_stride, int32_t film_off, int32_t silu,
+                           void* out_act_16, int32_t f16, float drop_p, uint64_t seed, int32_t layer, void* stream);
+/* F.linear(x, W, b) [+ SiLU] in fp32 (modules.py:77-78; time_embed, class_embed and every ResidualBlock.fc, unet.py:142,
+ * 287-295): x [rows, K], W [N, K], b [N] (required) -> out [rows, N]; K <= 1536.  The composed training step also forms the
+ * backward products with it (dX = dY W: pass W^T; dW = dY^T X: pass the transposed operands). */
+int vdt_op_linear(const float* x, const float* w, const float* b, float* out, int32_t rows, int32_t k, int32_t n,
+                  int32_t silu_out, void* stream);
+/* get_timestep_embedding(t, dim) (functions.py:10-29) for fp64 t [rows] -> fp32 [rows, dim] (sin | cos halves). */
+int vdt_op_timestep_embedding(const double* t, float* out, int32_t rows, int32_t dim, void* stream);
 /* attention on qkv 16-bit [B*N, 3*hid] (q | k | v thirds, heads contiguous inside each, the layout proj_in writes)
  * -> 16-bit [B*N, hid]; any N >= 1 (ragged last key / query tiles are masked) */
 int vdt_op_attention(const void* qkv_16, void* out_16, int32_t batch, int32_t n, int32_t heads,

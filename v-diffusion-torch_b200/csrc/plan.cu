@@ -1962,3 +1962,49 @@ extern "C" int vdt_op_sampler_step(const float* model_out, const float* x_t, con
     if (e2 != cudaSuccess) return fail("sampler_step failed: %s", cudaGetErrorString(e2));
     return 0;
 }
+
+// ---- entry points the composed training step (v-diffusion-torch_b200/training.py) adds to the kernel-level hooks ----------
+// norm2 -> FiLM -> act2 -> dropout of a ResidualBlock in .train() mode (unet.py:143-146) on a plain fp32 NHWC tensor: the
+// same kernel as vdt_op_groupnorm with the FiLM table and the dropout stream both given (drop_p = 0: no dropout).
+extern "C" int vdt_op_groupnorm_train(const void* src1, int32_t c1, int32_t batch, int32_t h, int32_t w, const float* gamma,
+                                      const float* beta, const float* film, int32_t film_stride, int32_t film_off, int32_t silu,
+                                      void* out_act, int32_t f16, float drop_p, uint64_t seed, int32_t layer, void* stream) {
+    if (!(drop_p >= 0.f && drop_p < 1.f)) return fail("drop_p must lie in [0, 1)");
+    if (drop_p == 0.f)
+        return op_groupnorm_impl(src1, c1, nullptr, 0, batch, h, w, gamma, beta, film, film_stride, film_off, silu, 0, out_act, nullptr,
+                                 nullptr, f16, nullptr, nullptr, 4, 0, 0.f, nullptr, 0, stream);
+    unsigned long long* ds = nullptr;
+    CK(cudaMalloc(&ds, sizeof(unsigned long long)));
+    const unsigned long long sv = seed;
+    cudaError_t e = cudaMemcpy(ds, &sv, sizeof(sv), cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? 0 : fail("seed upload failed: %s", cudaGetErrorString(e));
+    if (rc == 0)
+        rc = op_groupnorm_impl(src1, c1, nullptr, 0, batch, h, w, gamma, beta, film, film_stride, film_off, silu, 0, out_act, nullptr,
+                               nullptr, f16, nullptr, nullptr, 4, 0, drop_p, ds, layer, stream);
+    cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+    cudaFree(ds);
+    return rc;
+}
+
+// F.linear(x, W, b) [+ SiLU] in fp32 (modules.py:77-78), the kernel the embedding MLP and the FiLM projections run on:
+// x [rows, K], W [N, K], b [N] (required) -> out [rows, N].  K <= 1536 (one 8-row slab of x is staged in shared memory).
+extern "C" int vdt_op_linear(const float* x, const float* W, const float* b, float* out, int32_t rows, int32_t K, int32_t N,
+                             int32_t silu_out, void* stream) {
+    if (!x || !W || !b || !out) return fail("null argument");
+    if (rows < 0 || K < 1 || N < 1) return fail("bad linear shape (%d, %d, %d)", rows, K, N);
+    if ((size_t)K * 8 * sizeof(float) > 48 * 1024) return fail("linear: K = %d exceeds the 1536 columns one slab holds", K);
+    cudaError_t e = launch_linear_f32(x, W, b, out, rows, K, N, silu_out, reinterpret_cast<cudaStream_t>(stream));
+    ++g_launches;
+    if (e != cudaSuccess) return fail("linear launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// get_timestep_embedding(t, dim) (functions.py:20-25) for fp64 t: sin | cos halves of 1000 t exp(-k log(1e4) / (dim/2 - 1)).
+extern "C" int vdt_op_timestep_embedding(const double* t, float* out, int32_t rows, int32_t dim, void* stream) {
+    if (!t || !out) return fail("null argument");
+    if (rows < 0 || dim < 4) return fail("bad embedding shape (%d, %d)", rows, dim);
+    cudaError_t e = launch_timestep_embedding(t, out, rows, dim, nullptr, reinterpret_cast<cudaStream_t>(stream));
+    ++g_launches;
+    if (e != cudaSuccess) return fail("timestep embedding launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}

@@ -16,7 +16,8 @@ from . import _lib
 
 
 class AdamWEMA:
-    def __init__(self, named_params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_norm=1.0, ema_decay=0.9999):
+    def __init__(self, named_params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_norm=1.0, ema_decay=0.9999,
+                 use_ema=True):
         self.params = dict(named_params)
         for k, p in self.params.items():
             if p.device.type != "cuda" or p.dtype != torch.float32 or not p.is_contiguous():
@@ -25,7 +26,8 @@ class AdamWEMA:
         self.grad_norm, self.decay = grad_norm, ema_decay
         self.exp_avg = {k: torch.zeros_like(p) for k, p in self.params.items()}
         self.exp_avg_sq = {k: torch.zeros_like(p) for k, p in self.params.items()}
-        self.shadow = {k: p.detach().clone() for k, p in self.params.items()}           # utils.py:131-138
+        # the reference keeps the EMA on the leader rank only (train_utils.py:127-130): use_ema=False skips the shadow
+        self.shadow = {k: p.detach().clone() for k, p in self.params.items()} if use_ema else {}    # utils.py:131-138
         self.step_count = 0
         self.num_updates = 0
         dev = next(iter(self.params.values())).device
@@ -55,7 +57,7 @@ class AdamWEMA:
             if g.shape != p.shape or g.dtype != torch.float32:
                 raise ValueError(f"{k}: gradient must be fp32 with shape {tuple(p.shape)}")
             _lib.check(L.vdt_adamw_ema_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(self.exp_avg[k]), _lib.ptr(self.exp_avg_sq[k]),
-                                            _lib.ptr(self.shadow[k]), p.numel(), lr, self.betas[0], self.betas[1], self.eps,
+                                            _lib.ptr(self.shadow.get(k)), p.numel(), lr, self.betas[0], self.betas[1], self.eps,
                                             self.weight_decay, self.step_count, _lib.ptr(self._sq) if clip else None,
                                             float(self.grad_norm or 0.0), decay, st))
         return self._sq

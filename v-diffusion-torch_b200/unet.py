@@ -131,10 +131,15 @@ class UNet(nn.Module):
         # cuDNN convs use on GPU, same tcgen05 rate as bf16) or "bf16"
         self.operand_dtype = os.environ.get("VDT_OPERAND", "fp16")
         self._plans = {}
+        self._weights_epoch = 0            # bumped by whoever rewrites parameters behind torch's version counters (the optimizer kernel)
 
     # ------------------------------------------------------------------ plan management
     def _weights_signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self._weights_epoch,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def mark_weights_changed(self):
+        """Parameters were updated in place by a kernel (optim.AdamWEMA): the next forward / p_sample re-packs them."""
+        self._weights_epoch += 1
 
     def plan_for(self, resolution, device):
         """C-side plan (block list, packed bf16 weights, workspace) for one image resolution."""
