@@ -1,13 +1,14 @@
 """GPU: the composed training step (v-diffusion-torch_b200/training.py; SURVEY §8 f2, BASELINE configs[4]) on the real kernels.
 
-STATUS, stated plainly: this file was written after the round's GPU budget was spent.  The kernels it composes are each
-parity-tested on hardware (tests/test_gpu_kernels.py), the composition is checked against autograd on the CPU with a contract
-stand-in (tests/test_training_graph.py) -- but these end-to-end cases have NOT run on a B200 yet.  They are therefore marked
-``xfail(strict=False)``: a pass shows up as XPASS, a failure as xfail, neither hides or breaks the measured suite.  Each case
-runs in a child process (tests/train_step_worker.py) so a device fault cannot poison the tests after it.
+The kernels it composes are each parity-tested on their own (tests/test_gpu_kernels.py) and the composition is checked against
+autograd on the CPU with a contract stand-in (tests/test_training_graph.py); here the whole thing runs on the B200.  Each case
+runs in a child process (tests/train_step_worker.py) so a device fault in this newest path cannot poison the tests after it.
 
-Tolerances (fp16 operands; the reference is fp32 autograd through the oracle UNet on the CPU): network output rel-L2 <= 5e-3;
-every parameter gradient rel-L2 <= 3e-2 (one ResidualBlock / AttentionBlock alone measured 5.6e-4 / 7.7e-4); bf16: 4x those.
+Tolerances (the reference is fp32 autograd through the oracle UNet on the CPU; measured values in
+profiles/r2k_train_step_parity.txt): fp16 operands -- network output rel-L2 <= 3e-3 (measured 7.8e-4 on cifar10_cond, 9.3e-4 on
+the small net), every parameter gradient rel-L2 <= 8e-3 (measured worst 2.3e-3, median 1.4e-3 over 414 tensors); bf16 operands --
+2.5e-2 / 5e-2 (measured 7.4e-3 / 1.6e-2).  The two-rank case has not run on hardware (the round's budget ended at one GPU) and is
+the only one still marked xfail(strict=False).
 """
 import json
 import os
@@ -17,9 +18,8 @@ import sys
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="composed training step: written after the round's GPU budget was spent, "
-                                                     "not yet run on hardware (kernels and orchestration are tested separately)")]
+pytestmark = pytest.mark.gpu
+BARS = {"fp16": (3e-3, 8e-3), "bf16": (2.5e-2, 5e-2)}          # (output rel-L2, worst parameter-gradient rel-L2)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -39,24 +39,24 @@ def _run(*args, timeout=900):
 def test_unet_forward_backward_on_kernels_vs_autograd(case, B, operand):
     """Output and every parameter gradient of UNet forward + backward composed from the library's kernels against fp32
     autograd through the oracle UNet; `cifar_cond` is BASELINE configs[4]'s network (cifar10_cond.json) at batch 4."""
-    scale = 1.0 if operand == "fp16" else 4.0
     res = _run("graph_parity", case, B, operand)
     assert res["finite"] and res["launches"] > 100
-    assert res["out_rel"] <= 5e-3 * scale, res
-    assert res["grad_rel_worst"] <= 3e-2 * scale, res["worst"]
+    assert res["out_rel"] <= BARS[operand][0], res
+    assert res["grad_rel_worst"] <= BARS[operand][1], res["worst"]
 
 
 def test_training_steps_follow_the_reference_recipe():
     """Three optimizer steps of TrainingStep.step (Trainer.loss + Trainer.step, train_utils.py:137-166) against the same steps
     with the oracle UNet under autograd + clip_grad_norm_ + torch.optim.AdamW + the reference EMA, on the same (t, noise) draws:
-    loss within 2e-3, total gradient norm within 2e-2, parameter updates aligned (cosine >= 0.98; AdamW's first steps are
-    sign-like -- lr * g / |g| -- so entries whose gradient is below the fp16 rounding error may flip by 2 lr), EMA shadow within
-    2e-3 relative (it inherits those flips; the optimizer / EMA kernel itself is pinned to 1.6e-7 in test_gpu_unet.py)."""
+    loss within 1e-3 (measured 1.8e-4), total gradient norm within 2e-3 (2.3e-4), parameter updates aligned (cosine >= 0.999,
+    measured 0.9999; AdamW's first steps are sign-like -- lr * g / |g| -- so entries whose gradient is below the fp16 rounding
+    error may flip by 2 lr), EMA shadow within 3e-3 relative (7.3e-4: it inherits those flips; the optimizer / EMA kernel
+    itself is pinned to 1.6e-7 in test_gpu_unet.py)."""
     res = _run("train_steps", "small", 8, "fp16")
-    assert res["loss_rel_worst"] <= 2e-3, res
-    assert res["gnorm_rel_worst"] <= 2e-2, res
-    assert res["cosine_of_updates"] >= 0.98 and 0.95 <= res["update_norm_ratio"] <= 1.05, res
-    assert res["ema_rel_worst"] <= 2e-3, res
+    assert res["loss_rel_worst"] <= 1e-3, res
+    assert res["gnorm_rel_worst"] <= 2e-3, res
+    assert res["cosine_of_updates"] >= 0.999 and 0.999 <= res["update_norm_ratio"] <= 1.001, res
+    assert res["ema_rel_worst"] <= 3e-3, res
 
 
 def test_training_dropout_is_a_reproducible_stream():
@@ -66,6 +66,7 @@ def test_training_dropout_is_a_reproducible_stream():
     assert res["out_bias_grad_rel"] <= 1e-3, res
 
 
+@pytest.mark.xfail(strict=False, reason="not yet run on hardware: the round's GPU budget ended before a 2-GPU box could be used")
 def test_two_rank_training_step_keeps_replicas_identical():
     """DDP semantics over NCCL: two ranks with different data end every step with bit-identical parameters."""
     if torch.cuda.device_count() < 2:
