@@ -9,6 +9,11 @@ A "step" is one denoising step of the real sampling loop over the whole per-GPU 
 images/s = N_gpus * B * K / (100 * t_K).  Inputs are synthetic (seeded normal noise, random labels, random
 non-zero weights of the reference architecture); every tensor a step touches is far larger than L2.
 One process per GPU; multi-GPU is weak scaling with no collective in the loop.
+
+The N=1 line also carries, outside every timed region: `cpu_baseline` (the unmodified reference on the host cores),
+`reference_gpu_eager` (the unmodified reference in stock PyTorch eager on the same GPU) and `train_step` (BASELINE configs[4]:
+one cifar10_cond training step at batch 128 through v_diffusion_b200.training.TrainingStep beside the reference's own step under
+autograd, measured in a child process; the composition is parity-green but untuned).
 """
 import argparse
 import json
@@ -288,6 +293,107 @@ def reference_gpu_eager(net, diff, noise, label, device, batch=256, parity_batch
     return out
 
 
+def train_step_child(batch=128, steps=3, device=None):
+    """BASELINE configs[4], run in a child process of the N=1 bench (never inside its timed region): one training step of the
+    CIFAR-10 conditional v-objective network (cifar10_cond.json: drop_rate 0.2, snr_trunc re-weighting, p_uncond 0.1, AdamW
+    2e-4 / wd 1e-3, clip 1.0, EMA) on a synthetic batch of 128 images on one GPU -- through v_diffusion_b200.training.
+    TrainingStep (UNet forward + backward composed from this library's kernels, DESIGN.md section 7: a parity-green
+    composition, NOT tuned -- the kernel-level hooks allocate, pack weights and synchronise per call) and, beside it, the
+    unmodified reference (oracle/_ref) doing the same step under autograd in stock PyTorch eager on the same GPU.
+    Prints one line: TRAIN_STEP {json}."""
+    import torch
+    from v_diffusion_b200 import _lib
+    from v_diffusion_b200.training import TrainingStep
+    if device is None:
+        device = torch.device("cuda", 0)
+        torch.cuda.set_device(device)
+    net, diff = build_model(device, seed=0)
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    lr, wd, gn, decay = 2e-4, 0.001, 1.0, 0.9999                        # cifar10_cond.json "train"
+    g = torch.Generator().manual_seed(4321)
+    x = torch.randn(batch, 3, 32, 32, generator=g).clamp(-1, 1).to(device)
+    y = (torch.randint(10, (batch,), generator=g) + 1).to(device)
+    out = {"workload": "BASELINE configs[4]: cifar10_cond.json training step (v objective, continuous time, snr_trunc, "
+                       f"p_uncond 0.1, drop_rate 0.2, clip 1.0 + AdamW + EMA), synthetic batch {batch} on one GPU",
+           "batch": batch, "steps_timed": steps, "unit": "images/s"}
+
+    def timed(fn, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            last = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, float(last)
+
+    try:
+        net.train()
+        ts = TrainingStep(net, diff, timesteps=0, lr=lr, weight_decay=wd, grad_norm=gn, use_ema=True, ema_decay=decay)
+        n0 = _lib.lib().vdt_kernel_launches()
+        ms, loss = timed(lambda: ts.step(x, y.clone()), 1)
+        launches = (_lib.lib().vdt_kernel_launches() - n0) // (steps + 1)
+        out["this_path"] = {"ms_per_step": ms, "images_per_s": batch / (ms * 1e-3), "loss_last_step": loss,
+                            "kernels_per_step": int(launches), "operands": net.operand_dtype,
+                            "state": "parity-green composition over per-call kernel hooks, untuned (DESIGN.md section 7)"}
+        del ts
+    except Exception as e:                                              # noqa: BLE001 -- report, never break the bench line
+        out["this_path"] = {"error": repr(e)[:400]}
+    torch.cuda.empty_cache()
+    try:
+        if not reference_staged():
+            out["reference_gpu_eager"] = {"unavailable": "oracle/_ref not staged"}
+        else:
+            model, rdiff = reference_objects(sd0, device)
+            model.train()
+            opt = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=wd)
+            params = [p for p in model.parameters()]
+            shadow = [p.detach().clone() for p in params]
+            count = [0]
+
+            def ref_step():
+                t = torch.rand((batch,), dtype=torch.float64, device=device)                 # Trainer.loss, T = 0
+                noise = torch.randn_like(x)
+                loss = rdiff.train_loss(model, x_0=x, t=t, y=y.clone(), noise=noise).mean()
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(params, max_norm=gn)
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+                count[0] += 1
+                d = min(decay, (1 + count[0]) / (10 + count[0]))
+                with torch.no_grad():
+                    torch._foreach_lerp_(shadow, [p.detach() for p in params], 1 - d)      # EMA.update, utils.py:144-149
+                return loss.detach()
+            ref = {"note": "unmodified reference (oracle/_ref): train_loss + autograd + clip_grad_norm_ + AdamW + EMA, torch eager"}
+            saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            try:
+                for mode, tf32 in (("stock_flags_tf32_convs", True), ("strict_fp32", False)):
+                    torch.backends.cudnn.allow_tf32 = tf32
+                    ms, loss = timed(ref_step, 2)
+                    ref[mode] = {"ms_per_step": ms, "images_per_s": batch / (ms * 1e-3), "loss_last_step": loss}
+            finally:
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+            out["reference_gpu_eager"] = ref
+    except Exception as e:                                              # noqa: BLE001
+        out["reference_gpu_eager"] = {"error": repr(e)[:400]}
+    print("TRAIN_STEP " + json.dumps(out), flush=True)
+
+
+def train_step_block(timeout_s=300):
+    """Runs train_step_child in its own process (a fault there cannot touch this process's CUDA context or its bench line)."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--train-step-child"], capture_output=True, text=True,
+                           timeout=timeout_s, cwd=ROOT)
+        for ln in r.stdout.splitlines():
+            if ln.startswith("TRAIN_STEP "):
+                return json.loads(ln[len("TRAIN_STEP "):])
+        return {"error": f"child rc={r.returncode}: " + (r.stderr or r.stdout)[-400:]}
+    except Exception as e:                                              # noqa: BLE001
+        return {"error": repr(e)[:400]}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path on the host cores -- the unmodified
     reference staged under oracle/_ref (kind "reference"); the oracle port (kind "port") only if it is absent --
@@ -491,6 +597,8 @@ def run_b200(args, rank, world, local_rank):
             eager = line["reference_gpu_eager"].get("stock_flags_tf32_convs")
             if eager:
                 line["reference_gpu_eager"]["speedup_e2e_over_stock_eager"] = e2e["value"] / eager["images_per_s"]
+            if not args.no_train_step:
+                line["train_step"] = train_step_block()      # BASELINE configs[4], outside every timed region, own process
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -507,10 +615,15 @@ def main():
     ap.add_argument("--workload", default="cifar10_cond", choices=sorted(WORKLOADS))
     ap.add_argument("--max-rows", type=int, default=int(os.environ.get("VDT_MAX_ROWS", "1024")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the BASELINE configs[4] training-step block of the N=1 line")
+    ap.add_argument("--train-step-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.train_step_child:
+        train_step_child()
+        return
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -114,4 +114,30 @@ if __name__ == "__main__":
     r = W.train_steps("small", 2, "fp16", steps=2)
     print("train_steps", {k: v for k, v in r.items()})
     assert r["loss_rel_worst"] < 1e-5 and r["gnorm_rel_worst"] < 1e-4 and r["cosine_of_updates"] > 0.999 and r["ema_rel_worst"] < 1e-5, r
+    # bench.py's BASELINE configs[4] block (child process body), tiny batch, CPU stand-ins
+    import time
+    import bench
+
+    class _Ev:
+        def __init__(self, enable_timing=True):
+            self.t = None
+
+        def record(self):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+    torch.cuda.Event = _Ev
+    torch.cuda.empty_cache = lambda: None
+    bench.CIFAR_COND_MODEL = dict(bench.CIFAR_COND_MODEL, hid_channels=64, num_res_blocks=1)     # keep the dry run short
+    bench.stage_cfg = None
+    from oracle import stage_ref
+    _cfg0 = stage_ref.config
+
+    def _small(name):
+        c = _cfg0(name)
+        c["model"] = dict(c["model"], hid_channels=64, num_res_blocks=1)
+        return c
+    stage_ref.config = _small
+    bench.train_step_child(batch=2, steps=1, device=_dev("cpu"))
     print("dry run OK")
