@@ -293,7 +293,7 @@ def reference_gpu_eager(net, diff, noise, label, device, batch=256, parity_batch
     return out
 
 
-def train_step_child(batch=128, steps=3, device=None):
+def train_step_child(batch=128, steps=2, device=None):
     """BASELINE configs[4], run in a child process of the N=1 bench (never inside its timed region): one training step of the
     CIFAR-10 conditional v-objective network (cifar10_cond.json: drop_rate 0.2, snr_trunc re-weighting, p_uncond 0.1, AdamW
     2e-4 / wd 1e-3, clip 1.0, EMA) on a synthetic batch of 128 images on one GPU -- through v_diffusion_b200.training.
@@ -371,7 +371,7 @@ def train_step_child(batch=128, steps=3, device=None):
             try:
                 for mode, tf32 in (("stock_flags_tf32_convs", True), ("strict_fp32", False)):
                     torch.backends.cudnn.allow_tf32 = tf32
-                    ms, loss = timed(ref_step, 2)
+                    ms, loss = timed(ref_step, 1 if mode == "strict_fp32" else 2)
                     ref[mode] = {"ms_per_step": ms, "images_per_s": batch / (ms * 1e-3), "loss_last_step": loss}
             finally:
                 torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
@@ -381,7 +381,7 @@ def train_step_child(batch=128, steps=3, device=None):
     print("TRAIN_STEP " + json.dumps(out), flush=True)
 
 
-def train_step_block(timeout_s=300):
+def train_step_block(timeout_s=150):
     """Runs train_step_child in its own process (a fault there cannot touch this process's CUDA context or its bench line)."""
     try:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--train-step-child"], capture_output=True, text=True,
