@@ -114,6 +114,10 @@ if __name__ == "__main__":
     r = W.train_steps("small", 2, "fp16", steps=2)
     print("train_steps", {k: v for k, v in r.items()})
     assert r["loss_rel_worst"] < 1e-5 and r["gnorm_rel_worst"] < 1e-4 and r["cosine_of_updates"] > 0.999 and r["ema_rel_worst"] < 1e-5, r
+    from v_diffusion_b200 import UNet as _U
+    _U._forward_plan = lambda self, x, t, y=None: torch.zeros(x.shape[0], self.out_channels, x.shape[2], x.shape[3])   # plan path needs a GPU
+    r = W.autograd_step("small", 2, "fp16")
+    print("autograd_step", {k: r[k] for k in ("loss_rel", "grad_rel_worst", "grad_rel_median", "plan_path_finite")} if "skipped" not in r else r)
     # bench.py's BASELINE configs[4] block (child process body), tiny batch, CPU stand-ins
     import time
     import bench

@@ -7,8 +7,8 @@ runs in a child process (tests/train_step_worker.py) so a device fault in this n
 Tolerances (the reference is fp32 autograd through the oracle UNet on the CPU; measured values in
 profiles/r2k_train_step_parity.txt): fp16 operands -- network output rel-L2 <= 3e-3 (measured 7.8e-4 on cifar10_cond, 9.3e-4 on
 the small net), every parameter gradient rel-L2 <= 8e-3 (measured worst 2.3e-3, median 1.4e-3 over 414 tensors); bf16 operands --
-2.5e-2 / 5e-2 (measured 7.4e-3 / 1.6e-2).  The two-rank case has not run on hardware (the round's budget ended at one GPU) and is
-the only one still marked xfail(strict=False).
+2.5e-2 / 5e-2 (measured 7.4e-3 / 1.6e-2).  Two cases have not run on hardware and are the only ones marked
+xfail(strict=False): the two-rank NCCL step (the round's budget ended at one GPU) and the autograd-mode wrapper (added after it).
 """
 import json
 import os
@@ -64,6 +64,19 @@ def test_training_dropout_is_a_reproducible_stream():
     assert res["reproducible"] and res["finite"], res
     assert res["seed_changes_output"] > 1e-2 and res["eval_differs"] > 1e-2, res
     assert res["out_bias_grad_rel"] <= 1e-3, res
+
+
+@pytest.mark.xfail(strict=False, reason="not yet run on hardware: added after the round's GPU budget was spent (the same tape ran "
+                                        "green above; the autograd wrapper around it is checked on the CPU in test_training_graph.py)")
+def test_autograd_mode_under_the_reference_train_loss():
+    """UNet.autograd = True: the unmodified reference's train_loss + loss.mean().backward() drive this package's UNet on the
+    GPU; loss within 1e-3 and every .grad within the fp16 gradient bar of the same lines run with the oracle UNet on the CPU."""
+    res = _run("autograd_step", "small", 4, "fp16")
+    if "skipped" in res:
+        pytest.skip(res["skipped"])
+    assert res["plan_path_finite"]
+    assert res["loss_rel"] <= 1e-3, res
+    assert res["grad_rel_worst"] <= BARS["fp16"][1], res["worst"]
 
 
 @pytest.mark.xfail(strict=False, reason="not yet run on hardware: the round's GPU budget ended before a 2-GPU box could be used")

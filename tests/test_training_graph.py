@@ -405,3 +405,86 @@ def test_ctypes_argtypes_have_the_headers_arity():
             assert n == 0, f"{name}: {n} parameters in the header, no argtypes in _lib.py"
         else:
             assert len(at) == n, f"{name}: header has {n} parameters, _lib.py declares {len(at)}"
+
+
+def test_autograd_mode_runs_the_reference_training_lines_unchanged():
+    """UNet.autograd = True: the reference's own step -- loss = diffusion.train_loss(model, x_0, t, y, noise).mean();
+    loss.backward(); clip_grad_norm_; optimizer.step() (train_utils.py:137-163) -- written against this module exactly as
+    against the reference's, leaves in every .grad what autograd through the oracle UNet leaves (contract stand-in for the
+    kernels), and torch.optim.AdamW then moves the parameters identically."""
+    cfg = _cfg(hid=64, mult=(1, 2), nrb=1, attn=(False, True), num_classes=10)
+    sd, net = _build(cfg, seed=4)
+    net.autograd, net._train_ops = True, ContractOps()
+    net.train()
+    g = torch.Generator().manual_seed(12)
+    x0 = torch.randn(3, 3, 8, 8, generator=g).clamp(-1, 1)
+    t = torch.rand(3, generator=g, dtype=torch.float64)
+    noise = torch.randn(3, 3, 8, 8, generator=g)
+    y = torch.tensor([2, 0, 9])
+    from oracle import train_loss as oracle_train_loss
+
+    def run(denoise_fn, params):
+        opt = torch.optim.AdamW(params, lr=2e-4, weight_decay=0.001)
+        per, _ = oracle_train_loss(denoise_fn, x0, t, y.clone(), noise, model_out_type="v", reweight_type="snr_trunc")
+        loss = per.mean()
+        loss.backward()
+        total = torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)
+        opt.step()
+        return float(loss.detach()), float(total)
+
+    mine = run(lambda a, b, c: net(a.double(), b, c).float(), list(net.parameters()))
+    ref_p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = run(lambda a, b, c: _unet_forward(ref_p, cfg, a, b, c, None), list(ref_p.values()))
+    assert abs(mine[0] - ref[0]) <= 1e-5 * abs(ref[0]) and abs(mine[1] - ref[1]) <= 1e-4 * ref[1], (mine, ref)
+    for k, p in net.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape, k
+        step_mine, step_ref = p.detach().float() - sd[k], ref_p[k].detach() - sd[k]
+        # AdamW's first step is lr * g / (|g| + eps): entries with |g| ~ 1e-8 are sensitive to the last bit of g, the rest are not
+        d = (step_mine - step_ref).abs()
+        assert d.mean() <= 1e-6 and (d > 2e-5).float().mean() <= 1e-3 and d.max() <= 4.1e-4, (k, d.mean().item(), d.max().item())
+    # without grad mode (sampling) or with autograd off, forward() stays the plan path, which refuses a CPU tensor
+    net.autograd = False
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(x0, t, y)
+
+
+def test_reference_train_loss_drives_the_autograd_unet():
+    """The UNMODIFIED reference's GaussianDiffusion.train_loss (oracle/_ref, staged from /root/reference in the build
+    container) called with this package's UNet (autograd mode, contract stand-in for the kernels) as its denoise_fn, then
+    loss.mean().backward() as in Trainer.step: same loss and same gradients as with the oracle UNet as denoise_fn."""
+    from oracle import stage_ref
+    if not stage_ref.staged():
+        pytest.skip("oracle/_ref is staged only where /root/reference exists")
+    ref = stage_ref.load()
+    cfg = _cfg(hid=64, mult=(1, 1), nrb=1, attn=(True, False), num_classes=10)
+    sd, net = _build(cfg, seed=6)
+    net.autograd, net._train_ops = True, ContractOps()
+    net.train()
+    diffusion = ref.GaussianDiffusion(logsnr_fn=ref.get_logsnr_schedule("cosine", logsnr_min=-20., logsnr_max=20.), sample_timesteps=100,
+                                      model_out_type="v", model_var_type="fixed_medium", reweight_type="snr_trunc", loss_type="mse",
+                                      intp_frac=0.3, w_guide=0.1, p_uncond=0.1)
+    g = torch.Generator().manual_seed(13)
+    x0 = torch.randn(2, 3, 8, 8, generator=g).clamp(-1, 1)
+    t = torch.rand(2, generator=g, dtype=torch.float64)
+    noise = torch.randn(2, 3, 8, 8, generator=g)
+    y = torch.tensor([7, 1])
+    loss = diffusion.train_loss(lambda a, b, c: net(a.double(), b, c).float(), x_0=x0, t=t, y=y.clone(), noise=noise)
+    assert loss.shape == (2,)
+    loss.mean().backward()
+    ref_p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    want = diffusion.train_loss(lambda a, b, c: _unet_forward(ref_p, cfg, a, b, c, None), x_0=x0, t=t, y=y.clone(), noise=noise)
+    want.mean().backward()
+    assert torch.allclose(loss.detach(), want.detach(), rtol=1e-5)
+    for k, p in net.named_parameters():
+        w = ref_p[k].grad
+        err = (p.grad.double() - w.double()).norm().item() / (w.double().norm().item() + 2e-5 * math.sqrt(w.numel()))
+        assert err <= 2e-4, (k, err)
+
+
+def test_gpu_worker_and_bench_block_dry_run():
+    """tests/train_step_worker.py (the GPU suite's child process) and bench.py's train_step block, run here on the CPU with
+    stand-ins for everything that needs a device (scripts/dryrun_train_worker.py): guards their host logic against bit-rot."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "dryrun_train_worker.py")], cwd=ROOT, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "dry run OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]

@@ -152,10 +152,49 @@ def dropout(case, B, operand):
     return dict(reproducible=same, finite=finite, seed_changes_output=rel(c, a), eval_differs=rel(e, a), out_bias_grad_rel=bias_rel)
 
 
+def autograd_step(case, B, operand):
+    """UNet.autograd = True: the UNMODIFIED reference's GaussianDiffusion.train_loss (oracle/_ref) with this package's UNet
+    as denoise_fn on the GPU, then loss.mean().backward() as in Trainer.step (train_utils.py:149-151) -- loss and every
+    parameter's .grad against the same lines with the oracle UNet on the CPU."""
+    from oracle import stage_ref
+    if not stage_ref.staged():
+        return dict(skipped="oracle/_ref not staged")
+    ref = stage_ref.load()
+    cfg, R = CASES[case]["cfg"], CASES[case]["res"]
+    sd, net = build(cfg, 37, operand)
+    net.autograd = True
+    net.train()
+    diffusion = ref.GaussianDiffusion(logsnr_fn=ref.get_logsnr_schedule("cosine", logsnr_min=-20., logsnr_max=20.), sample_timesteps=100,
+                                      model_out_type="v", model_var_type="fixed_medium", reweight_type="snr_trunc", loss_type="mse",
+                                      intp_frac=0.3, w_guide=0.1, p_uncond=0.1)
+    g = torch.Generator().manual_seed(55)
+    x0 = torch.randn(B, cfg["in_channels"], R, R, generator=g).clamp(-1, 1)
+    t = torch.rand(B, generator=g, dtype=torch.float64)
+    noise = torch.randn(x0.shape, generator=g)
+    y = torch.randint(1, cfg["num_classes"] + 1, (B,), generator=g)
+    with torch.enable_grad():
+        loss = diffusion.train_loss(net, x_0=x0.cuda(), t=t.cuda(), y=y.clone().cuda(), noise=noise.cuda())
+        loss.mean().backward()
+    torch.cuda.synchronize()
+    ref_p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    with torch.enable_grad():
+        want = diffusion.train_loss(lambda a, b, c: _unet_forward(ref_p, cfg, a, b, c, None), x_0=x0, t=t, y=y.clone(), noise=noise)
+        want.mean().backward()
+    errs = {}
+    for k, p in net.named_parameters():
+        w = ref_p[k].grad
+        errs[k] = rel(p.grad, w, floor=1e-7 * math.sqrt(w.numel()))
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:3]
+    with torch.no_grad():
+        sampled = net(x0.cuda(), t.cuda(), y.cuda())                       # no grad mode: still the plan path (dropout 0 here)
+    return dict(loss_rel=rel(loss, want), grad_rel_worst=worst[0][1], worst=worst, grad_rel_median=sorted(errs.values())[len(errs) // 2],
+                plan_path_finite=bool(torch.isfinite(sampled).all()))
+
+
 if __name__ == "__main__":
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.cuda.set_device(0)
     kind, case, B, operand = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
-    res = {"graph_parity": graph_parity, "train_steps": train_steps, "dropout": dropout}[kind](case, B, operand)
+    res = {"graph_parity": graph_parity, "train_steps": train_steps, "dropout": dropout, "autograd_step": autograd_step}[kind](case, B, operand)
     print("RESULT " + json.dumps(res))

@@ -468,6 +468,30 @@ class UNetTrainGraph:
         return grads
 
 
+class _UNetFunction(torch.autograd.Function):
+    """One autograd node for the whole UNet: forward = UNetTrainGraph.forward, backward = UNetTrainGraph.backward (the kernel
+    tape), handing each parameter its gradient.  No gradient flows to the images, times or labels (training never needs one)."""
+
+    @staticmethod
+    def forward(ctx, graph, names, x, t, y, *params):
+        ctx.graph, ctx.names = graph, names
+        return graph.forward(x, t, y)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        grads = ctx.graph.backward(grad_out.contiguous())
+        return (None, None, None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
+def unet_autograd_forward(model, x, t, y=None):
+    """``UNet.forward`` with ``UNet.autograd = True`` under grad mode: a fresh graph (tape) per call, so several forwards may
+    be outstanding before their backwards, like any autograd graph."""
+    graph = UNetTrainGraph(model, _ops=getattr(model, "_train_ops", None))
+    named = list(model.named_parameters())
+    return _UNetFunction.apply(graph, tuple(k for k, _ in named), x.detach(), t, y, *(p for _, p in named))
+
+
 class GradBucketReducer:
     """What DistributedDataParallel does to the gradients (train.py wraps the model in DDP; the reference relies on its
     bucketed all-reduce): average them over the ranks.  Gradients are packed into flat buckets of ``bucket_bytes`` in the

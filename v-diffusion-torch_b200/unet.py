@@ -130,6 +130,12 @@ class UNet(nn.Module):
         # 16-bit tensor-core operand format: "fp16" (default: 10-bit mantissa like the TF32 the reference's own
         # cuDNN convs use on GPU, same tcgen05 rate as bf16) or "bf16"
         self.operand_dtype = os.environ.get("VDT_OPERAND", "fp16")
+        # autograd = True: forward() under torch.enable_grad() returns a tensor attached to the autograd graph -- its backward
+        # is the explicit kernel tape of training.UNetTrainGraph and fills every parameter's .grad -- so the reference's own
+        # training loop (loss.backward(); clip_grad_norm_; optimizer.step(), train_utils.py:149-166) runs unchanged on this
+        # module.  Off by default: forward() is then inference / forward-only, whatever the grad mode.
+        self.autograd = False
+        self._train_ops = None             # test seam of training.UNetTrainGraph (None: the CUDA kernels, no fallback)
         self._plans = {}
         self._weights_epoch = 0            # bumped by whoever rewrites parameters behind torch's version counters (the optimizer kernel)
 
@@ -194,8 +200,14 @@ class UNet(nn.Module):
             pass
 
     # ------------------------------------------------------------------ forward (unet.py:286-322)
-    @torch.no_grad()
     def forward(self, x, t, y=None):
+        if self.autograd and torch.is_grad_enabled():
+            from .training import unet_autograd_forward
+            return unet_autograd_forward(self, x, t, y)
+        return self._forward_plan(x, t, y)
+
+    @torch.no_grad()
+    def _forward_plan(self, x, t, y=None):
         # .train(): forward with dropout active (unet.py:135, 146); the masks come from the library's Philox stream, seeded
         # per call from torch's global CPU generator (nn.Dropout draws from the global generator too).  Forward only.
         train = bool(self.training and self.drop_rate > 0.)
