@@ -311,8 +311,14 @@ def train_step_child(batch=128, steps=2, device=None):
     sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
     lr, wd, gn, decay = 2e-4, 0.001, 1.0, 0.9999                        # cifar10_cond.json "train"
     g = torch.Generator().manual_seed(4321)
-    x = torch.randn(batch, 3, 32, 32, generator=g).clamp(-1, 1).to(device)
+    x = (torch.rand(batch, 3, 32, 32, generator=g) * 2 - 1).to(device)      # SURVEY 8(d) cfg 5: x0 ~ U[-1, 1], t ~ U[0, 1) fp64
     y = (torch.randint(10, (batch,), generator=g) + 1).to(device)
+    gf_per_sample = 112.92                                                # fwd + bwd of the cifar10_cond UNet
+    peak = read_peaks()["tflops"]
+
+    def rate(ms):
+        tf = gf_per_sample * batch / (ms * 1e-3) / 1e3
+        return {"ms_per_step": ms, "images_per_s": batch / (ms * 1e-3), "unet_tflops": tf, "frac_of_sustained_bf16_peak": tf / peak}
     out = {"workload": "BASELINE configs[4]: cifar10_cond.json training step (v objective, continuous time, snr_trunc, "
                        f"p_uncond 0.1, drop_rate 0.2, clip 1.0 + AdamW + EMA), synthetic batch {batch} on one GPU",
            "batch": batch, "steps_timed": steps, "unit": "images/s"}
@@ -335,7 +341,7 @@ def train_step_child(batch=128, steps=2, device=None):
         n0 = _lib.lib().vdt_kernel_launches()
         ms, loss = timed(lambda: ts.step(x, y.clone()), 1)
         launches = (_lib.lib().vdt_kernel_launches() - n0) // (steps + 1)
-        out["this_path"] = {"ms_per_step": ms, "images_per_s": batch / (ms * 1e-3), "loss_last_step": loss,
+        out["this_path"] = {**rate(ms), "loss_last_step": loss,
                             "kernels_per_step": int(launches), "operands": net.operand_dtype,
                             "state": "parity-green composition over per-call kernel hooks, untuned (DESIGN.md section 7)"}
         del ts
@@ -372,7 +378,7 @@ def train_step_child(batch=128, steps=2, device=None):
                 for mode, tf32 in (("stock_flags_tf32_convs", True), ("strict_fp32", False)):
                     torch.backends.cudnn.allow_tf32 = tf32
                     ms, loss = timed(ref_step, 1 if mode == "strict_fp32" else 2)
-                    ref[mode] = {"ms_per_step": ms, "images_per_s": batch / (ms * 1e-3), "loss_last_step": loss}
+                    ref[mode] = {**rate(ms), "loss_last_step": loss}
             finally:
                 torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
             out["reference_gpu_eager"] = ref
