@@ -92,7 +92,8 @@ int vdt_unet_forward(vdt_plan* plan, const float* x, const double* t, const void
 
 /* UNet.forward in .train() mode: the same network with nn.Dropout(drop_rate, inplace=True) active between act2 and conv2 of
  * every ResidualBlock (unet.py:135, 146).  The masks come from this library's Philox4x32-10 stream keyed by (seed, block,
- * element); drop_rate = 0 is bit-identical to vdt_unet_forward.  Forward only: the UNet backward is not part of this slice. */
+ * element); drop_rate = 0 is bit-identical to vdt_unet_forward.  Forward only (the plan keeps no activations): the differentiable path is
+ * the kernel tape of v-diffusion-torch_b200/training.py over the vdt_op_* entry points below. */
 int vdt_unet_forward_train(vdt_plan* plan, const float* x, const double* t, const void* y, float* out, int32_t batch,
                            float drop_rate, uint64_t seed, void* stream);
 
@@ -115,7 +116,7 @@ int vdt_p_sample_range(vdt_plan* plan, const vdt_sampler_config* sc, float* x, c
 int vdt_p_sample_host(vdt_plan* plan, const vdt_sampler_config* sc, const float* noise, const void* label,
                       const float* step_noise, float* out, int32_t batch);
 
-/* ---- training step, first slice: GaussianDiffusion.train_loss around the model call (diffusion.py:492-545) ------- */
+/* ---- training step: GaussianDiffusion.train_loss around the model call (diffusion.py:492-545) ------- */
 enum { VDT_REWEIGHT_CONSTANT = 0, VDT_REWEIGHT_SNR = 1, VDT_REWEIGHT_SNR_TRUNC = 2, VDT_REWEIGHT_SNR_1PLUS = 3 };
 /* Per-sample scalars from continuous times t in [0, 1] (HOST fp64 [B], Trainer.loss train_utils.py:137-147): out HOST
  * [B][16] floats, the vdt_step_coefficients slots 0-5, 11-13 (alpha, sigma, rsqrt(sigmoid l), exp(-l/2), sigmoid l,
@@ -184,7 +185,7 @@ int vdt_adamw_ema_step(float* param, const float* grad, float* exp_avg, float* e
 int vdt_op_conv(const void* x_16_nhwc, int32_t batch, int32_t h, int32_t w, int32_t cin, const float* w_oihw,
                 int32_t cout, int32_t ksize, const float* bias, const float* residual, float* out_nhwc, int32_t f16,
                 void* out16, void* stats_out, int32_t stat_cols, void* stream);
-/* Backward of a conv layer (F.conv2d under autograd, modules.py:141-144), first slice of the training step.
+/* Backward of a conv layer (F.conv2d under autograd, modules.py:141-144).
  * dgrad: dX fp32 NHWC [B, H, W, cin] = conv(dY, W rotated 180 degrees with its channel axes swapped) on the forward kernel;
  *        dy 16-bit NHWC [B, H, W, cout], w fp32 OIHW [cout, cin, k, k].
  * wgrad: dW fp32 OIHW [cout, cin, k, k] = sum over pixels of dY[p][co] * X[p + tap][ci] (tcgen05, both operands MN-major,

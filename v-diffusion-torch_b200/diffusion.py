@@ -206,10 +206,10 @@ class GaussianDiffusion:
     # ------------------------------------------------------------------ train_loss (diffusion.py:492-545)
     @torch.no_grad()
     def train_loss(self, denoise_fn, x_0, t, y, noise=None, return_grad=False):
-        """Forward half of the training step around the model call (first slice of SURVEY §8 f2): q_sample, the model
+        """Forward half of the training step around the model call: q_sample, the model
         call, from_model_out_to_pred and the re-weighted MSE, as two fused kernels.  Returns the per-sample loss (B,) on
         x_0's device; with ``return_grad`` also d loss.mean() / d model_out -- the tensor the reference's autograd hands
-        to the UNet's backward pass (the UNet backward itself is not part of this slice).
+        to the UNet's backward pass (training.TrainingStep passes its UNetTrainGraph as ``denoise_fn`` and feeds this gradient to the graph's backward).
 
         Reproduced as is: the label-dropout mask of ``p_uncond`` is applied to ``y`` in place AFTER the model call
         (diffusion.py:527-529 vs :508), so it changes the caller's tensor but never the loss; single-target reweightings

@@ -83,7 +83,7 @@ class UNet(nn.Module):
             apply_attn = [apply_attn] * levels
         self.apply_attn = list(apply_attn)
         self.num_res_blocks = num_res_blocks
-        self.drop_rate = drop_rate                              # active in .train() (forward only); identity in .eval()
+        self.drop_rate = drop_rate                              # active in .train(); identity in .eval()
         if head_dim is None and num_heads is None:
             num_heads = 1
         self.head_dim, self.num_heads = head_dim, num_heads
@@ -209,7 +209,8 @@ class UNet(nn.Module):
     @torch.no_grad()
     def _forward_plan(self, x, t, y=None):
         # .train(): forward with dropout active (unet.py:135, 146); the masks come from the library's Philox stream, seeded
-        # per call from torch's global CPU generator (nn.Dropout draws from the global generator too).  Forward only.
+        # per call from torch's global CPU generator (nn.Dropout draws from the global generator too).  Forward only: the
+        # differentiable path is training.UNetTrainGraph (self.autograd = True routes forward() to it under grad mode).
         train = bool(self.training and self.drop_rate > 0.)
         if x.ndim != 4 or x.shape[1] != self.in_channels or x.shape[2] != x.shape[3]:
             raise ValueError(f"expected x of shape (B, {self.in_channels}, R, R), got {tuple(x.shape)}")
