@@ -104,6 +104,16 @@ T.TrainingStep.__init__ = _init
 W.TrainingStep = T.TrainingStep
 _lib.lib().vdt_kernel_launches.restype = __import__("ctypes").c_uint64
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ddp":
+    # one rank of tests/train_step_ddp_worker.py (the two-GPU NCCL case) on the CPU over gloo; RANK / WORLD_SIZE / MASTER_* from the env
+    import torch.distributed as dist
+    _init_pg = dist.init_process_group
+    dist.init_process_group = lambda backend=None, **kw: _init_pg("gloo", **kw)
+    import tests.train_step_ddp_worker as D
+    D.TrainingStep = T.TrainingStep
+    D.main()
+    sys.exit(0)
+
 if __name__ == "__main__":
     r = W.graph_parity("small", 2, "fp16")
     print("graph_parity", {k: r[k] for k in ("out_rel", "grad_rel_worst", "grad_rel_median", "finite")})

@@ -488,3 +488,23 @@ def test_gpu_worker_and_bench_block_dry_run():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "dryrun_train_worker.py")], cwd=ROOT, capture_output=True,
                        text=True, timeout=900)
     assert r.returncode == 0 and "dry run OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_two_rank_training_step_dry_run_gloo():
+    """tests/train_step_ddp_worker.py (the two-GPU NCCL case of the GPU suite) on the CPU: two processes over gloo with the
+    same stand-ins -- loss reduce, bucketed gradient average, optimizer on every rank, EMA on the leader only; the replicas'
+    parameters stay bit-identical over three steps on different data, and they move."""
+    import json
+    import subprocess
+    port = 29800 + (os.getpid() % 1000)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "scripts", "dryrun_train_worker.py"), "ddp"], cwd=ROOT, env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\\n".join(o[1][-1500:] for o in outs)
+    lines = [ln for ln in outs[0][0].splitlines() if ln.startswith("RESULT ")]
+    assert lines, outs[0][0][-1000:]
+    res = json.loads(lines[-1][len("RESULT "):])
+    assert res["identical"] and res["finite"] and 0 < res["moved"] < 1e-2, res
