@@ -183,3 +183,29 @@ def build_train_inputs(case, cfg):
     noise = torch.randn(shape, generator=g)
     y = (torch.randint(10, (case["B"],), generator=g) + 1) if cfg["num_classes"] else None
     return x0, t, noise, y
+
+
+# ---- gradients of the training step, from the unmodified reference's autograd (tests/golden/make_train_grad_golden.py) ----
+# every block type of the CIFAR network at a quarter of the width: 128 / 256-channel norms, 1x1 skips, an avg-pool and a
+# nearest-upsample block, attention at 8x8 and (after the upsample) 16x16, class-conditional; objective of configs[4]
+TRAIN_GRAD_CASE = dict(cfg=_cfg(hid=128, mult=(1, 1), nrb=1, attn=(False, True), num_classes=10), wseed=51, seed=52, B=4, res=16,
+                       model_out_type="v", reweight_type="snr_trunc")
+
+
+def build_train_grad_inputs(case=TRAIN_GRAD_CASE):
+    cfg = case["cfg"]
+    g = torch.Generator().manual_seed(case["seed"])
+    shape = (case["B"], cfg["in_channels"], case["res"], case["res"])
+    x0 = torch.rand(shape, generator=g) * 2 - 1
+    t = torch.rand(case["B"], generator=g, dtype=torch.float64)
+    noise = torch.randn(shape, generator=g)
+    y = torch.randint(10, (case["B"],), generator=g) + 1
+    y[1] = 0                                                    # one unconditional row
+    return x0, t, noise, y
+
+
+def grad_probe(name, shape):
+    """Seeded N(0, 1) direction a gradient tensor is projected on (fixtures store |g| and <g, probe> per tensor)."""
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7fffffff)
+    return torch.randn(shape, generator=g, dtype=torch.float64)

@@ -1,6 +1,7 @@
 """CPU: the oracle restatement against fixtures produced by the unmodified reference
 (tests/golden/make_golden.py).  This is what pins the oracle."""
 import json
+import math
 import os
 
 import numpy as np
@@ -241,3 +242,34 @@ def test_numerics_model_of_the_cuda_path(golden_dir, name):
         err[mode] = (out - ref).abs().max().item()
     print(name, err)
     assert err["fp16"] <= 2e-2 and err["bf16"] > err["fp16"]
+
+
+def test_oracle_backward_matches_reference_gradients(golden_dir):
+    """The training step's gradients: torch autograd through the oracle UNet + the oracle train_loss against the gradients
+    the UNMODIFIED reference's own UNet / train_loss / autograd produced (tests/golden/make_train_grad_golden.py) -- loss,
+    every parameter gradient's norm and probe projection, and the small tensors in full.  This pins the checker the GPU
+    training tests compare the CUDA path with."""
+    from oracle import train_loss
+    from oracle.unet_ref import _unet_forward
+    from tests.cases import TRAIN_GRAD_CASE, build_train_grad_inputs, grad_probe
+    case = TRAIN_GRAD_CASE
+    cfg = case["cfg"]
+    g = _load(golden_dir, "train_grads_small.npz")
+    sd = {k: v.clone().requires_grad_(True) for k, v in make_state_dict(cfg, case["wseed"]).items()}
+    x0, t, noise, y = build_train_grad_inputs(case)
+    with torch.enable_grad():
+        loss, _ = train_loss(lambda a, b, c: _unet_forward(sd, cfg, a, b, c, None), x0, t, y, noise,
+                             model_out_type=case["model_out_type"], reweight_type=case["reweight_type"])
+        loss.mean().backward()
+    np.testing.assert_allclose(loss.detach().numpy(), g["loss"], rtol=1e-5)
+    names = [str(n) for n in g["names"]]
+    assert sorted(names) == sorted(sd)
+    for k in names:
+        gr = sd[k].grad.double()
+        n_ref = float(g["norm/" + k])
+        assert abs(gr.norm().item() - n_ref) <= 1e-4 * n_ref + 1e-9, k
+        p_ref = float(g["proj/" + k])
+        assert abs((gr * grad_probe(k, gr.shape)).sum().item() - p_ref) <= 1e-3 * n_ref + 1e-9, k
+        if ("full/" + k) in g.files:
+            full = torch.from_numpy(g["full/" + k]).double()
+            assert (gr - full).norm().item() <= 1e-4 * n_ref + 1e-9, k

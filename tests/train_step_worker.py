@@ -152,6 +152,38 @@ def dropout(case, B, operand):
     return dict(reproducible=same, finite=finite, seed_changes_output=rel(c, a), eval_differs=rel(e, a), out_bias_grad_rel=bias_rel)
 
 
+def grad_golden(case, B, operand):
+    """TrainingStep.loss_and_grads on the kernels against the gradients the UNMODIFIED reference's own UNet / train_loss /
+    autograd produced (tests/golden/train_grads_small.npz, made by tests/golden/make_train_grad_golden.py): per-sample loss,
+    every parameter gradient's norm and probe projection, the small tensors in full.  (case / B come from the fixture.)"""
+    import numpy as np
+    from tests.cases import TRAIN_GRAD_CASE, build_train_grad_inputs, grad_probe
+    c = TRAIN_GRAD_CASE
+    cfg = c["cfg"]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "train_grads_small.npz"))
+    sd, net = build(cfg, c["wseed"], operand)
+    net.train()
+    diff = GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), 1000, c["model_out_type"], "fixed_medium", c["reweight_type"],
+                             "mse", intp_frac=0.3, p_uncond=0.1)
+    ts = TrainingStep(net, diff, timesteps=0)
+    x0, t, noise, y = build_train_grad_inputs(c)
+    loss, grads = ts.loss_and_grads(x0.cuda(), y.cuda(), t=t.cuda(), noise=noise.cuda())
+    torch.cuda.synchronize()
+    loss_rel = float(np.abs(loss.cpu().numpy() - g["loss"]).max() / np.abs(g["loss"]).max())
+    norm_err, proj_err, full_err = {}, {}, {}
+    for k in (str(n) for n in g["names"]):
+        gr = grads[k].detach().double().cpu()
+        n_ref = float(g["norm/" + k])
+        norm_err[k] = abs(gr.norm().item() - n_ref) / n_ref
+        proj_err[k] = abs((gr * grad_probe(k, gr.shape)).sum().item() - float(g["proj/" + k])) / n_ref
+        if ("full/" + k) in g.files:
+            full_err[k] = (gr - torch.from_numpy(g["full/" + k]).double()).norm().item() / n_ref
+    top = lambda d: sorted(d.items(), key=lambda kv: -kv[1])[:3]
+    return dict(loss_rel=loss_rel, norm_rel_worst=top(norm_err)[0][1], proj_err_worst=top(proj_err)[0][1],
+                full_rel_worst=top(full_err)[0][1], n_params=len(norm_err), n_full=len(full_err),
+                worst=dict(norm=top(norm_err), proj=top(proj_err), full=top(full_err)))
+
+
 def autograd_step(case, B, operand):
     """UNet.autograd = True: the UNMODIFIED reference's GaussianDiffusion.train_loss (oracle/_ref) with this package's UNet
     as denoise_fn on the GPU, then loss.mean().backward() as in Trainer.step (train_utils.py:149-151) -- loss and every
@@ -196,5 +228,6 @@ if __name__ == "__main__":
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.cuda.set_device(0)
     kind, case, B, operand = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
-    res = {"graph_parity": graph_parity, "train_steps": train_steps, "dropout": dropout, "autograd_step": autograd_step}[kind](case, B, operand)
+    res = {"graph_parity": graph_parity, "train_steps": train_steps, "dropout": dropout, "autograd_step": autograd_step,
+           "grad_golden": grad_golden}[kind](case, B, operand)
     print("RESULT " + json.dumps(res))
