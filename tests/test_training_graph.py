@@ -508,3 +508,26 @@ def test_two_rank_training_step_dry_run_gloo():
     assert lines, outs[0][0][-1000:]
     res = json.loads(lines[-1][len("RESULT "):])
     assert res["identical"] and res["finite"] and 0 < res["moved"] < 1e-2, res
+
+
+def test_ema_weights_context_swaps_and_restores():
+    """``with step.ema():`` (the reference's ``with self.ema:``, utils.py:151-166): shadow in, live weights back out -- also
+    when the block raises -- and the model's plan cache is invalidated on both edges."""
+    from v_diffusion_b200.training import ema_weights
+    cfg = _cfg(hid=32, mult=(1,), nrb=1, attn=(False,))
+    _, net = _build(cfg, seed=2)
+    live = {k: p.detach().clone() for k, p in net.named_parameters()}
+    shadow = {k: v + 1.0 for k, v in live.items()}
+    e0 = net._weights_epoch
+    with ema_weights(net, shadow) as m:
+        assert m is net and net._weights_epoch == e0 + 1
+        assert all(torch.equal(p, shadow[k]) for k, p in net.named_parameters())
+    assert net._weights_epoch == e0 + 2
+    assert all(torch.equal(p, live[k]) for k, p in net.named_parameters())
+    with pytest.raises(ZeroDivisionError):
+        with ema_weights(net, shadow):
+            1 / 0
+    assert all(torch.equal(p, live[k]) for k, p in net.named_parameters())
+    with pytest.raises(RuntimeError, match="no EMA shadow"):
+        with ema_weights(net, {}):
+            pass

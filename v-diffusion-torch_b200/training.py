@@ -535,6 +535,37 @@ class GradBucketReducer:
         return out
 
 
+class ema_weights:
+    """``with self.ema:`` of the reference trainer (utils.py:151-166, used by Trainer.sample_fn train_utils.py:173-176): inside
+    the block the model's parameters hold the EMA shadow, afterwards the live weights are back.  Plain device copies; the
+    model's sampling plans are told to re-pack on both edges."""
+
+    def __init__(self, model, shadow):
+        self.model, self.shadow, self.backup = model, shadow, None
+
+    def _mark(self):
+        if hasattr(self.model, "mark_weights_changed"):
+            self.model.mark_weights_changed()
+
+    @torch.no_grad()
+    def __enter__(self):
+        if not self.shadow:
+            raise RuntimeError("this rank keeps no EMA shadow (use_ema=False, or not the leader: train_utils.py:127-130)")
+        self.backup = {k: p.detach().clone() for k, p in self.model.named_parameters()}
+        for k, p in self.model.named_parameters():
+            p.copy_(self.shadow[k])
+        self._mark()
+        return self.model
+
+    @torch.no_grad()
+    def __exit__(self, *exc):
+        for k, p in self.model.named_parameters():
+            p.copy_(self.backup[k])
+        self.backup = None
+        self._mark()
+        return False
+
+
 class TrainingStep:
     """``Trainer.loss`` + ``Trainer.step`` (train_utils.py:137-166) for one rank.
 
@@ -562,6 +593,30 @@ class TrainingStep:
         self.generator = torch.Generator(self.device).manual_seed(8191 + rank)          # train_utils.py:121
         self._accum, self._micro = None, 0
         self.last_grad_sq = None
+
+    def ema(self):
+        """Context manager: sample / evaluate with the EMA weights (``with self.ema:``, train_utils.py:173)."""
+        return ema_weights(self.model, self.optimizer.shadow)
+
+    @torch.no_grad()
+    def sample_fn(self, shape, label=None, use_ddim=False, seed=None, use_ema=True):
+        """Trainer.sample_fn (train_utils.py:168-186): ``p_sample`` of ``shape`` images on this rank with the EMA weights (where this
+        rank keeps them), gathered over the ranks when distributed.  Returns CPU fp32 images."""
+        import contextlib
+        import torch.distributed as dist
+        was_training = self.model.training
+        self.model.eval()
+        try:
+            with (self.ema() if (use_ema and self.optimizer.shadow) else contextlib.nullcontext()):
+                sample = self.diffusion.p_sample(denoise_fn=self.model, shape=tuple(shape), device=self.device, noise=None,
+                                                 label=label, seed=131071 + self.rank if seed is None else seed, use_ddim=use_ddim)
+        finally:
+            self.model.train(was_training)
+        if self.distributed:
+            parts = [torch.zeros(tuple(shape), device=self.device) for _ in range(self.world_size)]
+            dist.all_gather(parts, sample.to(self.device))
+            sample = torch.cat(parts, dim=0).cpu()
+        return sample
 
     def draw(self, x):
         """The random draws of Trainer.loss (train_utils.py:137-147): continuous or discrete fp64 times, then the noise."""
