@@ -531,3 +531,44 @@ def test_ema_weights_context_swaps_and_restores():
     with pytest.raises(RuntimeError, match="no EMA shadow"):
         with ema_weights(net, {}):
             pass
+
+
+def test_adamw_state_round_trips_through_torch_format():
+    """Checkpoint interop (train_utils.py:309-352): the moments leave and enter in torch.optim.AdamW.state_dict() form --
+    a state read from a real torch AdamW and written back loads into a fresh torch AdamW that then steps identically."""
+    from v_diffusion_b200.optim import torch_adamw_state, read_torch_adamw_state, strip_module_prefix
+    g = torch.Generator().manual_seed(4)
+    shapes = {"a.weight": (5, 3, 3, 3), "a.bias": (5,), "b.weight": (7, 4)}
+    names = list(shapes)
+
+    def fresh():
+        gg = torch.Generator().manual_seed(9)
+        ps = [torch.nn.Parameter(torch.randn(s, generator=gg)) for s in shapes.values()]
+        return ps, torch.optim.AdamW(ps, lr=2e-4, betas=(0.9, 0.999), weight_decay=0.001)
+
+    def run(ps, opt, n, seed):
+        gg = torch.Generator().manual_seed(seed)
+        for _ in range(n):
+            for p in ps:
+                p.grad = torch.randn(p.shape, generator=gg)
+            opt.step()
+    p1, o1 = fresh()
+    assert read_torch_adamw_state(o1.state_dict(), names)[2] == 0                  # fresh optimizer: no state yet
+    run(p1, o1, 3, 1)
+    exp_avg, exp_avg_sq, step, group = read_torch_adamw_state(o1.state_dict(), names)
+    assert step == 3 and group["lr"] == 2e-4 and set(exp_avg) == set(names)
+    emitted = torch_adamw_state(names, exp_avg, exp_avg_sq, step, group["lr"], group["betas"], group["eps"], group["weight_decay"])
+    p2, o2 = fresh()
+    with torch.no_grad():
+        for a, b in zip(p2, p1):
+            a.copy_(b)
+    import copy
+    o2.load_state_dict(copy.deepcopy(emitted))            # (torch's load_state_dict keeps same-dtype tensors by reference)
+    run(p1, o1, 2, 2)
+    run(p2, o2, 2, 2)
+    assert all(torch.equal(a, b) for a, b in zip(p1, p2))
+    assert strip_module_prefix({"module.x.weight": 1, "y": 2}) == {"x.weight": 1, "y": 2}
+    bad = o1.state_dict()
+    bad["param_groups"].append(dict(bad["param_groups"][0]))
+    with pytest.raises(RuntimeError, match="single AdamW parameter group"):
+        read_torch_adamw_state(bad, names)

@@ -15,6 +15,39 @@ import torch
 from . import _lib
 
 
+def torch_adamw_state(names, exp_avg, exp_avg_sq, step, lr, betas, eps, weight_decay):
+    """The moments in ``torch.optim.AdamW.state_dict()`` form (what the reference's checkpoints hold under "optimizer",
+    train_utils.py:328-352): parameter i of ``model.parameters()`` <-> names[i]."""
+    state = {}
+    if step > 0:
+        for i, k in enumerate(names):
+            state[i] = {"step": torch.tensor(float(step)), "exp_avg": exp_avg[k], "exp_avg_sq": exp_avg_sq[k]}
+    group = {"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay, "amsgrad": False, "maximize": False,
+             "foreach": None, "capturable": False, "differentiable": False, "fused": None, "params": list(range(len(names)))}
+    return {"state": state, "param_groups": [group]}
+
+
+def read_torch_adamw_state(sd, names):
+    """Inverse of torch_adamw_state for a checkpoint written by torch.optim.AdamW (one parameter group, every parameter in it,
+    in ``model.parameters()`` order).  Returns (exp_avg, exp_avg_sq, step, param_group); (None, None, 0, group) for a fresh one."""
+    groups = sd["param_groups"]
+    if len(groups) != 1 or list(groups[0]["params"]) != list(range(len(names))):
+        raise RuntimeError("expected the reference's single AdamW parameter group over model.parameters() (train.py:158)")
+    if not sd["state"]:
+        return None, None, 0, groups[0]
+    steps = {int(float(sd["state"][i]["step"])) for i in range(len(names))}
+    if len(steps) != 1:
+        raise RuntimeError(f"parameters disagree on the step count: {sorted(steps)}")
+    exp_avg = {k: sd["state"][i]["exp_avg"] for i, k in enumerate(names)}
+    exp_avg_sq = {k: sd["state"][i]["exp_avg_sq"] for i, k in enumerate(names)}
+    return exp_avg, exp_avg_sq, steps.pop(), groups[0]
+
+
+def strip_module_prefix(d):
+    """DDP checkpoints carry a "module." prefix on every key (generate.py:40-42, train_utils.py:320-324)."""
+    return {(k.split(".", 1)[1] if k.startswith("module.") else k): v for k, v in d.items()}
+
+
 class AdamWEMA:
     def __init__(self, named_params, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_norm=1.0, ema_decay=0.9999,
                  use_ema=True):
@@ -61,6 +94,34 @@ class AdamWEMA:
                                             self.weight_decay, self.step_count, _lib.ptr(self._sq) if clip else None,
                                             float(self.grad_norm or 0.0), decay, st))
         return self._sq
+
+    # ---- checkpoint interop with the reference trainer (train_utils.py:309-352): torch.optim.AdamW's and EMA's own formats
+    def state_dict(self):
+        return torch_adamw_state(list(self.params), self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas, self.eps,
+                                 self.weight_decay)
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        exp_avg, exp_avg_sq, step, group = read_torch_adamw_state(sd, list(self.params))
+        self.lr, self.betas, self.eps, self.weight_decay = group["lr"], tuple(group["betas"]), group["eps"], group["weight_decay"]
+        self.step_count = step
+        for k in self.params:
+            if exp_avg is None:
+                self.exp_avg[k].zero_(); self.exp_avg_sq[k].zero_()
+            else:
+                self.exp_avg[k].copy_(exp_avg[k]); self.exp_avg_sq[k].copy_(exp_avg_sq[k])
+
+    @torch.no_grad()
+    def load_ema_state_dict(self, d):
+        """``ckpt["ema"]`` of a reference checkpoint (utils.py:168-190); strict on the key set like EMA.load_state_dict."""
+        shadow = strip_module_prefix(d["shadow"])
+        if set(shadow) != set(self.params):
+            raise RuntimeError(f"EMA key mismatch: {sorted(set(shadow) ^ set(self.params))[:4]} ...")
+        if not self.shadow:
+            self.shadow = {k: p.detach().clone() for k, p in self.params.items()}
+        for k in self.params:
+            self.shadow[k].copy_(shadow[k])
+        self.decay, self.num_updates = d["decay"], int(d["num_updates"])
 
     def ema_state_dict(self):
         """The reference checkpoint's ``ckpt["ema"]`` entry (utils.py:168-173)."""

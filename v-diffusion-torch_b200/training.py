@@ -618,6 +618,37 @@ class TrainingStep:
             sample = torch.cat(parts, dim=0).cpu()
         return sample
 
+    # ---- checkpoints in the reference trainer's format (train_utils.py:309-352): {"model", "optimizer", "ema", "epoch", "rng"}
+    def checkpoint(self, epoch=0, **extra_info):
+        """``extra_info`` is merged in like Trainer.save_checkpoint(ckpt_path, **extra_info) does -- e.g. ``scheduler=
+        lr_scheduler.state_dict()`` (the learning-rate schedule is the caller's) or ``rng=[...]``."""
+        ckpt = {"model": {k: v.detach().cpu() for k, v in self.model.state_dict().items()},
+                "optimizer": self.optimizer.state_dict(), "epoch": int(epoch)}
+        if self.optimizer.shadow:
+            ckpt["ema"] = self.optimizer.ema_state_dict()
+        ckpt.update(extra_info)
+        return ckpt
+
+    def save_checkpoint(self, path, epoch=0, **extra_info):
+        if self.is_leader:
+            torch.save(self.checkpoint(epoch, **extra_info), path)
+
+    @torch.no_grad()
+    def load_checkpoint(self, path_or_dict, map_location="cpu"):
+        """Resume from a checkpoint written by this class or by the reference's Trainer.save_checkpoint (DDP "module." prefixes
+        accepted).  Returns the stored epoch."""
+        from .optim import strip_module_prefix
+        ckpt = path_or_dict if isinstance(path_or_dict, dict) else torch.load(path_or_dict, map_location=map_location)
+        if "rng" in ckpt:
+            self.generator.set_state(ckpt["rng"][int(self.rank)])
+        self.model.load_state_dict(strip_module_prefix(ckpt["model"]), strict=True)
+        if hasattr(self.model, "mark_weights_changed"):
+            self.model.mark_weights_changed()
+        self.optimizer.load_state_dict(ckpt["optimizer"])
+        if "ema" in ckpt and self.is_leader:
+            self.optimizer.load_ema_state_dict(ckpt["ema"])
+        return int(ckpt.get("epoch", 0))
+
     def draw(self, x):
         """The random draws of Trainer.loss (train_utils.py:137-147): continuous or discrete fp64 times, then the noise."""
         B, T = x.shape[0], self.timesteps
