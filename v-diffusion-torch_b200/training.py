@@ -29,14 +29,12 @@ seam tests/test_training_graph.py uses to check the *orchestration* -- which gra
 with a stand-in that models each call's contract in fp64.)
 """
 import ctypes as C
-import math
 
 import torch
 import torch.nn.functional as F
 
 from . import _lib
 
-_RESAMPLE = {"none": 0, "down": 1, "up": 2}
 _PAD = 128            # in_conv's im2col depth and out_conv's channel count are padded to this (tested GEMM shapes)
 
 
