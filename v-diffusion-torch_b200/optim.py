@@ -8,8 +8,6 @@ as two kernels per parameter tensor: a deterministic sum of squared gradients in
 weight decay + Adam moments + bias-corrected update + EMA in one pass (vdt_grad_sq_accumulate, vdt_adamw_ema_step).
 The learning-rate schedule (LambdaLR warm-up, train.py:161-162) stays with the caller: pass ``lr`` per step.
 """
-import ctypes as C
-
 import torch
 
 from . import _lib
