@@ -248,8 +248,10 @@ class UNetTrainGraph:
     def _unscale(inv, *ts):
         return tuple(t if (inv is None or t is None) else t * inv for t in ts)
 
-    def _conv_backward(self, a16, dy, w, ksize, need_dx=True):
-        dy16, inv = self._scaled(dy.contiguous())
+    def _conv_backward(self, a16, dy, w, ksize, need_dx=True, scaled=None):
+        """``scaled``: the (16-bit copy, inverse factor) pair of ``dy`` when the caller already made it (a block's output
+        gradient feeds both conv2's and the 1x1 skip conv's backward)."""
+        dy16, inv = scaled if scaled is not None else self._scaled(dy.contiguous())
         return self._unscale(inv, *self.ops.conv_backward(a16, dy16, w, ksize, need_dx))
 
     def _linear_nobias(self, x, w):
@@ -360,7 +362,8 @@ class UNetTrainGraph:
         out = ops.conv(a2, w2, b2, skip, 3)
 
         def backward(dout):
-            da2, dw2, db2 = self._conv_backward(a2, dout, w2, 3)
+            dout16 = self._scaled(dout.contiguous())
+            da2, dw2, db2 = self._conv_backward(a2, dout, w2, 3, scaled=dout16)
             self._acc(n + ".conv2.weight", dw2); self._acc(n + ".conv2.bias", db2)
             dh1, dg2, dbe2, dfilm = ops.groupnorm_backward(h1, da2.contiguous(), g2, be2, film, True, drop, seed, layer)
             self._acc(n + ".norm2.weight", dg2); self._acc(n + ".norm2.bias", dbe2)
@@ -375,7 +378,7 @@ class UNetTrainGraph:
             dx, dg1, dbe1, _ = ops.groupnorm_backward(xcat.contiguous(), da1.contiguous(), g1, be1, None, True, 0.0, 0, 0)
             self._acc(n + ".norm1.weight", dg1); self._acc(n + ".norm1.bias", dbe1)
             if has_skip:
-                ds, dws, dbs = self._conv_backward(raw16, dout, ws, 1)
+                ds, dws, dbs = self._conv_backward(raw16, dout, ws, 1, scaled=dout16)
                 self._acc(n + ".skip.weight", dws); self._acc(n + ".skip.bias", dbs)
                 dx = dx + ds
             else:
