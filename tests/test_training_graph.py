@@ -1,7 +1,7 @@
 """CPU tests of the composed training step's host logic (v-diffusion-torch_b200/training.py).
 
 The product runs ``UNetTrainGraph`` on ``KernelOps`` (ctypes into the CUDA library, no fallback).  What can be checked
-without a GPU is the *orchestration*: the block order read off the module tree, which tensor feeds which call, where every
+without a GPU is the *orchestration* (the tests monkeypatch the module's ``KernelOps`` name; the package has no backend switch): the block order read off the module tree, which tensor feeds which call, where every
 gradient flows (concat splits, the skip stack, resample adjoints, the FiLM / embedding chain, in_conv's im2col and out_conv's
 padded GEMM).  ``ContractOps`` below is test infrastructure: it models the documented contract of each kernel-level entry point
 (include/vdt_b200.h) with fp64 torch ops, so the graph's output and every parameter gradient can be compared with autograd
@@ -143,6 +143,15 @@ class ContractOps:
         return dq
 
 
+@pytest.fixture
+def contract_ops(monkeypatch):
+    """Every graph built inside the test gets this ContractOps instance instead of KernelOps (the package itself has no switch)."""
+    import v_diffusion_b200.training as T
+    ops = ContractOps()
+    monkeypatch.setattr(T, "KernelOps", lambda operand_dtype="fp16": ops)
+    return ops
+
+
 def _build(cfg, seed, drop_rate=0.0):
     sd = make_state_dict(cfg, seed)
     net = UNet(cfg["in_channels"], cfg["hid_channels"], cfg["out_channels"], cfg["ch_multipliers"], cfg["num_res_blocks"],
@@ -166,7 +175,7 @@ GRAPH_CASES = {
 
 
 @pytest.mark.parametrize("name", sorted(GRAPH_CASES))
-def test_graph_orchestration_matches_autograd(name):
+def test_graph_orchestration_matches_autograd(name, contract_ops):
     """Output and EVERY parameter gradient of the composed forward / backward (fp64 contract model in place of the kernels)
     against torch autograd through the oracle UNet (fp32) for d (sum of out * go)."""
     case = GRAPH_CASES[name]
@@ -183,8 +192,8 @@ def test_graph_orchestration_matches_autograd(name):
         y = torch.tensor(case["labels"])
     else:
         y = None
-    ops = ContractOps()
-    graph = UNetTrainGraph(net, _ops=ops)
+    ops = contract_ops
+    graph = UNetTrainGraph(net)
     out = graph.forward(x.double(), t, y)
     grads = graph.backward(go.double())
 
@@ -216,7 +225,7 @@ def test_graph_orchestration_matches_autograd(name):
         assert fam in ops.calls, fam
 
 
-def test_graph_dropout_uses_one_stream_for_forward_and_backward():
+def test_graph_dropout_uses_one_stream_for_forward_and_backward(contract_ops):
     """.train() with drop_rate > 0: the backward regenerates the forward's masks from (seed, layer); the gradient is the one
     autograd gives for the same masks (checked by finite differences on one weight), and a different seed changes the output."""
     cfg = _cfg(hid=32, mult=(1, 2), nrb=1, attn=(False, True), num_classes=0)
@@ -226,7 +235,7 @@ def test_graph_dropout_uses_one_stream_for_forward_and_backward():
     x = torch.randn(2, 3, 8, 8, generator=g).double()
     t = torch.rand(2, generator=g, dtype=torch.float64)
     go = torch.randn(2, 3, 8, 8, generator=g).double()
-    graph = UNetTrainGraph(net, _ops=ContractOps())
+    graph = UNetTrainGraph(net)
     out = graph.forward(x, t, None, seed=1234)
     grads = graph.backward(go)
     again = graph.forward(x, t, None, seed=1234)
@@ -344,7 +353,12 @@ def test_grad_bucket_reducer_single_rank_is_identity():
 
 
 def test_kernel_ops_is_the_only_product_backend():
-    """No fallback: the graph builds KernelOps unless a test hands it a stand-in, and KernelOps refuses CPU tensors."""
+    """No fallback, no switch: a graph always builds KernelOps (tests can only monkeypatch the name), and KernelOps refuses
+    CPU tensors."""
+    import inspect
+    from v_diffusion_b200.training import TrainingStep
+    assert list(inspect.signature(UNetTrainGraph.__init__).parameters) == ["self", "model"]
+    assert "ops" not in " ".join(inspect.signature(TrainingStep.__init__).parameters)
     from v_diffusion_b200.training import KernelOps
     cfg = _cfg(hid=32, mult=(1,), nrb=1, attn=(False,))
     _, net = _build(cfg, seed=1)
@@ -407,14 +421,14 @@ def test_ctypes_argtypes_have_the_headers_arity():
             assert len(at) == n, f"{name}: header has {n} parameters, _lib.py declares {len(at)}"
 
 
-def test_autograd_mode_runs_the_reference_training_lines_unchanged():
+def test_autograd_mode_runs_the_reference_training_lines_unchanged(contract_ops):
     """UNet.autograd = True: the reference's own step -- loss = diffusion.train_loss(model, x_0, t, y, noise).mean();
     loss.backward(); clip_grad_norm_; optimizer.step() (train_utils.py:137-163) -- written against this module exactly as
     against the reference's, leaves in every .grad what autograd through the oracle UNet leaves (contract stand-in for the
     kernels), and torch.optim.AdamW then moves the parameters identically."""
     cfg = _cfg(hid=64, mult=(1, 2), nrb=1, attn=(False, True), num_classes=10)
     sd, net = _build(cfg, seed=4)
-    net.autograd, net._train_ops = True, ContractOps()
+    net.autograd = True
     net.train()
     g = torch.Generator().manual_seed(12)
     x0 = torch.randn(3, 3, 8, 8, generator=g).clamp(-1, 1)
@@ -448,7 +462,7 @@ def test_autograd_mode_runs_the_reference_training_lines_unchanged():
         net(x0, t, y)
 
 
-def test_reference_train_loss_drives_the_autograd_unet():
+def test_reference_train_loss_drives_the_autograd_unet(contract_ops):
     """The UNMODIFIED reference's GaussianDiffusion.train_loss (oracle/_ref, staged from /root/reference in the build
     container) called with this package's UNet (autograd mode, contract stand-in for the kernels) as its denoise_fn, then
     loss.mean().backward() as in Trainer.step: same loss and same gradients as with the oracle UNet as denoise_fn."""
@@ -458,7 +472,7 @@ def test_reference_train_loss_drives_the_autograd_unet():
     ref = stage_ref.load()
     cfg = _cfg(hid=64, mult=(1, 1), nrb=1, attn=(True, False), num_classes=10)
     sd, net = _build(cfg, seed=6)
-    net.autograd, net._train_ops = True, ContractOps()
+    net.autograd = True
     net.train()
     diffusion = ref.GaussianDiffusion(logsnr_fn=ref.get_logsnr_schedule("cosine", logsnr_min=-20., logsnr_max=20.), sample_timesteps=100,
                                       model_out_type="v", model_var_type="fixed_medium", reweight_type="snr_trunc", loss_type="mse",

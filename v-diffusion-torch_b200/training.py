@@ -24,9 +24,9 @@ each such tensor is first multiplied by a power of two that brings its largest m
 multiplied back (exact, no host sync: the factor lives on the device), so d loss.mean() / d activations of order 1e-7 do
 not flush to zero; bf16 operands need no scaling.
 
-There is no CPU fallback: ``KernelOps`` is the only backend the product constructs.  (The private ``_ops`` parameter is the
-seam tests/test_training_graph.py uses to check the *orchestration* -- which gradient flows where -- against autograd
-with a stand-in that models each call's contract in fp64.)
+There is no CPU fallback and no backend switch: ``KernelOps`` is what every graph constructs.  (tests/test_training_graph.py
+checks the *orchestration* -- which gradient flows where -- against autograd by monkeypatching this module's ``KernelOps``
+name with a stand-in that models each call's contract in fp64; nothing in the package can select another backend.)
 """
 import ctypes as C
 
@@ -225,9 +225,9 @@ class UNetTrainGraph:
         grads = graph.backward(grad_out)            # {state_dict key: fp32 gradient}, what autograd leaves in .grad
     """
 
-    def __init__(self, model, _ops=None):
+    def __init__(self, model):
         self.model = model
-        self.ops = _ops if _ops is not None else KernelOps(model.operand_dtype)
+        self.ops = KernelOps(model.operand_dtype)
         self.blocks = block_list(model)
         if model.in_channels * 9 > _PAD or model.out_channels > _PAD:
             raise NotImplementedError(f"in_channels * 9 and out_channels must not exceed {_PAD}")
@@ -488,7 +488,7 @@ class _UNetFunction(torch.autograd.Function):
 def unet_autograd_forward(model, x, t, y=None):
     """``UNet.forward`` with ``UNet.autograd = True`` under grad mode: a fresh graph (tape) per call, so several forwards may
     be outstanding before their backwards, like any autograd graph."""
-    graph = UNetTrainGraph(model, _ops=getattr(model, "_train_ops", None))
+    graph = UNetTrainGraph(model)
     named = list(model.named_parameters())
     return _UNetFunction.apply(graph, tuple(k for k, _ in named), x.detach(), t, y, *(p for _, p in named))
 
@@ -578,7 +578,7 @@ class TrainingStep:
     """
 
     def __init__(self, model, diffusion, timesteps=0, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_norm=1.0,
-                 num_accum=1, use_ema=True, ema_decay=0.9999, distributed=False, rank=0, world_size=1, device=None, _ops=None):
+                 num_accum=1, use_ema=True, ema_decay=0.9999, distributed=False, rank=0, world_size=1, device=None):
         from .optim import AdamWEMA
         self.model, self.diffusion = model, diffusion
         self.timesteps, self.num_accum = int(timesteps), int(num_accum)
@@ -587,7 +587,7 @@ class TrainingStep:
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("v_diffusion_b200 trains on CUDA (sm_100a) only; there is no CPU fallback")
-        self.graph = UNetTrainGraph(model, _ops=_ops)
+        self.graph = UNetTrainGraph(model)
         # EMA lives on the leader only (train_utils.py:127-130)
         self.optimizer = AdamWEMA(model.named_parameters(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
                                   grad_norm=grad_norm, ema_decay=ema_decay, use_ema=bool(use_ema and self.is_leader))

@@ -135,7 +135,6 @@ class UNet(nn.Module):
         # training loop (loss.backward(); clip_grad_norm_; optimizer.step(), train_utils.py:149-166) runs unchanged on this
         # module.  Off by default: forward() is then inference / forward-only, whatever the grad mode.
         self.autograd = False
-        self._train_ops = None             # test seam of training.UNetTrainGraph (None: the CUDA kernels, no fallback)
         self._plans = {}
         self._weights_epoch = 0            # bumped by whoever rewrites parameters behind torch's version counters (the optimizer kernel)
 
