@@ -124,7 +124,7 @@ if __name__ == "__main__":
     r = W.train_steps("small", 2, "fp16", steps=2)
     print("train_steps", {k: v for k, v in r.items()})
     assert r["loss_rel_worst"] < 1e-5 and r["gnorm_rel_worst"] < 1e-4 and r["cosine_of_updates"] > 0.999 and r["ema_rel_worst"] < 1e-5, r
-    r = W.grad_golden("fixture", 0, "fp16")
+    r = W.grad_golden("small", 0, "fp16")
     print("grad_golden", {k: r[k] for k in ("loss_rel", "norm_rel_worst", "proj_err_worst", "full_rel_worst", "n_params", "n_full")})
     assert r["loss_rel"] < 1e-5 and r["norm_rel_worst"] < 1e-4 and r["proj_err_worst"] < 1e-3 and r["full_rel_worst"] < 1e-4, r
     from v_diffusion_b200 import UNet as _U

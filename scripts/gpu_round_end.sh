@@ -10,7 +10,7 @@ for wl in celeba cifar10_uncond mnist28; do
   timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_${wl}.json 2> gpurun_out/${tag}_bench_${wl}.err; echo "== bench $wl exit $?"
 done
 # the composed training step: parity cases one by one, then three steps at batch 128 with wall-clock per step
-for spec in "graph_parity cifar_cond 4 fp16" "graph_parity small 3 bf16" "train_steps small 8 fp16" "dropout small 4 fp16" "grad_golden fixture 0 fp16" "autograd_step small 4 fp16"; do
+for spec in "graph_parity cifar_cond 4 fp16" "graph_parity small 3 bf16" "train_steps small 8 fp16" "dropout small 4 fp16" "grad_golden small 0 fp16" "grad_golden cifar 0 fp16" "autograd_step small 4 fp16"; do
   timeout 600 python -m tests.train_step_worker $spec > gpurun_out/${tag}_train_$(echo $spec | tr " " _).log 2>&1; echo "== train_step_worker $spec exit $?"
 done
 timeout 300 python scripts/quick_train_step.py 128 > gpurun_out/${tag}_quick_train_step_b128.log 2>&1; echo "== quick_train_step exit $?"

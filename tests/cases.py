@@ -192,6 +192,11 @@ TRAIN_GRAD_CASE = dict(cfg=_cfg(hid=128, mult=(1, 1), nrb=1, attn=(False, True),
                        model_out_type="v", reweight_type="snr_trunc")
 
 
+# BASELINE configs[4]'s own network (cifar10_cond.json) at batch 4, 32x32
+TRAIN_GRAD_CASE_CIFAR = dict(cfg=CIFAR_COND, wseed=53, seed=54, B=4, res=32, model_out_type="v", reweight_type="snr_trunc")
+TRAIN_GRAD_CASES = {"small": TRAIN_GRAD_CASE, "cifar": TRAIN_GRAD_CASE_CIFAR}
+
+
 def build_train_grad_inputs(case=TRAIN_GRAD_CASE):
     cfg = case["cfg"]
     g = torch.Generator().manual_seed(case["seed"])

@@ -4,8 +4,8 @@
 
 The reference's own UNet (the oracle's deterministic weights strict-loaded, drop_rate 0) under the reference's own
 GaussianDiffusion.train_loss and torch autograd, `loss.mean().backward()` as in Trainer.step (train_utils.py:149-151), on the
-seeded inputs of tests/cases.py:TRAIN_GRAD_CASE.  Stored: the per-sample loss and, for every parameter, the gradient's norm and
-its projection on a seeded probe direction (cases.grad_probe); tensors of at most 4096 entries are stored in full.
+seeded inputs of tests/cases.py:TRAIN_GRAD_CASES (a small network with every block type, and cifar10_cond.json's own).  Stored: the per-sample loss and, for every parameter, the gradient's norm and
+its projection on a seeded probe direction (cases.grad_probe); tensors of at most 4096 (cifar: 1024) entries are stored in full.
 """
 import os
 import sys
@@ -24,11 +24,15 @@ sys.path.insert(0, "/root/reference")
 from v_diffusion import UNet, GaussianDiffusion, get_logsnr_schedule      # noqa: E402
 
 from oracle.unet_ref import make_state_dict                              # noqa: E402
-from tests.cases import TRAIN_GRAD_CASE, build_train_grad_inputs, grad_probe   # noqa: E402
+from tests.cases import TRAIN_GRAD_CASES, build_train_grad_inputs, grad_probe   # noqa: E402
 
 
 def main():
-    case = TRAIN_GRAD_CASE
+    for name, case in TRAIN_GRAD_CASES.items():
+        one(name, case)
+
+
+def one(name, case):
     cfg = case["cfg"]
     net = UNet(cfg["in_channels"], cfg["hid_channels"], cfg["out_channels"], cfg["ch_multipliers"], cfg["num_res_blocks"],
                cfg["apply_attn"], embedding_dim=cfg["embedding_dim"], drop_rate=0., head_dim=cfg["head_dim"],
@@ -49,11 +53,11 @@ def main():
         names.append(k)
         out["norm/" + k] = np.float64(g.norm().item())
         out["proj/" + k] = np.float64((g * grad_probe(k, g.shape)).sum().item())
-        if g.numel() <= 4096:
+        if g.numel() <= (4096 if name == "small" else 1024):
             out["full/" + k] = p.grad.numpy()
     out["names"] = np.array(names)
-    np.savez_compressed(os.path.join(HERE, "train_grads_small.npz"), **out)
-    print("train_grads_small:", len(names), "parameters, loss", loss.detach().numpy(),
+    np.savez_compressed(os.path.join(HERE, f"train_grads_{name}.npz"), **out)
+    print(f"train_grads_{name}:", len(names), "parameters, loss", loss.detach().numpy(),
           "total grad norm", float(torch.sqrt(sum(p.grad.double().pow(2).sum() for p in net.parameters()))))
 
 

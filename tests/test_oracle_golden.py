@@ -244,17 +244,18 @@ def test_numerics_model_of_the_cuda_path(golden_dir, name):
     assert err["fp16"] <= 2e-2 and err["bf16"] > err["fp16"]
 
 
-def test_oracle_backward_matches_reference_gradients(golden_dir):
+@pytest.mark.parametrize("which", ["small", "cifar"])
+def test_oracle_backward_matches_reference_gradients(golden_dir, which):
     """The training step's gradients: torch autograd through the oracle UNet + the oracle train_loss against the gradients
     the UNMODIFIED reference's own UNet / train_loss / autograd produced (tests/golden/make_train_grad_golden.py) -- loss,
     every parameter gradient's norm and probe projection, and the small tensors in full.  This pins the checker the GPU
     training tests compare the CUDA path with."""
     from oracle import train_loss
     from oracle.unet_ref import _unet_forward
-    from tests.cases import TRAIN_GRAD_CASE, build_train_grad_inputs, grad_probe
-    case = TRAIN_GRAD_CASE
+    from tests.cases import TRAIN_GRAD_CASES, build_train_grad_inputs, grad_probe
+    case = TRAIN_GRAD_CASES[which]                                      # "cifar": cifar10_cond.json's own network (configs[4])
     cfg = case["cfg"]
-    g = _load(golden_dir, "train_grads_small.npz")
+    g = _load(golden_dir, f"train_grads_{which}.npz")
     sd = {k: v.clone().requires_grad_(True) for k, v in make_state_dict(cfg, case["wseed"]).items()}
     x0, t, noise, y = build_train_grad_inputs(case)
     with torch.enable_grad():

@@ -4,6 +4,7 @@ line.  (A child, so that a device fault in this newest code path cannot take the
     python -m tests.train_step_worker graph_parity cifar_cond 4 fp16
     python -m tests.train_step_worker train_steps small 8 fp16
     python -m tests.train_step_worker dropout small 4 fp16
+    python -m tests.train_step_worker grad_golden cifar 0 fp16
 """
 import json
 import math
@@ -154,12 +155,12 @@ def dropout(case, B, operand):
 def grad_golden(case, B, operand):
     """TrainingStep.loss_and_grads on the kernels against the gradients the UNMODIFIED reference's own UNet / train_loss /
     autograd produced (tests/golden/train_grads_small.npz, made by tests/golden/make_train_grad_golden.py): per-sample loss,
-    every parameter gradient's norm and probe projection, the small tensors in full.  (case / B come from the fixture.)"""
+    every parameter gradient's norm and probe projection, the small tensors in full.  (B comes from the fixture.)"""
     import numpy as np
-    from tests.cases import TRAIN_GRAD_CASE, build_train_grad_inputs, grad_probe
-    c = TRAIN_GRAD_CASE
+    from tests.cases import TRAIN_GRAD_CASES, build_train_grad_inputs, grad_probe
+    c = TRAIN_GRAD_CASES[case]                                         # "small" | "cifar" (cifar10_cond.json's own network)
     cfg = c["cfg"]
-    g = np.load(os.path.join(ROOT, "tests", "golden", "train_grads_small.npz"))
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"train_grads_{case}.npz"))
     sd, net = build(cfg, c["wseed"], operand)
     net.train()
     diff = GaussianDiffusion(get_logsnr_schedule("cosine", -20., 20.), 1000, c["model_out_type"], "fixed_medium", c["reweight_type"],
