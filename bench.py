@@ -387,7 +387,7 @@ def train_step_child(batch=128, steps=2, device=None):
     print("TRAIN_STEP " + json.dumps(out), flush=True)
 
 
-def train_step_block(timeout_s=150):
+def train_step_block(timeout_s=120):
     """Runs train_step_child in its own process (a fault there cannot touch this process's CUDA context or its bench line)."""
     try:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--train-step-child"], capture_output=True, text=True,
