@@ -586,3 +586,13 @@ def test_adamw_state_round_trips_through_torch_format():
     bad["param_groups"].append(dict(bad["param_groups"][0]))
     with pytest.raises(RuntimeError, match="single AdamW parameter group"):
         read_torch_adamw_state(bad, names)
+
+
+def test_bench_train_step_block_never_breaks_the_bench_line():
+    """bench.py's train_step block runs in a child process; when the child fails (here: no GPU) the block comes back as an
+    {"error": ...} entry instead of an exception, so the headline JSON line is still printed."""
+    if torch.cuda.is_available():
+        pytest.skip("meant for the CPU-only container")
+    import bench
+    out = bench.train_step_block(timeout_s=120)
+    assert set(out) == {"error"} and "child rc=" in out["error"], out
